@@ -1,0 +1,94 @@
+"""ctypes binding of libcmdlmc_b200.so (the C ABI declared in include/cmdlmc_b200.h).
+
+The product path is CUDA-only: if the shared library has not been built, or no CUDA device can
+be bound, every entry point raises -- there is no CPU fallback and nothing here imports the
+oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcmdlmc_b200.so")
+
+
+class CmdError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("libcmdlmc_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+lp = C.POINTER(C.c_int64)
+u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/cmdlmc_b200.h declares
+SIGNATURES = {
+    "cmd_abi_version": (C.c_int, []),
+    "cmd_last_error": (C.c_char_p, []),
+    "cmd_init": (C.c_int, [C.c_int]),
+    "cmd_shutdown": (C.c_int, []),
+    "cmd_device_count": (C.c_int, [ip]),
+    "cmd_set_stream": (C.c_int, [vp]),
+    "cmd_sync": (C.c_int, []),
+    "cmd_launch_count": (C.c_int64, []),
+    "cmd_fp64_peak": (C.c_int, [C.c_int, dp]),
+    "cmd_box_create": (C.c_int, [dp, C.c_int, ip, C.POINTER(vp)]),
+    "cmd_box_set_hinv": (C.c_int, [vp, dp]),
+    "cmd_box_n_images": (C.c_int, [vp]),
+    "cmd_box_set_conversion": (C.c_int, [vp, C.c_int, dp]),
+    "cmd_box_query": (C.c_int, [vp, dp, dp, dp, dp]),
+    "cmd_box_destroy": (None, [vp]),
+    "cmd_length": (C.c_int, [vp, dp, dp, C.c_int64, dp]),
+    "cmd_distance": (C.c_int, [vp, dp, dp, C.c_int64, dp]),
+    "cmd_length_all_to_all": (C.c_int, [vp, dp, C.c_int64, dp, C.c_int64, dp]),
+    "cmd_angle": (C.c_int, [vp, dp, dp, dp, C.c_int64, dp]),
+    "cmd_next_neighbor": (C.c_int, [vp, dp, dp, C.c_int64, ip, dp]),
+    "cmd_position_extended_box": (C.c_int, [vp, C.c_int, dp, C.c_int, dp]),
+    "cmd_next_neighbor_extended_box": (C.c_int, [vp, C.c_int, dp, C.c_int, dp, C.c_int, ip, dp]),
+    "cmd_length_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp]),
+    "cmd_distance_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp]),
+    "cmd_length_all_to_all_dev": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64, vp]),
+    "cmd_angle_dev": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp]),
+    "cmd_rates": (C.c_int, [C.c_int, dp, dp, dp, C.c_int64, dp]),
+    "cmd_rates_dev": (C.c_int, [C.c_int, dp, vp, vp, C.c_int64, vp]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ImportError(
+                "%s is missing: build it with `python -m cmdlmc_b200.build` (nvcc, sm_100a). "
+                "cmdlmc_b200 has no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise CmdError(code, lib().cmd_last_error().decode("utf-8", "replace"))
+    return code
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def as_i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def ptr(a, typ=C.c_double):
+    return a.ctypes.data_as(C.POINTER(typ)) if a is not None else None

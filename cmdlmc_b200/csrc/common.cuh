@@ -1,0 +1,74 @@
+// common.cuh -- shared host/device declarations of libcmdlmc_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cmdlmc_b200.h"
+
+#define CMD_MAX_IMAGES 26
+
+// Box parameters as the kernels see them (passed by value as a __grid_constant__ argument).
+// Mirrors the state of the reference's AtomBox family (PBCHelper.pyx:30-32,216-226,248-260).
+struct BoxParams {
+    int kind;        // 0 orthorhombic (AtomBoxCubic), 1 general cell (AtomBoxMonoclinic)
+    int conv;        // CMD_CONV_*
+    double L[3];     // periodic_boundaries_extended (ortho)
+    double hL[3];    // L/2
+    double h[9];     // row-major, columns = cell vectors (extended)
+    double hinv[9];  // row-major inverse of h
+    double conv_par[5];
+    // images (i,j,k) != 0 that can beat the fractionally wrapped vector by more than rounding
+    // noise somewhere in the wrap cube; used by the FAST filter only (the exact stage always
+    // walks all 27 images in the reference order, numpyatom.pyx:111-123).
+    int n_img;
+    double img[CMD_MAX_IMAGES][3];  // Cartesian shift i*a + j*b + k*c
+};
+
+struct cmd_box {
+    BoxParams p;
+    int n_values;             // 3 or 9
+    double pbc[9];            // periodic_boundaries as given
+    double pbc_extended[9];   // periodic_boundaries_extended
+    double pbc_matrix[9];     // rows = cell vectors (NOT extended, PBCHelper.pyx:219-222,260)
+    int mult[3];
+};
+
+struct CmdGlobal {
+    bool inited = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = 0;
+    int64_t launches = 0;
+    // stream-ordered scratch for the host-pointer entry points
+    void *scratch[6] = {0, 0, 0, 0, 0, 0};
+    size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
+};
+
+CmdGlobal &cmd_global();
+int cmd_set_error(int code, const char *fmt, ...);
+int cmd_scratch(int slot, size_t bytes, void **out);  // grows slot to >= bytes
+
+#define CMD_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return cmd_set_error(CMD_ECUDA, "%s failed: %s (%s:%d)", #expr,                 \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);               \
+    } while (0)
+
+#define CMD_REQUIRE_INIT()                                                                  \
+    do {                                                                                    \
+        if (!cmd_global().inited)                                                           \
+            return cmd_set_error(CMD_ENODEV, "cmd_init() has not succeeded: no CUDA device " \
+                                             "bound (there is no CPU fallback)");           \
+    } while (0)
+
+#define CMD_LAUNCHED()                                                                      \
+    do {                                                                                    \
+        cmd_global().launches++;                                                            \
+        CMD_CUDA(cudaGetLastError());                                                       \
+    } while (0)
+
+static inline int cmd_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

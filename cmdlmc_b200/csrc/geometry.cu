@@ -1,0 +1,663 @@
+// geometry.cu -- library state, AtomBox handles and the batched geometry kernels
+// (AtomBox.length / distance / length_all_to_all / angle / next_neighbor, PBCHelper.pyx:56-185)
+// plus the stand-alone jump-rate kernel (jumprate_generators.py:33-43).
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "pbc.cuh"
+
+// ------------------------------------------------------------------ global state / errors ------
+static thread_local char g_err[512] = "";
+
+CmdGlobal &cmd_global()
+{
+    static CmdGlobal g;
+    return g;
+}
+
+int cmd_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cmd_scratch(int slot, size_t bytes, void **out)
+{
+    CmdGlobal &g = cmd_global();
+    if (bytes == 0) bytes = 16;
+    if (g.scratch_bytes[slot] < bytes) {
+        if (g.scratch[slot]) {
+            CMD_CUDA(cudaStreamSynchronize(g.stream));
+            CMD_CUDA(cudaFree(g.scratch[slot]));
+            g.scratch[slot] = nullptr;
+            g.scratch_bytes[slot] = 0;
+        }
+        size_t want = bytes + bytes / 4;
+        if (cudaMalloc(&g.scratch[slot], want) != cudaSuccess) {
+            cudaGetLastError();
+            return cmd_set_error(CMD_ENOMEM, "cudaMalloc of %zu scratch bytes failed", want);
+        }
+        g.scratch_bytes[slot] = want;
+    }
+    *out = g.scratch[slot];
+    return CMD_OK;
+}
+
+extern "C" int cmd_abi_version(void) { return CMD_ABI_VERSION; }
+extern "C" const char *cmd_last_error(void) { return g_err; }
+
+extern "C" int cmd_device_count(int *n)
+{
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        c = 0;
+    }
+    if (n) *n = c;
+    return CMD_OK;
+}
+
+extern "C" int cmd_init(int device)
+{
+    CmdGlobal &g = cmd_global();
+    int n = 0;
+    cmd_device_count(&n);
+    if (n <= 0)
+        return cmd_set_error(CMD_ENODEV, "no CUDA device visible: libcmdlmc_b200 has no CPU "
+                                         "fallback and cannot run here");
+    if (device < 0 || device >= n)
+        return cmd_set_error(CMD_EINVAL, "device %d out of range (%d devices)", device, n);
+    CMD_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CMD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return cmd_set_error(CMD_ENODEV, "device %d is sm_%d%d; this library is built for "
+                                         "sm_100a (B200) only", device, prop.major, prop.minor);
+    g.device = device;
+    g.sm_count = prop.multiProcessorCount;
+    g.inited = true;
+    return CMD_OK;
+}
+
+extern "C" int cmd_shutdown(void)
+{
+    CmdGlobal &g = cmd_global();
+    if (!g.inited) return CMD_OK;
+    cudaStreamSynchronize(g.stream);
+    for (int i = 0; i < 6; i++) {
+        if (g.scratch[i]) cudaFree(g.scratch[i]);
+        g.scratch[i] = nullptr;
+        g.scratch_bytes[i] = 0;
+    }
+    g.inited = false;
+    return CMD_OK;
+}
+
+extern "C" int cmd_set_stream(void *s)
+{
+    CMD_REQUIRE_INIT();
+    cmd_global().stream = (cudaStream_t)s;
+    return CMD_OK;
+}
+
+extern "C" int cmd_sync(void)
+{
+    CMD_REQUIRE_INIT();
+    CMD_CUDA(cudaStreamSynchronize(cmd_global().stream));
+    return CMD_OK;
+}
+
+extern "C" int64_t cmd_launch_count(void) { return cmd_global().launches; }
+
+// ------------------------------------------------------------------ FP64 peak probe -----------
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-6;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int cmd_fp64_peak(int iters, double *tflops)
+{
+    CMD_REQUIRE_INIT();
+    CmdGlobal &g = cmd_global();
+    int blocks = g.sm_count * 8, threads = 256;
+    void *buf;
+    int rc = cmd_scratch(5, (size_t)blocks * threads * sizeof(double), &buf);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    CMD_CUDA(cudaEventCreate(&e0));
+    CMD_CUDA(cudaEventCreate(&e1));
+    k_fp64_peak<<<blocks, threads, 0, g.stream>>>((double *)buf, iters / 8 + 1);  // warm-up
+    CMD_LAUNCHED();
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CMD_CUDA(cudaEventRecord(e0, g.stream));
+        k_fp64_peak<<<blocks, threads, 0, g.stream>>>((double *)buf, iters);
+        CMD_LAUNCHED();
+        CMD_CUDA(cudaEventRecord(e1, g.stream));
+        CMD_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        CMD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return CMD_OK;
+}
+
+// ------------------------------------------------------------------ AtomBox handle ------------
+static void invert3(const double *m, double *inv)
+{
+    // adjugate / determinant -- np.linalg.inv (LAPACK) differs in the last bits; callers that need
+    // the reference's exact h_inv pass it through cmd_box_set_hinv (the Python layer does).
+    double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    inv[0] = (e * i - f * h) / det; inv[1] = (c * h - b * i) / det; inv[2] = (b * f - c * e) / det;
+    inv[3] = (f * g - d * i) / det; inv[4] = (a * i - c * g) / det; inv[5] = (c * d - a * f) / det;
+    inv[6] = (d * h - e * g) / det; inv[7] = (b * g - a * h) / det; inv[8] = (a * e - b * d) / det;
+}
+
+static void box_prune_images(BoxParams &p)
+{
+    p.n_img = 0;
+    if (p.kind == 0) return;
+    for (int i = -1; i < 2; i++)
+        for (int j = -1; j < 2; j++)
+            for (int k = -1; k < 2; k++) {
+                if (!i && !j && !k) continue;
+                double T[3], g[3];
+                for (int c = 0; c < 3; c++) T[c] = i * p.h[3 * c] + j * p.h[3 * c + 1] + k * p.h[3 * c + 2];
+                double t2 = T[0] * T[0] + T[1] * T[1] + T[2] * T[2];
+                // g = h^T T ; the image can shorten the wrapped vector h s (|s_c| <= 1/2) iff
+                // |T|^2 < sum_c |g_c|
+                double sum = 0;
+                for (int c = 0; c < 3; c++) {
+                    g[c] = p.h[c] * T[0] + p.h[3 + c] * T[1] + p.h[6 + c] * T[2];
+                    sum += fabs(g[c]);
+                }
+                if (sum - t2 > 1e-13 * t2) {
+                    for (int c = 0; c < 3; c++) p.img[p.n_img][c] = T[c];
+                    p.n_img++;
+                }
+            }
+}
+
+extern "C" int cmd_box_create(const double *pb, int n_values, const int mult_in[3], cmd_box **out)
+{
+    if (!pb || !out || (n_values != 3 && n_values != 9))
+        return cmd_set_error(CMD_EINVAL, "periodic_boundaries must have 3 or 9 values");
+    int mult[3] = {1, 1, 1};
+    if (mult_in) memcpy(mult, mult_in, sizeof(mult));
+    for (int i = 0; i < 3; i++)
+        if (mult[i] < 1) return cmd_set_error(CMD_EINVAL, "box_multiplier must be >= 1");
+    cmd_box *b = (cmd_box *)calloc(1, sizeof(cmd_box));
+    if (!b) return cmd_set_error(CMD_ENOMEM, "out of host memory");
+    b->n_values = n_values;
+    memcpy(b->mult, mult, sizeof(mult));
+    memcpy(b->pbc, pb, n_values * sizeof(double));
+    BoxParams &p = b->p;
+    if (n_values == 3) {  // PBCHelper.pyx:216-226
+        p.kind = 0;
+        for (int i = 0; i < 3; i++) {
+            if (!(pb[i] > 0) || !isfinite(pb[i])) {
+                free(b);
+                return cmd_set_error(CMD_EINVAL, "box length %d must be positive and finite", i);
+            }
+            b->pbc_matrix[4 * i] = pb[i];
+            b->pbc_extended[i] = pb[i] * mult[i];
+            p.L[i] = b->pbc_extended[i];
+            p.hL[i] = p.L[i] / 2;
+            p.h[4 * i] = p.L[i];
+            p.hinv[4 * i] = 1.0 / p.L[i];
+        }
+    } else {  // PBCHelper.pyx:248-260
+        p.kind = 1;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                if (!isfinite(pb[3 * i + j])) {
+                    free(b);
+                    return cmd_set_error(CMD_EINVAL, "cell entries must be finite");
+                }
+                b->pbc_matrix[3 * i + j] = pb[3 * i + j];
+                b->pbc_extended[3 * i + j] = pb[3 * i + j] * mult[i];
+            }
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) p.h[3 * j + i] = b->pbc_extended[3 * i + j];
+        invert3(p.h, p.hinv);
+        for (int i = 0; i < 9; i++)
+            if (!isfinite(p.hinv[i])) {
+                free(b);
+                return cmd_set_error(CMD_EINVAL, "cell matrix is singular");
+            }
+        for (int i = 0; i < 3; i++) {
+            p.L[i] = sqrt(p.h[i] * p.h[i] + p.h[3 + i] * p.h[3 + i] + p.h[6 + i] * p.h[6 + i]);
+            p.hL[i] = p.L[i] / 2;
+        }
+    }
+    box_prune_images(p);
+    *out = b;
+    return CMD_OK;
+}
+
+// The reference computes h_inv with np.linalg.inv (PBCHelper.pyx:259); the Python layer hands
+// that exact matrix over so that device results are bit-identical with the oracle.
+extern "C" int cmd_box_set_hinv(cmd_box *b, const double hinv[9])
+{
+    if (!b || !hinv || b->p.kind != 1) return cmd_set_error(CMD_EINVAL, "general-cell box required");
+    memcpy(b->p.hinv, hinv, 9 * sizeof(double));
+    return CMD_OK;
+}
+
+extern "C" int cmd_box_set_conversion(cmd_box *b, int kind, const double par[5])
+{
+    if (!b || kind < CMD_CONV_NONE || kind > CMD_CONV_RAMP)
+        return cmd_set_error(CMD_EINVAL, "bad conversion kind");
+    if (b->p.kind != 0) return cmd_set_error(CMD_EINVAL, "AtomBoxWater is orthorhombic only");
+    b->p.conv = kind;
+    if (par) memcpy(b->p.conv_par, par, 5 * sizeof(double));
+    return CMD_OK;
+}
+
+extern "C" int cmd_box_query(const cmd_box *b, double *ext, double *pbcm, double *h, double *hinv)
+{
+    if (!b) return cmd_set_error(CMD_EINVAL, "null box");
+    if (ext) memcpy(ext, b->pbc_extended, b->n_values * sizeof(double));
+    if (pbcm) memcpy(pbcm, b->pbc_matrix, 9 * sizeof(double));
+    if (h) memcpy(h, b->p.h, 9 * sizeof(double));
+    if (hinv) memcpy(hinv, b->p.hinv, 9 * sizeof(double));
+    return CMD_OK;
+}
+
+extern "C" int cmd_box_n_images(const cmd_box *b) { return b ? b->p.n_img : -1; }
+
+extern "C" void cmd_box_destroy(cmd_box *b) { free(b); }
+
+// PBCHelper.pyx:39-53: atom = index % n, image = index / n, (i, j, k) with k fastest
+static void position_extended(const cmd_box *b, int index, const double *frame, int n, double *pos)
+{
+    int atom = index % n, box = index / n;
+    int i = box / (b->mult[1] * b->mult[2]), j = (box / b->mult[2]) % b->mult[1], k = box % b->mult[2];
+    for (int c = 0; c < 3; c++)
+        pos[c] = frame[3 * atom + c] + i * b->pbc_matrix[c] + j * b->pbc_matrix[3 + c] +
+                 k * b->pbc_matrix[6 + c];
+}
+
+extern "C" int cmd_position_extended_box(const cmd_box *b, int index, const double *frame, int n,
+                                         double out[3])
+{
+    if (!b || !frame || n <= 0 || index < 0) return cmd_set_error(CMD_EINVAL, "bad argument");
+    position_extended(b, index, frame, n, out);
+    return CMD_OK;
+}
+
+// ------------------------------------------------------------------ batched kernels -----------
+__device__ __forceinline__ void load3(const double *p, int64_t i, double v[3])
+{
+    v[0] = __ldg(p + 3 * i); v[1] = __ldg(p + 3 * i + 1); v[2] = __ldg(p + 3 * i + 2);
+}
+
+__global__ void __launch_bounds__(256) k_length(const __grid_constant__ BoxParams bx,
+                                                const double *__restrict__ a,
+                                                const double *__restrict__ b, int64_t n,
+                                                double *__restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double pa[3], pb[3];
+        load3(a, i, pa);
+        load3(b, i, pb);
+        out[i] = length_exact(bx, pa, pb);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_distance(const __grid_constant__ BoxParams bx,
+                                                  const double *__restrict__ a,
+                                                  const double *__restrict__ b, int64_t n,
+                                                  double *__restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double pa[3], pb[3], d[3];
+        load3(a, i, pa);
+        load3(b, i, pb);
+        distance_exact(bx, pa, pb, d);
+        out[3 * i] = d[0]; out[3 * i + 1] = d[1]; out[3 * i + 2] = d[2];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_angle(const __grid_constant__ BoxParams bx,
+                                               const double *__restrict__ a1,
+                                               const double *__restrict__ a2,
+                                               const double *__restrict__ a3, int64_t n,
+                                               double *__restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double p1[3], p2[3], p3[3];
+        load3(a1, i, p1);
+        load3(a2, i, p2);
+        load3(a3, i, p3);
+        out[i] = angle_exact(bx, p1, p2, p3);
+    }
+}
+
+// out[i][j] = length(a[i], b[j]); a 32x8 thread tile walks j fastest so stores coalesce and the
+// a-row is a broadcast; b rows come from L1/L2.
+__global__ void __launch_bounds__(256) k_all_to_all(const __grid_constant__ BoxParams bx,
+                                                    const double *__restrict__ a, int64_t n,
+                                                    const double *__restrict__ b, int64_t m,
+                                                    double *__restrict__ out)
+{
+    int64_t j = blockIdx.x * 32ll + threadIdx.x;
+    if (j >= m) return;
+    double pb[3];
+    load3(b, j, pb);
+    for (int64_t i = blockIdx.y * 8ll + threadIdx.y; i < n; i += (int64_t)gridDim.y * 8) {
+        double pa[3];
+        load3(a, i, pa);
+        out[i * m + j] = length_exact(bx, pa, pb);
+    }
+}
+
+// first index of the minimum length (strict '<' scan of the reference, PBCHelper.pyx:161-165)
+__global__ void __launch_bounds__(1024) k_next_neighbor(const __grid_constant__ BoxParams bx,
+                                                        const double *__restrict__ pos,
+                                                        const double *__restrict__ frame,
+                                                        int64_t n, int vector_norm,
+                                                        int *idx, double *dist)
+{
+    __shared__ double sd[32];
+    __shared__ int si[32];
+    double p[3] = {pos[0], pos[1], pos[2]};
+    double best = 1e30;
+    int bi = -1;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+        double q[3];
+        load3(frame, j, q);
+        double l;
+        if (vector_norm) {  // length_extended_box_ptr (PBCHelper.pyx:97-105): |distance_vector|
+            double d[3];
+            distance_exact(bx, p, q, d);
+            l = convert_distance(bx, sqrt(norm2_exact(d)));
+        } else {
+            l = length_exact(bx, p, q);
+        }
+        if (l < best) { best = l; bi = (int)j; }
+    }
+    auto better = [](double d1, int i1, double d2, int i2) {
+        // (d1,i1) beats (d2,i2): smaller distance, or equal distance and smaller valid index
+        if (i1 < 0) return false;
+        if (i2 < 0) return true;
+        return d1 < d2 || (d1 == d2 && i1 < i2);
+    };
+    for (int o = 16; o > 0; o >>= 1) {
+        double od = __shfl_down_sync(0xffffffffu, best, o);
+        int oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (better(od, oi, best, bi)) { best = od; bi = oi; }
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sd[w] = best; si[w] = bi; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        best = l < nw ? sd[l] : 1e30;
+        bi = l < nw ? si[l] : -1;
+        for (int o = 16; o > 0; o >>= 1) {
+            double od = __shfl_down_sync(0xffffffffu, best, o);
+            int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (better(od, oi, best, bi)) { best = od; bi = oi; }
+        }
+        if (l == 0) { *idx = bi; *dist = best; }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_rates(const __grid_constant__ RateParams rp,
+                                               const double *__restrict__ x,
+                                               const double *__restrict__ theta, int64_t n,
+                                               double *__restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = rate_eval(rp, x[i], theta ? theta[i] : 0.0);
+}
+
+static int grid_for(int64_t n, int threads)
+{
+    int64_t blocks = (n + threads - 1) / threads;
+    int64_t cap = (int64_t)cmd_global().sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ------------------------------------------------------------------ device-pointer entry points
+extern "C" int cmd_length_dev(const cmd_box *box, const double *a, const double *b, int64_t n,
+                              double *out)
+{
+    CMD_REQUIRE_INIT();
+    if (!box || n < 0) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (n == 0) return CMD_OK;
+    k_length<<<grid_for(n, 256), 256, 0, cmd_global().stream>>>(box->p, a, b, n, out);
+    CMD_LAUNCHED();
+    return CMD_OK;
+}
+
+extern "C" int cmd_distance_dev(const cmd_box *box, const double *a, const double *b, int64_t n,
+                                double *out)
+{
+    CMD_REQUIRE_INIT();
+    if (!box || n < 0) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (n == 0) return CMD_OK;
+    k_distance<<<grid_for(n, 256), 256, 0, cmd_global().stream>>>(box->p, a, b, n, out);
+    CMD_LAUNCHED();
+    return CMD_OK;
+}
+
+extern "C" int cmd_angle_dev(const cmd_box *box, const double *a1, const double *a2,
+                             const double *a3, int64_t n, double *out)
+{
+    CMD_REQUIRE_INIT();
+    if (!box || n < 0) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (n == 0) return CMD_OK;
+    k_angle<<<grid_for(n, 256), 256, 0, cmd_global().stream>>>(box->p, a1, a2, a3, n, out);
+    CMD_LAUNCHED();
+    return CMD_OK;
+}
+
+extern "C" int cmd_length_all_to_all_dev(const cmd_box *box, const double *a, int64_t n,
+                                         const double *b, int64_t m, double *out)
+{
+    CMD_REQUIRE_INIT();
+    if (!box || n < 0 || m < 0) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (n == 0 || m == 0) return CMD_OK;
+    dim3 block(32, 8);
+    int64_t gy = (n + 7) / 8;
+    if (gy > 4096) gy = 4096;
+    dim3 grid((unsigned)((m + 31) / 32), (unsigned)gy);
+    k_all_to_all<<<grid, block, 0, cmd_global().stream>>>(box->p, a, n, b, m, out);
+    CMD_LAUNCHED();
+    return CMD_OK;
+}
+
+extern "C" int cmd_rates_dev(int kind, const double par[CMD_RATE_NPAR], const double *x,
+                             const double *theta, int64_t n, double *out)
+{
+    CMD_REQUIRE_INIT();
+    if (kind < 0 || kind > CMD_RATE_EXP || !par || n < 0) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (kind == CMD_RATE_FERMI_ANGLE && !theta)
+        return cmd_set_error(CMD_EINVAL, "FermiAngle needs the angle array");
+    if (n == 0) return CMD_OK;
+    RateParams rp;
+    rp.kind = kind;
+    memcpy(rp.par, par, sizeof(rp.par));
+    k_rates<<<grid_for(n, 256), 256, 0, cmd_global().stream>>>(rp, x, theta, n, out);
+    CMD_LAUNCHED();
+    return CMD_OK;
+}
+
+// ------------------------------------------------------------------ host-pointer entry points -
+// Drop-in forms: copy in, launch, copy out, all stream-ordered on the library stream.
+static int upload(int slot, const void *h, size_t bytes, void **d)
+{
+    int rc = cmd_scratch(slot, bytes, d);
+    if (rc) return rc;
+    if (bytes) CMD_CUDA(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, cmd_global().stream));
+    return CMD_OK;
+}
+
+static int download(void *h, const void *d, size_t bytes)
+{
+    if (bytes) CMD_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, cmd_global().stream));
+    CMD_CUDA(cudaStreamSynchronize(cmd_global().stream));
+    return CMD_OK;
+}
+
+extern "C" int cmd_length(const cmd_box *box, const double *a, const double *b, int64_t n,
+                          double *out)
+{
+    CMD_REQUIRE_INIT();
+    if (!box || n < 0 || (n && (!a || !b || !out))) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (n == 0) return CMD_OK;
+    void *da, *db, *dout;
+    int rc;
+    if ((rc = upload(0, a, n * 24, &da)) || (rc = upload(1, b, n * 24, &db)) ||
+        (rc = cmd_scratch(2, n * 8, &dout)) ||
+        (rc = cmd_length_dev(box, (double *)da, (double *)db, n, (double *)dout)))
+        return rc;
+    return download(out, dout, n * 8);
+}
+
+extern "C" int cmd_distance(const cmd_box *box, const double *a, const double *b, int64_t n,
+                            double *out)
+{
+    CMD_REQUIRE_INIT();
+    if (!box || n < 0 || (n && (!a || !b || !out))) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (n == 0) return CMD_OK;
+    void *da, *db, *dout;
+    int rc;
+    if ((rc = upload(0, a, n * 24, &da)) || (rc = upload(1, b, n * 24, &db)) ||
+        (rc = cmd_scratch(2, n * 24, &dout)) ||
+        (rc = cmd_distance_dev(box, (double *)da, (double *)db, n, (double *)dout)))
+        return rc;
+    return download(out, dout, n * 24);
+}
+
+extern "C" int cmd_angle(const cmd_box *box, const double *a1, const double *a2, const double *a3,
+                         int64_t n, double *out)
+{
+    CMD_REQUIRE_INIT();
+    if (!box || n < 0 || (n && (!a1 || !a2 || !a3 || !out)))
+        return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (n == 0) return CMD_OK;
+    void *d1, *d2, *d3, *dout;
+    int rc;
+    if ((rc = upload(0, a1, n * 24, &d1)) || (rc = upload(1, a2, n * 24, &d2)) ||
+        (rc = upload(3, a3, n * 24, &d3)) || (rc = cmd_scratch(2, n * 8, &dout)) ||
+        (rc = cmd_angle_dev(box, (double *)d1, (double *)d2, (double *)d3, n, (double *)dout)))
+        return rc;
+    return download(out, dout, n * 8);
+}
+
+extern "C" int cmd_length_all_to_all(const cmd_box *box, const double *a, int64_t n,
+                                     const double *b, int64_t m, double *out)
+{
+    CMD_REQUIRE_INIT();
+    if (!box || n < 0 || m < 0 || (n && m && (!a || !b || !out)))
+        return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (n == 0 || m == 0) return CMD_OK;
+    void *da, *db, *dout;
+    int rc;
+    if ((rc = upload(0, a, n * 24, &da)) || (rc = upload(1, b, m * 24, &db)) ||
+        (rc = cmd_scratch(2, (size_t)n * m * 8, &dout)) ||
+        (rc = cmd_length_all_to_all_dev(box, (double *)da, n, (double *)db, m, (double *)dout)))
+        return rc;
+    return download(out, dout, (size_t)n * m * 8);
+}
+
+static int next_neighbor_impl(const cmd_box *box, const double *pos, const double *frame,
+                              int64_t n, int vector_norm, int *idx, double *dist)
+{
+    CMD_REQUIRE_INIT();
+    if (!box || n < 0 || !pos || !idx || !dist) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (n == 0) {  // the reference returns (-1, 1e30) for an empty frame
+        *idx = -1;
+        *dist = 1e30;
+        return CMD_OK;
+    }
+    void *dp, *df, *dres;
+    int rc;
+    if ((rc = upload(0, pos, 24, &dp)) || (rc = upload(1, frame, n * 24, &df)) ||
+        (rc = cmd_scratch(2, 16, &dres)))
+        return rc;
+    int threads = n >= 1024 ? 1024 : (int)((n + 31) / 32 * 32);
+    k_next_neighbor<<<1, threads, 0, cmd_global().stream>>>(box->p, (double *)dp, (double *)df, n,
+                                                            vector_norm, (int *)((char *)dres + 8),
+                                                            (double *)dres);
+    CMD_LAUNCHED();
+    char res[16];
+    if ((rc = download(res, dres, 16))) return rc;
+    memcpy(dist, res, 8);
+    memcpy(idx, res + 8, 4);
+    return CMD_OK;
+}
+
+extern "C" int cmd_next_neighbor(const cmd_box *box, const double *pos, const double *frame,
+                                 int64_t n, int *idx, double *dist)
+{
+    return next_neighbor_impl(box, pos, frame, n, 0, idx, dist);
+}
+
+// PBCHelper.pyx:169-185: both atoms are placed in the extended box first, then the wrapped
+// length in the extended cell is minimised over all images of frame_2.
+extern "C" int cmd_next_neighbor_extended_box(const cmd_box *box, int index_1, const double *f1,
+                                              int n1, const double *f2, int n2, int *idx,
+                                              double *dist)
+{
+    CMD_REQUIRE_INIT();
+    if (!box || !f1 || !f2 || n1 <= 0 || n2 <= 0 || index_1 < 0)
+        return cmd_set_error(CMD_EINVAL, "bad argument");
+    int nimg = box->mult[0] * box->mult[1] * box->mult[2];
+    double p1[3];
+    if (nimg == 1) {  // PBCHelper.pyx:145-146: plain indexing, no image shift
+        if (index_1 >= n1) return cmd_set_error(CMD_EINVAL, "index out of range");
+        memcpy(p1, f1 + 3 * index_1, 24);
+        return next_neighbor_impl(box, p1, f2, n2, 1, idx, dist);
+    }
+    position_extended(box, index_1, f1, n1, p1);
+    int64_t total = (int64_t)n2 * nimg;
+    double *ext = (double *)malloc(total * 24);
+    if (!ext) return cmd_set_error(CMD_ENOMEM, "out of host memory");
+    for (int64_t k = 0; k < total; k++) position_extended(box, (int)k, f2, n2, ext + 3 * k);
+    int rc = next_neighbor_impl(box, p1, ext, total, 1, idx, dist);
+    free(ext);
+    return rc;
+}
+
+extern "C" int cmd_rates(int kind, const double par[CMD_RATE_NPAR], const double *x,
+                         const double *theta, int64_t n, double *out)
+{
+    CMD_REQUIRE_INIT();
+    if (n < 0 || (n && (!x || !out))) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (n == 0) return CMD_OK;
+    void *dx, *dt = nullptr, *dout;
+    int rc;
+    if ((rc = upload(0, x, n * 8, &dx))) return rc;
+    if (theta && (rc = upload(1, theta, n * 8, &dt))) return rc;
+    if ((rc = cmd_scratch(2, n * 8, &dout)) ||
+        (rc = cmd_rates_dev(kind, par, (double *)dx, (double *)dt, n, (double *)dout)))
+        return rc;
+    return download(out, dout, n * 8);
+}

@@ -1,0 +1,216 @@
+// pbc.cuh -- device-side periodic-boundary geometry.
+//
+// Two families:
+//   *_exact : the reference's arithmetic, operation by operation, with explicit round-to-nearest
+//             intrinsics so that nvcc never contracts a*b+c into an FMA.  Results are bit-identical
+//             to the CPU oracle (oracle/cmdlmc_oracle.c, compiled with -ffp-contract=off) and
+//             agree with the reference build (which is -ffast-math) to ~1e-15 relative.
+//   *_fast  : FMA arithmetic with a pruned image set, used only as a conservative FILTER in the
+//             all-pairs kernels; every pair that survives the filter is re-evaluated exactly.
+#pragma once
+#include "common.cuh"
+
+// ---- A1: numpyatom.pyx:33-42 (diff_ptr): repeated +-L while outside [-L/2, L/2] (strict) ------
+__device__ __forceinline__ double wrap_ortho_exact(double d, double L, double hL)
+{
+    // Safety valve (documented divergence): the reference loops |d|/L times; beyond 64 box
+    // lengths we first remove whole boxes with one rounding and then finish with the exact loop.
+    if (fabs(d) > 64.0 * L) d = __dadd_rn(d, -__dmul_rn(L, rint(d / L)));
+    if (!(fabs(d) <= 128.0 * L)) return d;  // inf / nan: the reference would never return
+    while (d < -hL) d = __dadd_rn(d, L);
+    while (d > hL) d = __dadd_rn(d, -L);
+    return d;
+}
+
+__device__ __forceinline__ void diff_ortho_exact(const BoxParams &bx, const double a[3],
+                                                 const double b[3], double d[3])
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++) d[i] = wrap_ortho_exact(__dadd_rn(b[i], -a[i]), bx.L[i], bx.hL[i]);
+}
+
+// dx*dx + dy*dy + dz*dz in the reference's order, no FMA (numpyatom.pyx:179)
+__device__ __forceinline__ double norm2_exact(const double d[3])
+{
+    return __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));
+}
+
+// math_helper.pyx:50-60 (matrix_mult_ptr): r_i = ((0 + m_i0 v0) + m_i1 v1) + m_i2 v2
+__device__ __forceinline__ void matvec3_exact(const double m[9], double v[3])
+{
+    double r[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        r[i] = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(m[3 * i], v[0])),
+                                   __dmul_rn(m[3 * i + 1], v[1])),
+                         __dmul_rn(m[3 * i + 2], v[2]));
+    v[0] = r[0]; v[1] = r[1]; v[2] = r[2];
+}
+
+// ---- A3: numpyatom.pyx:61-74 (diff_ptr_nonortho); round = C99 round, half away from zero ------
+__device__ __forceinline__ void diff_general_exact(const BoxParams &bx, const double a[3],
+                                                   const double b[3], double d[3])
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++) d[i] = __dadd_rn(b[i], -a[i]);
+    matvec3_exact(bx.hinv, d);
+#pragma unroll
+    for (int i = 0; i < 3; i++) d[i] = __dadd_rn(d[i], -round(d[i]));
+    matvec3_exact(bx.h, d);
+}
+
+// ---- A4: numpyatom.pyx:101-123: min over the 27 images of the wrapped vector, squared ---------
+__device__ __forceinline__ double min_image_norm2_exact(const BoxParams &bx, const double d[3])
+{
+    double mind = 1e6;
+#pragma unroll 1
+    for (int i = -1; i < 2; i++) {
+        double u[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) u[c] = __dadd_rn(d[c], i * bx.h[3 * c]);
+#pragma unroll
+        for (int j = -1; j < 2; j++) {
+            double w[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) w[c] = __dadd_rn(u[c], j * bx.h[3 * c + 1]);
+#pragma unroll
+            for (int k = -1; k < 2; k++) {
+                double v[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) v[c] = __dadd_rn(w[c], k * bx.h[3 * c + 2]);
+                double n2 = norm2_exact(v);
+                if (n2 < mind) mind = n2;
+            }
+        }
+    }
+    return mind;
+}
+
+// squared reference length of (b - a), before sqrt and before the water conversion
+__device__ __forceinline__ double length2_exact(const BoxParams &bx, const double a[3],
+                                                const double b[3])
+{
+    double d[3];
+    if (bx.kind == 0) {
+        diff_ortho_exact(bx, a, b, d);
+        return norm2_exact(d);
+    }
+    diff_general_exact(bx, a, b, d);
+    return min_image_norm2_exact(bx, d);
+}
+
+// PBCHelper.pyx:318-324, 342-351 (convert_distance)
+__device__ __forceinline__ double convert_distance(const BoxParams &bx, double d)
+{
+    if (bx.conv == CMD_CONV_NONE) return d;
+    if (bx.conv_par[3] < d && d < bx.conv_par[4]) {
+        if (bx.conv == CMD_CONV_LINEAR) return __dadd_rn(__dmul_rn(bx.conv_par[0], d), bx.conv_par[1]);
+        if (d < bx.conv_par[2]) return bx.conv_par[1];
+        return __dadd_rn(__dmul_rn(bx.conv_par[0], __dadd_rn(d, -bx.conv_par[2])), bx.conv_par[1]);
+    }
+    return d;
+}
+
+// AtomBox.length_ptr dispatch (PBCHelper.pyx:228-232, 262-268, 300-303)
+__device__ __forceinline__ double length_exact(const BoxParams &bx, const double a[3],
+                                               const double b[3])
+{
+    return convert_distance(bx, sqrt(length2_exact(bx, a, b)));
+}
+
+// AtomBox.distance_vector dispatch (PBCHelper.pyx:234-235, 270-271)
+__device__ __forceinline__ void distance_exact(const BoxParams &bx, const double a[3],
+                                               const double b[3], double d[3])
+{
+    if (bx.kind == 0) diff_ortho_exact(bx, a, b, d);
+    else diff_general_exact(bx, a, b, d);
+}
+
+// math_helper.pyx:16-23 (dot_product_ptr): ((0 + a0 b0) + a1 b1) + a2 b2
+__device__ __forceinline__ double dot3_exact(const double a[3], const double b[3])
+{
+    return __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(a[0], b[0])), __dmul_rn(a[1], b[1])),
+                     __dmul_rn(a[2], b[2]));
+}
+
+// ---- A5: AtomBox.angle_ptr: angle at p2 between p1 and p3 -------------------------------------
+// ortho (numpyatom.pyx:244-264, wraps '>' first then '<'); general (numpyatom.pyx:280-291,
+// fractional wrap only).
+__device__ __forceinline__ double angle_exact(const BoxParams &bx, const double p1[3],
+                                              const double p2[3], const double p3[3])
+{
+    double v1[3], v2[3];
+    if (bx.kind == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            // same fixed point as diff_ptr: the two loops commute for a finite box
+            v1[i] = wrap_ortho_exact(__dadd_rn(p1[i], -p2[i]), bx.L[i], bx.hL[i]);
+            v2[i] = wrap_ortho_exact(__dadd_rn(p3[i], -p2[i]), bx.L[i], bx.hL[i]);
+        }
+    } else {
+        diff_general_exact(bx, p2, p1, v1);
+        diff_general_exact(bx, p2, p3, v2);
+    }
+    return acos(dot3_exact(v1, v2) / sqrt(dot3_exact(v1, v1)) / sqrt(dot3_exact(v2, v2)));
+}
+
+// ---- FAST filter: a value within ~1e-14 relative of the reference length^2 ---------------------
+// rint via the 1.5*2^52 trick (2 DADD on the FP64 pipe instead of a conversion instruction);
+// valid for |x| < 2^51, which holds for fractional coordinates of any sane trajectory.
+__device__ __forceinline__ double rint_magic(double x)
+{
+    const double magic = 6755399441055744.0;
+    return __dadd_rn(__dadd_rn(x, magic), -magic);
+}
+
+__device__ __forceinline__ double length2_fast(const BoxParams &bx, double dx, double dy, double dz)
+{
+    if (bx.kind == 0) {
+        dx -= bx.L[0] * rint_magic(dx * (1.0 / bx.L[0]));
+        dy -= bx.L[1] * rint_magic(dy * (1.0 / bx.L[1]));
+        dz -= bx.L[2] * rint_magic(dz * (1.0 / bx.L[2]));
+        return fma(dz, dz, fma(dy, dy, dx * dx));
+    }
+    double s0 = fma(bx.hinv[2], dz, fma(bx.hinv[1], dy, bx.hinv[0] * dx));
+    double s1 = fma(bx.hinv[5], dz, fma(bx.hinv[4], dy, bx.hinv[3] * dx));
+    double s2 = fma(bx.hinv[8], dz, fma(bx.hinv[7], dy, bx.hinv[6] * dx));
+    s0 -= rint_magic(s0);
+    s1 -= rint_magic(s1);
+    s2 -= rint_magic(s2);
+    double cx = fma(bx.h[2], s2, fma(bx.h[1], s1, bx.h[0] * s0));
+    double cy = fma(bx.h[5], s2, fma(bx.h[4], s1, bx.h[3] * s0));
+    double cz = fma(bx.h[8], s2, fma(bx.h[7], s1, bx.h[6] * s0));
+    double best = fma(cz, cz, fma(cy, cy, cx * cx));
+    for (int m = 0; m < bx.n_img; m++) {
+        double vx = cx + bx.img[m][0], vy = cy + bx.img[m][1], vz = cz + bx.img[m][2];
+        best = fmin(best, fma(vz, vz, fma(vy, vy, vx * vx)));
+    }
+    return best;
+}
+
+// ---- jump rates (A9 / A9') ---------------------------------------------------------------------
+struct RateParams {
+    int kind;
+    double par[CMD_RATE_NPAR];
+};
+
+#define CMD_KB_EV 8.617333262e-5
+
+__device__ __forceinline__ double rate_eval(const RateParams &r, double x, double theta)
+{
+    switch (r.kind) {
+    case CMD_RATE_FERMI:  // jumprate_generators.py:33-34
+        return r.par[0] / (1.0 + exp((x - r.par[1]) / r.par[2]));
+    case CMD_RATE_FERMI_ANGLE:  // jumprate_generators.py:42-43
+        return theta < r.par[3] ? 0.0 : r.par[0] / (1.0 + exp((x - r.par[1]) / r.par[2]));
+    case CMD_RATE_AE: {  // IO/config_parser.py:334-342 (specification text; parity unpinned)
+        double u = x - r.par[3];
+        if (!(u > 0)) return r.par[0];
+        double e = r.par[1] * u / sqrt(r.par[2] + 1.0 / (u * u));
+        return r.par[0] * exp(-e / (CMD_KB_EV * r.par[4]));
+    }
+    case CMD_RATE_EXP:  // IO/config_parser.py:344-345
+        return r.par[0] * exp(r.par[1] * x);
+    }
+    return 0.0;
+}

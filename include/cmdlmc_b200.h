@@ -1,0 +1,216 @@
+/*
+ * cmdlmc_b200.h -- C ABI of the B200-native cMD/LMC hot path (libcmdlmc_b200.so).
+ *
+ * The reference has no FFI: its only native seam is the Cython `cdef class AtomBox` method
+ * table (mdlmc/cython_exts/LMC/PBCHelper.pxd:1-43) plus the duck-typed Python protocols that
+ * main.py:73-158 wires together.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative CMD_E* code on failure; the message is
+ *     available from cmd_last_error() (thread-local).  Nothing throws across the boundary.
+ *   - plain pointers and sizes only.  `h_` arguments are HOST pointers borrowed for the call,
+ *     `d_` arguments are DEVICE pointers (current device) used on the stream set with
+ *     cmd_set_stream().  Positions are float64 [n][3], C-contiguous, like the reference
+ *     (PBCHelper.pyx:60-61,78-79,88).
+ *   - one host thread per process drives one GPU (one process per GPU); not re-entrant.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     CMD_ENODEV.
+ */
+#ifndef CMDLMC_B200_H
+#define CMDLMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMD_ABI_VERSION 1
+
+#define CMD_OK 0
+#define CMD_EINVAL (-1)    /* bad argument */
+#define CMD_ENODEV (-2)    /* no CUDA device / cmd_init not called */
+#define CMD_ECUDA (-3)     /* CUDA runtime error (see cmd_last_error) */
+#define CMD_ENOMEM (-4)    /* allocation failed */
+#define CMD_ECAPACITY (-5) /* an internal fixed-capacity buffer overflowed; retry with more */
+#define CMD_ESTATE (-6)    /* object used in the wrong state */
+
+/* jump-rate function kinds (mdlmc/LMC/jumprate_generators.py:14-43; legacy kinds from the
+ * specification text mdlmc/IO/config_parser.py:322-349, parity unpinned) */
+#define CMD_RATE_FERMI 0       /* par = a, b, c            w = a / (1 + exp((x - b) / c))      */
+#define CMD_RATE_FERMI_ANGLE 1 /* par = a, b, c, theta0    0 where theta < theta0 else Fermi   */
+#define CMD_RATE_AE 2          /* par = A, a, b, d0, T     w = A exp(-E/(kB T)), E = a u / sqrt(b + 1/u^2), u = x - d0 */
+#define CMD_RATE_EXP 3         /* par = a, b               w = a exp(b x)                      */
+#define CMD_RATE_NPAR 8
+
+/* distance conversions of AtomBoxWater* (PBCHelper.pyx:306-351) */
+#define CMD_CONV_NONE 0
+#define CMD_CONV_LINEAR 1 /* par = a, b, -, left, right */
+#define CMD_CONV_RAMP 2   /* par = a, b, d0, left, right */
+
+typedef struct cmd_box cmd_box;
+typedef struct cmd_topo cmd_topo;
+typedef struct cmd_kmc cmd_kmc;
+
+/* ---------------------------------------------------------------- lifecycle ------------- */
+int cmd_abi_version(void);
+const char *cmd_last_error(void);
+/* Selects the CUDA device of this process (one process per GPU) and creates the library's
+ * stream-ordered scratch state.  Fails with CMD_ENODEV when no device is present. */
+int cmd_init(int device);
+int cmd_shutdown(void);
+int cmd_device_count(int *n);
+/* Stream used by every kernel the library launches (a cudaStream_t passed as void*; NULL
+ * selects the legacy default stream).  PyTorch callers pass
+ * torch.cuda.current_stream().cuda_stream so that torch.cuda.Event timing sees the work. */
+int cmd_set_stream(void *cuda_stream);
+int cmd_sync(void);
+/* Number of kernels this library has launched since cmd_init (bench.py's gpu_launches). */
+int64_t cmd_launch_count(void);
+/* Measured-peak helper: runs a dependent-free DFMA loop on every SM and returns the achieved
+ * FP64 rate in TFLOP/s (the roofline denominator of the FP64-bound kernels). */
+int cmd_fp64_peak(int iters, double *tflops);
+
+/* ---------------------------------------------------------------- AtomBox --------------- */
+/* Replaces AtomBoxCubic.__cinit__ (n_values == 3, PBCHelper.pyx:216-226) and
+ * AtomBoxMonoclinic.__cinit__ (n_values == 9, rows = cell vectors, PBCHelper.pyx:248-260). */
+int cmd_box_create(const double *h_periodic_boundaries, int n_values,
+                   const int h_box_multiplier[3], cmd_box **out);
+/* The reference inverts h with np.linalg.inv (PBCHelper.pyx:259); a caller that wants device
+ * results bit-identical with the reference's h_inv hands that matrix over here. */
+int cmd_box_set_hinv(cmd_box *box, const double h_hinv[9]);
+/* number of periodic images the fast pair filter has to look at for this cell (0 for ortho) */
+int cmd_box_n_images(const cmd_box *box);
+/* AtomBoxWaterLinearConversion / AtomBoxWaterRampConversion (PBCHelper.pyx:306-351). */
+int cmd_box_set_conversion(cmd_box *box, int conv_kind, const double h_par[5]);
+/* public attributes of the Cython class (PBCHelper.pxd:3-8,40-43): periodic_boundaries_extended
+ * (3 or 9 values), pbc_matrix[9], h[9], h_inv[9]; any output pointer may be NULL. */
+int cmd_box_query(const cmd_box *box, double *h_pbc_extended, double *h_pbc_matrix, double *h_h,
+                  double *h_hinv);
+void cmd_box_destroy(cmd_box *box);
+
+/* AtomBox.length (PBCHelper.pyx:74-85): out[i] = |min-image(b[i] - a[i])| (27-image search for
+ * general cells, numpyatom.pyx:101-123; water conversion applied). */
+int cmd_length(const cmd_box *box, const double *h_a, const double *h_b, int64_t n, double *h_out);
+/* AtomBox.distance (PBCHelper.pyx:56-70): out[i][3] = wrapped vector b[i] - a[i] (fractional
+ * wrap only for general cells, numpyatom.pyx:61-74). */
+int cmd_distance(const cmd_box *box, const double *h_a, const double *h_b, int64_t n,
+                 double *h_out);
+/* AtomBox.length_all_to_all (PBCHelper.pyx:88-95): out[i][j] = length(a[i], b[j]). */
+int cmd_length_all_to_all(const cmd_box *box, const double *h_a, int64_t n, const double *h_b,
+                          int64_t m, double *h_out);
+/* AtomBox.angle (PBCHelper.pyx:133-134,237-239,273-275): angle at a2 between a1 and a3. */
+int cmd_angle(const cmd_box *box, const double *h_a1, const double *h_a2, const double *h_a3,
+              int64_t n, double *h_out);
+/* AtomBox.next_neighbor (PBCHelper.pyx:153-167): first index of the smallest length. */
+int cmd_next_neighbor(const cmd_box *box, const double *h_pos, const double *h_frame, int64_t n,
+                      int *idx, double *dist);
+/* AtomBox.position_extended_box (PBCHelper.pyx:34-53), host arithmetic. */
+int cmd_position_extended_box(const cmd_box *box, int index, const double *h_frame, int n_atoms,
+                              double h_out[3]);
+/* AtomBox.next_neighbor_extended_box (PBCHelper.pyx:169-185). */
+int cmd_next_neighbor_extended_box(const cmd_box *box, int index_1, const double *h_frame_1,
+                                   int n1, const double *h_frame_2, int n2, int *idx,
+                                   double *dist);
+
+/* Device-pointer forms of the same operations (inputs already resident in HBM). */
+int cmd_length_dev(const cmd_box *box, const double *d_a, const double *d_b, int64_t n,
+                   double *d_out);
+int cmd_distance_dev(const cmd_box *box, const double *d_a, const double *d_b, int64_t n,
+                     double *d_out);
+int cmd_length_all_to_all_dev(const cmd_box *box, const double *d_a, int64_t n,
+                              const double *d_b, int64_t m, double *d_out);
+int cmd_angle_dev(const cmd_box *box, const double *d_a1, const double *d_a2, const double *d_a3,
+                  int64_t n, double *d_out);
+
+/* ---------------------------------------------------------------- jump rates ------------ */
+/* Fermi.__call__ / FermiAngle.__call__ (jumprate_generators.py:33-34,42-43) and the legacy
+ * kinds.  h_theta may be NULL unless kind == CMD_RATE_FERMI_ANGLE. */
+int cmd_rates(int kind, const double h_par[CMD_RATE_NPAR], const double *h_x,
+              const double *h_theta, int64_t n, double *h_out);
+int cmd_rates_dev(int kind, const double h_par[CMD_RATE_NPAR], const double *d_x,
+                  const double *d_theta, int64_t n, double *d_out);
+
+/* ---------------------------------------------------------------- neighbour topology ---- */
+/* A cmd_topo owns, in HBM, the neighbour lists and jump rates of a block of frames:
+ *   frame f -> P_f directed pairs stored at [f * stride, f * stride + P_f) of
+ *   start i32, dest i32, dist f64, omega f64   (stride = per-frame capacity),
+ * in the reference order of NeighborTopology.get_topology_bruteforce (topology.py:55-72):
+ * both directions of every pair, row-major, columns ascending; pairs at exactly 0.0 dropped. */
+
+/* mode of cmd_topo_build */
+#define CMD_TOPO_BRUTEFORCE 0 /* topology_bruteforce_generator (topology.py:74-78): rebuild every frame */
+#define CMD_TOPO_VERLET 1     /* topology_verlet_list_generator (topology.py:80-114) */
+
+/* Creates an empty topology object for n_atoms donor sites; capacity_per_frame = 0 lets the
+ * library size it from the first frame. */
+int cmd_topo_create(const cmd_box *box, int n_atoms, double cutoff, double buffer, int mode,
+                    int rate_kind, const double h_rate_par[CMD_RATE_NPAR],
+                    int64_t capacity_per_frame, cmd_topo **out);
+void cmd_topo_destroy(cmd_topo *t);
+/* Processes the next block of frames (device-resident f64 [nframes][n_atoms][3]); frames are
+ * consecutive in time across calls (the Verlet displacement state is carried).  Results of the
+ * previous block are overwritten. */
+int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t nframes);
+/* Same with host frames: uploads, then builds.  dtype_bytes is 8 (float64) or 4 (float32, as
+ * stored by HDF5Trajectory, IO/trajectory_parser.py:324, up-cast on the device). */
+int cmd_topo_build(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes);
+/* Per-frame results of the last block.  Pointers may be NULL. h_counts: P_f, h_rebuilt: 1 when
+ * frame f's list was rebuilt, h_rate_sum: sum of omega over all listed pairs of the frame. */
+int cmd_topo_frame_info(const cmd_topo *t, int64_t *h_counts, uint8_t *h_rebuilt,
+                        double *h_rate_sum);
+int64_t cmd_topo_stride(const cmd_topo *t);
+int64_t cmd_topo_nframes(const cmd_topo *t);
+/* Copies frame f of the last block to host arrays of at least P_f elements (any may be NULL):
+ * the (row, col, data) triple get_topology_bruteforce returns, plus the rates. */
+int cmd_topo_get_frame(const cmd_topo *t, int64_t f, int *h_start, int *h_dest, double *h_dist,
+                       double *h_omega);
+/* Device views of the last block (valid until the next build / destroy). */
+int cmd_topo_device_arrays(const cmd_topo *t, const int **d_start, const int **d_dest,
+                           const double **d_dist, const double **d_omega,
+                           const int **d_counts);
+/* Tie audit: number of evaluated pairs of the last block whose distance is
+ * within 1e-11 relative of cutoff+buffer. */
+int64_t cmd_topo_tie_count(const cmd_topo *t);
+
+/* ---------------------------------------------------------------- KMC ------------------- */
+#define CMD_RNG_REPLAY 0 /* host-pregenerated uniforms, bit-exact replay of the reference stream */
+#define CMD_RNG_PHILOX 1 /* counter-based Philox4x32-10, key = (seed, replica) */
+
+/* KMCLattice (MDMC.py:28-226) for n_replicas independent replicas on one topology stream.
+ * h_lattices: int32 [n_replicas][n_sites], labels 1..P (MDMC.py:68-72). */
+int cmd_kmc_create(const cmd_box *box, int n_sites, int n_replicas, const int *h_lattices,
+                   double time_step, int rng_mode, uint64_t seed, cmd_kmc **out);
+void cmd_kmc_destroy(cmd_kmc *k);
+/* Replay stream: h_u float64 [n_replicas][n_per_replica]; draw 2e is np.random.random()
+ * (MDMC.py:148), draw 2e+1 the u of np.random.uniform(0, S) == S*u (MDMC.py:110). */
+int cmd_kmc_set_replay_stream(cmd_kmc *k, const double *h_u, int64_t n_per_replica);
+/* Event log capacity per replica (0 disables logging). */
+int cmd_kmc_set_event_log(cmd_kmc *k, int64_t max_events_per_replica);
+/* Observables (MDMC.py:179-208, output.py): MSD per axis and covalent autocorrelation every
+ * print_frequency frames, reset every reset_frequency frames. d_positions are the donor
+ * positions of the frames handed to cmd_kmc_advance. 0/0 disables. */
+int cmd_kmc_set_observables(cmd_kmc *k, int reset_frequency, int print_frequency);
+/* Consumes the frames of the topology's current block (KMCLattice.continuous_output,
+ * MDMC.py:77-99, fastforward_to_next_jump :121-171, move_proton :101-119).  d_positions:
+ * f64 [nframes][n_sites][3] of the same block (needed only when observables are enabled). */
+int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_positions);
+/* State read-back. Any pointer may be NULL. */
+int cmd_kmc_get_state(const cmd_kmc *k, int *h_lattices, double *h_time, int64_t *h_frame,
+                      int64_t *h_n_events, int64_t *h_site_updates);
+/* Event log of one replica: returns the number of logged events in *n (<= capacity). */
+int cmd_kmc_get_events(const cmd_kmc *k, int replica, int64_t capacity, int64_t *n,
+                       int64_t *h_frame, double *h_time, int *h_start, int *h_dest,
+                       int *h_proton);
+/* Observable rows of one replica: (frame, time, msd_x, msd_y, msd_z, autocorr) per row. */
+int cmd_kmc_get_observables(const cmd_kmc *k, int replica, int64_t capacity, int64_t *n,
+                            double *h_rows6);
+/* Tie audit: decisions (time stepping / selection) within 1e-9 relative of a boundary. */
+int64_t cmd_kmc_tie_count(const cmd_kmc *k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
