@@ -57,6 +57,31 @@ SIGNATURES = {
     "cmd_angle_dev": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp]),
     "cmd_rates": (C.c_int, [C.c_int, dp, dp, dp, C.c_int64, dp]),
     "cmd_rates_dev": (C.c_int, [C.c_int, dp, vp, vp, C.c_int64, vp]),
+    "cmd_topo_create": (C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, dp,
+                                  C.c_int64, C.POINTER(vp)]),
+    "cmd_topo_destroy": (None, [vp]),
+    "cmd_topo_build_dev": (C.c_int, [vp, vp, C.c_int64]),
+    "cmd_topo_build": (C.c_int, [vp, vp, C.c_int, C.c_int64]),
+    "cmd_topo_frame_info": (C.c_int, [vp, lp, u8p, dp]),
+    "cmd_topo_stride": (C.c_int64, [vp]),
+    "cmd_topo_nframes": (C.c_int64, [vp]),
+    "cmd_topo_get_frame": (C.c_int, [vp, C.c_int64, ip, ip, dp, dp]),
+    "cmd_topo_device_arrays": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                         C.POINTER(vp), C.POINTER(vp)]),
+    "cmd_topo_tie_count": (C.c_int64, [vp]),
+    "cmd_topo_positions": (C.c_int, [vp, C.POINTER(vp)]),
+    "cmd_kmc_create": (C.c_int, [vp, C.c_int, C.c_int, ip, C.c_double, C.c_int, C.c_uint64,
+                                 C.POINTER(vp)]),
+    "cmd_kmc_destroy": (None, [vp]),
+    "cmd_kmc_set_replay_stream": (C.c_int, [vp, dp, C.c_int64]),
+    "cmd_kmc_set_event_log": (C.c_int, [vp, C.c_int64]),
+    "cmd_kmc_set_observables": (C.c_int, [vp, C.c_int, C.c_int]),
+    "cmd_kmc_advance": (C.c_int, [vp, vp, vp]),
+    "cmd_kmc_get_state": (C.c_int, [vp, ip, dp, lp, lp, lp]),
+    "cmd_kmc_get_status": (C.c_int, [vp, ip, ip, lp]),
+    "cmd_kmc_get_events": (C.c_int, [vp, C.c_int, C.c_int64, lp, lp, dp, ip, ip, ip]),
+    "cmd_kmc_get_observables": (C.c_int, [vp, C.c_int, C.c_int64, lp, dp]),
+    "cmd_kmc_tie_count": (C.c_int64, [vp]),
 }
 
 

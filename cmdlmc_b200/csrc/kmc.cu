@@ -1,0 +1,965 @@
+// kmc.cu -- time-dependent-rate KMC over the per-frame topology (rows A10-A13 of SURVEY.md 8):
+//   jumprate_generator / filter_allowed_transitions   MDMC.py:229-248
+//   KMCLattice.fastforward_to_next_jump                MDMC.py:121-171
+//   KMCLattice.move_proton / continuous_output         MDMC.py:101-119, 77-99
+//   MeanSquareDisplacement / CovalentAutocorrelation   output.py:6-49, MDMC.py:179-208
+//
+// One WARP per replica, several replicas per CTA.  All replicas walk the frames of a topology
+// block in the same order; the warps of a CTA are kept on the same frame by one barrier per
+// frame so that the frame's (start, dest, omega) arrays are served from L1 for every replica
+// after the first.  Per-replica state (lattice, occupancy bits, the allowed-mask of the last
+// consumed frame) lives in shared memory; scalars are kept redundantly in every lane.
+//
+// Exactness: the state machine reproduces the reference's control flow including its quirks
+// (Q1 stale current_rate, Q2 same-frame events re-mask the last consumed
+// frame, Q3/Q4 cached frames stamped with the event time and seen with the pre-jump lattice,
+// Q6 Python // and %, Q7 searchsorted side='left').  Two arithmetic flavours:
+//   replay mode  every sum in NumPy's own order (np.sum pairwise tree, sequential np.cumsum), no
+//                FMA contraction, time selectors taken from the host stream: bit-identical to the
+//                CPU oracle on the same rates (the reference amplifies rounding noise through Q1,
+//                so anything less drifts apart after a few hundred events);
+//   Philox mode  warp-parallel sums in a fixed order (deterministic in the seed), for throughput.
+// Every decision closer than 1e-9 relative to its boundary is counted by the tie audit
+// (cmd_kmc_tie_count).
+#include <math.h>
+#include <stdlib.h>
+
+#include "pbc.cuh"
+
+#define KMC_PHASE_START 0
+#define KMC_PHASE_SCAN 2
+#define KMC_PHASE_HALT 3
+
+struct KmcState {  // one per replica, global memory, persistent across cmd_kmc_advance calls
+    double kmc_time, current_rate, time_selector, current_probsum, delta_t;
+    long long sweep, delta_frame, n_events, site_updates, draws, frames_seen, n_rows, pending_row;
+    long long cursor;   // position in the current replay stream
+    long long log_pos;  // events logged since the last cmd_kmc_set_event_log
+    int phase, reason;  // reason: 1 replay stream exhausted, 2 no allowed transition
+};
+
+struct cmd_kmc {
+    BoxParams bx;
+    int n_sites, n_replicas, n_protons_max;
+    double dt;
+    int rng_mode;
+    uint64_t seed;
+    int *d_lattice;      // [R][n_sites]
+    int *d_lattice0;     // [R][n_sites] autocorrelation reference (output.py:10-11)
+    KmcState *d_state;   // [R]
+    double *d_u;         // replay stream [R][n_u]
+    int64_t n_u;
+    // event log
+    int64_t ev_cap;
+    long long *d_ev_frame;
+    double *d_ev_time;
+    int *d_ev_start, *d_ev_dest, *d_ev_proton;
+    // observables
+    int reset_freq, print_freq;
+    int64_t row_cap;
+    double *d_rows;      // [R][row_cap][6]
+    double *d_snapshot;  // [R][n_sites][3]  indexed by proton label - 1
+    double *d_disp;      // [R][n_sites][3]
+    unsigned long long *d_ties;
+    int64_t frames_total;
+    // exact-replay scratch (per replica): the compacted allowed list of the last consumed frame
+    void *d_exact;
+    size_t exact_bytes;
+};
+
+struct KmcArgs {
+    int n_sites, n_replicas, rng_mode, replicas_per_cta, mask_words, occ_words;
+    double dt;
+    uint64_t seed;
+    int64_t stride, nframes, frames_base, n_u, ev_cap, row_cap;
+    int reset_freq, print_freq;
+    const int *start, *dest, *counts;
+    const double *omega, *positions, *u;
+    int *lattice, *lattice0;
+    KmcState *state;
+    long long *ev_frame;
+    double *ev_time;
+    int *ev_start, *ev_dest, *ev_proton;
+    double *rows, *snapshot, *disp;
+    unsigned long long *ties;
+    // exact-replay scratch, one slice per replica (see kmc_consume_exact)
+    int exact;
+    int64_t x_cap, x_leaves;
+    double *x_comp, *x_cum, *x_lsum;
+    int *x_cidx, *x_loff, *x_ln;
+};
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter = (event#, 0, replica, 0), key = seed -------
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b)
+{
+    return ((a >> 5) * 67108864.0 + (b >> 6)) / 9007199254740992.0;  // NumPy random_sample layout
+}
+
+// CPython / NumPy float floor-division and modulo (MDMC.py:152,156)
+__device__ __forceinline__ double py_floordiv(double a, double b)
+{
+    double mod = fmod(a, b);
+    double div = (a - mod) / b;
+    if (mod != 0 && ((b < 0) != (mod < 0))) div -= 1.0;
+    if (div != 0) {
+        double fl = floor(div);
+        if (div - fl > 0.5) fl += 1.0;
+        return fl;
+    }
+    return copysign(0.0, a / b);
+}
+
+__device__ __forceinline__ double py_mod(double a, double b)
+{
+    double mod = fmod(a, b);
+    if (mod != 0) { if ((b < 0) != (mod < 0)) mod += b; }
+    else mod = copysign(0.0, b);
+    return mod;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct WarpCtx {
+    int lane;
+    int *lat;            // [n_sites] labels
+    unsigned *occ;       // occupancy bits
+    unsigned *mask0;     // allowed-at-consumption bits of the last consumed frame
+    int64_t base;        // element offset of the last consumed frame
+    int p;               // its pair count
+    // exact-replay mode: the allowed transitions of the last consumed frame, compacted in list
+    // order (what jumprate_generator yields, MDMC.py:229-238), in global scratch
+    double *comp, *cum, *lsum;
+    int *cidx, *loff, *ln;
+    int m;
+};
+
+__device__ __forceinline__ bool occupied(const WarpCtx &c, int s) { return (c.occ[s >> 5] >> (s & 31)) & 1u; }
+
+// jumprate_generator + np.sum (MDMC.py:229-238, :85): total rate of the allowed transitions of
+// frame f for this replica; records the allowed mask (remember_last_element, MDMC.py:83-84)
+__device__ double kmc_consume(const KmcArgs &a, WarpCtx &c, int64_t f)
+{
+    const int p = a.counts[f];
+    const int64_t base = f * a.stride;
+    c.base = base;
+    c.p = p;
+    double s = 0.0;
+    for (int k0 = 0; k0 < p; k0 += 32) {
+        int k = k0 + c.lane;
+        bool ok = false;
+        if (k < p) {
+            int st = __ldg(a.start + base + k), de = __ldg(a.dest + base + k);
+            ok = occupied(c, st) && !occupied(c, de);
+            if (ok) s += __ldg(a.omega + base + k);
+        }
+        unsigned bits = __ballot_sync(0xffffffffu, ok);
+        if (c.lane == 0) c.mask0[k0 >> 5] = bits;
+    }
+    __syncwarp();
+    return warp_sum(s);
+}
+
+// ---- exact-replay arithmetic ------------------------------------------------------------------
+// The reference's time stepping feeds rounding noise back into kmc_time with gain S_0/S_t per
+// event (quirk Q1: the partial-frame interval always uses the total rate of frame 0), so a replay
+// only stays bit-identical if every sum is formed in NumPy's own order:
+//   np.sum   (MDMC.py:85)  -> pairwise summation, 8 accumulators per block of <= 128 elements,
+//                             halves rounded down to a multiple of 8 (NumPy's add.reduce)
+//   np.cumsum (MDMC.py:109) -> strictly sequential
+// np_sum_warp evaluates exactly that tree over the compacted allowed rates c.comp[0..m).
+__device__ double np_sum_warp(WarpCtx &c, int m)
+{
+    const double *a = c.comp;
+    if (m < 8) {  // every lane forms the same sequential sum
+        double res = 0.;
+        for (int i = 0; i < m; i++) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    // 1. leaves of the recursion, left to right (lane 0)
+    int nleaf = 0;
+    if (c.lane == 0) {
+        int so[40], sn[40], sp = 1;
+        so[0] = 0; sn[0] = m;
+        while (sp) {
+            --sp;
+            int off = so[sp], n = sn[sp];
+            if (n <= 128) { c.loff[nleaf] = off; c.ln[nleaf] = n; nleaf++; }
+            else {
+                int n2 = n / 2;
+                n2 -= n2 % 8;
+                so[sp] = off + n2; sn[sp] = n - n2; sp++;   // right half below, left half on top
+                so[sp] = off; sn[sp] = n2; sp++;
+            }
+        }
+    }
+    nleaf = __shfl_sync(0xffffffffu, nleaf, 0);
+    __syncwarp();
+    // 2. leaf sums: 8 lanes = the 8 accumulators of one leaf, 4 leaves per pass
+    const int g = c.lane >> 3, j = c.lane & 7;
+    for (int l0 = 0; l0 < nleaf; l0 += 4) {
+        const int l = l0 + g;
+        const bool act = l < nleaf;
+        int off = 0, n = 0;
+        if (act) { off = c.loff[l]; n = c.ln[l]; }
+        double r = 0.0;
+        if (act) {
+            r = a[off + j];
+            for (int i = 8; i < n - (n % 8); i += 8) r = __dadd_rn(r, a[off + i + j]);
+        }
+        // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); IEEE addition commutes, so every lane of the
+        // group ends with the same bits
+        r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+        if (act && j == 0) {
+            for (int i = n - (n % 8); i < n; i++) r = __dadd_rn(r, a[off + i]);
+            c.lsum[l] = r;
+        }
+    }
+    __syncwarp();
+    // 3. combine the leaves along the recursion tree (lane 0)
+    double ret = 0.0;
+    if (c.lane == 0) {
+        double val[40];
+        int sn[40], sp = 1, li = 0;
+        signed char ph[40];
+        bool have = false;
+        sn[0] = m; ph[0] = 0;
+        while (sp > 0) {
+            const int t = sp - 1;
+            if (have) {
+                if (ph[t] == 1) {  // left value arrived: descend into the right half
+                    val[t] = ret; ph[t] = 2; have = false;
+                    int n = sn[t], n2 = n / 2;
+                    n2 -= n2 % 8;
+                    sn[sp] = n - n2; ph[sp] = 0; sp++;
+                } else {
+                    ret = __dadd_rn(val[t], ret);
+                    sp--;
+                }
+            } else {
+                int n = sn[t];
+                if (n <= 128) { ret = c.lsum[li++]; have = true; sp--; }
+                else {
+                    ph[t] = 1;
+                    int n2 = n / 2;
+                    n2 -= n2 % 8;
+                    sn[sp] = n2; ph[sp] = 0; sp++;
+                }
+            }
+        }
+    }
+    return __shfl_sync(0xffffffffu, ret, 0);
+}
+
+// exact-replay form of kmc_consume: compacts the allowed transitions (list order) into the
+// replica's scratch and sums them like np.sum
+__device__ double kmc_consume_exact(const KmcArgs &a, WarpCtx &c, int64_t f)
+{
+    const int p = a.counts[f];
+    const int64_t base = f * a.stride;
+    c.base = base;
+    c.p = p;
+    int m = 0;
+    for (int k0 = 0; k0 < p; k0 += 32) {
+        int k = k0 + c.lane;
+        bool ok = false;
+        double om = 0.0;
+        if (k < p) {
+            int st = __ldg(a.start + base + k), de = __ldg(a.dest + base + k);
+            ok = occupied(c, st) && !occupied(c, de);
+            if (ok) om = __ldg(a.omega + base + k);
+        }
+        unsigned bits = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            int e = m + __popc(bits & ((1u << c.lane) - 1u));
+            c.comp[e] = om;
+            c.cidx[e] = k;
+        }
+        m += __popc(bits);
+    }
+    __syncwarp();
+    c.m = m;
+    return np_sum_warp(c, m);
+}
+
+// exact-replay form of kmc_move (MDMC.py:101-119): the arrays of the last consumed frame were
+// filtered at consumption (c.comp / c.cidx); they are filtered again with the current lattice
+// (it differs after a same-frame event, Q2), np.cumsum runs sequentially, draw = S*u,
+// searchsorted(side='left').
+__device__ bool kmc_move_exact(const KmcArgs &a, WarpCtx &c, double u, int *o_start, int *o_dest,
+                               int *o_proton, unsigned long long *ties)
+{
+    const int m = c.m;
+    const int64_t base = c.base;
+    double cum = 0.0;
+    bool any = false;
+    for (int e0 = 0; e0 < m; e0 += 32) {
+        int e = e0 + c.lane;
+        double om = 0.0;
+        bool ok = false;
+        if (e < m) {
+            int k = c.cidx[e];
+            int st = __ldg(a.start + base + k), de = __ldg(a.dest + base + k);
+            ok = occupied(c, st) && !occupied(c, de);
+            if (ok) om = c.comp[e];
+        }
+        unsigned okbits = __ballot_sync(0xffffffffu, ok);
+        any |= okbits != 0u;
+        double mine = 0.0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {  // sequential running sum, formed redundantly by every lane
+            cum = __dadd_rn(cum, __shfl_sync(0xffffffffu, om, i));   // + 0.0 leaves cum unchanged
+            if (i == c.lane) mine = cum;
+        }
+        if (e < m) c.cum[e] = mine;
+        if (c.lane == 0) c.mask0[e0 >> 5] = okbits;
+    }
+    __syncwarp();
+    if (!any) return false;  // empty cumsum: IndexError upstream
+    const double total = cum;
+    const double draw = __dadd_rn(0.0, __dmul_rn(__dadd_rn(total, -0.0), u));  // uniform(0, S)
+    int found = -1;
+    for (int e0 = 0; e0 < m && found < 0; e0 += 32) {
+        int e = e0 + c.lane;
+        bool ok = e < m && ((c.mask0[e0 >> 5] >> c.lane) & 1u);
+        double cv = ok ? c.cum[e] : 0.0;
+        unsigned hit = __ballot_sync(0xffffffffu, ok && cv >= draw);  // side='left'
+        if (hit) {
+            int l = __ffs(hit) - 1;
+            found = e0 + l;
+            double cl = __shfl_sync(0xffffffffu, cv, l);
+            double prev = cl - c.comp[found];
+            if (c.lane == 0 && (fabs(cl - draw) < 1e-9 * total || fabs(draw - prev) < 1e-9 * total))
+                atomicAdd(ties, 1ull);
+        }
+    }
+    if (found < 0) return false;  // cannot happen for u < 1 (draw <= cumsum[-1])
+    const int k = c.cidx[found];
+    int st = __ldg(a.start + base + k), de = __ldg(a.dest + base + k);
+    int proton = c.lat[st];
+    __syncwarp();
+    if (c.lane == 0) {
+        c.lat[de] = proton;
+        c.lat[st] = 0;
+        c.occ[de >> 5] |= 1u << (de & 31);
+        c.occ[st >> 5] &= ~(1u << (st & 31));
+    }
+    __syncwarp();
+    *o_start = st; *o_dest = de; *o_proton = proton;
+    return true;
+}
+
+// move_proton (MDMC.py:101-119) on the last consumed frame: re-mask, cumsum, draw = S*u,
+// searchsorted(left), move the label.  Returns false when nothing is allowed (the reference
+// raises IndexError there).
+__device__ bool kmc_move(const KmcArgs &a, WarpCtx &c, double u, int *o_start, int *o_dest,
+                         int *o_proton, unsigned long long *ties)
+{
+    const int p = c.p;
+    const int64_t base = c.base;
+    double s = 0.0;
+    int n_allowed = 0;
+    for (int k0 = 0; k0 < p; k0 += 32) {
+        int k = k0 + c.lane;
+        if (k < p && ((c.mask0[k0 >> 5] >> c.lane) & 1u)) {
+            int st = __ldg(a.start + base + k), de = __ldg(a.dest + base + k);
+            if (occupied(c, st) && !occupied(c, de)) { s += __ldg(a.omega + base + k); n_allowed++; }
+        }
+    }
+    const double total = warp_sum(s);
+    if (!__any_sync(0xffffffffu, n_allowed > 0)) return false;  // empty cumsum: IndexError upstream
+    const double draw = 0.0 + (total - 0.0) * u;  // np.random.uniform(0, cumsum[-1])
+    double running = 0.0;
+    int found = -1, last_ok = -1;
+    for (int k0 = 0; k0 < p && found < 0; k0 += 32) {
+        int k = k0 + c.lane;
+        double om = 0.0;
+        bool ok = false;
+        if (k < p && ((c.mask0[k0 >> 5] >> c.lane) & 1u)) {
+            int st = __ldg(a.start + base + k), de = __ldg(a.dest + base + k);
+            ok = occupied(c, st) && !occupied(c, de);
+            if (ok) om = __ldg(a.omega + base + k);
+        }
+        double inc = om;  // inclusive scan across the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (c.lane >= o) inc += t;
+        }
+        double cum = running + inc;
+        unsigned okbits = __ballot_sync(0xffffffffu, ok);
+        unsigned hit = __ballot_sync(0xffffffffu, ok && cum >= draw);  // side='left'
+        if (hit) {
+            int l = __ffs(hit) - 1;
+            found = k0 + l;
+            double cl = __shfl_sync(0xffffffffu, cum, l);
+            double prev = cl - __shfl_sync(0xffffffffu, om, l);
+            if (c.lane == 0 && (fabs(cl - draw) < 1e-9 * total || fabs(draw - prev) < 1e-9 * total))
+                atomicAdd(ties, 1ull);
+        }
+        if (okbits) last_ok = k0 + 31 - __clz(okbits);
+        running += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (found < 0) {
+        // draw beyond the parallel running total by rounding only: the sequential cumsum's last
+        // entry is the reference's own draw bound -> take the last allowed transition
+        if (last_ok < 0) return false;
+        found = last_ok;
+        if (c.lane == 0) atomicAdd(ties, 1ull);
+    }
+    int st = __ldg(a.start + base + found), de = __ldg(a.dest + base + found);
+    int proton = c.lat[st];
+    __syncwarp();
+    if (c.lane == 0) {
+        c.lat[de] = proton;
+        c.lat[st] = 0;
+        c.occ[de >> 5] |= 1u << (de & 31);
+        c.occ[st >> 5] &= ~(1u << (st & 31));
+    }
+    __syncwarp();
+    *o_start = st; *o_dest = de; *o_proton = proton;
+    return true;
+}
+
+// observables on a consumed frame (MDMC.py:198-208 + output.py); the lattice a frame is seen
+// with is the lattice at consumption == the pre-jump lattice at the flush (Q4)
+__device__ void kmc_observe(const KmcArgs &a, const BoxParams &bx, WarpCtx &c, int r, int64_t f,
+                            KmcState &st)
+{
+    const int64_t gf = a.frames_base + f;
+    const double *pos = a.positions + f * (int64_t)a.n_sites * 3;
+    double *snap = a.snapshot + (int64_t)r * a.n_sites * 3;
+    double *disp = a.disp + (int64_t)r * a.n_sites * 3;
+    int *lat0 = a.lattice0 + (int64_t)r * a.n_sites;
+    if (gf == 0) {  // MDMC.py:193-196: first frame initialises both observables
+        for (int s = c.lane; s < a.n_sites; s += 32) {
+            int l = c.lat[s];
+            lat0[s] = l;
+            if (l > 0) {
+                for (int k = 0; k < 3; k++) { snap[3 * (l - 1) + k] = pos[3 * s + k]; disp[3 * (l - 1) + k] = 0.0; }
+            }
+        }
+        __syncwarp();
+        return;
+    }
+    const bool reset = a.reset_freq > 0 && (gf % a.reset_freq) == 0;
+    double m[3] = {0, 0, 0};
+    int nprot = 0, same = 0;
+    for (int s = c.lane; s < a.n_sites; s += 32) {
+        int l = c.lat[s];
+        if (reset) lat0[s] = l;
+        if (l > 0) {
+            nprot++;
+            double pa[3], pb[3], d[3];
+            for (int k = 0; k < 3; k++) { pa[k] = snap[3 * (l - 1) + k]; pb[k] = pos[3 * s + k]; }
+            distance_exact(bx, pa, pb, d);  // output.py:41: atombox.distance(snapshot, new)
+            for (int k = 0; k < 3; k++) {
+                double v = __dadd_rn(reset ? 0.0 : disp[3 * (l - 1) + k], d[k]);
+                disp[3 * (l - 1) + k] = v;
+                snap[3 * (l - 1) + k] = pb[k];
+                m[k] += v * v;
+            }
+            same += (lat0[s] == l);
+        }
+    }
+    __syncwarp();
+    if (a.print_freq > 0 && (gf % a.print_freq) == 0) {
+        for (int k = 0; k < 3; k++) m[k] = warp_sum(m[k]);
+        for (int o = 16; o > 0; o >>= 1) {
+            nprot += __shfl_xor_sync(0xffffffffu, nprot, o);
+            same += __shfl_xor_sync(0xffffffffu, same, o);
+        }
+        if (c.lane == 0 && st.n_rows < a.row_cap) {
+            double *row = a.rows + ((int64_t)r * a.row_cap + st.n_rows) * 6;
+            row[0] = (double)gf;
+            row[1] = nan("");
+            row[2] = m[0] / nprot; row[3] = m[1] / nprot; row[4] = m[2] / nprot;
+            row[5] = (double)same;
+        }
+        if (st.n_rows < a.row_cap) st.n_rows++;
+    }
+}
+
+// event bookkeeping shared by both branches of fastforward_to_next_jump: stamp the cached
+// frames' rows with the event time (Q3), select + move, log.  Returns false if the replica halts.
+__device__ bool kmc_event(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
+{
+    if (c.lane == 0)
+        for (long long q = st.pending_row; q < st.n_rows; q++)
+            a.rows[((int64_t)r * a.row_cap + q) * 6 + 1] = st.kmc_time;
+    st.pending_row = st.n_rows;
+    double u;
+    if (a.rng_mode == CMD_RNG_REPLAY) {
+        if (st.cursor + 1 >= a.n_u) { st.reason = 1; return false; }
+        u = a.u[(int64_t)r * a.n_u + st.cursor + 1];
+    } else {
+        uint32_t ctr[4] = {(uint32_t)st.n_events, (uint32_t)((uint64_t)st.n_events >> 32), (uint32_t)r, 0u};
+        philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        u = u53(ctr[2], ctr[3]);
+    }
+    int es, ed, ep;
+    const bool moved = a.exact ? kmc_move_exact(a, c, u, &es, &ed, &ep, a.ties)
+                               : kmc_move(a, c, u, &es, &ed, &ep, a.ties);
+    if (!moved) { st.reason = 2; return false; }
+    if (c.lane == 0 && st.log_pos < a.ev_cap) {
+        int64_t q = (int64_t)r * a.ev_cap + st.log_pos;
+        a.ev_frame[q] = st.sweep;
+        a.ev_time[q] = st.kmc_time;
+        a.ev_start[q] = es; a.ev_dest[q] = ed; a.ev_proton[q] = ep;
+    }
+    st.n_events++;
+    if (st.log_pos < a.ev_cap) st.log_pos++;
+    st.draws += 2;
+    st.cursor += 2;
+    return true;
+}
+
+// runs the reference's `while True` loop (MDMC.py:147-171) until it needs another frame
+__device__ void kmc_run_until_frame_needed(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
+{
+    for (;;) {
+        if (a.rng_mode == CMD_RNG_REPLAY) {
+            if (st.cursor + 1 >= a.n_u) { st.phase = KMC_PHASE_HALT; st.reason = 1; return; }
+            // the stream carries -np.log(1 - np.random.random()) as the host evaluated it
+            st.time_selector = a.u[(int64_t)r * a.n_u + st.cursor];   // MDMC.py:148
+        } else {
+            uint32_t ctr[4] = {(uint32_t)st.n_events, (uint32_t)((uint64_t)st.n_events >> 32), (uint32_t)r, 0u};
+            philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            st.time_selector = -log(1 - u53(ctr[0], ctr[1]));         // MDMC.py:148
+        }
+        double t_trial = st.time_selector / st.current_rate;  // Q1: the rate of frame 0, forever
+        double x = st.kmc_time + t_trial;
+        if (c.lane == 0) {  // tie audit of the floor-division decision
+            double rm = py_mod(x, a.dt);
+            if (rm < 1e-9 * a.dt || a.dt - rm < 1e-9 * a.dt) atomicAdd(a.ties, 1ull);
+        }
+        if (py_floordiv(x, a.dt) == py_floordiv(st.kmc_time, a.dt)) {
+            st.kmc_time = x;
+            st.delta_frame = 0;
+            if (!kmc_event(a, c, r, st)) { st.phase = KMC_PHASE_HALT; return; }
+        } else {
+            st.delta_t = a.dt - py_mod(st.kmc_time, a.dt);
+            st.delta_frame = 1;
+            st.current_probsum = st.current_rate * st.delta_t;
+            st.phase = KMC_PHASE_SCAN;
+            return;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) k_kmc_advance(const __grid_constant__ BoxParams bx,
+                                                        const __grid_constant__ KmcArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * a.replicas_per_cta + w;
+    const bool active = r < a.n_replicas;
+    const size_t per_warp = (size_t)a.n_sites * 4 + (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4;
+    WarpCtx c;
+    c.lane = lane;
+    c.lat = (int *)(smem_raw + per_warp * w);
+    c.occ = (unsigned *)(c.lat + a.n_sites);
+    c.mask0 = c.occ + a.occ_words;
+    c.base = 0;
+    c.p = 0;
+    c.m = 0;
+    c.comp = c.cum = c.lsum = nullptr;
+    c.cidx = c.loff = c.ln = nullptr;
+    if (a.exact && active) {
+        c.comp = a.x_comp + (int64_t)r * a.x_cap;
+        c.cum = a.x_cum + (int64_t)r * a.x_cap;
+        c.cidx = a.x_cidx + (int64_t)r * a.x_cap;
+        c.lsum = a.x_lsum + (int64_t)r * a.x_leaves;
+        c.loff = a.x_loff + (int64_t)r * a.x_leaves;
+        c.ln = a.x_ln + (int64_t)r * a.x_leaves;
+    }
+    KmcState st;
+    memset(&st, 0, sizeof(st));
+    st.phase = KMC_PHASE_HALT;
+    if (active) {
+        st = a.state[r];
+        for (int s = lane; s < a.n_sites; s += 32) c.lat[s] = a.lattice[(int64_t)r * a.n_sites + s];
+        __syncwarp();
+        for (int q = lane; q < a.occ_words; q += 32) {
+            unsigned bits = 0;
+            for (int b = 0; b < 32; b++) {
+                int s = q * 32 + b;
+                if (s < a.n_sites && c.lat[s] > 0) bits |= 1u << b;
+            }
+            c.occ[q] = bits;
+        }
+        __syncwarp();
+    }
+    for (int64_t f = 0; f < a.nframes; f++) {
+        if (active && st.phase != KMC_PHASE_HALT) {
+            if (a.positions) kmc_observe(a, bx, c, r, f, st);
+            double rate = a.exact ? kmc_consume_exact(a, c, f) : kmc_consume(a, c, f);
+            st.site_updates += c.p;
+            st.frames_seen++;
+            if (st.phase == KMC_PHASE_START) {  // MDMC.py:146
+                st.current_rate = rate;
+                kmc_run_until_frame_needed(a, c, r, st);
+            } else {  // KMC_PHASE_SCAN, MDMC.py:158-165
+                // explicit roundings: no FMA contraction anywhere in the decision arithmetic
+                double next_probsum = __dadd_rn(st.current_probsum, __dmul_rn(rate, a.dt));
+                if (lane == 0 && fabs(next_probsum - st.time_selector) < 1e-9 * st.time_selector)
+                    atomicAdd(a.ties, 1ull);
+                if (next_probsum < st.time_selector) {
+                    st.delta_frame += 1;
+                    st.current_probsum = next_probsum;
+                } else {
+                    double rest = st.time_selector - st.current_probsum;
+                    st.delta_t = __dadd_rn(st.delta_t,
+                                           __dadd_rn(__dmul_rn((double)(st.delta_frame - 1), a.dt),
+                                                     __ddiv_rn(rest, rate)));
+                    st.kmc_time += st.delta_t;
+                    st.sweep += st.delta_frame;
+                    if (!kmc_event(a, c, r, st)) st.phase = KMC_PHASE_HALT;
+                    else kmc_run_until_frame_needed(a, c, r, st);
+                }
+            }
+        }
+        __syncthreads();  // keep the CTA's replicas on the same frame (L1 reuse of the frame data)
+    }
+    if (active) {
+        __syncwarp();
+        for (int s = lane; s < a.n_sites; s += 32) a.lattice[(int64_t)r * a.n_sites + s] = c.lat[s];
+        if (lane == 0) a.state[r] = st;
+    }
+}
+
+// ------------------------------------------------------------------ host side ------------------
+extern "C" void cmd_kmc_destroy(cmd_kmc *k)
+{
+    if (!k) return;
+    cudaStreamSynchronize(cmd_global().stream);
+    cudaFree(k->d_lattice); cudaFree(k->d_lattice0); cudaFree(k->d_state); cudaFree(k->d_u);
+    cudaFree(k->d_ev_frame); cudaFree(k->d_ev_time); cudaFree(k->d_ev_start); cudaFree(k->d_ev_dest);
+    cudaFree(k->d_ev_proton); cudaFree(k->d_rows); cudaFree(k->d_snapshot); cudaFree(k->d_disp);
+    cudaFree(k->d_ties); cudaFree(k->d_exact);
+    free(k);
+}
+
+#define KALLOC(ptr, bytes)                                                     \
+    if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) {                 \
+        cudaGetLastError();                                                    \
+        return cmd_set_error(CMD_ENOMEM, "cudaMalloc failed for %s (%zu bytes)", #ptr, (size_t)(bytes)); \
+    }
+
+extern "C" int cmd_kmc_create(const cmd_box *box, int n_sites, int n_replicas, const int *lattices,
+                              double dt, int rng_mode, uint64_t seed, cmd_kmc **out)
+{
+    CMD_REQUIRE_INIT();
+    if (!box || !out || !lattices || n_sites < 1 || n_replicas < 1 || !(dt > 0))
+        return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (rng_mode != CMD_RNG_REPLAY && rng_mode != CMD_RNG_PHILOX)
+        return cmd_set_error(CMD_EINVAL, "bad rng mode");
+    cmd_kmc *k = (cmd_kmc *)calloc(1, sizeof(cmd_kmc));
+    if (!k) return cmd_set_error(CMD_ENOMEM, "out of host memory");
+    k->bx = box->p;
+    k->n_sites = n_sites;
+    k->n_replicas = n_replicas;
+    k->dt = dt;
+    k->rng_mode = rng_mode;
+    k->seed = seed;
+    cudaStream_t st = cmd_global().stream;
+    size_t nl = (size_t)n_replicas * n_sites;
+    int rc = CMD_OK;
+    do {
+        if (cudaMalloc((void **)&k->d_lattice, nl * 4) != cudaSuccess ||
+            cudaMalloc((void **)&k->d_lattice0, nl * 4) != cudaSuccess ||
+            cudaMalloc((void **)&k->d_state, (size_t)n_replicas * sizeof(KmcState)) != cudaSuccess ||
+            cudaMalloc((void **)&k->d_ties, 8) != cudaSuccess) {
+            cudaGetLastError();
+            rc = cmd_set_error(CMD_ENOMEM, "cudaMalloc failed for the KMC state");
+            break;
+        }
+        cudaMemcpyAsync(k->d_lattice, lattices, nl * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(k->d_lattice0, lattices, nl * 4, cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(k->d_state, 0, (size_t)n_replicas * sizeof(KmcState), st);
+        cudaMemsetAsync(k->d_ties, 0, 8, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) {
+            rc = cmd_set_error(CMD_ECUDA, "KMC state upload failed: %s",
+                               cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+    } while (0);
+    if (rc) { cmd_kmc_destroy(k); return rc; }
+    *out = k;
+    return CMD_OK;
+}
+
+__global__ void k_kmc_reset_cursor(KmcState *st, int n, int what)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) {
+        if (what == 0) st[r].cursor = 0;
+        else st[r].log_pos = 0;
+    }
+}
+
+extern "C" int cmd_kmc_get_status(const cmd_kmc *k, int *phase, int *reason, int64_t *cursor)
+{
+    CMD_REQUIRE_INIT();
+    if (!k) return cmd_set_error(CMD_EINVAL, "bad argument");
+    cudaStream_t st = cmd_global().stream;
+    KmcState *hs = (KmcState *)malloc((size_t)k->n_replicas * sizeof(KmcState));
+    if (!hs) return cmd_set_error(CMD_ENOMEM, "out of host memory");
+    cudaError_t e = cudaMemcpyAsync(hs, k->d_state, (size_t)k->n_replicas * sizeof(KmcState),
+                                    cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess)
+        for (int r = 0; r < k->n_replicas; r++) {
+            if (phase) phase[r] = hs[r].phase;
+            if (reason) reason[r] = hs[r].reason;
+            if (cursor) cursor[r] = hs[r].cursor;
+        }
+    free(hs);
+    CMD_CUDA(e);
+    return CMD_OK;
+}
+
+extern "C" int cmd_kmc_set_replay_stream(cmd_kmc *k, const double *u, int64_t n)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || !u || n < 2) return cmd_set_error(CMD_EINVAL, "bad argument");
+    cudaStream_t st = cmd_global().stream;
+    CMD_CUDA(cudaStreamSynchronize(st));
+    cudaFree(k->d_u);
+    k->d_u = nullptr;
+    KALLOC(k->d_u, (size_t)k->n_replicas * n * 8);
+    CMD_CUDA(cudaMemcpyAsync(k->d_u, u, (size_t)k->n_replicas * n * 8, cudaMemcpyHostToDevice, st));
+    k_kmc_reset_cursor<<<(k->n_replicas + 255) / 256, 256, 0, st>>>(k->d_state, k->n_replicas, 0);
+    CMD_LAUNCHED();
+    CMD_CUDA(cudaStreamSynchronize(st));
+    k->n_u = n;
+    return CMD_OK;
+}
+
+extern "C" int cmd_kmc_set_event_log(cmd_kmc *k, int64_t cap)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || cap < 0) return cmd_set_error(CMD_EINVAL, "bad argument");
+    cudaStream_t st = cmd_global().stream;
+    if (cap > k->ev_cap) {
+        CMD_CUDA(cudaStreamSynchronize(st));
+        cudaFree(k->d_ev_frame); cudaFree(k->d_ev_time); cudaFree(k->d_ev_start);
+        cudaFree(k->d_ev_dest); cudaFree(k->d_ev_proton);
+        k->d_ev_frame = nullptr; k->d_ev_time = nullptr;
+        k->d_ev_start = k->d_ev_dest = k->d_ev_proton = nullptr;
+        k->ev_cap = 0;
+        size_t n = (size_t)k->n_replicas * cap;
+        KALLOC(k->d_ev_frame, n * 8);
+        KALLOC(k->d_ev_time, n * 8);
+        KALLOC(k->d_ev_start, n * 4);
+        KALLOC(k->d_ev_dest, n * 4);
+        KALLOC(k->d_ev_proton, n * 4);
+        k->ev_cap = cap;
+    }
+    if (cap == 0) k->ev_cap = 0;
+    k_kmc_reset_cursor<<<(k->n_replicas + 255) / 256, 256, 0, st>>>(k->d_state, k->n_replicas, 1);
+    CMD_LAUNCHED();
+    return CMD_OK;
+}
+
+extern "C" int cmd_kmc_set_observables(cmd_kmc *k, int reset_frequency, int print_frequency)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || reset_frequency < 0 || print_frequency < 0) return cmd_set_error(CMD_EINVAL, "bad argument");
+    k->reset_freq = reset_frequency;
+    k->print_freq = print_frequency;
+    if (print_frequency > 0 && !k->d_snapshot) {
+        size_t n = (size_t)k->n_replicas * k->n_sites * 3 * 8;
+        KALLOC(k->d_snapshot, n);
+        KALLOC(k->d_disp, n);
+        CMD_CUDA(cudaMemsetAsync(k->d_snapshot, 0, n, cmd_global().stream));
+        CMD_CUDA(cudaMemsetAsync(k->d_disp, 0, n, cmd_global().stream));
+    }
+    return CMD_OK;
+}
+
+extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_positions)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || !t) return cmd_set_error(CMD_EINVAL, "bad argument");
+    const int *d_start, *d_dest, *d_counts;
+    const double *d_dist, *d_omega;
+    int rc = cmd_topo_device_arrays(t, &d_start, &d_dest, &d_dist, &d_omega, &d_counts);
+    if (rc) return rc;
+    if (k->rng_mode == CMD_RNG_REPLAY && !k->d_u)
+        return cmd_set_error(CMD_ESTATE, "replay mode needs cmd_kmc_set_replay_stream first");
+    const bool obs = k->print_freq > 0;
+    if (obs && !d_positions)
+        return cmd_set_error(CMD_EINVAL, "observables need the donor positions of the block");
+    CmdGlobal &g = cmd_global();
+    cudaStream_t st = g.stream;
+    int64_t nframes = cmd_topo_nframes(t), stride = cmd_topo_stride(t);
+    // observable rows: grow to hold this block's prints
+    if (obs) {
+        int64_t need = (k->frames_total + nframes) / k->print_freq + 2;
+        if (need > k->row_cap) {
+            int64_t cap = need + need / 2 + 16;
+            double *nr = nullptr;
+            KALLOC(nr, (size_t)k->n_replicas * cap * 6 * 8);
+            if (k->d_rows) {
+                CMD_CUDA(cudaMemcpy2DAsync(nr, cap * 48, k->d_rows, k->row_cap * 48, k->row_cap * 48,
+                                           k->n_replicas, cudaMemcpyDeviceToDevice, st));
+                CMD_CUDA(cudaStreamSynchronize(st));
+                cudaFree(k->d_rows);
+            }
+            k->d_rows = nr;
+            k->row_cap = cap;
+        }
+    }
+    KmcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_sites = k->n_sites; a.n_replicas = k->n_replicas; a.rng_mode = k->rng_mode;
+    a.dt = k->dt; a.seed = k->seed; a.stride = stride; a.nframes = nframes;
+    a.frames_base = k->frames_total; a.n_u = k->n_u; a.ev_cap = k->ev_cap; a.row_cap = k->row_cap;
+    a.reset_freq = k->reset_freq; a.print_freq = k->print_freq;
+    a.start = d_start; a.dest = d_dest; a.counts = d_counts; a.omega = d_omega;
+    a.positions = obs ? d_positions : nullptr;
+    a.u = k->d_u; a.lattice = k->d_lattice; a.lattice0 = k->d_lattice0; a.state = k->d_state;
+    a.ev_frame = k->d_ev_frame; a.ev_time = k->d_ev_time; a.ev_start = k->d_ev_start;
+    a.ev_dest = k->d_ev_dest; a.ev_proton = k->d_ev_proton;
+    a.rows = k->d_rows; a.snapshot = k->d_snapshot; a.disp = k->d_disp; a.ties = k->d_ties;
+    a.exact = k->rng_mode == CMD_RNG_REPLAY ? 1 : 0;
+    if (a.exact) {
+        // per replica: comp f64[cap], cum f64[cap], lsum f64[leaves], cidx i32[cap],
+        // loff i32[leaves], ln i32[leaves]
+        a.x_cap = stride;
+        a.x_leaves = stride / 64 + 4;
+        size_t R = (size_t)k->n_replicas;
+        size_t need = R * ((size_t)a.x_cap * 20 + (size_t)a.x_leaves * 16);
+        if (need > k->exact_bytes) {
+            CMD_CUDA(cudaStreamSynchronize(st));
+            cudaFree(k->d_exact);
+            k->d_exact = nullptr;
+            k->exact_bytes = 0;
+            KALLOC(k->d_exact, need);
+            k->exact_bytes = need;
+        }
+        a.x_comp = (double *)k->d_exact;
+        a.x_cum = a.x_comp + R * a.x_cap;
+        a.x_lsum = a.x_cum + R * a.x_cap;
+        a.x_cidx = (int *)(a.x_lsum + R * a.x_leaves);
+        a.x_loff = a.x_cidx + R * a.x_cap;
+        a.x_ln = a.x_loff + R * a.x_leaves;
+    }
+    a.occ_words = (k->n_sites + 31) / 32;
+    a.mask_words = (int)((stride + 31) / 32) + 1;
+    size_t per_warp = (size_t)a.n_sites * 4 + (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4;
+    int rpc = (k->n_replicas + g.sm_count - 1) / g.sm_count;
+    if (rpc < 1) rpc = 1;
+    if (rpc > 16) rpc = 16;
+    while (rpc > 1 && per_warp * rpc > 200 * 1024) rpc--;
+    if (per_warp * rpc > 226 * 1024)
+        return cmd_set_error(CMD_ECAPACITY, "KMC per-replica state (%zu bytes) exceeds shared memory", per_warp);
+    a.replicas_per_cta = rpc;
+    size_t smem = per_warp * rpc;
+    CMD_CUDA(cudaFuncSetAttribute(k_kmc_advance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = (k->n_replicas + rpc - 1) / rpc;
+    k_kmc_advance<<<blocks, rpc * 32, smem, st>>>(k->bx, a);
+    CMD_LAUNCHED();
+    k->frames_total += nframes;
+    return CMD_OK;
+}
+
+extern "C" int cmd_kmc_get_state(const cmd_kmc *k, int *lattices, double *time, int64_t *frame,
+                                 int64_t *n_events, int64_t *site_updates)
+{
+    CMD_REQUIRE_INIT();
+    if (!k) return cmd_set_error(CMD_EINVAL, "bad argument");
+    cudaStream_t st = cmd_global().stream;
+    KmcState *hs = (KmcState *)malloc((size_t)k->n_replicas * sizeof(KmcState));
+    if (!hs) return cmd_set_error(CMD_ENOMEM, "out of host memory");
+    cudaError_t e = cudaMemcpyAsync(hs, k->d_state, (size_t)k->n_replicas * sizeof(KmcState),
+                                    cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && lattices)
+        e = cudaMemcpyAsync(lattices, k->d_lattice, (size_t)k->n_replicas * k->n_sites * 4,
+                            cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess)
+        for (int r = 0; r < k->n_replicas; r++) {
+            if (time) time[r] = hs[r].kmc_time;
+            if (frame) frame[r] = hs[r].sweep;
+            if (n_events) n_events[r] = hs[r].n_events;
+            if (site_updates) site_updates[r] = hs[r].site_updates;
+        }
+    free(hs);
+    CMD_CUDA(e);
+    return CMD_OK;
+}
+
+extern "C" int cmd_kmc_get_events(const cmd_kmc *k, int replica, int64_t capacity, int64_t *n,
+                                  int64_t *frame, double *time, int *start, int *dest, int *proton)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || replica < 0 || replica >= k->n_replicas || !n) return cmd_set_error(CMD_EINVAL, "bad argument");
+    cudaStream_t st = cmd_global().stream;
+    KmcState hs;
+    CMD_CUDA(cudaMemcpyAsync(&hs, k->d_state + replica, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
+    int64_t have = hs.log_pos < k->ev_cap ? hs.log_pos : k->ev_cap;
+    if (have > capacity) have = capacity;
+    *n = have;
+    int64_t off = (int64_t)replica * k->ev_cap;
+    if (have > 0) {
+        if (frame) CMD_CUDA(cudaMemcpyAsync(frame, k->d_ev_frame + off, have * 8, cudaMemcpyDeviceToHost, st));
+        if (time) CMD_CUDA(cudaMemcpyAsync(time, k->d_ev_time + off, have * 8, cudaMemcpyDeviceToHost, st));
+        if (start) CMD_CUDA(cudaMemcpyAsync(start, k->d_ev_start + off, have * 4, cudaMemcpyDeviceToHost, st));
+        if (dest) CMD_CUDA(cudaMemcpyAsync(dest, k->d_ev_dest + off, have * 4, cudaMemcpyDeviceToHost, st));
+        if (proton) CMD_CUDA(cudaMemcpyAsync(proton, k->d_ev_proton + off, have * 4, cudaMemcpyDeviceToHost, st));
+        CMD_CUDA(cudaStreamSynchronize(st));
+    }
+    return CMD_OK;
+}
+
+extern "C" int cmd_kmc_get_observables(const cmd_kmc *k, int replica, int64_t capacity, int64_t *n,
+                                       double *rows)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || replica < 0 || replica >= k->n_replicas || !n) return cmd_set_error(CMD_EINVAL, "bad argument");
+    cudaStream_t st = cmd_global().stream;
+    KmcState hs;
+    CMD_CUDA(cudaMemcpyAsync(&hs, k->d_state + replica, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
+    // only rows whose frames were flushed by an event carry a time stamp (MDMC.py:94-96)
+    int64_t have = hs.pending_row;
+    if (have > capacity) have = capacity;
+    *n = have;
+    if (have > 0 && rows) {
+        CMD_CUDA(cudaMemcpyAsync(rows, k->d_rows + (int64_t)replica * k->row_cap * 6, have * 48,
+                                 cudaMemcpyDeviceToHost, st));
+        CMD_CUDA(cudaStreamSynchronize(st));
+    }
+    return CMD_OK;
+}
+
+extern "C" int64_t cmd_kmc_tie_count(const cmd_kmc *k)
+{
+    if (!k || !cmd_global().inited) return -1;
+    unsigned long long v = 0;
+    cudaStream_t st = cmd_global().stream;
+    if (cudaMemcpyAsync(&v, k->d_ties, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    cudaStreamSynchronize(st);
+    return (int64_t)v;
+}

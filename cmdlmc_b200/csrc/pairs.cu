@@ -43,6 +43,7 @@ struct cmd_topo {
     int *d_rebuild_ids, *d_refresh_ids, *d_head;
     double *d_upload;
     size_t upload_bytes;
+    const double *d_frames_last;  // frames of the last block (device)
     int64_t total_frames;
 };
 
@@ -113,8 +114,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums, int *
 
 // ------------------------------------------------------------------ all-pairs kernel ----------
 // grid.x = number of frames to (re)build; frame index = ids ? ids[blockIdx.x] : blockIdx.x
-template <int KIND>
-__global__ void __launch_bounds__(1024, 1)
+template <int KIND, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ RateParams rp,
               const double *__restrict__ frames, const int *__restrict__ ids,
               const int *__restrict__ n_ids, int n, double rc, double t2, double t2_fast,
@@ -447,7 +448,7 @@ static int topo_configure(cmd_topo *t, int64_t stride)
     stride = (stride + 63) / 64 * 64;
     int hit_cap = (int)(stride / 2);
     size_t smem = dense_smem_bytes(t->n, hit_cap);
-    if (smem > 227 * 1024)
+    if (smem > 226 * 1024)
         return cmd_set_error(CMD_ECAPACITY,
                              "dense pair kernel needs %zu bytes of shared memory for n=%d, "
                              "capacity %lld (limit 232448): use the cell-list path", smem, t->n,
@@ -526,19 +527,23 @@ static int launch_dense(cmd_topo *t, const double *d_frames, const int *ids, con
                         int hit_cap, size_t smem)
 {
     cudaStream_t st = cmd_global().stream;
-    if (t->bx.kind == 0) {
-        CMD_CUDA(cudaFuncSetAttribute(k_pairs_dense<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        k_pairs_dense<0><<<(unsigned)grid, t->threads, smem, st>>>(
-            t->bx, t->rate, d_frames, ids, n_ids, t->n, t->rc, t->t2, t->t2, stride, hit_cap, start,
-            dest, dist, omega, counts, rate_sum, rebuilt, t->d_err, t->d_ties);
+    const bool ortho = t->bx.kind == 0;
+#define DENSE_LAUNCH(K, MT, MB)                                                                  \
+    do {                                                                                         \
+        CMD_CUDA(cudaFuncSetAttribute(k_pairs_dense<K, MT, MB>,                                  \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        k_pairs_dense<K, MT, MB><<<(unsigned)grid, t->threads, smem, st>>>(                      \
+            t->bx, t->rate, d_frames, ids, n_ids, t->n, t->rc, t->t2, t->t2_fast, stride,        \
+            hit_cap, start, dest, dist, omega, counts, rate_sum, rebuilt, t->d_err, t->d_ties);  \
+    } while (0)
+    if (t->threads <= 256) {
+        if (ortho) DENSE_LAUNCH(0, 256, 3); else DENSE_LAUNCH(1, 256, 3);
+    } else if (t->threads <= 512) {
+        if (ortho) DENSE_LAUNCH(0, 512, 2); else DENSE_LAUNCH(1, 512, 2);
     } else {
-        CMD_CUDA(cudaFuncSetAttribute(k_pairs_dense<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        k_pairs_dense<1><<<(unsigned)grid, t->threads, smem, st>>>(
-            t->bx, t->rate, d_frames, ids, n_ids, t->n, t->rc, t->t2, t->t2_fast, stride, hit_cap,
-            start, dest, dist, omega, counts, rate_sum, rebuilt, t->d_err, t->d_ties);
+        if (ortho) DENSE_LAUNCH(0, 1024, 1); else DENSE_LAUNCH(1, 1024, 1);
     }
+#undef DENSE_LAUNCH
     CMD_LAUNCHED();
     return CMD_OK;
 }
@@ -565,7 +570,7 @@ static int topo_autosize(cmd_topo *t, const double *d_frame)
     int64_t p0 = cnt < 0 ? -cnt : cnt;
     int64_t want = p0 + p0 / 2 + 128;
     // shrink to what the shared-memory hit list can hold
-    while (want > p0 + 64 && dense_smem_bytes(t->n, (int)((want + 63) / 64 * 64 / 2)) > 227 * 1024)
+    while (want > p0 + 64 && dense_smem_bytes(t->n, (int)((want + 63) / 64 * 64 / 2)) > 226 * 1024)
         want -= 64;
     return topo_configure(t, want);
 }
@@ -619,6 +624,7 @@ extern "C" int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t n
         }
     }
     t->nframes = nframes;
+    t->d_frames_last = d_frames;
     if (t->mode == CMD_TOPO_BRUTEFORCE) {
         rc = launch_dense(t, d_frames, nullptr, nullptr, nframes, t->d_start, t->d_dest, t->d_dist,
                           t->d_omega, t->d_counts, t->d_rate_sum, t->d_rebuilt, t->stride,
@@ -652,8 +658,7 @@ extern "C" int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t n
         CMD_CUDA(cudaMemcpyAsync(t->d_last, d_frames + (nframes - 1) * (int64_t)t->n * 3,
                                  (size_t)t->n * 24, cudaMemcpyDeviceToDevice, st));
         // after this block the head, if any, lives in the carry
-        int minus1 = -1;
-        CMD_CUDA(cudaMemcpyAsync(t->d_sched + 2, &minus1, sizeof(int), cudaMemcpyHostToDevice, st));
+        CMD_CUDA(cudaMemsetAsync(t->d_sched + 2, 0xff, sizeof(int), st));
         t->have_last = true;
     }
     t->total_frames += nframes;
@@ -755,6 +760,13 @@ extern "C" int cmd_topo_device_arrays(const cmd_topo *t, const int **start, cons
     if (dist) *dist = t->d_dist;
     if (omega) *omega = t->d_omega;
     if (counts) *counts = t->d_counts;
+    return CMD_OK;
+}
+
+extern "C" int cmd_topo_positions(const cmd_topo *t, const double **d_frames)
+{
+    if (!t || t->nframes < 1 || !d_frames) return cmd_set_error(CMD_ESTATE, "no block has been built");
+    *d_frames = t->d_frames_last;
     return CMD_OK;
 }
 

@@ -1,0 +1,226 @@
+"""Neighbour topology -- host mirror of mdlmc/topo/topology.py:18-121 on top of the C ABI.
+
+`NeighborTopology` keeps the reference's constructor, generators and output contract
+(`(start int32[P], destination int32[P], distance float64[P])` in LIL->COO order); the work is
+done by the CUDA kernels of csrc/pairs.cu on blocks of frames.
+"""
+import ctypes as C
+import logging
+from collections import deque
+
+import numpy as np
+
+from . import _abi, runtime
+from ._abi import as_f64, check, ptr
+from .jumprate import NPAR
+
+logger = logging.getLogger(__name__)
+
+MODE_BRUTEFORCE = 0
+MODE_VERLET = 1
+
+
+class DeviceTopology:
+    """Thin owner of a `cmd_topo` handle: neighbour lists + rates of a block of frames in HBM."""
+
+    def __init__(self, atom_box, n_atoms, cutoff, buffer, mode, jumprate=None, capacity=0):
+        runtime.ensure_init()
+        self.atom_box = atom_box          # keeps the box handle alive
+        self.n_atoms = int(n_atoms)
+        self.mode = mode
+        kind = jumprate.kind if jumprate is not None else 0
+        if kind == 1:  # FermiAngle needs the angle colvar (AngleTopology); rates come later
+            kind = 0
+        par = jumprate._par() if jumprate is not None else np.array([0.0, 0.0, 1.0] + [0.0] * 5)
+        self._args = (atom_box, n_atoms, cutoff, buffer, mode, kind, par)
+        self._handle = C.c_void_p()
+        check(_abi.lib().cmd_topo_create(atom_box.handle, int(n_atoms), float(cutoff),
+                                         float(buffer), int(mode), int(kind), ptr(par),
+                                         int(capacity), C.byref(self._handle)))
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                _abi.lib().cmd_topo_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    @property
+    def handle(self):
+        return self._handle
+
+    @property
+    def stride(self):
+        return int(_abi.lib().cmd_topo_stride(self._handle))
+
+    @property
+    def nframes(self):
+        return int(_abi.lib().cmd_topo_nframes(self._handle))
+
+    def build(self, frames):
+        """frames: host ndarray [F, n, 3] float64 or float32."""
+        frames = np.ascontiguousarray(frames)
+        if frames.dtype not in (np.float32, np.float64):
+            frames = frames.astype(np.float64)
+        if frames.ndim != 3 or frames.shape[1:] != (self.n_atoms, 3):
+            raise ValueError("frames must have shape [F, %d, 3]" % self.n_atoms)
+        check(_abi.lib().cmd_topo_build(self._handle, frames.ctypes.data_as(C.c_void_p),
+                                        frames.dtype.itemsize, frames.shape[0]))
+
+    def build_dev(self, data_ptr, nframes):
+        """Frames already in HBM: raw device pointer to float64 [F, n, 3]."""
+        check(_abi.lib().cmd_topo_build_dev(self._handle, C.c_void_p(int(data_ptr)), int(nframes)))
+
+    def frame_info(self):
+        n = self.nframes
+        counts = np.zeros(n, np.int64)
+        rebuilt = np.zeros(n, np.uint8)
+        rate_sum = np.zeros(n)
+        check(_abi.lib().cmd_topo_frame_info(self._handle, ptr(counts, C.c_int64),
+                                             ptr(rebuilt, C.c_uint8), ptr(rate_sum)))
+        return counts, rebuilt.astype(bool), rate_sum
+
+    def get_frame(self, f, count=None):
+        if count is None:
+            count = int(self.frame_info()[0][f])
+        start, dest = np.empty(count, np.int32), np.empty(count, np.int32)
+        dist, omega = np.empty(count), np.empty(count)
+        check(_abi.lib().cmd_topo_get_frame(self._handle, int(f), ptr(start, C.c_int),
+                                            ptr(dest, C.c_int), ptr(dist), ptr(omega)))
+        return start, dest, dist, omega
+
+    def tie_count(self):
+        return int(_abi.lib().cmd_topo_tie_count(self._handle))
+
+    def positions_ptr(self):
+        """Device pointer of the frames the last block was built from."""
+        p = C.c_void_p()
+        check(_abi.lib().cmd_topo_positions(self._handle, C.byref(p)))
+        return p
+
+
+def build_with_retry(make, frames):
+    """Runs make(capacity).build(frames); on a capacity overflow re-creates the object with the
+    capacity the library asked for (plus head-room) and builds again."""
+    capacity = 0
+    for _ in range(6):
+        topo = make(capacity)
+        try:
+            topo.build(frames)
+            return topo
+        except _abi.CmdError as e:
+            if e.code != -5:
+                raise
+            import re
+            m = re.search(r"has (\d+) directed pairs", str(e))
+            need = int(m.group(1)) if m else max(64, topo.stride * 2)
+            capacity = need + need // 4 + 64
+    raise RuntimeError("could not size the per-frame pair capacity")
+
+
+class NeighborTopology:
+    """Keeps track of the connections between donor/acceptor atoms.
+    Given a cutoff distance, for each atom the atoms within this
+    distance will be determined.  (mdlmc/topo/topology.py:18-121)"""
+    __show_in_config__ = True
+    __no_config_parameter__ = ["trajectory", "atom_box"]
+
+    #: frames pulled from the trajectory and sent to the GPU per launch
+    chunk_size = 256
+
+    def __init__(self, trajectory, atom_box, *, donor_atoms: str, cutoff: float = 3.0,
+                 buffer: float = 2.0) -> None:
+        self._raw_trajectory = trajectory
+        self._cache = deque()
+        self.trajectory = trajectory
+        self.trajectory_time_step = trajectory.time_step
+        self.cutoff = cutoff
+        self.buffer = buffer
+        self.atombox = atom_box
+        self.donor_atoms = donor_atoms
+        self._jumprate = None
+
+    # -- frame cache with the semantics of misc/tools.py:249-261 as installed at topology.py:43:
+    # every frame handed downstream is remembered until get_cached_frames() drains it
+    def get_cached_frames(self):
+        while self._cache:
+            yield self._cache.popleft()
+
+    def attach_jumprate(self, jumprate):
+        """Lets the device pipeline evaluate the jump rate inside the topology kernels."""
+        self._jumprate = jumprate
+
+    def _determine_colvars(self, start_indices, destination_indices, distances, frame):
+        """Per convention, the first collective variable is the distance (topology.py:50-53)."""
+        return start_indices, destination_indices, distances
+
+    # -- topology.py:55-72
+    def get_topology_bruteforce(self, frame):
+        """Determine the distance for each atom pair.  If it is below cutoff + buffer, add it to
+        the list of connections."""
+        frame = as_f64(frame)
+        topo = build_with_retry(
+            lambda cap: DeviceTopology(self.atombox, frame.shape[0], self.cutoff, self.buffer,
+                                       MODE_BRUTEFORCE, self._jumprate, cap), frame[None])
+        start, dest, dist, _ = topo.get_frame(0)
+        return start, dest, dist
+
+    def _donor_positions(self, full_frame):
+        return np.asarray(full_frame[self.donor_atoms].atom_positions, dtype=float)
+
+    def _chunks(self):
+        it = iter(self.trajectory)
+        while True:
+            frames = []
+            for full_frame in it:
+                frames.append(full_frame)
+                if len(frames) == self.chunk_size:
+                    break
+            if not frames:
+                return
+            yield frames
+            if len(frames) < self.chunk_size:
+                return
+
+    def device_blocks(self, mode=MODE_VERLET, chunk_size=None):
+        """Yields (DeviceTopology, full_frames, donor_positions) per block of frames: the block's
+        neighbour lists and rates stay in HBM for the KMC kernel (no per-frame host traffic)."""
+        if chunk_size is not None:
+            self.chunk_size = int(chunk_size)
+        topo = None
+        for full_frames in self._chunks():
+            pos = np.stack([self._donor_positions(f) for f in full_frames])
+            if topo is None:
+                topo = build_with_retry(
+                    lambda cap: DeviceTopology(self.atombox, pos.shape[1], self.cutoff,
+                                               self.buffer, mode, self._jumprate, cap), pos)
+            else:
+                topo.build(pos)   # a capacity overflow mid-trajectory raises CmdError(-5)
+            yield topo, full_frames, pos
+
+    def _generate(self, mode):
+        for topo, full_frames, _ in self.device_blocks(mode):
+            counts, _, _ = topo.frame_info()
+            for k, full_frame in enumerate(full_frames):
+                start, dest, dist, _ = topo.get_frame(k, int(counts[k]))
+                self._cache.append(full_frame)
+                yield start, dest, dist, full_frame
+
+    # -- topology.py:74-78
+    def topology_bruteforce_generator(self):
+        yield from self._generate(MODE_BRUTEFORCE)
+
+    # -- topology.py:80-114
+    def topology_verlet_list_generator(self):
+        """Keep track of the two maximum atom displacements.  As soon as their sum is larger
+        than the buffer region, update the neighbor topology."""
+        yield from self._generate(MODE_VERLET)
+
+    def __iter__(self):
+        for topo in self.topology_verlet_list_generator():
+            yield self._determine_colvars(*topo)
+
+    def update_time_of_last_jump(self, proton_idx, new_time):
+        pass

@@ -1,0 +1,122 @@
+"""Frame and the Trajectory protocol -- the input boundary of the hot path
+(mdlmc/IO/trajectory_parser.py:43-135).  Parsing xyz / HDF5 files is host I/O and out of scope
+(SURVEY.md section 8(f) F3); array-backed trajectories feed the GPU pipeline directly."""
+from abc import ABCMeta, abstractmethod
+
+import numpy as np
+
+
+class Frame:
+    """Names + positions (+ time) of all atoms of one MD step; selectable by atom name or by
+    index (trajectory_parser.py:43-113)."""
+
+    def __init__(self, names, positions, *, time=None):
+        self._names = names
+        self._positions = positions
+        self._time = time
+
+    @classmethod
+    def from_recarray(cls, array, *, time=None):
+        return cls(array["name"], array["pos"], time=time)
+
+    def __getitem__(self, item):
+        if isinstance(item, str):
+            sel = self._names == item
+        elif isinstance(item, (list, np.ndarray)):
+            sel = item
+        else:
+            raise ValueError(f"Selection {item} not understood")
+        return Frame(self._names[sel], self._positions[sel], time=self._time)
+
+    def __repr__(self):
+        body = "\n".join(f"{n}    {p[0]:20.10f} {p[1]:20.10f} {p[2]:20.10f}"
+                         for n, p in zip(self.atom_names, self.atom_positions))
+        return f"{self.atom_number}\n\n{body}"
+
+    def append(self, f2):
+        return Frame(np.hstack([self.atom_names, f2.atom_names]),
+                     np.vstack([self.atom_positions, f2.atom_positions]))
+
+    @property
+    def atom_names(self):
+        return self._names
+
+    @atom_names.setter
+    def atom_names(self, name):
+        self._names[:] = name
+
+    @property
+    def atom_positions(self):
+        return self._positions
+
+    @property
+    def atom_number(self):
+        return self._names.size
+
+    @property
+    def time(self):
+        return self._time
+
+
+class Trajectory(metaclass=ABCMeta):
+    """Iterable of Frame objects with a `time_step` attribute (trajectory_parser.py:116-135)."""
+    __show_in_config__ = True
+
+    @abstractmethod
+    def __iter__(self):
+        pass
+
+    @property
+    @abstractmethod
+    def current_frame_number(self):
+        pass
+
+    @abstractmethod
+    def __len__(self):
+        pass
+
+
+class ArrayTrajectory(Trajectory):
+    """In-memory trajectory: positions [frames, atoms, 3] (float32 as HDF5Trajectory stores it,
+    trajectory_parser.py:324, or float64) + atom names [atoms].  The GPU pipeline uploads whole
+    frame blocks of `positions` instead of iterating Frame objects."""
+
+    def __init__(self, positions, atom_names, *, time_step: float, repeat: bool = False):
+        self.positions = np.asarray(positions)
+        if self.positions.ndim != 3 or self.positions.shape[2] != 3:
+            raise ValueError("positions must have shape [frames, atoms, 3]")
+        self.atom_names = np.asarray(atom_names)
+        if self.atom_names.shape[0] != self.positions.shape[1]:
+            raise ValueError("atom_names must have one entry per atom")
+        self.time_step = time_step
+        self.repeat = repeat
+        self._current_frame_number = 0
+
+    def __iter__(self):
+        step = 0
+        while True:
+            for pos in self.positions:
+                self._current_frame_number = step
+                yield Frame(self.atom_names, np.asarray(pos, dtype=float), time=step * self.time_step)
+                step += 1
+            if not self.repeat:
+                break
+
+    def __len__(self):
+        return self.positions.shape[0]
+
+    @property
+    def current_frame_number(self):
+        return self._current_frame_number
+
+    def selection(self, name):
+        """Indices of the atoms called `name`."""
+        return np.where(self.atom_names == name)[0]
+
+    def block(self, name, start, stop):
+        """float64 [stop-start, n_selected, 3] donor positions of a frame block."""
+        sel = self.selection(name)
+        blk = self.positions[start:stop]
+        if sel.size != blk.shape[1]:
+            blk = blk[:, sel]
+        return np.ascontiguousarray(blk, dtype=np.float64)

@@ -171,6 +171,8 @@ int cmd_topo_get_frame(const cmd_topo *t, int64_t f, int *h_start, int *h_dest, 
 int cmd_topo_device_arrays(const cmd_topo *t, const int **d_start, const int **d_dest,
                            const double **d_dist, const double **d_omega,
                            const int **d_counts);
+/* Device pointer of the frames the last block was built from (float64 [nframes][n_atoms][3]). */
+int cmd_topo_positions(const cmd_topo *t, const double **d_frames);
 /* Tie audit: number of evaluated pairs of the last block whose distance is
  * within 1e-11 relative of cutoff+buffer. */
 int64_t cmd_topo_tie_count(const cmd_topo *t);
@@ -184,10 +186,14 @@ int64_t cmd_topo_tie_count(const cmd_topo *t);
 int cmd_kmc_create(const cmd_box *box, int n_sites, int n_replicas, const int *h_lattices,
                    double time_step, int rng_mode, uint64_t seed, cmd_kmc **out);
 void cmd_kmc_destroy(cmd_kmc *k);
-/* Replay stream: h_u float64 [n_replicas][n_per_replica]; draw 2e is np.random.random()
- * (MDMC.py:148), draw 2e+1 the u of np.random.uniform(0, S) == S*u (MDMC.py:110). */
+/* Replay stream: h_u float64 [n_replicas][n_per_replica]; consumed strictly alternating per
+ * event e: h_u[2e] is the TIME SELECTOR -log(1 - r) of the event's np.random.random() draw r
+ * (MDMC.py:148), evaluated by the caller with the reference's own log (NumPy) so that no
+ * log-implementation difference enters; h_u[2e+1] is the u of its np.random.uniform(0, S) == S*u
+ * (MDMC.py:110).  Replaces the previous stream and rewinds every replica's cursor. */
 int cmd_kmc_set_replay_stream(cmd_kmc *k, const double *h_u, int64_t n_per_replica);
-/* Event log capacity per replica (0 disables logging). */
+/* Event log capacity per replica (0 disables logging); (re)starts the log: events are logged
+ * from slot 0 again, so a caller drains the log after every cmd_kmc_advance. */
 int cmd_kmc_set_event_log(cmd_kmc *k, int64_t max_events_per_replica);
 /* Observables (MDMC.py:179-208, output.py): MSD per axis and covalent autocorrelation every
  * print_frequency frames, reset every reset_frequency frames. d_positions are the donor
@@ -200,6 +206,10 @@ int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_positions);
 /* State read-back. Any pointer may be NULL. */
 int cmd_kmc_get_state(const cmd_kmc *k, int *h_lattices, double *h_time, int64_t *h_frame,
                       int64_t *h_n_events, int64_t *h_site_updates);
+/* Per replica: phase (0 start, 2 running, 3 halted), halt reason (1 replay stream exhausted,
+ * 2 no allowed transition -- the reference raises IndexError there) and the number of replay
+ * draws consumed from the current stream. */
+int cmd_kmc_get_status(const cmd_kmc *k, int *h_phase, int *h_reason, int64_t *h_cursor);
 /* Event log of one replica: returns the number of logged events in *n (<= capacity). */
 int cmd_kmc_get_events(const cmd_kmc *k, int replica, int64_t capacity, int64_t *n,
                        int64_t *h_frame, double *h_time, int *h_start, int *h_dest,

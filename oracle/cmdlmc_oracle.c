@@ -339,10 +339,12 @@ ORC_API double orc_np_sum(const double *a, long n) { return pairwise_sum(a, n); 
 
 /* ---- A10-A12: mdlmc/LMC/MDMC.py:77-171, 229-248 -------------------------------------------
  * One KMC replica in exact-replay mode.  The per-frame topology + rates are given as CSR-like
- * concatenated arrays: frame f owns pairs [fptr[f], fptr[f+1]).  `u` is the uniform stream the
- * reference would draw from the global legacy RandomState after its initial shuffle: strictly
- * alternating  u[2e] -> np.random.random() (MDMC.py:148),  u[2e+1] -> np.random.uniform(0,S)
- * == S*u (MDMC.py:110).  All quirks of the reference are kept:
+ * concatenated arrays: frame f owns pairs [fptr[f], fptr[f+1]).  `u` is derived from the uniform
+ * stream the reference would draw from the global legacy RandomState after its initial shuffle,
+ * strictly alternating:  u[2e] = -np.log(1 - np.random.random()) (MDMC.py:148; evaluated by NumPy
+ * on the host so that no libm/NumPy log difference can enter -- the reference feeds rounding
+ * noise back into kmc_time with gain S_0/S_t per event, quirk Q1),  u[2e+1] -> the u of
+ * np.random.uniform(0,S) == S*u (MDMC.py:110).  All quirks of the reference are kept:
  *   Q1 current_rate is the total of frame 0 forever (MDMC.py:146);
  *   Q2 a same-frame event re-masks the arrays of the last consumed frame (MDMC.py:98,105-108);
  *   Q5 np.sum (pairwise) for totals, sequential cumsum for selection; Q6 Python // and %;
@@ -376,7 +378,7 @@ static double py_mod(double a, double b)
 
 /* ---- A11 alone: MDMC.py:121-171 (fastforward_to_next_jump) on a given stream of per-frame
  * total rates (cycled when `cycle` != 0, like itertools.cycle in tests/LMC/test_MDMC.py).
- * u[e] is the e-th np.random.random() draw.  rows[e] = (sweep, delta_frame, kmc_time). */
+ * u[e] = -np.log(1 - r_e) for the e-th np.random.random() draw r_e (NumPy-evaluated).  rows[e] = (sweep, delta_frame, kmc_time). */
 ORC_API long orc_fastforward(const double *rates, long nrates, int cycle, double dt,
                              const double *u, long nevents, double *rows)
 {
@@ -386,7 +388,7 @@ ORC_API long orc_fastforward(const double *rates, long nrates, int cycle, double
     double current_rate;
     NEXT_RATE(current_rate);
     while (nev < nevents) {
-        double time_selector = -log(1 - u[nev]);
+        double time_selector = u[nev]; /* = -np.log(1 - np.random.random()) evaluated by NumPy */
         double t_trial = time_selector / current_rate;
         long delta_frame;
         if (py_floordiv(kmc_time + t_trial, dt) == py_floordiv(kmc_time, dt)) {
@@ -463,7 +465,7 @@ ORC_API long orc_kmc_replay(const long *fptr, const int *start, const int *dest,
     double kmc_time = 0.0, current_rate;
     if (!kmc_next_rate(&s, &current_rate)) goto done;
     while (nev < max_events) {
-        double time_selector = -log(1 - u[2 * nev]);
+        double time_selector = u[2 * nev]; /* = -np.log(1 - np.random.random()), MDMC.py:148 */
         double t_trial = time_selector / current_rate;
         long delta_frame;
         if (py_floordiv(kmc_time + t_trial, dt) == py_floordiv(kmc_time, dt)) {

@@ -255,7 +255,7 @@ def kmc_replay(fptr, start, dest, omega, lattice, dt, u, max_events, trace_latti
     Returns dict of event arrays (+ frame_event, lattice_trace)."""
     fptr = np.ascontiguousarray(fptr, dtype=np.int64)
     start, dest, omega = _i(start), _i(dest), _d(omega)
-    u = _d(u)
+    u = time_selectors(u)
     assert lattice.dtype == np.int32 and lattice.flags.c_contiguous
     nframes = fptr.shape[0] - 1
     nsites = lattice.shape[0]
@@ -283,10 +283,18 @@ def kmc_replay(fptr, start, dest, omega, lattice, dt, u, max_events, trace_latti
     return out
 
 
+def time_selectors(u):
+    """Uniform stream (random(), uniform-u, random(), ...) -> stream whose even entries are the
+    reference's time selectors -np.log(1 - u) (MDMC.py:148), evaluated by NumPy like upstream."""
+    u = np.array(u, dtype=np.float64)
+    u[0::2] = -np.log(1 - u[0::2])
+    return u
+
+
 def fastforward(rates, dt, u, n_events, cycle=True):
     """MDMC.py:121-171 on a stream of per-frame total rates.  Returns f64[n,3] rows of
     (sweep, delta_frame, kmc_time)."""
-    rates, u = _d(rates), _d(u)
+    rates, u = _d(rates), -np.log(1 - _d(u))
     rows = np.zeros((n_events, 3))
     n = lib().orc_fastforward(_p(rates), rates.shape[0], int(cycle), float(dt), _p(u), n_events,
                               _p(rows))

