@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the cMD/LMC per-frame hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                          # the CPU path (reference arm)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W      # one rank per GPU
+
+Workload (config.workload): BASELINE.json configs[1] -- "C2": CsH2PO4-like monoclinic cell, 400 O,
+Fermi jump rate, synthetic trajectory (cmdlmc_b200/synth.py, seed 1).  One STEP = one pass of the
+geometry -> neighbour list -> jump rate stages (SURVEY.md 8(d) metric M1) over one block of
+`frames_per_step` frames per GPU, every unordered O-O pair of every frame evaluated
+(NeighborTopology.topology_bruteforce_generator semantics, topology.py:55-78), the per-frame
+lists (start, dest, dist, omega) materialised in HBM in the reference's order, followed -- when
+more than one GPU runs -- by one NCCL all-reduce of the block statistics.  Frame blocks are
+independent, so GPUs take disjoint blocks (weak scaling, no data-path collective).
+
+    value    frames x O-pairs / s, whole job, inputs resident in HBM
+    e2e      the same through the host-pointer C-ABI calls (cmd_topo_build + cmd_topo_frame_info):
+             pinned-host -> device copy of the block and device -> host read of the per-frame
+             results inside the timed region
+    roofline the dense pair kernel (k_pairs_dense) against the measured FP64 pipe peak
+    m2       KMC site-updates / s (SURVEY.md 8(d) metric M2): Verlet-mode topology of a sub-block
+             + Philox-mode KMC of `--replicas` replicas, timed on its own
+    cpu_baseline  the oracle's C port of the same step (OpenMP, all host cores) on a bounded
+             sample, plus the reference's own Cython AtomBox on a few frames when oracle/_ref
+             is present
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "frames*O-pairs/s"
+UNIT = "pairs/s"
+# algorithmic FP64 cost per unordered O-O pair
+FLOP_ORTHO = 20
+FLOP_GENERAL_REFERENCE = 279      # the reference's 27-image algorithm
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--frames-per-step", type=int, default=16384)
+    ap.add_argument("--replicas", type=int, default=1024)
+    ap.add_argument("--kmc-frames", type=int, default=2048)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0,
+                    help="target CPU time of the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-m2", action="store_true")
+    return ap.parse_args()
+
+
+def pairs_per_frame(n):
+    return n * (n - 1) // 2
+
+
+def flop_per_pair_executed(box_n_images, kind):
+    """FP64 flop the dense kernel issues per candidate pair: ortho 20;
+    general cell 3 sub + 2 mat-vec (15 each) + 3 x (2 add rint + 1 sub) + 5 norm
+    + n_img x (3 add + 5 norm + 1 min)."""
+    if kind == 0:
+        return FLOP_ORTHO
+    return 3 + 30 + 9 + 5 + box_n_images * 9
+
+
+# ------------------------------------------------------------------------------ clocks --------
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ CPU legs ------
+def cpu_port_rate(w, seconds, threads=None):
+    """The oracle's C port of the step (all-pairs topology + rates per frame, OpenMP over frames)
+    on a bounded sample of the same workload.  Returns (pairs/s, cores, sample text)."""
+    from oracle import oracle as orc
+    from cmdlmc_b200 import synth
+    cores = threads or os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    orc.build()
+    box = orc.OracleBox(w.cell)
+    rc = w.cutoff + w.buffer
+    ppf = pairs_per_frame(w.n_oxygen)
+    probe = max(cores, 8)
+    fr = synth.trajectory(w, probe)
+    orc.bench_frames(box, fr, rc, w.rate_kind, w.rate_params)   # warm the thread pool
+    t = time.perf_counter()
+    orc.bench_frames(box, fr, rc, w.rate_kind, w.rate_params)
+    dt = time.perf_counter() - t
+    nfr = int(max(probe, min(16384, seconds / max(dt / probe, 1e-9))))
+    nfr = (nfr + cores - 1) // cores * cores
+    fr = synth.trajectory(w, nfr)
+    best = None
+    for _ in range(2):
+        t = time.perf_counter()
+        orc.bench_frames(box, fr, rc, w.rate_kind, w.rate_params)
+        dt = time.perf_counter() - t
+        best = dt if best is None or dt < best else best
+    sample = "%d frames of %s (%d O, %d pairs/frame), best of 2, gcc -O2 -fopenmp port" % (
+        nfr, w.name, w.n_oxygen, ppf)
+    return nfr * ppf / best, cores, sample, nfr, best
+
+
+def reference_cython_rate(w, frames=2):
+    """The reference's own compiled AtomBox (oracle/_ref): length_all_to_all on a few frames,
+    one core (the reference is single-threaded).  None when oracle/_ref did not travel."""
+    try:
+        from oracle import ref_import
+        from cmdlmc_b200 import synth
+        mod = ref_import.import_ref_atombox()
+    except Exception:
+        return None
+    cell = np.asarray(w.cell, dtype=float)
+    box = mod.AtomBoxCubic(cell) if cell.size == 3 else mod.AtomBoxMonoclinic(cell)
+    fr = synth.trajectory(w, frames)
+    t = time.perf_counter()
+    for f in fr:
+        box.length_all_to_all(f, f)
+    dt = time.perf_counter() - t
+    # length_all_to_all evaluates the full n x n table = 2 x the unordered pairs (+ diagonal)
+    return frames * w.n_oxygen * w.n_oxygen / 2.0 / dt
+
+
+def run_reference(args):
+    """Reference arm: the CPU implementation of the same step on the host cores (the oracle's C
+    port with OpenMP; oracle/_ref's Cython AtomBox is timed beside it as `reference_cython`)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from cmdlmc_b200 import synth
+    w = synth.workload(args.workload)
+    ppf = pairs_per_frame(w.n_oxygen)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    # bounded sample per step so that the whole run ends within a few minutes
+    budget = min(args.cpu_seconds, 120.0 / (steps + warm))
+    rate, cores, sample, nfr, _ = cpu_port_rate(w, budget)
+    from oracle import oracle as orc
+    box = orc.OracleBox(w.cell)
+    fr = synth.trajectory(w, nfr)
+    rc = w.cutoff + w.buffer
+    for _ in range(warm):
+        orc.bench_frames(box, fr, rc, w.rate_kind, w.rate_params)
+    t = time.perf_counter()
+    for _ in range(steps):
+        orc.bench_frames(box, fr, rc, w.rate_kind, w.rate_params)
+    dt = time.perf_counter() - t
+    value = steps * nfr * ppf / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "gpu_launches": 0,
+        "config": workload_config(w, nfr, "bruteforce", extra={"l2": "n/a (CPU)"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample,
+                         "reference_cython_pairs_per_s_1core": reference_cython_rate(w)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(w, frames_per_step, mode, extra=None):
+    cfg = {"workload": "%s: %s cell, %d O, %s jump rate, synthetic trajectory (seed %d)" % (
+        w.name, "orthorhombic" if w.is_ortho else "monoclinic/triclinic", w.n_oxygen,
+        w.rate_kind, w.seed),
+        "frames_per_step_per_gpu": frames_per_step,
+        "o_pairs_per_frame": pairs_per_frame(w.n_oxygen),
+        "cutoff_plus_buffer": w.cutoff + w.buffer, "topology_mode": mode,
+        "parallelism": "frame-block per GPU"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------ GPU arm -------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from cmdlmc_b200 import AtomBoxCubic, AtomBoxMonoclinic, Fermi, ActivationEnergy, runtime, synth
+    from cmdlmc_b200 import _abi
+    from cmdlmc_b200.topology import DeviceTopology, MODE_BRUTEFORCE, MODE_VERLET
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    runtime.init(local)
+    runtime.use_torch_stream()
+    dev = torch.device("cuda", local)
+
+    w = synth.workload(args.workload)
+    n, B = w.n_oxygen, args.frames_per_step
+    ppf = pairs_per_frame(n)
+    cell = np.asarray(w.cell, dtype=float)
+    box = AtomBoxCubic(cell) if cell.size == 3 else AtomBoxMonoclinic(cell)
+    rate = Fermi(*w.rate_params) if w.rate_kind == "Fermi" else ActivationEnergy(*w.rate_params)
+
+    # this rank's frame block of the synthetic trajectory, in pinned host memory and in HBM
+    host = torch.empty((B, n, 3), dtype=torch.float64, pin_memory=True)
+    host.numpy()[...] = synth.trajectory(w, B, start=rank * B)
+    d_frames = host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    in_bytes = B * n * 24
+
+    topo = DeviceTopology(box, n, w.cutoff, w.buffer, MODE_BRUTEFORCE, rate, 0)
+    stats = torch.zeros(2, dtype=torch.float64, device=dev)
+
+    def step_resident():
+        topo.build_dev(d_frames.data_ptr(), B)
+        if world > 1:
+            dist.all_reduce(stats)       # block statistics (pair count, rate sum): 16 bytes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+    counts, _, rate_sum = topo.frame_info()
+    assert (counts >= 0).all()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    K = args.steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(K)]
+    l0 = runtime.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        ev[k][0].record()
+        topo.build_dev(d_frames.data_ptr(), B)
+        ev[k][1].record()
+        if world > 1:
+            dist.all_reduce(stats)
+    e1.record()
+    barrier()
+    launches = runtime.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region -------------
+    hptr = host.data_ptr()
+    import ctypes as C
+    lib = _abi.lib()
+    h_counts = np.zeros(B, np.int64)
+    h_rebuilt = np.zeros(B, np.uint8)
+    h_rsum = np.zeros(B)
+
+    def step_e2e():
+        _abi.check(lib.cmd_topo_build(topo.handle, C.c_void_p(hptr), 8, B))
+        _abi.check(lib.cmd_topo_frame_info(topo.handle, _abi.ptr(h_counts, C.c_int64),
+                                           _abi.ptr(h_rebuilt, C.c_uint8), _abi.ptr(h_rsum)))
+        if world > 1:
+            dist.all_reduce(stats)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_e2e()
+    f1.record()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = max(f0.elapsed_time(f1), e2e_wall * 1e3)
+    clocks = sampler.stop()
+
+    # max over ranks
+    tm = torch.tensor([ms_total, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, kernel_ms = [float(x) for x in tm.tolist()]
+
+    value = world * K * B * ppf / (ms_total * 1e-3)
+    e2e_value = world * K * B * ppf / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_pairs_dense), FP64 pipe --------------------------
+    peak_tf = runtime.fp64_peak_tflops(40000)
+    n_img = int(lib.cmd_box_n_images(box.handle))
+    kind = 0 if cell.size == 3 else 1
+    flop_exec = flop_per_pair_executed(n_img, kind)
+    flop_ref = FLOP_ORTHO if kind == 0 else FLOP_GENERAL_REFERENCE
+    achieved = B * ppf * flop_exec / (kernel_ms * 1e-3) / 1e12
+    out_bytes = float(counts.sum()) * 24.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {
+        "kernel": "k_pairs_dense", "bound": "fp64", "achieved": achieved, "peak": peak_tf,
+        "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+        "peak_source": "cmd_fp64_peak: DFMA loop on every SM, measured in this run "
+                       "(MEASURED_PEAKS.json has no FP64 figure)",
+        "flop_per_pair_executed": flop_exec, "images_kept": n_img,
+        "flop_per_pair_reference_algorithm": flop_ref,
+        "achieved_reference_equivalent_tflops": B * ppf * flop_ref / (kernel_ms * 1e-3) / 1e12,
+        "kernel_ms_per_launch": kernel_ms,
+        "hbm_algorithmic_gbs": (in_bytes + out_bytes) / (kernel_ms * 1e-3) / 1e9,
+        "hbm_peak_gbs": hbm_peak,
+        "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_total / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(w, B, "bruteforce", extra={
+            "l2": "inputs (%.0f MB) and outputs (%.0f MB) per step exceed the 126 MB L2" % (
+                in_bytes / 1e6, out_bytes / 1e6),
+            "directed_pairs_per_frame_mean": float(counts.mean())}),
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": B * 13 + 4, "ms_per_step": e2e_ms / K,
+                "api": "cmd_topo_build(host f64 frames) + cmd_topo_frame_info"},
+        "roofline": roofline, "clocks": clocks,
+    }
+
+    # ---- M2: KMC site-updates/s (own timed region) --------------------------------------------
+    if not args.no_m2:
+        line["m2"] = run_m2(args, w, box, rate, d_frames, world, dev, dist, barrier)
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample, _, _ = cpu_port_rate(w, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": sample,
+                                "reference_cython_pairs_per_s_1core": reference_cython_rate(w)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_m2(args, w, box, rate, d_frames, world, dev, dist, barrier):
+    """Verlet-mode topology of a sub-block + Philox KMC of R replicas per GPU (replica-sharded:
+    every GPU walks its own replicas over its own frames; statistics all-reduced)."""
+    import torch
+    from cmdlmc_b200 import runtime, synth
+    from cmdlmc_b200.kmc import DeviceKMC, RNG_PHILOX
+    from cmdlmc_b200.topology import DeviceTopology, MODE_VERLET
+    F = min(args.kmc_frames, d_frames.shape[0])
+    R = args.replicas
+    n = w.n_oxygen
+    topo = DeviceTopology(box, n, w.cutoff, w.buffer, MODE_VERLET, rate, 0)
+    topo.build_dev(d_frames.data_ptr(), F)
+    counts, rebuilt, _ = topo.frame_info()
+    lattices = np.stack([synth.initial_lattice(n, w.n_protons, 4000 + r)[0] for r in range(R)])
+    times = []
+    updates = 0
+    events = 0
+    reps = 3
+    for it in range(reps + 1):
+        kmc = DeviceKMC(box, lattices, w.time_step, RNG_PHILOX, seed=11 + it)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        kmc.advance(topo)
+        b.record()
+        barrier()
+        st = kmc.state()
+        if it > 0:
+            times.append(a.elapsed_time(b))
+            updates = int(st["site_updates"].sum())
+            events = int(st["n_events"].sum())
+    ms = float(np.mean(times))
+    tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(updates), float(events)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    ms = float(tm.item())
+    updates, events = [float(x) for x in tot.tolist()]
+    rate_su = updates / (ms * 1e-3)
+    return {"metric": "KMC site-updates/s", "value": rate_su, "unit": "site-updates/s",
+            "replicas_per_gpu": R, "frames": F, "ms": ms, "events": events,
+            "rng": "philox4x32-10", "directed_pairs_per_frame_mean": float(counts.mean()),
+            "verlet_rebuilds": int(rebuilt.sum()),
+            "implied_onchip_gbs": rate_su * 16 / 1e9,
+            "hbm_algorithmic_gbs": float(counts.sum()) * 16.0 / (ms * 1e-3) / 1e9}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
