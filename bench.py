@@ -69,12 +69,12 @@ def pairs_per_frame(n):
 
 
 def flop_per_pair_executed(box_n_images, kind):
-    """FP64 flop the dense kernel issues per candidate pair (DESIGN.md section 4): ortho 20;
-    general cell 3 sub + 2 mat-vec (15 each) + 3 x (2 add rint + 1 sub) + 5 norm
-    + n_img x (3 add + 5 norm + 1 min)."""
+    """FP64 flop the dense kernel's filter issues per unordered pair:
+    ortho 20; general cell 3 sub (pre-wrapped fractional coordinates) + 3 x (2 add rint + 1 sub)
+    + 1 mat-vec (3 mul + 6 fma = 15) + norm (1 mul + 2 fma = 5) + n_img x (3 add + 5 norm + 1 min)."""
     if kind == 0:
         return FLOP_ORTHO
-    return 3 + 30 + 9 + 5 + box_n_images * 9
+    return 3 + 9 + 15 + 5 + box_n_images * 9
 
 
 # ------------------------------------------------------------------------------ clocks --------
@@ -351,7 +351,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (k_pairs_dense), FP64 pipe --------------------------
     peak_tf = runtime.fp64_peak_tflops(40000)
-    n_img = int(lib.cmd_box_n_images(box.handle))
+    n_img = topo.n_images
     kind = 0 if cell.size == 3 else 1
     flop_exec = flop_per_pair_executed(n_img, kind)
     flop_ref = FLOP_ORTHO if kind == 0 else FLOP_GENERAL_REFERENCE

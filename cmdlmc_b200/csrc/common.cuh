@@ -24,6 +24,7 @@ struct BoxParams {
     // walks all 27 images in the reference order, numpyatom.pyx:111-123).
     int n_img;
     double img[CMD_MAX_IMAGES][3];  // Cartesian shift i*a + j*b + k*c
+    int img_ijk[CMD_MAX_IMAGES][3]; // the (i, j, k) of each kept image
 };
 
 struct cmd_box {
@@ -49,6 +50,9 @@ struct CmdGlobal {
 CmdGlobal &cmd_global();
 int cmd_set_error(int code, const char *fmt, ...);
 int cmd_scratch(int slot, size_t bytes, void **out);  // grows slot to >= bytes
+// Rebuilds p.img / p.img_ijk: the periodic images a pair filter with radius `rc` has to look at
+// besides the fractionally wrapped vector (rc < 0: no radius, every image that can beat it).
+void cmd_box_prune_images(BoxParams &p, double rc);
 
 #define CMD_CUDA(expr)                                                                      \
     do {                                                                                    \

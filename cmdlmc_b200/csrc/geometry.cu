@@ -170,26 +170,43 @@ static void invert3(const double *m, double *inv)
     inv[6] = (d * h - e * g) / det; inv[7] = (b * g - a * h) / det; inv[8] = (a * e - b * d) / det;
 }
 
-static void box_prune_images(BoxParams &p)
+// Which of the 26 neighbour images can matter for a wrapped vector v = h s, |s_c| <= 1/2 ?
+//  (1) image T can be shorter than v somewhere in the wrap cube iff |T|^2 < sum_c |(h^T T)_c|;
+//  (2) |v + T| <= rc needs v inside the ball B(-T, rc); the lattice point -T lies at least
+//      height_c / 2 outside the wrap parallelepiped along every axis c with T_c != 0
+//      (height_c = 1 / |row c of h^-1|), so the image is irrelevant below that radius.
+// Both tests are conservative (1e-6 relative slack on rc); a kept image costs flops, a wrongly
+// dropped one would lose neighbours.
+void cmd_box_prune_images(BoxParams &p, double rc)
 {
     p.n_img = 0;
     if (p.kind == 0) return;
+    double height[3];
+    for (int c = 0; c < 3; c++)
+        height[c] = 1.0 / sqrt(p.hinv[3 * c] * p.hinv[3 * c] + p.hinv[3 * c + 1] * p.hinv[3 * c + 1] +
+                               p.hinv[3 * c + 2] * p.hinv[3 * c + 2]);
     for (int i = -1; i < 2; i++)
         for (int j = -1; j < 2; j++)
             for (int k = -1; k < 2; k++) {
                 if (!i && !j && !k) continue;
+                const int ijk[3] = {i, j, k};
                 double T[3], g[3];
                 for (int c = 0; c < 3; c++) T[c] = i * p.h[3 * c] + j * p.h[3 * c + 1] + k * p.h[3 * c + 2];
                 double t2 = T[0] * T[0] + T[1] * T[1] + T[2] * T[2];
-                // g = h^T T ; the image can shorten the wrapped vector h s (|s_c| <= 1/2) iff
-                // |T|^2 < sum_c |g_c|
                 double sum = 0;
                 for (int c = 0; c < 3; c++) {
                     g[c] = p.h[c] * T[0] + p.h[3 + c] * T[1] + p.h[6 + c] * T[2];
                     sum += fabs(g[c]);
                 }
-                if (sum - t2 > 1e-13 * t2) {
-                    for (int c = 0; c < 3; c++) p.img[p.n_img][c] = T[c];
+                bool keep = sum - t2 > -1e-9 * t2;
+                if (keep && rc >= 0) {
+                    double lb = 0;
+                    for (int c = 0; c < 3; c++)
+                        if (ijk[c] && 0.5 * height[c] > lb) lb = 0.5 * height[c];
+                    keep = lb <= rc * (1.0 + 1e-6) + 1e-9 * lb;
+                }
+                if (keep) {
+                    for (int c = 0; c < 3; c++) { p.img[p.n_img][c] = T[c]; p.img_ijk[p.n_img][c] = ijk[c]; }
                     p.n_img++;
                 }
             }
@@ -247,7 +264,7 @@ extern "C" int cmd_box_create(const double *pb, int n_values, const int mult_in[
             p.hL[i] = p.L[i] / 2;
         }
     }
-    box_prune_images(p);
+    cmd_box_prune_images(p, -1.0);
     *out = b;
     return CMD_OK;
 }

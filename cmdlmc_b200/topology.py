@@ -56,6 +56,11 @@ class DeviceTopology:
         return int(_abi.lib().cmd_topo_stride(self._handle))
 
     @property
+    def n_images(self):
+        """Periodic images the pair filter evaluates besides the wrapped vector."""
+        return int(_abi.lib().cmd_topo_n_images(self._handle))
+
+    @property
     def nframes(self):
         return int(_abi.lib().cmd_topo_nframes(self._handle))
 

@@ -162,6 +162,9 @@ int cmd_topo_build(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t n
 int cmd_topo_frame_info(const cmd_topo *t, int64_t *h_counts, uint8_t *h_rebuilt,
                         double *h_rate_sum);
 int64_t cmd_topo_stride(const cmd_topo *t);
+/* Number of periodic images, besides the fractionally wrapped vector, that the pair filter of
+ * this topology evaluates (general cells; depends on cutoff + buffer against the cell heights). */
+int cmd_topo_n_images(const cmd_topo *t);
 int64_t cmd_topo_nframes(const cmd_topo *t);
 /* Copies frame f of the last block to host arrays of at least P_f elements (any may be NULL):
  * the (row, col, data) triple get_topology_bruteforce returns, plus the rates. */
