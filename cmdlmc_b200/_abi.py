@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcmdlmc_b200.so")
+# CMDLMC_B200_LIB lets a developer A/B-test another build of the same library
+LIB_PATH = os.environ.get("CMDLMC_B200_LIB") or os.path.join(HERE, "libcmdlmc_b200.so")
 
 
 class CmdError(RuntimeError):

@@ -15,7 +15,11 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include "pbc.cuh"
+#include "pairs_dense.cuh"
+
+#ifndef DENSE_SPLIT_MID
+#define DENSE_SPLIT_MID 2
+#endif
 
 struct cmd_topo {
     BoxParams bx;
@@ -23,7 +27,7 @@ struct cmd_topo {
     int n;
     double cutoff, buffer, rc;
     double t2;       // largest d2 with sqrt(d2) <= rc  (exact decision on the squared length)
-    double lsum;     // sum |h_ij|: scale of the filter's rounding-error allowance
+    FilterParams fp; // FP32 fixed-point filter of the dense kernel
     int mode;
     int64_t stride;  // per-frame pair capacity
     int hit_cap;     // unordered hits per frame that fit the CTA's shared-memory list
@@ -46,304 +50,6 @@ struct cmd_topo {
     const double *d_frames_last;  // frames of the last block (device)
     int64_t total_frames;
 };
-
-// ------------------------------------------------------------------ shared-memory layout ------
-struct DenseSmem {
-    double *cx, *cy, *cz;   // [n] Cartesian coordinates of the frame (SoA)
-    double *sx, *sy, *sz;   // [n] wrapped fractional coordinates (general cells only)
-    double *hit_d;          // [hit_cap] candidate d^2 (ortho) -> distance of a hit, < 0 otherwise
-    unsigned *mask;         // [n][W] adjacency bit matrix
-    unsigned *hit_ij;       // [hit_cap] (i << 16) | j
-    int *rowoff;            // [n + 1]
-    int *misc;              // [0] ncand, [1] total, [2..33] warp sums
-    double *red;            // [34] block reductions
-};
-
-__host__ __device__ inline size_t dense_smem_bytes(int n, int hit_cap, int kind)
-{
-    int W = (n + 31) / 32;
-    size_t b = 0;
-    b += (kind ? 6 : 3) * (size_t)n * 8;
-    b += (size_t)hit_cap * 8;
-    b += 40 * 8;
-    b += (size_t)n * W * 4;
-    b += (size_t)hit_cap * 4;
-    b += ((size_t)n + 1) * 4;
-    b += 40 * 4;
-    return b + 16;
-}
-
-__device__ __forceinline__ DenseSmem dense_carve(unsigned char *base, int n, int hit_cap, int kind)
-{
-    DenseSmem s;
-    int W = (n + 31) / 32;
-    s.cx = (double *)base;
-    s.cy = s.cx + n;
-    s.cz = s.cy + n;
-    double *nx = s.cz + n;
-    s.sx = s.sy = s.sz = nullptr;
-    if (kind) { s.sx = nx; s.sy = s.sx + n; s.sz = s.sy + n; nx = s.sz + n; }
-    s.hit_d = nx;
-    s.red = s.hit_d + hit_cap;
-    s.mask = (unsigned *)(s.red + 40);
-    s.hit_ij = s.mask + (size_t)n * W;
-    s.rowoff = (int *)(s.hit_ij + hit_cap);
-    s.misc = s.rowoff + n + 1;
-    return s;
-}
-
-// exclusive scan of one int per thread over the CTA; returns the exclusive prefix, total in *tot
-__device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums, int *tot)
-{
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) warp_sums[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        int ws = lane < nw ? warp_sums[lane] : 0;
-        int winc = ws;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        if (lane < nw) warp_sums[lane] = winc - ws;
-        if (lane == 31) *tot = winc;
-    }
-    __syncthreads();
-    return inc - v + warp_sums[w];
-}
-
-// squared reference length over the zero image + the kept images, in the reference's operation
-// order ((d + i a) + j b) + k c (numpyatom.pyx:111-118).  Equals the reference's 27-image minimum
-// whenever that minimum is <= cutoff + buffer (cmd_box_prune_images, test 2).
-__device__ __forceinline__ double min_image_norm2_kept(const BoxParams &bx, const double d[3])
-{
-    double mind = fmin(1e6, norm2_exact(d));   // image (0,0,0): d + 0*a + 0*b + 0*c == d
-    for (int m = 0; m < bx.n_img; m++) {
-        const int i = bx.img_ijk[m][0], j = bx.img_ijk[m][1], k = bx.img_ijk[m][2];
-        double v[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-            v[c] = __dadd_rn(__dadd_rn(__dadd_rn(d[c], i * bx.h[3 * c]), j * bx.h[3 * c + 1]),
-                             k * bx.h[3 * c + 2]);
-        double n2 = norm2_exact(v);
-        if (n2 < mind) mind = n2;
-    }
-    return mind;
-}
-
-// ------------------------------------------------------------------ all-pairs kernel ----------
-// One CTA per frame.  grid.x = number of frames to (re)build; frame = ids ? ids[blockIdx.x] :
-// blockIdx.x.  Three phases, all out of shared memory:
-//   1 filter   every unordered pair once (cyclic pairing, thread i <-> row i): FMA arithmetic on
-//              pre-wrapped fractional coordinates (general cells) or the exact orthorhombic wrap;
-//              pairs within the (conservatively widened) radius are appended to a candidate list
-//              with one warp-aggregated shared-memory atomic -- no divergent heavy path;
-//   2 exact    the candidates, densely packed over the CTA, in the reference's arithmetic: the
-//              `dist <= cutoff + buffer` decision, sqrt, adjacency bits;
-//   3 emit     row offsets from the adjacency bit matrix (popc scan) and the ordered write of
-//              (start, dest, dist, omega) with the jump rate evaluated per hit.
-template <int KIND, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ RateParams rp,
-              const double *__restrict__ frames, const int *__restrict__ ids,
-              const int *__restrict__ n_ids, int n, double rc, double t2, double lsum,
-              int64_t stride, int hit_cap, int *__restrict__ out_start, int *__restrict__ out_dest,
-              double *__restrict__ out_dist, double *__restrict__ out_omega,
-              int *__restrict__ out_counts, double *__restrict__ out_rate_sum,
-              uint8_t *__restrict__ out_rebuilt, int *__restrict__ err,
-              unsigned long long *__restrict__ ties)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    if (n_ids && (int)blockIdx.x >= *n_ids) return;
-    const int64_t f = ids ? ids[blockIdx.x] : blockIdx.x;
-    DenseSmem s = dense_carve(smem_raw, n, hit_cap, KIND);
-    const int W = (n + 31) / 32;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const double *fr = frames + f * (int64_t)n * 3;
-
-    // stage the frame: contiguous, coalesced read of 3n doubles, de-interleaved into SoA
-    for (int k = tid; k < 3 * n; k += blockDim.x) {
-        double v = __ldg(fr + k);
-        int a = k / 3, c = k - 3 * a;
-        (c == 0 ? s.cx : c == 1 ? s.cy : s.cz)[a] = v;
-    }
-    for (int k = tid; k < n * W; k += blockDim.x) s.mask[k] = 0u;
-    if (tid == 0) { s.misc[0] = 0; s.misc[1] = 0; }
-    __syncthreads();
-
-    const int i = tid;
-    double t2f = t2;
-    if (KIND == 1) {
-        // wrapped fractional coordinates, once per atom; e bounds their rounding error
-        double e = 0.0;
-        if (i < n) {
-            const double x = s.cx[i], y = s.cy[i], z = s.cz[i];
-            double q[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                double v = fma(bx.hinv[3 * c + 2], z, fma(bx.hinv[3 * c + 1], y, bx.hinv[3 * c] * x));
-                double a = fma(fabs(bx.hinv[3 * c + 2]), fabs(z),
-                               fma(fabs(bx.hinv[3 * c + 1]), fabs(y), fabs(bx.hinv[3 * c] * x)));
-                e = fmax(e, a);
-                q[c] = v - rint(v);
-            }
-            s.sx[i] = q[0]; s.sy[i] = q[1]; s.sz[i] = q[2];
-        }
-        for (int o = 16; o > 0; o >>= 1) e = fmax(e, __shfl_xor_sync(0xffffffffu, e, o));
-        if (lane == 0) s.red[wid] = e;
-        __syncthreads();
-        e = 0.0;
-        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) e = fmax(e, s.red[w]);
-        // filter radius: rc widened by 1e-9 relative plus the worst Cartesian error of a wrapped
-        // difference (8 ulp of the largest fractional magnitude times sum |h|)
-        const double thr = rc * (1.0 + 1e-9) + 8.0 * 2.3e-16 * (e + 1.0) * lsum;
-        t2f = thr * thr;
-    }
-
-    // ---- phase 1: filter -------------------------------------------------------------------
-    {
-        const int half = n >> 1;
-        const bool even = (n & 1) == 0;
-        double xi = 0, yi = 0, zi = 0;
-        if (i < n) {
-            if (KIND == 1) { xi = s.sx[i]; yi = s.sy[i]; zi = s.sz[i]; }
-            else { xi = s.cx[i]; yi = s.cy[i]; zi = s.cz[i]; }
-        }
-        const double pi_[3] = {xi, yi, zi};
-        // cyclic pairing: thread i owns pairs (i, i+k mod n), k = 1..floor(n/2); for even n the
-        // k = n/2 column is owned by the lower half only -> every unordered pair exactly once
-        for (int k = 1; k <= half; k++) {
-            const bool valid = i < n && !(even && k == half && i >= half);
-            int j = i + k;
-            if (j >= n) j -= n;
-            if (!valid) j = 0;
-            double d2;
-            bool cand;
-            if (KIND == 0) {
-                // reference: length(frame[hi], frame[lo]) (topology.py:62-66); the arithmetic is
-                // sign-symmetric, so the direction does not change a bit
-                const double pj[3] = {s.cx[j], s.cy[j], s.cz[j]};
-                double d[3];
-                diff_ortho_exact(bx, pi_, pj, d);
-                d2 = norm2_exact(d);
-                cand = bx.conv == CMD_CONV_NONE ? d2 <= t2 : convert_distance(bx, sqrt(d2)) <= rc;
-            } else {
-                double a = s.sx[j] - xi, b = s.sy[j] - yi, c = s.sz[j] - zi;
-                a -= rint_magic(a); b -= rint_magic(b); c -= rint_magic(c);
-                const double vx = fma(bx.h[2], c, fma(bx.h[1], b, bx.h[0] * a));
-                const double vy = fma(bx.h[5], c, fma(bx.h[4], b, bx.h[3] * a));
-                const double vz = fma(bx.h[8], c, fma(bx.h[7], b, bx.h[6] * a));
-                d2 = fma(vz, vz, fma(vy, vy, vx * vx));
-                for (int m = 0; m < bx.n_img; m++) {
-                    double ux = vx + bx.img[m][0], uy = vy + bx.img[m][1], uz = vz + bx.img[m][2];
-                    d2 = fmin(d2, fma(uz, uz, fma(uy, uy, ux * ux)));
-                }
-                cand = d2 <= t2f;
-            }
-            cand = cand && valid;
-            const unsigned bal = __ballot_sync(0xffffffffu, cand);
-            if (bal) {
-                int slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&s.misc[0], __popc(bal));
-                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
-                if (cand && slot < hit_cap) {
-                    s.hit_ij[slot] = ((unsigned)i << 16) | (unsigned)j;
-                    if (KIND == 0) s.hit_d[slot] = d2;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    const int ncand = s.misc[0];
-    if (ncand > hit_cap) {  // capacity probe / overflow: report the (upper bound of the) need
-        if (tid == 0) {
-            out_counts[f] = -2 * ncand;
-            if (out_rebuilt) out_rebuilt[f] = 1;
-            atomicMax(err, 2 * ncand);
-        }
-        return;
-    }
-
-    // ---- phase 2: exact evaluation of the candidates ----------------------------------------
-    unsigned long long my_ties = 0;
-    for (int c = tid; c < ncand; c += blockDim.x) {
-        const unsigned ij = s.hit_ij[c];
-        const int a = ij >> 16, b = ij & 0xffff;
-        double d2;
-        if (KIND == 0) d2 = s.hit_d[c];
-        else {
-            const double pa[3] = {s.cx[a], s.cy[a], s.cz[a]}, pb[3] = {s.cx[b], s.cy[b], s.cz[b]};
-            double d[3];
-            diff_general_exact(bx, pa, pb, d);
-            d2 = min_image_norm2_kept(bx, d);
-        }
-        const double dist = convert_distance(bx, sqrt(d2));
-        const bool hit = (bx.conv == CMD_CONV_NONE ? d2 <= t2 : dist <= rc) && dist != 0.0;
-        if (fabs(dist - rc) <= 1e-11 * rc) my_ties++;
-        s.hit_d[c] = hit ? dist : -1.0;
-        if (hit) {
-            atomicOr(&s.mask[a * W + (b >> 5)], 1u << (b & 31));
-            atomicOr(&s.mask[b * W + (a >> 5)], 1u << (a & 31));
-        }
-    }
-    if (my_ties) atomicAdd(ties, my_ties);
-    __syncthreads();
-
-    // ---- phase 3: row counts -> exclusive offsets (LIL->COO order is row-major), write-out ---
-    int cnt = 0;
-    if (i < n)
-        for (int w = 0; w < W; w++) cnt += __popc(s.mask[i * W + w]);
-    int off = block_exclusive_scan(cnt, s.misc + 2, &s.misc[1]);
-    if (i < n) s.rowoff[i] = off;
-    __syncthreads();
-    const int total = s.misc[1];
-    if (tid == 0) {
-        out_counts[f] = total > stride ? -total : total;
-        if (out_rebuilt) out_rebuilt[f] = 1;
-        if (total > stride) atomicMax(err, total);
-    }
-    if (total > stride) return;
-
-    // position of (a -> b) = rowoff[a] + #set bits of row a below column b
-    const int64_t base = f * stride;
-    double rsum = 0.0;
-    for (int h = tid; h < ncand; h += blockDim.x) {
-        const double dist = s.hit_d[h];
-        if (dist < 0.0) continue;
-        const unsigned ij = s.hit_ij[h];
-        const int a = ij >> 16, b = ij & 0xffff;
-        const double om = rate_eval(rp, dist, 0.0);
-        rsum += om;
-        int pa = s.rowoff[a], pb = s.rowoff[b];
-        for (int w = 0; w < (b >> 5); w++) pa += __popc(s.mask[a * W + w]);
-        pa += __popc(s.mask[a * W + (b >> 5)] & ((1u << (b & 31)) - 1u));
-        for (int w = 0; w < (a >> 5); w++) pb += __popc(s.mask[b * W + w]);
-        pb += __popc(s.mask[b * W + (a >> 5)] & ((1u << (a & 31)) - 1u));
-        out_start[base + pa] = a; out_dest[base + pa] = b;
-        out_dist[base + pa] = dist; out_omega[base + pa] = om;
-        out_start[base + pb] = b; out_dest[base + pb] = a;
-        out_dist[base + pb] = dist; out_omega[base + pb] = om;
-    }
-    if (out_rate_sum) {
-        // informational per-frame total of all listed rates (both directions)
-        for (int o = 16; o > 0; o >>= 1) rsum += __shfl_down_sync(0xffffffffu, rsum, o);
-        if (lane == 0) s.red[wid] = rsum;
-        __syncthreads();
-        if (tid == 0) {
-            double t = 0;
-            for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) t += s.red[w];
-            out_rate_sum[f] = 2.0 * t;
-        }
-    }
-}
 
 // ------------------------------------------------------------------ Verlet pieces -------------
 // dr[f][i] = length(frame[f-1][i], frame[f][i])  (topology.py:98); f = 0 uses the carried frame
@@ -543,12 +249,54 @@ extern "C" void cmd_topo_destroy(cmd_topo *t)
     free(t);
 }
 
+// FP32 side of the dense filter: h = Q R (Gram-Schmidt on the cell vectors = columns of h);
+// |h s| = |R s|, so the filter works in the rotated frame where the cell matrix is upper
+// triangular (6 multiply-adds instead of 9).  R carries the 2^-32 of the fixed-point unit.
+// Radius: rc (or the water-conversion window's right edge, beyond which convert_distance is the
+// identity) widened by far more than the FP32 error of a wrapped difference (~3e-7 * sum|R|).
+static void topo_filter_params(cmd_topo *t)
+{
+    FilterParams &fp = t->fp;
+    const BoxParams &bx = t->bx;
+    double c[3][3], q[3][3], R[3][3] = {{0}};
+    for (int k = 0; k < 3; k++)
+        for (int r = 0; r < 3; r++) c[k][r] = bx.h[3 * r + k];   // column k of h
+    for (int k = 0; k < 3; k++) {
+        double u[3] = {c[k][0], c[k][1], c[k][2]};
+        for (int m = 0; m < k; m++) {
+            R[m][k] = q[m][0] * c[k][0] + q[m][1] * c[k][1] + q[m][2] * c[k][2];
+            for (int r = 0; r < 3; r++) u[r] -= R[m][k] * q[m][r];
+        }
+        R[k][k] = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        for (int r = 0; r < 3; r++) q[k][r] = u[r] / R[k][k];
+    }
+    const double unit = 1.0 / 4294967296.0;
+    const double rr[6] = {R[0][0], R[0][1], R[0][2], R[1][1], R[1][2], R[2][2]};
+    double rsum = 0;
+    for (int k = 0; k < 6; k++) { fp.R[k] = (float)(rr[k] * unit); rsum += fabs(rr[k]); }
+    double radius = t->rc;
+    if (bx.conv != CMD_CONV_NONE && bx.conv_par[4] > radius) radius = bx.conv_par[4];
+    const double thr = radius * (1.0 + 1e-5) + 1e-5 * rsum;
+    fp.t2 = nextafterf((float)(thr * thr * (1.0 + 1e-6)), INFINITY);
+    fp.n_img = bx.n_img;
+    for (int m = 0; m < bx.n_img; m++)   // shift of image m in the R frame: Q^T T
+        for (int k = 0; k < 3; k++)
+            fp.img[m][k] = (float)(q[k][0] * bx.img[m][0] + q[k][1] * bx.img[m][1] +
+                                   q[k][2] * bx.img[m][2]);
+}
+
+static int dense_threads(int n)
+{
+    int th = ((n + 1) / 2 + 31) / 32 * 32;   // two rows per thread
+    return th < 32 ? 32 : th;
+}
+
 static int topo_configure(cmd_topo *t, int64_t stride)
 {
     // per-frame capacity and the matching shared-memory hit list
     stride = (stride + 63) / 64 * 64;
     int hit_cap = (int)(stride / 2);
-    size_t smem = dense_smem_bytes(t->n, hit_cap, t->bx.kind);
+    size_t smem = dense_smem_bytes(t->n, hit_cap);
     if (smem > 226 * 1024)
         return cmd_set_error(CMD_ECAPACITY,
                              "dense pair kernel needs %zu bytes of shared memory for n=%d, "
@@ -557,8 +305,7 @@ static int topo_configure(cmd_topo *t, int64_t stride)
     t->stride = stride;
     t->hit_cap = hit_cap;
     t->smem_bytes = smem;
-    int th = (t->n + 31) / 32 * 32;
-    t->threads = th < 64 ? 64 : th;
+    t->threads = dense_threads(t->n);
     return CMD_OK;
 }
 
@@ -588,8 +335,7 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
     t->t2 = exact_sq_threshold(t->rc);
     // the filter only has to look at the images that can come within rc of the origin
     cmd_box_prune_images(t->bx, t->rc);
-    t->lsum = 0;
-    for (int c = 0; c < 9; c++) t->lsum += fabs(t->bx.h[c]);
+    topo_filter_params(t);
     t->mode = mode;
     int rc = topo_configure(t, capacity > 0 ? capacity : 0);
     if (rc) { free(t); return rc; }
@@ -625,21 +371,25 @@ static int launch_dense(cmd_topo *t, const double *d_frames, const int *ids, con
 {
     cudaStream_t st = cmd_global().stream;
     const bool ortho = t->bx.kind == 0;
-#define DENSE_LAUNCH(K, MT, MB)                                                                  \
+#define DENSE_LAUNCH(K, IM, SP, MT, MB)                                                          \
     do {                                                                                         \
-        CMD_CUDA(cudaFuncSetAttribute(k_pairs_dense<K, MT, MB>,                                  \
+        CMD_CUDA(cudaFuncSetAttribute(k_pairs_dense<K, IM, SP, MT, MB>,                          \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        k_pairs_dense<K, MT, MB><<<(unsigned)grid, t->threads, smem, st>>>(                      \
-            t->bx, t->rate, d_frames, ids, n_ids, t->n, t->rc, t->t2, t->lsum, stride,           \
-            hit_cap, start, dest, dist, omega, counts, rate_sum, rebuilt, t->d_err, t->d_ties);  \
+        k_pairs_dense<K, IM, SP, MT, MB><<<(unsigned)grid, t->threads * SP, smem, st>>>(         \
+            t->bx, t->rate, t->fp, d_frames, ids, n_ids, t->n, t->rc, t->t2, stride, hit_cap,    \
+            start, dest, dist, omega, counts, rate_sum, rebuilt, t->d_err, t->d_ties);           \
     } while (0)
-    if (t->threads <= 256) {
-        if (ortho) DENSE_LAUNCH(0, 256, 3); else DENSE_LAUNCH(1, 256, 3);
-    } else if (t->threads <= 512) {
-        if (ortho) DENSE_LAUNCH(0, 512, 2); else DENSE_LAUNCH(1, 512, 2);
-    } else {
-        if (ortho) DENSE_LAUNCH(0, 1024, 1); else DENSE_LAUNCH(1, 1024, 1);
-    }
+#define DENSE_PICK(SP, MT, MB)                                                                   \
+    do {                                                                                         \
+        if (ortho) DENSE_LAUNCH(0, false, SP, MT, MB);                                           \
+        else if (t->fp.n_img == 0) DENSE_LAUNCH(1, false, SP, MT, MB);                           \
+        else DENSE_LAUNCH(1, true, SP, MT, MB);                                                  \
+    } while (0)
+    // t->threads = one thread per two rows; small frames run two copies of the row set
+    if (t->threads <= 128) DENSE_PICK(2, 256, 2);
+    else if (t->threads <= 256) DENSE_PICK(DENSE_SPLIT_MID, 256 * DENSE_SPLIT_MID, 2);
+    else DENSE_PICK(1, 512, 1);
+#undef DENSE_PICK
 #undef DENSE_LAUNCH
     CMD_LAUNCHED();
     return CMD_OK;
@@ -653,8 +403,8 @@ static int topo_autosize(cmd_topo *t, const double *d_frame)
     int *d_cnt;
     int rc = cmd_scratch(4, 64, (void **)&d_cnt);
     if (rc) return rc;
-    t->threads = ((t->n + 31) / 32 * 32) < 64 ? 64 : (t->n + 31) / 32 * 32;
-    size_t smem = dense_smem_bytes(t->n, 0, t->bx.kind);
+    t->threads = dense_threads(t->n);
+    size_t smem = dense_smem_bytes(t->n, 0);
     CMD_CUDA(cudaMemsetAsync(t->d_err, 0, sizeof(int), st));
     rc = launch_dense(t, d_frame, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, d_cnt,
                       nullptr, nullptr, 0, 0, smem);
@@ -667,7 +417,7 @@ static int topo_autosize(cmd_topo *t, const double *d_frame)
     int64_t p0 = cnt < 0 ? -cnt : cnt;
     int64_t want = p0 + p0 / 2 + 128;
     // shrink to what the shared-memory hit list can hold
-    while (want > p0 + 64 && dense_smem_bytes(t->n, (int)((want + 63) / 64 * 64 / 2), t->bx.kind) > 226 * 1024)
+    while (want > p0 + 64 && dense_smem_bytes(t->n, (int)((want + 63) / 64 * 64 / 2)) > 226 * 1024)
         want -= 64;
     return topo_configure(t, want);
 }

@@ -47,6 +47,20 @@ __device__ __forceinline__ void matvec3_exact(const double m[9], double v[3])
     v[0] = r[0]; v[1] = r[1]; v[2] = r[2];
 }
 
+// x - round(x) with C99 round (half away from zero), bit for bit, without libm's round():
+// r = rint(x) by the 1.5*2^52 trick (exact for |x| < 2^51), x - r is exact, and round() differs
+// from rint() only on ties that rint resolved towards zero.
+__device__ __forceinline__ double sub_round_exact(double x)
+{
+    if (!(fabs(x) < 2251799813685248.0)) return __dadd_rn(x, -round(x));   // cold: |x| >= 2^51, nan
+    const double magic = 6755399441055744.0;
+    const double r = __dadd_rn(__dadd_rn(x, magic), -magic);
+    double w = __dadd_rn(x, -r);
+    if (w == 0.5 && x > 0.0) w = -0.5;
+    if (w == -0.5 && x < 0.0) w = 0.5;
+    return w;
+}
+
 // ---- A3: numpyatom.pyx:61-74 (diff_ptr_nonortho); round = C99 round, half away from zero ------
 __device__ __forceinline__ void diff_general_exact(const BoxParams &bx, const double a[3],
                                                    const double b[3], double d[3])
@@ -55,7 +69,7 @@ __device__ __forceinline__ void diff_general_exact(const BoxParams &bx, const do
     for (int i = 0; i < 3; i++) d[i] = __dadd_rn(b[i], -a[i]);
     matvec3_exact(bx.hinv, d);
 #pragma unroll
-    for (int i = 0; i < 3; i++) d[i] = __dadd_rn(d[i], -round(d[i]));
+    for (int i = 0; i < 3; i++) d[i] = sub_round_exact(d[i]);
     matvec3_exact(bx.h, d);
 }
 
@@ -213,4 +227,17 @@ __device__ __forceinline__ double rate_eval(const RateParams &r, double x, doubl
         return r.par[0] * exp(r.par[1] * x);
     }
     return 0.0;
+}
+
+// two independent evaluations behind ONE dispatch, so their FP64 chains can interleave
+__device__ __forceinline__ void rate_eval2(const RateParams &r, double x0, double x1, double out[2])
+{
+    if (r.kind == CMD_RATE_FERMI) {
+        const double e0 = exp((x0 - r.par[1]) / r.par[2]), e1 = exp((x1 - r.par[1]) / r.par[2]);
+        out[0] = r.par[0] / (1.0 + e0);
+        out[1] = r.par[0] / (1.0 + e1);
+    } else {
+        out[0] = rate_eval(r, x0, 0.0);
+        out[1] = rate_eval(r, x1, 0.0);
+    }
 }
