@@ -61,6 +61,8 @@ SIGNATURES = {
     "cmd_topo_create": (C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, dp,
                                   C.c_int64, C.POINTER(vp)]),
     "cmd_topo_destroy": (None, [vp]),
+    "cmd_topo_set_path": (C.c_int, [vp, C.c_int]),
+    "cmd_topo_path": (C.c_int, [vp]),
     "cmd_topo_build_dev": (C.c_int, [vp, vp, C.c_int64]),
     "cmd_topo_build": (C.c_int, [vp, vp, C.c_int, C.c_int64]),
     "cmd_topo_frame_info": (C.c_int, [vp, lp, u8p, dp]),

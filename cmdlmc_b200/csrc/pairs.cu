@@ -15,7 +15,7 @@
 #include <math.h>
 #include <stdlib.h>
 
-#include "pairs_dense.cuh"
+#include "pairs_cell.cuh"
 
 #ifndef DENSE_SPLIT_MID
 #define DENSE_SPLIT_MID 2
@@ -33,6 +33,14 @@ struct cmd_topo {
     int hit_cap;     // unordered hits per frame that fit the CTA's shared-memory list
     size_t smem_bytes;
     int threads;
+    // cell-list path (boxes the one-CTA-per-frame kernel cannot hold)
+    int path;        // 0 dense, 1 cell list
+    int force_path;  // -1 automatic (cmd_topo_set_path)
+    CellGrid cg;
+    int rowcap, cell_batch;
+    int4 *d_fxu, *d_sorted;
+    int *d_slot, *d_cell_start, *d_rowcount, *d_rowoff, *d_tmp_j, *d_cap_need;
+    double *d_tmp_d;
     // block results
     int64_t cap_frames, nframes;
     int *d_start, *d_dest, *d_counts, *d_err;
@@ -146,6 +154,7 @@ k_schedule(const double *__restrict__ dr, double *__restrict__ displacement, int
 
 // Refresh of a kept list (topology.py:110): dist = length(frame[row], frame[col]), same pairs.
 // One CTA per refreshed frame; the head list is either a frame of this block or the carry.
+template <bool STAGE>
 __global__ void __launch_bounds__(256)
 k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RateParams rp,
           const double *__restrict__ frames, const int *__restrict__ ids,
@@ -158,11 +167,13 @@ k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RatePara
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if ((int)blockIdx.x >= *n_ids) return;
-    double *sp = (double *)smem_raw;  // [3n] AoS copy of the frame
     const int64_t f = ids[blockIdx.x];
     const int hd = head[f];
     const double *fr = frames + f * (int64_t)n * 3;
-    for (int k = threadIdx.x; k < 3 * n; k += blockDim.x) sp[k] = __ldg(fr + k);
+    // [3n] AoS copy of the frame; frames too large for shared memory are read through L1/L2
+    const double *sp = STAGE ? (const double *)smem_raw : fr;
+    if (STAGE)
+        for (int k = threadIdx.x; k < 3 * n; k += blockDim.x) ((double *)smem_raw)[k] = __ldg(fr + k);
     // out_counts of a head frame in this block is final: the build kernel ran before us
     const int p = hd < 0 ? *carry_count : out_counts[hd];
     const int *hs = hd < 0 ? carry_start : out_start + hd * stride;
@@ -238,6 +249,16 @@ static void topo_free_block(cmd_topo *t)
     t->cap_frames = 0;
 }
 
+static void cell_free(cmd_topo *t)
+{
+    cudaFree(t->d_fxu); cudaFree(t->d_sorted); cudaFree(t->d_slot); cudaFree(t->d_cell_start);
+    cudaFree(t->d_rowcount); cudaFree(t->d_rowoff); cudaFree(t->d_tmp_j); cudaFree(t->d_tmp_d);
+    t->d_fxu = t->d_sorted = nullptr;
+    t->d_slot = t->d_cell_start = t->d_rowcount = t->d_rowoff = t->d_tmp_j = nullptr;
+    t->d_tmp_d = nullptr;
+    t->cell_batch = 0;
+}
+
 extern "C" void cmd_topo_destroy(cmd_topo *t)
 {
     if (!t) return;
@@ -245,7 +266,8 @@ extern "C" void cmd_topo_destroy(cmd_topo *t)
     topo_free_block(t);
     cudaFree(t->d_err); cudaFree(t->d_ties); cudaFree(t->d_last); cudaFree(t->d_displacement);
     cudaFree(t->d_carry_start); cudaFree(t->d_carry_dest); cudaFree(t->d_carry_count);
-    cudaFree(t->d_sched); cudaFree(t->d_upload);
+    cudaFree(t->d_sched); cudaFree(t->d_upload); cudaFree(t->d_cap_need);
+    cell_free(t);
     free(t);
 }
 
@@ -291,21 +313,56 @@ static int dense_threads(int n)
     return th < 32 ? 32 : th;
 }
 
+// Cells per fractional axis: the cell must be at least one filter radius thick.
+static void topo_cell_grid(cmd_topo *t)
+{
+    const BoxParams &bx = t->bx;
+    double radius = t->rc;
+    if (bx.conv != CMD_CONV_NONE && bx.conv_par[4] > radius) radius = bx.conv_par[4];
+    radius *= 1.0 + 1e-6;
+    CellGrid &cg = t->cg;
+    for (int c = 0; c < 3; c++) {
+        const double height = 1.0 / sqrt(bx.hinv[3 * c] * bx.hinv[3 * c] + bx.hinv[3 * c + 1] * bx.hinv[3 * c + 1] +
+                                         bx.hinv[3 * c + 2] * bx.hinv[3 * c + 2]);
+        double q = radius > 0 ? floor(height / radius) : 64.0;
+        int nc = q > 64.0 ? 64 : (int)q;
+        if (nc < 3) nc = 1;
+        cg.nc[c] = nc;
+    }
+    // more cells than atoms buys nothing; keep the per-frame count table inside shared memory
+    while ((int64_t)cg.nc[0] * cg.nc[1] * cg.nc[2] > 32768 ||
+           ((int64_t)cg.nc[0] * cg.nc[1] * cg.nc[2] > 4 * (int64_t)t->n + 64 && cg.nc[0] * cg.nc[1] * cg.nc[2] > 27)) {
+        int big = 0;
+        for (int c = 1; c < 3; c++) if (cg.nc[c] > cg.nc[big]) big = c;
+        if (cg.nc[big] <= 3) break;
+        cg.nc[big]--;
+    }
+    for (int c = 0; c < 3; c++) cg.span[c] = cg.nc[c] >= 3 ? 3 : 1;
+    cg.ncell = cg.nc[0] * cg.nc[1] * cg.nc[2];
+}
+
 static int topo_configure(cmd_topo *t, int64_t stride)
 {
     // per-frame capacity and the matching shared-memory hit list
     stride = (stride + 63) / 64 * 64;
     int hit_cap = (int)(stride / 2);
     size_t smem = dense_smem_bytes(t->n, hit_cap);
-    if (smem > 226 * 1024)
-        return cmd_set_error(CMD_ECAPACITY,
-                             "dense pair kernel needs %zu bytes of shared memory for n=%d, "
-                             "capacity %lld (limit 232448): use the cell-list path", smem, t->n,
-                             (long long)stride);
     t->stride = stride;
+    t->threads = dense_threads(t->n);
+    const bool fits = t->n <= 1024 && smem <= 226 * 1024;
+    if (!fits && t->force_path == 0)
+        return cmd_set_error(CMD_ECAPACITY, "dense pair kernel needs %zu bytes of shared memory for "
+                             "n=%d, capacity %lld (limit 231424)", smem, t->n, (long long)stride);
+    if (!fits || t->force_path == 1) {   // too large for one CTA per frame: cell list
+        t->path = 1;
+        t->hit_cap = 0;
+        t->smem_bytes = 0;
+        if (t->rowcap < 8) t->rowcap = 40;
+        return CMD_OK;
+    }
+    t->path = 0;
     t->hit_cap = hit_cap;
     t->smem_bytes = smem;
-    t->threads = dense_threads(t->n);
     return CMD_OK;
 }
 
@@ -315,9 +372,6 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
 {
     CMD_REQUIRE_INIT();
     if (!box || !out || n < 1) return cmd_set_error(CMD_EINVAL, "bad argument");
-    if (n > 1024)
-        return cmd_set_error(CMD_EINVAL, "dense topology supports n_atoms <= 1024 (got %d); "
-                                         "larger systems need the cell-list path", n);
     if (mode != CMD_TOPO_BRUTEFORCE && mode != CMD_TOPO_VERLET)
         return cmd_set_error(CMD_EINVAL, "bad topology mode %d", mode);
     if (rate_kind < 0 || rate_kind > CMD_RATE_EXP || rate_kind == CMD_RATE_FERMI_ANGLE)
@@ -336,7 +390,9 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
     // the filter only has to look at the images that can come within rc of the origin
     cmd_box_prune_images(t->bx, t->rc);
     topo_filter_params(t);
+    topo_cell_grid(t);
     t->mode = mode;
+    t->force_path = -1;
     int rc = topo_configure(t, capacity > 0 ? capacity : 0);
     if (rc) { free(t); return rc; }
     if (capacity <= 0) t->stride = 0;  // sized from the first frame
@@ -352,11 +408,13 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
     TALLOC(t->d_displacement, (size_t)n * 8);
     TALLOC(t->d_carry_count, sizeof(int));
     TALLOC(t->d_sched, 4 * sizeof(int));
+    TALLOC(t->d_cap_need, sizeof(int));
     cudaStream_t st = cmd_global().stream;
     CMD_CUDA(cudaMemsetAsync(t->d_err, 0, sizeof(int), st));
     CMD_CUDA(cudaMemsetAsync(t->d_ties, 0, sizeof(unsigned long long), st));
     CMD_CUDA(cudaMemsetAsync(t->d_displacement, 0, (size_t)n * 8, st));
     CMD_CUDA(cudaMemsetAsync(t->d_carry_count, 0, sizeof(int), st));
+    CMD_CUDA(cudaMemsetAsync(t->d_cap_need, 0, sizeof(int), st));
     int sched0[4] = {0, 0, -1, 0};
     CMD_CUDA(cudaMemcpyAsync(t->d_sched, sched0, sizeof(sched0), cudaMemcpyHostToDevice, st));
     CMD_CUDA(cudaStreamSynchronize(st));
@@ -395,6 +453,113 @@ static int launch_dense(cmd_topo *t, const double *d_frames, const int *ids, con
     return CMD_OK;
 }
 
+
+// ---- cell-list path ----------------------------------------------------------------------------
+static int cell_reserve(cmd_topo *t, int batch)
+{
+    if (batch <= t->cell_batch) return CMD_OK;
+    CMD_CUDA(cudaStreamSynchronize(cmd_global().stream));
+    cell_free(t);
+    const size_t n = (size_t)t->n, B = (size_t)batch;
+#define CALLOC(ptr, bytes)                                                                       \
+    if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) {                                   \
+        cudaGetLastError();                                                                      \
+        cell_free(t);                                                                            \
+        return cmd_set_error(CMD_ENOMEM, "cudaMalloc of %zu bytes failed for %s", (size_t)(bytes), #ptr); \
+    }
+    CALLOC(t->d_fxu, B * n * 16);
+    CALLOC(t->d_sorted, B * n * 16);
+    CALLOC(t->d_slot, B * n * 4);
+    CALLOC(t->d_cell_start, B * (t->cg.ncell + 1) * 4);
+    CALLOC(t->d_rowcount, B * n * 4);
+    CALLOC(t->d_rowoff, B * (n + 1) * 4);
+    CALLOC(t->d_tmp_j, B * n * t->rowcap * 4);
+    CALLOC(t->d_tmp_d, B * n * t->rowcap * 8);
+#undef CALLOC
+    t->cell_batch = batch;
+    return CMD_OK;
+}
+
+static int cell_batch_size(const cmd_topo *t, int64_t want)
+{
+    const size_t per = (size_t)t->n * (40 + 12 * (size_t)t->rowcap) + (size_t)(t->cg.ncell + 1) * 4 + 8;
+    int64_t b = (int64_t)((size_t)1 << 30) / (int64_t)per;
+    if (b < 1) b = 1;
+    if (b > 8192) b = 8192;
+    return (int)(b < want ? b : want);
+}
+
+// Builds the lists of `count` frames (ids[first..] or frames first..first+count) through the cell
+// list.  emit = false stops after the per-frame totals (capacity probe).
+static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, const int *n_ids,
+                       int64_t count, int *start, int *dest, double *dist, double *omega,
+                       int *counts, double *rate_sum, uint8_t *rebuilt, int64_t stride, bool emit)
+{
+    cudaStream_t st = cmd_global().stream;
+    const bool ortho = t->bx.kind == 0;
+    const int n = t->n;
+    for (int64_t first = 0; first < count;) {
+        int batch = cell_batch_size(t, count - first);
+        int rc = cell_reserve(t, batch);
+        if (rc) return rc;
+        batch = t->cell_batch < count - first ? t->cell_batch : (int)(count - first);
+        const size_t bsm = (size_t)(t->cg.ncell + 1 + 40) * 4;
+        if (ortho) {
+            CMD_CUDA(cudaFuncSetAttribute(k_cell_build<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+            k_cell_build<0><<<batch, 1024, bsm, st>>>(t->bx, t->cg, d_frames, ids, n_ids, (int)first, n,
+                                                     t->d_fxu, t->d_slot, t->d_sorted, t->d_cell_start);
+        } else {
+            CMD_CUDA(cudaFuncSetAttribute(k_cell_build<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+            k_cell_build<1><<<batch, 1024, bsm, st>>>(t->bx, t->cg, d_frames, ids, n_ids, (int)first, n,
+                                                     t->d_fxu, t->d_slot, t->d_sorted, t->d_cell_start);
+        }
+        CMD_LAUNCHED();
+        int tpb = 128;
+        while (tpb > 32 && (size_t)t->rowcap * tpb * 12 > 160 * 1024) tpb >>= 1;
+        const size_t psm = (size_t)t->rowcap * tpb * 12;
+        dim3 pgrid((unsigned)((n + tpb - 1) / tpb), (unsigned)batch);
+#define CELL_PAIRS(K, IM)                                                                        \
+    do {                                                                                         \
+        CMD_CUDA(cudaFuncSetAttribute(k_cell_pairs<K, IM>,                                       \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));   \
+        k_cell_pairs<K, IM><<<pgrid, tpb, psm, st>>>(                                            \
+            t->bx, t->fp, t->cg, d_frames, ids, n_ids, (int)first, n, t->rc, t->t2, t->rowcap,   \
+            t->d_sorted, t->d_cell_start, t->d_rowcount, t->d_tmp_j, t->d_tmp_d, t->d_cap_need,  \
+            t->d_ties);                                                                          \
+    } while (0)
+        if (ortho) CELL_PAIRS(0, false);
+        else if (t->fp.n_img == 0) CELL_PAIRS(1, false);
+        else CELL_PAIRS(1, true);
+#undef CELL_PAIRS
+        CMD_LAUNCHED();
+        // scratch rows too short?  (one 4-byte read-back per batch)
+        int need = 0;
+        CMD_CUDA(cudaMemcpyAsync(&need, t->d_cap_need, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CMD_CUDA(cudaStreamSynchronize(st));
+        if (need > t->rowcap) {
+            CMD_CUDA(cudaMemsetAsync(t->d_cap_need, 0, sizeof(int), st));
+            if ((size_t)(need + 8) * 32 * 12 > 200 * 1024)
+                return cmd_set_error(CMD_ECAPACITY, "an atom has %d neighbour candidates: more than "
+                                     "the cell-list kernel can hold per row", need);
+            t->rowcap = need + 8;
+            cell_free(t);
+            continue;   // redo this batch with longer rows
+        }
+        k_cell_scan<<<batch, 1024, 0, st>>>(ids, n_ids, (int)first, n, stride, t->d_rowcount,
+                                            t->d_rowoff, counts, rebuilt, rate_sum, t->d_err);
+        CMD_LAUNCHED();
+        if (emit) {
+            dim3 egrid((unsigned)((n + 255) / 256), (unsigned)batch);
+            k_cell_emit<<<egrid, 256, 0, st>>>(t->rate, ids, n_ids, (int)first, n, stride, t->rowcap,
+                                               t->d_rowoff, t->d_tmp_j, t->d_tmp_d, start, dest, dist,
+                                               omega, rate_sum);
+            CMD_LAUNCHED();
+        }
+        first += batch;
+    }
+    return CMD_OK;
+}
+
 // sizes the per-frame capacity from a probe of one frame (count-only: nothing fits, so the
 // kernel reports -P through out_counts and err)
 static int topo_autosize(cmd_topo *t, const double *d_frame)
@@ -406,8 +571,14 @@ static int topo_autosize(cmd_topo *t, const double *d_frame)
     t->threads = dense_threads(t->n);
     size_t smem = dense_smem_bytes(t->n, 0);
     CMD_CUDA(cudaMemsetAsync(t->d_err, 0, sizeof(int), st));
-    rc = launch_dense(t, d_frame, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, d_cnt,
-                      nullptr, nullptr, 0, 0, smem);
+    if (t->n <= 1024 && smem <= 226 * 1024 && t->force_path != 1) {
+        rc = launch_dense(t, d_frame, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, d_cnt,
+                          nullptr, nullptr, 0, 0, smem);
+    } else {
+        if (t->rowcap < 8) t->rowcap = 40;
+        rc = launch_cell(t, d_frame, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, d_cnt,
+                         nullptr, nullptr, (int64_t)1 << 40, false);
+    }
     if (rc) return rc;
     int cnt = 0;
     CMD_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -416,10 +587,32 @@ static int topo_autosize(cmd_topo *t, const double *d_frame)
     CMD_CUDA(cudaMemsetAsync(t->d_ties, 0, sizeof(unsigned long long), st));
     int64_t p0 = cnt < 0 ? -cnt : cnt;
     int64_t want = p0 + p0 / 2 + 128;
-    // shrink to what the shared-memory hit list can hold
-    while (want > p0 + 64 && dense_smem_bytes(t->n, (int)((want + 63) / 64 * 64 / 2)) > 226 * 1024)
+    // prefer the dense kernel: shrink the head-room to what its shared-memory hit list can hold
+    while (t->n <= 1024 && t->force_path != 1 && want > p0 + p0 / 4 + 64 &&
+           dense_smem_bytes(t->n, (int)((want + 63) / 64 * 64 / 2)) > 226 * 1024)
         want -= 64;
     return topo_configure(t, want);
+}
+
+// all-pairs lists of `grid` frames (or of the ids[0 .. *n_ids) frames) by the configured path
+static int launch_pairs(cmd_topo *t, const double *d_frames, const int *ids, const int *n_ids,
+                        int64_t grid, int *start, int *dest, double *dist, double *omega,
+                        int *counts, double *rate_sum, uint8_t *rebuilt)
+{
+    if (t->path == 0)
+        return launch_dense(t, d_frames, ids, n_ids, grid, start, dest, dist, omega, counts,
+                            rate_sum, rebuilt, t->stride, t->hit_cap, t->smem_bytes);
+    int64_t count = grid;
+    if (n_ids) {   // Verlet: the number of rebuild frames lives on the device
+        int h = 0;
+        cudaStream_t st = cmd_global().stream;
+        CMD_CUDA(cudaMemcpyAsync(&h, n_ids, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CMD_CUDA(cudaStreamSynchronize(st));
+        count = h;
+        if (count <= 0) return CMD_OK;
+    }
+    return launch_cell(t, d_frames, ids, n_ids, count, start, dest, dist, omega, counts, rate_sum,
+                       rebuilt, t->stride, true);
 }
 
 static int topo_reserve(cmd_topo *t, int64_t nframes)
@@ -473,9 +666,8 @@ extern "C" int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t n
     t->nframes = nframes;
     t->d_frames_last = d_frames;
     if (t->mode == CMD_TOPO_BRUTEFORCE) {
-        rc = launch_dense(t, d_frames, nullptr, nullptr, nframes, t->d_start, t->d_dest, t->d_dist,
-                          t->d_omega, t->d_counts, t->d_rate_sum, t->d_rebuilt, t->stride,
-                          t->hit_cap, t->smem_bytes);
+        rc = launch_pairs(t, d_frames, nullptr, nullptr, nframes, t->d_start, t->d_dest, t->d_dist,
+                          t->d_omega, t->d_counts, t->d_rate_sum, t->d_rebuilt);
         if (rc) return rc;
     } else {
         int blocks = cmd_div_up(nframes * t->n, 256);
@@ -489,12 +681,17 @@ extern "C" int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t n
                                       t->total_frames == 0 ? 1 : 0, t->d_sched, t->d_rebuild_ids,
                                       t->d_refresh_ids, t->d_head, t->d_rebuilt);
         CMD_LAUNCHED();
-        rc = launch_dense(t, d_frames, t->d_rebuild_ids, t->d_sched, nframes, t->d_start, t->d_dest,
-                          t->d_dist, t->d_omega, t->d_counts, t->d_rate_sum, nullptr, t->stride,
-                          t->hit_cap, t->smem_bytes);
+        rc = launch_pairs(t, d_frames, t->d_rebuild_ids, t->d_sched, nframes, t->d_start, t->d_dest,
+                          t->d_dist, t->d_omega, t->d_counts, t->d_rate_sum, nullptr);
         if (rc) return rc;
         size_t rsmem = (size_t)t->n * 24;
-        k_refresh<<<(unsigned)nframes, 256, rsmem, st>>>(
+        if (rsmem > 40 * 1024)
+            k_refresh<false><<<(unsigned)nframes, 256, 0, st>>>(
+                t->bx, t->rate, d_frames, t->d_refresh_ids, t->d_sched + 1, t->d_head, t->n, t->stride,
+                t->d_carry_start, t->d_carry_dest, t->d_carry_count, t->d_start, t->d_dest, t->d_dist,
+                t->d_omega, t->d_counts, t->d_rate_sum);
+        else
+        k_refresh<true><<<(unsigned)nframes, 256, rsmem, st>>>(
             t->bx, t->rate, d_frames, t->d_refresh_ids, t->d_sched + 1, t->d_head, t->n, t->stride,
             t->d_carry_start, t->d_carry_dest, t->d_carry_count, t->d_start, t->d_dest, t->d_dist,
             t->d_omega, t->d_counts, t->d_rate_sum);
@@ -575,6 +772,18 @@ extern "C" int cmd_topo_frame_info(const cmd_topo *t, int64_t *counts, uint8_t *
     CMD_CUDA(cudaStreamSynchronize(st));
     return CMD_OK;
 }
+
+extern "C" int cmd_topo_set_path(cmd_topo *t, int path)
+{
+    if (!t || path < -1 || path > 1) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (t->nframes > 0 || t->total_frames > 0)
+        return cmd_set_error(CMD_ESTATE, "the search path is fixed once a block has been built");
+    t->force_path = path;
+    if (t->stride > 0) return topo_configure(t, t->stride);
+    return CMD_OK;
+}
+
+extern "C" int cmd_topo_path(const cmd_topo *t) { return t ? t->path : -1; }
 
 extern "C" int64_t cmd_topo_stride(const cmd_topo *t) { return t ? t->stride : -1; }
 extern "C" int cmd_topo_n_images(const cmd_topo *t) { return t ? t->bx.n_img : -1; }

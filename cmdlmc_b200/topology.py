@@ -23,7 +23,8 @@ MODE_VERLET = 1
 class DeviceTopology:
     """Thin owner of a `cmd_topo` handle: neighbour lists + rates of a block of frames in HBM."""
 
-    def __init__(self, atom_box, n_atoms, cutoff, buffer, mode, jumprate=None, capacity=0):
+    def __init__(self, atom_box, n_atoms, cutoff, buffer, mode, jumprate=None, capacity=0,
+                 path=-1):
         runtime.ensure_init()
         self.atom_box = atom_box          # keeps the box handle alive
         self.n_atoms = int(n_atoms)
@@ -37,6 +38,13 @@ class DeviceTopology:
         check(_abi.lib().cmd_topo_create(atom_box.handle, int(n_atoms), float(cutoff),
                                          float(buffer), int(mode), int(kind), ptr(par),
                                          int(capacity), C.byref(self._handle)))
+        if path != -1:   # -1 auto, 0 dense (one CTA per frame), 1 cell list
+            check(_abi.lib().cmd_topo_set_path(self._handle, int(path)))
+
+    @property
+    def path(self):
+        """Search path the library chose (0 dense, 1 cell list); final after the first build."""
+        return int(_abi.lib().cmd_topo_path(self._handle))
 
     def __del__(self):
         h = getattr(self, "_handle", None)

@@ -150,6 +150,15 @@ int cmd_topo_create(const cmd_box *box, int n_atoms, double cutoff, double buffe
                     int rate_kind, const double h_rate_par[CMD_RATE_NPAR],
                     int64_t capacity_per_frame, cmd_topo **out);
 void cmd_topo_destroy(cmd_topo *t);
+/* Neighbour search path: CMD_PATH_DENSE = one CTA per frame, all N(N-1)/2 pairs out of shared
+ * memory (N <= 1024); CMD_PATH_CELL = cell list for large boxes (north_star: "cell-list build and
+ * warp-ballot/prefix-sum compaction for large boxes").  CMD_PATH_AUTO (default) picks by size.
+ * Both produce identical lists.  Must be called before the first build. */
+#define CMD_PATH_AUTO (-1)
+#define CMD_PATH_DENSE 0
+#define CMD_PATH_CELL 1
+int cmd_topo_set_path(cmd_topo *t, int path);
+int cmd_topo_path(const cmd_topo *t);
 /* Processes the next block of frames (device-resident f64 [nframes][n_atoms][3]); frames are
  * consecutive in time across calls (the Verlet displacement state is carried).  Results of the
  * previous block are overwritten. */

@@ -178,3 +178,82 @@ def test_float32_frames_and_full_size_properties():
         assert all(fwd[(d, s)] == v for (s, d), v in fwd.items())   # symmetric, bitwise
         assert (dist <= w.cutoff + w.buffer).all() and (dist > 0).all()
         assert (omega > 0).all() and (omega <= w.rate_params[0]).all()
+
+
+@pytest.mark.parametrize("cfg,nfr", [("C1", 6), ("C2", 6), ("C4", 3)])
+def test_cell_list_path_equals_dense(orc, cfg, nfr):
+    """The cell-list search (large boxes) and the dense search give the same arrays, bit for bit."""
+    from cmdlmc_b200.topology import DeviceTopology, build_with_retry
+    import cmdlmc_b200 as cm
+    w = synth.workload(cfg)
+    frames = synth.trajectory(w, nfr)
+    box = make_box(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    res = []
+    for path in (0, 1):
+        t = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, 0, rate,
+                                                        cap, path=path), frames)
+        assert t.path == path
+        counts = t.frame_info()[0]
+        res.append([t.get_frame(f, int(counts[f])) for f in range(nfr)])
+    for fa, fb in zip(*res):
+        for a, b in zip(fa, fb):
+            np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("cfg,nfr", [("C3", 3)])
+def test_large_box_vs_oracle(orc, cfg, nfr):
+    """C3: 2048 O in a triclinic cell, activation-energy rate -- cell-list path vs the oracle's
+    all-pairs loop (index sets and distances bit-exact, rates 1e-10)."""
+    from cmdlmc_b200.topology import DeviceTopology, build_with_retry
+    import cmdlmc_b200 as cm
+    w = synth.workload(cfg)
+    frames = synth.trajectory(w, nfr)
+    box, obox = make_box(w.cell), orc.OracleBox(w.cell)
+    rate = cm.ActivationEnergy(*w.rate_params)
+    t = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, 0, rate, cap),
+                         frames)
+    assert t.path == 1
+    counts = t.frame_info()[0]
+    for f in range(nfr):
+        start, dest, dist, omega = t.get_frame(f, int(counts[f]))
+        want = orc.topology_bruteforce(obox, frames[f], w.cutoff, w.buffer)
+        np.testing.assert_array_equal(start, want[0])
+        np.testing.assert_array_equal(dest, want[1])
+        np.testing.assert_array_equal(dist, want[2])
+        np.testing.assert_allclose(omega, orc.rates("ActivationEnergy", w.rate_params, want[2]),
+                                   rtol=1e-10)
+
+
+def test_cell_list_random_boxes(orc):
+    """Random orthorhombic and triclinic boxes through the cell list, incl. axes with fewer than
+    three cells (collapsed) and a Verlet run across blocks."""
+    from cmdlmc_b200.topology import NeighborTopology, DeviceTopology, build_with_retry
+    rng = np.random.RandomState(11)
+    cells = [np.array([31.0, 12.0, 47.0]),                              # y: 2 cells -> collapsed
+             np.array([40.0, 0, 0, 7.0, 36.0, 0, -5.0, 9.0, 33.0]),
+             np.array([14.0, 0, 0, 3.0, 13.0, 0, 2.0, 1.0, 60.0])]      # x, y collapsed
+    for cell in cells:
+        box, obox = make_box(cell), orc.OracleBox(cell)
+        hm = np.diag(cell) if cell.size == 3 else cell.reshape(3, 3)
+        for n in (1500, 2100):
+            p = rng.uniform(-0.3, 1.3, size=(n, 3)) @ hm      # also outside the cell
+            top = NeighborTopology(make_traj(p[None]), box, cutoff=3.2, buffer=1.0, donor_atoms="O")
+            got = top.get_topology_bruteforce(p)
+            want = orc.topology_bruteforce(obox, p, 3.2, 1.0)
+            for a, b in zip(got, want):
+                np.testing.assert_array_equal(a, b)
+    # Verlet schedule + refresh on the cell path, blocks of 7 frames
+    w = synth.workload("C3")
+    frames = synth.trajectory(w, 20)
+    box, obox = make_box(w.cell), orc.OracleBox(w.cell)
+    top = NeighborTopology(make_traj(frames, w.time_step), box, donor_atoms="O", cutoff=w.cutoff,
+                           buffer=w.buffer)
+    top.chunk_size = 7
+    gen = orc.verlet_generator(obox, frames, w.cutoff, w.buffer)
+    k = -1
+    for k, ((row, col, dist, _), want) in enumerate(zip(top.topology_verlet_list_generator(), gen)):
+        np.testing.assert_array_equal(row, want[0])
+        np.testing.assert_array_equal(col, want[1])
+        np.testing.assert_array_equal(dist, want[2])
+    assert k == 19
