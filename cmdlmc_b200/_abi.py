@@ -65,6 +65,8 @@ SIGNATURES = {
     "cmd_topo_path": (C.c_int, [vp]),
     "cmd_topo_build_dev": (C.c_int, [vp, vp, C.c_int64]),
     "cmd_topo_build": (C.c_int, [vp, vp, C.c_int, C.c_int64]),
+    "cmd_topo_skip_dev": (C.c_int, [vp, vp, C.c_int64]),
+    "cmd_topo_skip": (C.c_int, [vp, vp, C.c_int, C.c_int64]),
     "cmd_topo_frame_info": (C.c_int, [vp, lp, u8p, dp]),
     "cmd_topo_stride": (C.c_int64, [vp]),
     "cmd_topo_n_images": (C.c_int, [vp]),
@@ -73,6 +75,11 @@ SIGNATURES = {
     "cmd_topo_device_arrays": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                          C.POINTER(vp), C.POINTER(vp)]),
     "cmd_topo_tie_count": (C.c_int64, [vp]),
+    "cmd_topo_distance_histogram": (C.c_int, [vp, C.c_double, C.c_double, C.c_int, lp]),
+    "cmd_topo_distance_histogram_dev": (C.c_int, [vp, C.c_double, C.c_double, C.c_int, vp]),
+    "cmd_kmc_get_event_distances": (C.c_int, [vp, C.c_int, C.c_int64, lp, dp]),
+    "cmd_kmc_jump_histogram": (C.c_int, [vp, C.c_double, C.c_double, C.c_int, lp]),
+    "cmd_kmc_jump_histogram_dev": (C.c_int, [vp, C.c_double, C.c_double, C.c_int, vp]),
     "cmd_topo_positions": (C.c_int, [vp, C.POINTER(vp)]),
     "cmd_kmc_create": (C.c_int, [vp, C.c_int, C.c_int, ip, C.c_double, C.c_int, C.c_uint64,
                                  C.POINTER(vp)]),

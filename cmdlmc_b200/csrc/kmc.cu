@@ -54,6 +54,7 @@ struct cmd_kmc {
     long long *d_ev_frame;
     double *d_ev_time;
     int *d_ev_start, *d_ev_dest, *d_ev_proton;
+    double *d_ev_dist;   // O-O distance of the jump pair at the event (jumpstat histogram)
     // observables
     int reset_freq, print_freq;
     int64_t row_cap;
@@ -74,12 +75,13 @@ struct KmcArgs {
     int64_t stride, nframes, frames_base, n_u, ev_cap, row_cap;
     int reset_freq, print_freq;
     const int *start, *dest, *counts;
-    const double *omega, *positions, *u;
+    const double *omega, *positions, *u, *dist;
     int *lattice, *lattice0;
     KmcState *state;
     long long *ev_frame;
     double *ev_time;
     int *ev_start, *ev_dest, *ev_proton;
+    double *ev_dist;
     double *rows, *snapshot, *disp;
     unsigned long long *ties;
     // exact-replay scratch, one slice per replica (see kmc_consume_exact)
@@ -305,7 +307,7 @@ __device__ double kmc_consume_exact(const KmcArgs &a, WarpCtx &c, int64_t f)
 // (it differs after a same-frame event, Q2), np.cumsum runs sequentially, draw = S*u,
 // searchsorted(side='left').
 __device__ bool kmc_move_exact(const KmcArgs &a, WarpCtx &c, double u, int *o_start, int *o_dest,
-                               int *o_proton, unsigned long long *ties)
+                               int *o_proton, int *o_index, unsigned long long *ties)
 {
     const int m = c.m;
     const int64_t base = c.base;
@@ -363,7 +365,7 @@ __device__ bool kmc_move_exact(const KmcArgs &a, WarpCtx &c, double u, int *o_st
         c.occ[st >> 5] &= ~(1u << (st & 31));
     }
     __syncwarp();
-    *o_start = st; *o_dest = de; *o_proton = proton;
+    *o_start = st; *o_dest = de; *o_proton = proton; *o_index = k;
     return true;
 }
 
@@ -371,7 +373,7 @@ __device__ bool kmc_move_exact(const KmcArgs &a, WarpCtx &c, double u, int *o_st
 // searchsorted(left), move the label.  Returns false when nothing is allowed (the reference
 // raises IndexError there).
 __device__ bool kmc_move(const KmcArgs &a, WarpCtx &c, double u, int *o_start, int *o_dest,
-                         int *o_proton, unsigned long long *ties)
+                         int *o_proton, int *o_index, unsigned long long *ties)
 {
     const int p = c.p;
     const int64_t base = c.base;
@@ -435,7 +437,7 @@ __device__ bool kmc_move(const KmcArgs &a, WarpCtx &c, double u, int *o_start, i
         c.occ[st >> 5] &= ~(1u << (st & 31));
     }
     __syncwarp();
-    *o_start = st; *o_dest = de; *o_proton = proton;
+    *o_start = st; *o_dest = de; *o_proton = proton; *o_index = found;
     return true;
 }
 
@@ -515,15 +517,16 @@ __device__ bool kmc_event(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
         philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
         u = u53(ctr[2], ctr[3]);
     }
-    int es, ed, ep;
-    const bool moved = a.exact ? kmc_move_exact(a, c, u, &es, &ed, &ep, a.ties)
-                               : kmc_move(a, c, u, &es, &ed, &ep, a.ties);
+    int es, ed, ep, ek;
+    const bool moved = a.exact ? kmc_move_exact(a, c, u, &es, &ed, &ep, &ek, a.ties)
+                               : kmc_move(a, c, u, &es, &ed, &ep, &ek, a.ties);
     if (!moved) { st.reason = 2; return false; }
     if (c.lane == 0 && st.log_pos < a.ev_cap) {
         int64_t q = (int64_t)r * a.ev_cap + st.log_pos;
         a.ev_frame[q] = st.sweep;
         a.ev_time[q] = st.kmc_time;
         a.ev_start[q] = es; a.ev_dest[q] = ed; a.ev_proton[q] = ep;
+        a.ev_dist[q] = __ldg(a.dist + c.base + ek);
     }
     st.n_events++;
     if (st.log_pos < a.ev_cap) st.log_pos++;
@@ -653,7 +656,7 @@ extern "C" void cmd_kmc_destroy(cmd_kmc *k)
     cudaStreamSynchronize(cmd_global().stream);
     cudaFree(k->d_lattice); cudaFree(k->d_lattice0); cudaFree(k->d_state); cudaFree(k->d_u);
     cudaFree(k->d_ev_frame); cudaFree(k->d_ev_time); cudaFree(k->d_ev_start); cudaFree(k->d_ev_dest);
-    cudaFree(k->d_ev_proton); cudaFree(k->d_rows); cudaFree(k->d_snapshot); cudaFree(k->d_disp);
+    cudaFree(k->d_ev_proton); cudaFree(k->d_ev_dist); cudaFree(k->d_rows); cudaFree(k->d_snapshot); cudaFree(k->d_disp);
     cudaFree(k->d_ties); cudaFree(k->d_exact);
     free(k);
 }
@@ -762,8 +765,8 @@ extern "C" int cmd_kmc_set_event_log(cmd_kmc *k, int64_t cap)
     if (cap > k->ev_cap) {
         CMD_CUDA(cudaStreamSynchronize(st));
         cudaFree(k->d_ev_frame); cudaFree(k->d_ev_time); cudaFree(k->d_ev_start);
-        cudaFree(k->d_ev_dest); cudaFree(k->d_ev_proton);
-        k->d_ev_frame = nullptr; k->d_ev_time = nullptr;
+        cudaFree(k->d_ev_dest); cudaFree(k->d_ev_proton); cudaFree(k->d_ev_dist);
+        k->d_ev_frame = nullptr; k->d_ev_time = nullptr; k->d_ev_dist = nullptr;
         k->d_ev_start = k->d_ev_dest = k->d_ev_proton = nullptr;
         k->ev_cap = 0;
         size_t n = (size_t)k->n_replicas * cap;
@@ -772,6 +775,7 @@ extern "C" int cmd_kmc_set_event_log(cmd_kmc *k, int64_t cap)
         KALLOC(k->d_ev_start, n * 4);
         KALLOC(k->d_ev_dest, n * 4);
         KALLOC(k->d_ev_proton, n * 4);
+        KALLOC(k->d_ev_dist, n * 8);
         k->ev_cap = cap;
     }
     if (cap == 0) k->ev_cap = 0;
@@ -835,11 +839,11 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
     a.dt = k->dt; a.seed = k->seed; a.stride = stride; a.nframes = nframes;
     a.frames_base = k->frames_total; a.n_u = k->n_u; a.ev_cap = k->ev_cap; a.row_cap = k->row_cap;
     a.reset_freq = k->reset_freq; a.print_freq = k->print_freq;
-    a.start = d_start; a.dest = d_dest; a.counts = d_counts; a.omega = d_omega;
+    a.start = d_start; a.dest = d_dest; a.counts = d_counts; a.omega = d_omega; a.dist = d_dist;
     a.positions = obs ? d_positions : nullptr;
     a.u = k->d_u; a.lattice = k->d_lattice; a.lattice0 = k->d_lattice0; a.state = k->d_state;
     a.ev_frame = k->d_ev_frame; a.ev_time = k->d_ev_time; a.ev_start = k->d_ev_start;
-    a.ev_dest = k->d_ev_dest; a.ev_proton = k->d_ev_proton;
+    a.ev_dest = k->d_ev_dest; a.ev_proton = k->d_ev_proton; a.ev_dist = k->d_ev_dist;
     a.rows = k->d_rows; a.snapshot = k->d_snapshot; a.disp = k->d_disp; a.ties = k->d_ties;
     a.exact = k->rng_mode == CMD_RNG_REPLAY ? 1 : 0;
     if (a.exact) {
@@ -930,6 +934,75 @@ extern "C" int cmd_kmc_get_events(const cmd_kmc *k, int replica, int64_t capacit
         if (proton) CMD_CUDA(cudaMemcpyAsync(proton, k->d_ev_proton + off, have * 4, cudaMemcpyDeviceToHost, st));
         CMD_CUDA(cudaStreamSynchronize(st));
     }
+    return CMD_OK;
+}
+
+extern "C" int cmd_kmc_get_event_distances(const cmd_kmc *k, int replica, int64_t capacity,
+                                           int64_t *n, double *dist)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || replica < 0 || replica >= k->n_replicas || !n) return cmd_set_error(CMD_EINVAL, "bad argument");
+    cudaStream_t st = cmd_global().stream;
+    KmcState hs;
+    CMD_CUDA(cudaMemcpyAsync(&hs, k->d_state + replica, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
+    int64_t have = hs.log_pos < k->ev_cap ? hs.log_pos : k->ev_cap;
+    if (have > capacity) have = capacity;
+    *n = have;
+    if (have > 0 && dist) {
+        CMD_CUDA(cudaMemcpyAsync(dist, k->d_ev_dist + (int64_t)replica * k->ev_cap, have * 8,
+                                 cudaMemcpyDeviceToHost, st));
+        CMD_CUDA(cudaStreamSynchronize(st));
+    }
+    return CMD_OK;
+}
+
+// jump-pair distances of the logged events of every replica -> histogram (jumpstat numerator)
+__global__ void __launch_bounds__(256)
+k_jump_hist(const KmcState *__restrict__ state, const double *__restrict__ ev_dist, int64_t ev_cap,
+            int n_replicas, double lo, double inv_width, int nbins, unsigned long long *__restrict__ hist)
+{
+    const int r = blockIdx.x;
+    if (r >= n_replicas) return;
+    long long have = state[r].log_pos < ev_cap ? state[r].log_pos : ev_cap;
+    for (long long e = threadIdx.x; e < have; e += blockDim.x) {
+        const double d = ev_dist[(int64_t)r * ev_cap + e];
+        const double b = floor((d - lo) * inv_width);
+        if (b >= 0 && b < nbins) atomicAdd(hist + (int)b, 1ull);
+    }
+}
+
+extern "C" int cmd_kmc_jump_histogram_dev(const cmd_kmc *k, double lo, double hi, int nbins,
+                                          unsigned long long *d_hist)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || !d_hist || nbins < 1 || !(hi > lo)) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (k->ev_cap <= 0) return cmd_set_error(CMD_ESTATE, "the event log is disabled");
+    k_jump_hist<<<k->n_replicas, 256, 0, cmd_global().stream>>>(k->d_state, k->d_ev_dist, k->ev_cap,
+                                                                 k->n_replicas, lo, nbins / (hi - lo),
+                                                                 nbins, d_hist);
+    CMD_LAUNCHED();
+    return CMD_OK;
+}
+
+extern "C" int cmd_kmc_jump_histogram(const cmd_kmc *k, double lo, double hi, int nbins,
+                                      int64_t *h_hist)
+{
+    CMD_REQUIRE_INIT();
+    if (!h_hist || nbins < 1) return cmd_set_error(CMD_EINVAL, "bad argument");
+    void *d;
+    int rc = cmd_scratch(3, (size_t)nbins * 8, &d);
+    if (rc) return rc;
+    cudaStream_t st = cmd_global().stream;
+    CMD_CUDA(cudaMemsetAsync(d, 0, (size_t)nbins * 8, st));
+    if ((rc = cmd_kmc_jump_histogram_dev(k, lo, hi, nbins, (unsigned long long *)d))) return rc;
+    int64_t *tmp = (int64_t *)malloc((size_t)nbins * 8);
+    if (!tmp) return cmd_set_error(CMD_ENOMEM, "out of host memory");
+    cudaError_t e = cudaMemcpyAsync(tmp, d, (size_t)nbins * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) for (int b = 0; b < nbins; b++) h_hist[b] += tmp[b];
+    free(tmp);
+    CMD_CUDA(e);
     return CMD_OK;
 }
 

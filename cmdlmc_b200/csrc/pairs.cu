@@ -646,7 +646,26 @@ static int topo_reserve(cmd_topo *t, int64_t nframes)
     return CMD_OK;
 }
 
+static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes, bool skip);
+
 extern "C" int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t nframes)
+{
+    return topo_build_impl(t, d_frames, nframes, false);
+}
+
+// Frame-block sharding of a Verlet run: a rank whose block starts at frame s walks frames [0, s)
+// through the (cheap, sequential) displacement / rebuild-decision pass only and builds just the
+// list of the last rebuild frame, which leaves exactly the state a sequential run has at s.
+extern "C" int cmd_topo_skip_dev(cmd_topo *t, const double *d_frames, int64_t nframes)
+{
+    if (t && t->mode != CMD_TOPO_VERLET) {   // brute force keeps no state between frames
+        t->total_frames += nframes;
+        return CMD_OK;
+    }
+    return topo_build_impl(t, d_frames, nframes, true);
+}
+
+static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes, bool skip)
 {
     CMD_REQUIRE_INIT();
     if (!t || !d_frames || nframes < 1) return cmd_set_error(CMD_EINVAL, "bad argument");
@@ -663,7 +682,7 @@ extern "C" int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t n
             return cmd_set_error(CMD_ENOMEM, "cudaMalloc failed for the carried pair list");
         }
     }
-    t->nframes = nframes;
+    t->nframes = skip ? 0 : nframes;
     t->d_frames_last = d_frames;
     if (t->mode == CMD_TOPO_BRUTEFORCE) {
         rc = launch_pairs(t, d_frames, nullptr, nullptr, nframes, t->d_start, t->d_dest, t->d_dist,
@@ -681,6 +700,16 @@ extern "C" int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t n
                                       t->total_frames == 0 ? 1 : 0, t->d_sched, t->d_rebuild_ids,
                                       t->d_refresh_ids, t->d_head, t->d_rebuilt);
         CMD_LAUNCHED();
+        if (skip) {
+            int sched[3] = {0, 0, -1};
+            CMD_CUDA(cudaMemcpyAsync(sched, t->d_sched, sizeof(sched), cudaMemcpyDeviceToHost, st));
+            CMD_CUDA(cudaStreamSynchronize(st));
+            if (sched[0] > 0) {
+                rc = launch_pairs(t, d_frames, t->d_rebuild_ids + sched[0] - 1, nullptr, 1, t->d_start,
+                                  t->d_dest, t->d_dist, t->d_omega, t->d_counts, t->d_rate_sum, nullptr);
+                if (rc) return rc;
+            }
+        } else {
         rc = launch_pairs(t, d_frames, t->d_rebuild_ids, t->d_sched, nframes, t->d_start, t->d_dest,
                           t->d_dist, t->d_omega, t->d_counts, t->d_rate_sum, nullptr);
         if (rc) return rc;
@@ -696,6 +725,7 @@ extern "C" int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t n
             t->d_carry_start, t->d_carry_dest, t->d_carry_count, t->d_start, t->d_dest, t->d_dist,
             t->d_omega, t->d_counts, t->d_rate_sum);
         CMD_LAUNCHED();
+        }
         k_carry<<<8, 256, 0, st>>>(t->d_sched, t->d_start, t->d_dest, t->d_counts, t->stride,
                                    t->d_carry_start, t->d_carry_dest, t->d_carry_count);
         CMD_LAUNCHED();
@@ -719,11 +749,9 @@ extern "C" int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t n
     return CMD_OK;
 }
 
-extern "C" int cmd_topo_build(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes)
+// host frames -> the topology's staging buffer in HBM (float32 blocks are up-cast on the device)
+static int topo_stage(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes)
 {
-    CMD_REQUIRE_INIT();
-    if (!t || !h_frames || nframes < 1 || (dtype_bytes != 4 && dtype_bytes != 8))
-        return cmd_set_error(CMD_EINVAL, "bad argument");
     cudaStream_t st = cmd_global().stream;
     size_t elems = (size_t)nframes * t->n * 3;
     size_t need = elems * 8 + (dtype_bytes == 4 ? elems * 4 : 0);
@@ -748,7 +776,28 @@ extern "C" int cmd_topo_build(cmd_topo *t, const void *h_frames, int dtype_bytes
         k_upcast_f32<<<blocks, 256, 0, st>>>(d32, t->d_upload, (int64_t)elems);
         CMD_LAUNCHED();
     }
+    return CMD_OK;
+}
+
+extern "C" int cmd_topo_build(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || !h_frames || nframes < 1 || (dtype_bytes != 4 && dtype_bytes != 8))
+        return cmd_set_error(CMD_EINVAL, "bad argument");
+    int rc = topo_stage(t, h_frames, dtype_bytes, nframes);
+    if (rc) return rc;
     return cmd_topo_build_dev(t, t->d_upload, nframes);
+}
+
+extern "C" int cmd_topo_skip(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || !h_frames || nframes < 1 || (dtype_bytes != 4 && dtype_bytes != 8))
+        return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (t->mode != CMD_TOPO_VERLET) return cmd_topo_skip_dev(t, nullptr, nframes);
+    int rc = topo_stage(t, h_frames, dtype_bytes, nframes);
+    if (rc) return rc;
+    return cmd_topo_skip_dev(t, t->d_upload, nframes);
 }
 
 extern "C" int cmd_topo_frame_info(const cmd_topo *t, int64_t *counts, uint8_t *rebuilt,
@@ -824,6 +873,65 @@ extern "C" int cmd_topo_positions(const cmd_topo *t, const double **d_frames)
 {
     if (!t || t->nframes < 1 || !d_frames) return cmd_set_error(CMD_ESTATE, "no block has been built");
     *d_frames = t->d_frames_last;
+    return CMD_OK;
+}
+
+// ---- K5: histogram of the listed pair distances of the last block -------------
+// One CTA per frame slice; shared-memory bins, one global atomic per non-empty bin per CTA.
+__global__ void __launch_bounds__(256)
+k_pair_hist(const double *__restrict__ dist, const int *__restrict__ counts, int64_t stride,
+            int64_t nframes, double lo, double inv_width, int nbins,
+            unsigned long long *__restrict__ hist)
+{
+    extern __shared__ unsigned int bins[];
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) bins[b] = 0u;
+    __syncthreads();
+    for (int64_t f = blockIdx.x; f < nframes; f += gridDim.x) {
+        const int p = counts[f];
+        const double *d = dist + f * stride;
+        for (int k = threadIdx.x; k < p; k += blockDim.x) {
+            const double b = floor((d[k] - lo) * inv_width);
+            if (b >= 0 && b < nbins) atomicAdd(&bins[(int)b], 1u);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+        if (bins[b]) atomicAdd(hist + b, (unsigned long long)bins[b]);
+}
+
+extern "C" int cmd_topo_distance_histogram_dev(const cmd_topo *t, double lo, double hi, int nbins,
+                                               unsigned long long *d_hist)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || !d_hist || nbins < 1 || nbins > 8192 || !(hi > lo))
+        return cmd_set_error(CMD_EINVAL, "bad argument (1 <= nbins <= 8192, hi > lo)");
+    if (t->nframes < 1) return cmd_set_error(CMD_ESTATE, "no block has been built");
+    int64_t blocks = t->nframes < (int64_t)cmd_global().sm_count * 8 ? t->nframes
+                                                                     : (int64_t)cmd_global().sm_count * 8;
+    k_pair_hist<<<(unsigned)blocks, 256, (size_t)nbins * 4, cmd_global().stream>>>(
+        t->d_dist, t->d_counts, t->stride, t->nframes, lo, nbins / (hi - lo), nbins, d_hist);
+    CMD_LAUNCHED();
+    return CMD_OK;
+}
+
+extern "C" int cmd_topo_distance_histogram(const cmd_topo *t, double lo, double hi, int nbins,
+                                           int64_t *h_hist)
+{
+    CMD_REQUIRE_INIT();
+    if (!h_hist || nbins < 1) return cmd_set_error(CMD_EINVAL, "bad argument");
+    void *d;
+    int rc = cmd_scratch(3, (size_t)nbins * 8, &d);
+    if (rc) return rc;
+    cudaStream_t st = cmd_global().stream;
+    CMD_CUDA(cudaMemsetAsync(d, 0, (size_t)nbins * 8, st));
+    if ((rc = cmd_topo_distance_histogram_dev(t, lo, hi, nbins, (unsigned long long *)d))) return rc;
+    int64_t *tmp = (int64_t *)malloc((size_t)nbins * 8);
+    if (!tmp) return cmd_set_error(CMD_ENOMEM, "out of host memory");
+    cudaError_t e = cudaMemcpyAsync(tmp, d, (size_t)nbins * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) for (int b = 0; b < nbins; b++) h_hist[b] += tmp[b];
+    free(tmp);
+    CMD_CUDA(e);
     return CMD_OK;
 }
 

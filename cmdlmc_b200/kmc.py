@@ -100,8 +100,19 @@ class DeviceKMC:
                                             ptr(frame, C.c_int64), ptr(time), ptr(start, C.c_int),
                                             ptr(dest, C.c_int), ptr(proton, C.c_int)))
         k = n.value
+        dist = np.zeros(cap)
+        check(_abi.lib().cmd_kmc_get_event_distances(self._handle, int(replica), cap, C.byref(n),
+                                                     ptr(dist)))
         return dict(frame=frame[:k], time=time[:k], start=start[:k], dest=dest[:k],
-                    proton=proton[:k])
+                    proton=proton[:k], dist=dist[:k])
+
+    def jump_histogram(self, lo, hi, nbins, out=None):
+        """Adds the histogram of the O-O distances of all logged jumps (every replica) to `out`."""
+        if out is None:
+            out = np.zeros(int(nbins), np.int64)
+        check(_abi.lib().cmd_kmc_jump_histogram(self._handle, float(lo), float(hi), int(nbins),
+                                                ptr(out, C.c_int64)))
+        return out
 
     def observables(self, replica=0, capacity=1 << 20):
         n = C.c_int64(0)
@@ -255,7 +266,7 @@ class KMCLattice:
     @property
     def event_log(self):
         """All events so far: dict of arrays frame (sweep), time, start, dest, proton."""
-        keys = ("frame", "time", "start", "dest", "proton")
+        keys = ("frame", "time", "start", "dest", "proton", "dist")
         if not self._event_blocks:
             return {k: np.zeros(0) for k in keys}
         return {k: np.concatenate([b[k] for b in self._event_blocks]) for k in keys}

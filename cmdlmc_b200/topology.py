@@ -82,6 +82,24 @@ class DeviceTopology:
         check(_abi.lib().cmd_topo_build(self._handle, frames.ctypes.data_as(C.c_void_p),
                                         frames.dtype.itemsize, frames.shape[0]))
 
+    def skip(self, frames):
+        """Walks frames that precede this rank's block through the Verlet schedule pass only
+        (frame-block sharding, cmd_topo_skip); produces no per-frame results."""
+        frames = np.ascontiguousarray(frames)
+        if frames.dtype not in (np.float32, np.float64):
+            frames = frames.astype(np.float64)
+        check(_abi.lib().cmd_topo_skip(self._handle, frames.ctypes.data_as(C.c_void_p),
+                                       frames.dtype.itemsize, frames.shape[0]))
+
+    def distance_histogram(self, lo, hi, nbins, out=None):
+        """Adds the histogram of the listed pair distances of the last block to `out` (int64
+        [nbins]; created when None).  Every unordered pair counts twice (both directions)."""
+        if out is None:
+            out = np.zeros(int(nbins), np.int64)
+        check(_abi.lib().cmd_topo_distance_histogram(self._handle, float(lo), float(hi), int(nbins),
+                                                     ptr(out, C.c_int64)))
+        return out
+
     def build_dev(self, data_ptr, nframes):
         """Frames already in HBM: raw device pointer to float64 [F, n, 3]."""
         check(_abi.lib().cmd_topo_build_dev(self._handle, C.c_void_p(int(data_ptr)), int(nframes)))

@@ -166,6 +166,12 @@ int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t nframes);
 /* Same with host frames: uploads, then builds.  dtype_bytes is 8 (float64) or 4 (float32, as
  * stored by HDF5Trajectory, IO/trajectory_parser.py:324, up-cast on the device). */
 int cmd_topo_build(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes);
+/* Frame-block sharding across GPUs: walks a block of frames that precedes this rank's own block
+ * through the Verlet displacement / rebuild-decision pass only (topology.py:96-107) and builds
+ * just the list of its last rebuild frame -- the state a sequential run has at the block end.
+ * No per-frame results are produced.  A no-op (besides counting frames) in brute-force mode. */
+int cmd_topo_skip_dev(cmd_topo *t, const double *d_frames, int64_t nframes);
+int cmd_topo_skip(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes);
 /* Per-frame results of the last block.  Pointers may be NULL. h_counts: P_f, h_rebuilt: 1 when
  * frame f's list was rebuilt, h_rate_sum: sum of omega over all listed pairs of the frame. */
 int cmd_topo_frame_info(const cmd_topo *t, int64_t *h_counts, uint8_t *h_rebuilt,
@@ -188,6 +194,15 @@ int cmd_topo_positions(const cmd_topo *t, const double **d_frames);
 /* Tie audit: number of evaluated pairs of the last block whose distance is
  * within 1e-11 relative of cutoff+buffer. */
 int64_t cmd_topo_tie_count(const cmd_topo *t);
+
+/* K5 / "jumpstat" (README.md:57-58): histogram of the listed O-O distances of the
+ * last block over nbins equal bins of [lo, hi).  Every unordered pair is listed in both
+ * directions and counted twice.  Counts are ADDED to the caller's array (int64 on the host,
+ * unsigned 64-bit on the device -- e.g. a torch tensor that is all-reduced across GPUs). */
+int cmd_topo_distance_histogram(const cmd_topo *t, double lo, double hi, int nbins,
+                                int64_t *h_hist);
+int cmd_topo_distance_histogram_dev(const cmd_topo *t, double lo, double hi, int nbins,
+                                    unsigned long long *d_hist);
 
 /* ---------------------------------------------------------------- KMC ------------------- */
 #define CMD_RNG_REPLAY 0 /* host-pregenerated uniforms, bit-exact replay of the reference stream */
@@ -226,6 +241,15 @@ int cmd_kmc_get_status(const cmd_kmc *k, int *h_phase, int *h_reason, int64_t *h
 int cmd_kmc_get_events(const cmd_kmc *k, int replica, int64_t capacity, int64_t *n,
                        int64_t *h_frame, double *h_time, int *h_start, int *h_dest,
                        int *h_proton);
+/* O-O distance of the jump pair of every logged event of one replica (same order as
+ * cmd_kmc_get_events). */
+int cmd_kmc_get_event_distances(const cmd_kmc *k, int replica, int64_t capacity, int64_t *n,
+                                double *h_dist);
+/* Histogram of those distances over all replicas (numerator of the jump probability vs distance
+ * statistic); counts are added to the caller's array. */
+int cmd_kmc_jump_histogram(const cmd_kmc *k, double lo, double hi, int nbins, int64_t *h_hist);
+int cmd_kmc_jump_histogram_dev(const cmd_kmc *k, double lo, double hi, int nbins,
+                               unsigned long long *d_hist);
 /* Observable rows of one replica: (frame, time, msd_x, msd_y, msd_z, autocorr) per row. */
 int cmd_kmc_get_observables(const cmd_kmc *k, int replica, int64_t capacity, int64_t *n,
                             double *h_rows6);

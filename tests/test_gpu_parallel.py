@@ -1,0 +1,111 @@
+"""GPU side of the sharding rows and the histogram kernels (K5): ranks emulated
+one after the other on one GPU must reproduce the sequential run exactly."""
+import numpy as np
+import pytest
+
+from cmdlmc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def make_box(cell):
+    import cmdlmc_b200 as cm
+    cell = np.asarray(cell, dtype=float)
+    return cm.AtomBoxCubic(cell) if cell.size == 3 else cm.AtomBoxMonoclinic(cell)
+
+
+@pytest.mark.parametrize("cfg,nfr,world", [("C1", 240, 2), ("C2", 150, 4)])
+def test_frame_block_sharding_is_exact(cfg, nfr, world):
+    """Verlet mode across frame blocks: skip pass + own block == sequential run, frame by frame,
+    bit for bit (index arrays, distances, rates, rebuilt flags except at the block head)."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.parallel import ShardedTopology
+    from cmdlmc_b200.topology import DeviceTopology, MODE_VERLET, build_with_retry
+    w = synth.workload(cfg)
+    frames = synth.trajectory(w, nfr)
+    box = make_box(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    seq = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer,
+                                                      MODE_VERLET, rate, cap), frames)
+    counts, rebuilt, rsum = seq.frame_info()
+    want = [seq.get_frame(f, int(counts[f])) for f in range(nfr)]
+    seen = 0
+    for rank in range(world):
+        sh = ShardedTopology(box, w.n_oxygen, w.cutoff, w.buffer, MODE_VERLET, rate,
+                             lambda a, b: frames[a:b], nfr, rank=rank, world=world, chunk=29)
+        for first, topo in sh.blocks():
+            c, r, s = topo.frame_info()
+            for k in range(len(c)):
+                f = first + k
+                got = topo.get_frame(k, int(c[k]))
+                for a, b in zip(got, want[f]):
+                    np.testing.assert_array_equal(a, b)
+                assert s[k] == pytest.approx(rsum[f], rel=1e-12)
+                if not (rank > 0 and f == sh.start):
+                    assert bool(r[k]) == bool(rebuilt[f])
+                seen += 1
+    assert seen == nfr
+
+
+def test_pair_distance_histogram(orc):
+    """K5: histogram of all listed distances of a block == numpy on the same lists; float32
+    (HDF5-style) blocks and the cell-list path give the same counts."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.topology import DeviceTopology, build_with_retry
+    w = synth.workload("C2")
+    frames = synth.trajectory(w, 40)
+    box = make_box(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    topo = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, 0, rate,
+                                                       cap), frames)
+    counts = topo.frame_info()[0]
+    alld = np.concatenate([topo.get_frame(f, int(counts[f]))[2] for f in range(40)])
+    nb = 500
+    want = np.floor((alld - 0.0) * (nb / 5.0)).astype(np.int64)
+    want = np.bincount(want[(want >= 0) & (want < nb)], minlength=nb)
+    got = topo.distance_histogram(0.0, 5.0, nb)
+    np.testing.assert_array_equal(got, want)
+    assert got.sum() == counts.sum()
+    got2 = topo.distance_histogram(0.0, 5.0, nb, out=got.copy())      # accumulates
+    np.testing.assert_array_equal(got2, 2 * want)
+    cell = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, 0, rate,
+                                                       cap, path=1), frames)
+    np.testing.assert_array_equal(cell.distance_histogram(0.0, 5.0, nb), want)
+
+
+def test_jump_histogram_and_event_distances():
+    """jumpstat numerator: distances of the jump pairs, logged per event, histogrammed on the
+    device over all replicas."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.kmc import DeviceKMC, RNG_PHILOX
+    from cmdlmc_b200.topology import DeviceTopology, MODE_VERLET, build_with_retry
+    w = synth.workload("C1")
+    frames = synth.trajectory(w, 200)
+    box = make_box(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    topo = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer,
+                                                       MODE_VERLET, rate, cap), frames)
+    counts = topo.frame_info()[0]
+    R = 6
+    lat = np.stack([synth.initial_lattice(w.n_oxygen, w.n_protons, 50 + r)[0] for r in range(R)])
+    kmc = DeviceKMC(box, lat, w.time_step, RNG_PHILOX, seed=3)
+    kmc.set_event_log(4000)
+    kmc.advance(topo)
+    nb = 100
+    want = np.zeros(nb, np.int64)
+    total = 0
+    for r in range(R):
+        ev = kmc.events(r)
+        assert len(ev["dist"]) == len(ev["frame"]) > 0
+        # the logged distance is the listed distance of (start, dest) in the event's frame
+        for e in range(0, len(ev["frame"]), 37):
+            f = int(ev["frame"][e])
+            s, d, dist, _ = topo.get_frame(f, int(counts[f]))
+            k = np.flatnonzero((s == ev["start"][e]) & (d == ev["dest"][e]))
+            assert len(k) == 1 and dist[k[0]] == ev["dist"][e]
+        b = np.floor(ev["dist"] * (nb / 5.0)).astype(np.int64)
+        want += np.bincount(b[(b >= 0) & (b < nb)], minlength=nb)
+        total += len(ev["dist"])
+    got = kmc.jump_histogram(0.0, 5.0, nb)
+    np.testing.assert_array_equal(got, want)
+    assert got.sum() == total
