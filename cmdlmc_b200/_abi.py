@@ -93,6 +93,13 @@ SIGNATURES = {
     "cmd_kmc_get_events": (C.c_int, [vp, C.c_int, C.c_int64, lp, lp, dp, ip, ip, ip]),
     "cmd_kmc_get_observables": (C.c_int, [vp, C.c_int, C.c_int64, lp, dp]),
     "cmd_kmc_tie_count": (C.c_int64, [vp]),
+    "cmd_lmc_create": (C.c_int, [C.c_int, C.c_int, ip, C.c_int, C.c_uint64, C.POINTER(vp)]),
+    "cmd_lmc_destroy": (None, [vp]),
+    "cmd_lmc_set_replay_stream": (C.c_int, [vp, ip, dp, C.c_int64]),
+    "cmd_lmc_enable_jump_matrix": (C.c_int, [vp, C.c_int]),
+    "cmd_lmc_advance": (C.c_int, [vp, vp, C.c_double, C.c_int]),
+    "cmd_lmc_get_state": (C.c_int, [vp, ip, lp, lp, lp, ip]),
+    "cmd_lmc_get_jump_matrix": (C.c_int, [vp, lp]),
 }
 
 

@@ -256,6 +256,27 @@ int cmd_kmc_get_observables(const cmd_kmc *k, int replica, int64_t capacity, int
 /* Tie audit: decisions (time stepping / selection) within 1e-9 relative of a boundary. */
 int64_t cmd_kmc_tie_count(const cmd_kmc *k);
 
+/* ---------------------------------------------------------------- legacy LMC sweep ------ */
+/* PARITY UNPINNED: the legacy engine (LMCHelper.pyx, LMCRoutine.sweep / sweep_with_jumpmatrix) is
+ * not in the reference tree; restated from mdlmc/IO/config_parser.py:182-189 and the .bak tests
+ * (tests/cython_exts/LMC/test_LMCRoutine.py.bak:11-42, tests/LMC/test_MDMC.py.bak:61-84).
+ * One sweep on a frame = P attempts; attempt: pair k uniform in [0, P), u uniform in [0, 1);
+ * hop start[k] -> dest[k] iff start occupied, dest empty and u < omega[k] * prob_scale. */
+typedef struct cmd_lmc cmd_lmc;
+int cmd_lmc_create(int n_sites, int n_replicas, const int *h_lattices, int rng_mode, uint64_t seed,
+                   cmd_lmc **out);
+void cmd_lmc_destroy(cmd_lmc *k);
+/* Replay streams (e.g. GSL gsl_rng_uniform_int(P) / gsl_rng_uniform from a seeded MT19937):
+ * h_pick int32 [n_replicas][n], h_acc float64 [n_replicas][n], one entry per attempt. */
+int cmd_lmc_set_replay_stream(cmd_lmc *k, const int *h_pick, const double *h_acc, int64_t n);
+/* sweep_with_jumpmatrix: counts hops per (start, dest), summed over replicas. */
+int cmd_lmc_enable_jump_matrix(cmd_lmc *k, int enable);
+/* sweeps_per_frame sweeps on every frame of the topology's current block; prob_scale = dt. */
+int cmd_lmc_advance(cmd_lmc *k, const cmd_topo *t, double prob_scale, int sweeps_per_frame);
+int cmd_lmc_get_state(const cmd_lmc *k, int *h_lattices, int64_t *h_jumps, int64_t *h_attempts,
+                      int64_t *h_sweeps, int *h_halted);
+int cmd_lmc_get_jump_matrix(const cmd_lmc *k, int64_t *h_matrix);
+
 #ifdef __cplusplus
 }
 #endif

@@ -244,3 +244,22 @@ def test_legacy_rates_and_mt(orc):
     mt = orc.MT19937(7)
     ks = [mt.gsl_uniform_int(1000) for _ in range(1000)]
     assert 0 <= min(ks) and max(ks) < 1000
+
+
+def test_gsl_stream_helper_matches_oracle_mt(orc):
+    """cmdlmc_b200.lmc.gsl_streams (host helper feeding the LMC replay mode) == the oracle's
+    MT19937 with GSL's uniform_int / uniform conventions (PARITY UNPINNED upstream)."""
+    from cmdlmc_b200 import lmc
+    counts = [7, 0, 1000, 3, 4093]
+    pick, acc = lmc.gsl_streams(99, counts, sweeps_per_frame=2)
+    mt = orc.MT19937(99)
+    k = 0
+    for p in np.repeat(counts, 2):
+        for _ in range(int(p)):
+            assert pick[k] == mt.gsl_uniform_int(int(p))
+            assert acc[k] == mt.gsl_uniform()
+            k += 1
+    assert k == len(pick)
+    raw = lmc.mt19937_u32(5, 10)
+    mt = orc.MT19937(5)
+    assert [int(x) for x in raw] == [mt.u32() for _ in range(10)]
