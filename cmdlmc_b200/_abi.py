@@ -80,6 +80,8 @@ SIGNATURES = {
     "cmd_kmc_get_event_distances": (C.c_int, [vp, C.c_int, C.c_int64, lp, dp]),
     "cmd_kmc_jump_histogram": (C.c_int, [vp, C.c_double, C.c_double, C.c_int, lp]),
     "cmd_kmc_jump_histogram_dev": (C.c_int, [vp, C.c_double, C.c_double, C.c_int, vp]),
+    "cmd_topo_row_offsets": (C.c_int, [vp, C.POINTER(vp)]),
+    "cmd_topo_n_atoms": (C.c_int, [vp]),
     "cmd_topo_positions": (C.c_int, [vp, C.POINTER(vp)]),
     "cmd_kmc_create": (C.c_int, [vp, C.c_int, C.c_int, ip, C.c_double, C.c_int, C.c_uint64,
                                  C.POINTER(vp)]),

@@ -75,4 +75,7 @@ void cmd_box_prune_images(BoxParams &p, double rc);
         CMD_CUDA(cudaGetLastError());                                                       \
     } while (0)
 
+// row pitch (ints) of the per-frame row index: n + 1 entries padded to 16 bytes (TMA bulk copies)
+__host__ __device__ inline int cmd_ro_pitch(int n) { return (n + 4) & ~3; }
+
 static inline int cmd_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -85,6 +85,9 @@ struct KmcArgs {
     double *ev_dist;
     double *rows, *snapshot, *disp;
     unsigned long long *ties;
+    // streaming (Philox) kernel: row index of the block's lists, smem ring geometry
+    int fast, ro_pitch, nst_max;
+    const int *rowoff;
     // exact-replay scratch, one slice per replica (see kmc_consume_exact)
     int exact;
     int64_t x_cap, x_leaves;
@@ -133,6 +136,12 @@ struct WarpCtx {
     double *comp, *cum, *lsum;
     int *cidx, *loff, *ln;
     int m;
+    // streaming kernel: psum[stage][lane] = allowed rate of the pairs k = stage*1024 + i*32 + lane,
+    // the frame's row index (shared memory) and the running per-lane total
+    double *psum;
+    const int *ro;
+    double lane_total;
+    int nst;
 };
 
 __device__ __forceinline__ bool occupied(const WarpCtx &c, int s) { return (c.occ[s >> 5] >> (s & 31)) & 1u; }
@@ -424,6 +433,128 @@ __device__ bool kmc_move(const KmcArgs &a, WarpCtx &c, double u, int *o_start, i
     return true;
 }
 
+
+// ---- streaming (Philox) flavour ------------------------------------------------------------------
+// The frame's (start, dest, omega) arrays come through a TMA-fed shared-memory ring shared by all
+// replicas of the CTA; a lane accumulates the allowed rates of ITS pairs (k mod 32 == lane) per
+// 1024-pair stage without any shuffle.  Selection walks the transitions in (lane, stage, i) order
+// instead of list order -- the probability of picking transition k is omega_k / S either way.
+__device__ __forceinline__ void kmc_consume_stage(WarpCtx &c, const int *s_start, const int *s_dest,
+                                                  const double *s_omega, int k0, int cnt, int stage)
+{
+    double acc = 0.0;
+#pragma unroll 4
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+        const int k = i0 + c.lane;
+        bool ok = false;
+        if (k < cnt) {
+            const int st = s_start[k], de = s_dest[k];
+            ok = occupied(c, st) && !occupied(c, de);
+            if (ok) acc += s_omega[k];
+        }
+        const unsigned bits = __ballot_sync(0xffffffffu, ok);
+        if (c.lane == 0) c.mask0[(k0 + i0) >> 5] = bits;
+    }
+    c.psum[stage * 32 + c.lane] = acc;
+    c.lane_total += acc;
+}
+
+// removes transition k of the last consumed frame from the allowed set (bit, partial sum)
+__device__ __forceinline__ void kmc_disallow(const KmcArgs &a, WarpCtx &c, int k)
+{
+    const unsigned bit = 1u << (k & 31);
+    if (c.mask0[k >> 5] & bit) {
+        atomicAnd(&c.mask0[k >> 5], ~bit);
+        atomicAdd(&c.psum[(k >> 10) * 32 + (k & 31)], -__ldg(a.omega + c.base + k));
+    }
+}
+
+__device__ bool kmc_move_fast(const KmcArgs &a, WarpCtx &c, double u, int *o_start, int *o_dest,
+                              int *o_proton, int *o_index, unsigned long long *ties)
+{
+    // lane totals -> inclusive scan over lanes; the last value is the total the draw refers to
+    double lt = 0.0;
+    for (int s = 0; s < c.nst; s++) lt += c.psum[s * 32 + c.lane];
+    lt = fmax(lt, 0.0);   // removals leave rounding residue only
+    double inc = lt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (c.lane >= o) inc += t;
+    }
+    const double total = __shfl_sync(0xffffffffu, inc, 31);
+    if (!(total > 0.0)) return false;   // nothing allowed: IndexError upstream
+    const double draw = total * u;
+    const unsigned have = __ballot_sync(0xffffffffu, lt > 0.0);
+    if (!have) return false;
+    const unsigned hit = __ballot_sync(0xffffffffu, lt > 0.0 && inc >= draw);
+    const int L = hit ? __ffs(hit) - 1 : 31 - __clz(have);
+    double run = __shfl_sync(0xffffffffu, inc - lt, L);   // rate in front of lane L's pairs
+    // lane L's stages, in order (every lane walks the same values)
+    int sfound = -1;
+    double run_before = run;
+    for (int s = 0; s < c.nst; s++) {
+        const double v = c.psum[s * 32 + L];
+        if (v > 0.0) {
+            sfound = s;
+            run_before = run;
+            if (run + v >= draw) break;
+            run += v;
+        }
+    }
+    if (sfound < 0) return false;
+    run = run_before;
+    // its <= 32 pairs k = sfound*1024 + i*32 + L, one per lane
+    const int k = sfound * 1024 + c.lane * 32 + L;
+    const bool ok = k < c.p && ((c.mask0[k >> 5] >> L) & 1u);
+    const double om = ok ? __ldg(a.omega + c.base + k) : 0.0;
+    double inc2 = om;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc2, o);
+        if (c.lane >= o) inc2 += t;
+    }
+    const unsigned okbits = __ballot_sync(0xffffffffu, ok);
+    if (!okbits) return false;
+    unsigned hit2 = __ballot_sync(0xffffffffu, ok && run + inc2 >= draw);
+    int isel;
+    if (hit2) isel = __ffs(hit2) - 1;
+    else {   // partial sums and the scan round differently: the last allowed pair of the stage
+        isel = 31 - __clz(okbits);
+        if (c.lane == 0) atomicAdd(ties, 1ull);
+    }
+    const int found = sfound * 1024 + isel * 32 + L;
+    const int st = __ldg(a.start + c.base + found), de = __ldg(a.dest + c.base + found);
+    const int proton = c.lat[st];
+    __syncwarp();
+    if (c.lane == 0) {
+        c.lat[de] = proton;
+        c.lat[st] = 0;
+        c.occ[de >> 5] |= 1u << (de & 31);
+        c.occ[st >> 5] &= ~(1u << (st & 31));
+    }
+    __syncwarp();
+    // Same-frame follow-up events see the arrays filtered at consumption, filtered again with the
+    // new lattice (Q2): transitions only ever LEAVE the set -- those starting at st (now empty)
+    // and those ending at de (now occupied).
+    const int r0 = c.ro[st], r1 = c.ro[st + 1];
+    for (int q = r0 + c.lane; q < r1; q += 32) kmc_disallow(a, c, q);
+    __syncwarp();
+    const int d0 = c.ro[de], d1 = c.ro[de + 1];
+    for (int q = d0 + c.lane; q < d1; q += 32) {
+        const int x = __ldg(a.dest + c.base + q);          // neighbour of de; find (x -> de) in row x
+        int lo = c.ro[x], hi = c.ro[x + 1] - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(a.dest + c.base + mid) < de) lo = mid + 1; else hi = mid;
+        }
+        if (lo < c.ro[x + 1] && __ldg(a.dest + c.base + lo) == de) kmc_disallow(a, c, lo);
+    }
+    __syncwarp();
+    *o_start = st; *o_dest = de; *o_proton = proton; *o_index = found;
+    return true;
+}
+
 // observables on a consumed frame (MDMC.py:198-208 + output.py); the lattice a frame is seen
 // with is the lattice at consumption == the pre-jump lattice at the flush (Q4)
 __device__ void kmc_observe(const KmcArgs &a, const BoxParams &bx, WarpCtx &c, int r, int64_t f,
@@ -502,7 +633,8 @@ __device__ bool kmc_event(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
     }
     int es, ed, ep, ek;
     const bool moved = a.exact ? kmc_move_exact(a, c, u, &es, &ed, &ep, &ek, a.ties)
-                               : kmc_move(a, c, u, &es, &ed, &ep, &ek, a.ties);
+                       : a.fast ? kmc_move_fast(a, c, u, &es, &ed, &ep, &ek, a.ties)
+                                : kmc_move(a, c, u, &es, &ed, &ep, &ek, a.ties);
     if (!moved) { st.reason = 2; return false; }
     if (c.lane == 0 && st.log_pos < a.ev_cap) {
         int64_t q = (int64_t)r * a.ev_cap + st.log_pos;
@@ -547,6 +679,34 @@ __device__ void kmc_run_until_frame_needed(const KmcArgs &a, WarpCtx &c, int r, 
             st.current_probsum = st.current_rate * st.delta_t;
             st.phase = KMC_PHASE_SCAN;
             return;
+        }
+    }
+}
+
+// the reference's per-frame step once the frame's total allowed rate is known (MDMC.py:146-171)
+__device__ void kmc_after_consume(const KmcArgs &a, WarpCtx &c, int r, KmcState &st, double rate)
+{
+    const int lane = c.lane;
+    if (st.phase == KMC_PHASE_START) {  // MDMC.py:146
+        st.current_rate = rate;
+        kmc_run_until_frame_needed(a, c, r, st);
+    } else {  // KMC_PHASE_SCAN, MDMC.py:158-165
+        // explicit roundings: no FMA contraction anywhere in the decision arithmetic
+        double next_probsum = __dadd_rn(st.current_probsum, __dmul_rn(rate, a.dt));
+        if (lane == 0 && fabs(next_probsum - st.time_selector) < 1e-9 * st.time_selector)
+            atomicAdd(a.ties, 1ull);
+        if (next_probsum < st.time_selector) {
+            st.delta_frame += 1;
+            st.current_probsum = next_probsum;
+        } else {
+            double rest = st.time_selector - st.current_probsum;
+            st.delta_t = __dadd_rn(st.delta_t,
+                           __dadd_rn(__dmul_rn((double)(st.delta_frame - 1), a.dt),
+                                     __ddiv_rn(rest, rate)));
+            st.kmc_time += st.delta_t;
+            st.sweep += st.delta_frame;
+            if (!kmc_event(a, c, r, st)) st.phase = KMC_PHASE_HALT;
+            else kmc_run_until_frame_needed(a, c, r, st);
         }
     }
 }
@@ -600,30 +760,166 @@ __global__ void __launch_bounds__(512, 1) k_kmc_advance(const __grid_constant__ 
             double rate = a.exact ? kmc_consume_exact(a, c, f) : kmc_consume(a, c, f);
             st.site_updates += c.p;
             st.frames_seen++;
-            if (st.phase == KMC_PHASE_START) {  // MDMC.py:146
-                st.current_rate = rate;
-                kmc_run_until_frame_needed(a, c, r, st);
-            } else {  // KMC_PHASE_SCAN, MDMC.py:158-165
-                // explicit roundings: no FMA contraction anywhere in the decision arithmetic
-                double next_probsum = __dadd_rn(st.current_probsum, __dmul_rn(rate, a.dt));
-                if (lane == 0 && fabs(next_probsum - st.time_selector) < 1e-9 * st.time_selector)
-                    atomicAdd(a.ties, 1ull);
-                if (next_probsum < st.time_selector) {
-                    st.delta_frame += 1;
-                    st.current_probsum = next_probsum;
-                } else {
-                    double rest = st.time_selector - st.current_probsum;
-                    st.delta_t = __dadd_rn(st.delta_t,
-                                           __dadd_rn(__dmul_rn((double)(st.delta_frame - 1), a.dt),
-                                                     __ddiv_rn(rest, rate)));
-                    st.kmc_time += st.delta_t;
-                    st.sweep += st.delta_frame;
-                    if (!kmc_event(a, c, r, st)) st.phase = KMC_PHASE_HALT;
-                    else kmc_run_until_frame_needed(a, c, r, st);
-                }
-            }
+            kmc_after_consume(a, c, r, st, rate);
         }
         __syncthreads();  // keep the CTA's replicas on the same frame (L1 reuse of the frame data)
+    }
+    if (active) {
+        __syncwarp();
+        for (int s = lane; s < a.n_sites; s += 32) a.lattice[(int64_t)r * a.n_sites + s] = c.lat[s];
+        if (lane == 0) a.state[r] = st;
+    }
+}
+
+
+// ---- TMA / mbarrier plumbing of the streaming kernel ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     "selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+#define KMC_STAGE 1024   // pairs per ring stage: 4 KB start + 4 KB dest + 8 KB omega
+
+// Streaming KMC kernel (Philox mode).  One warp per replica; the replicas of a CTA consume the
+// frames' arrays from a two-stage shared-memory ring filled by TMA bulk copies (thread 0 issues
+// stage i+1 while stage i is consumed).  Per replica-frame the work is one pass over the pairs out
+// of shared memory; events cost O(neighbours) thanks to the per-(stage, lane) partial sums.
+__global__ void __launch_bounds__(512, 1) k_kmc_stream(const __grid_constant__ BoxParams bx,
+                                                       const __grid_constant__ KmcArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int r = blockIdx.x * a.replicas_per_cta + w;
+    const bool active = r < a.n_replicas;
+    // ring: 2 x (start, dest, omega), 2 x row index, 2 mbarriers; then the per-warp state
+    int *ring_start[2], *ring_dest[2], *ring_ro[2];
+    double *ring_omega[2];
+    unsigned char *q = smem_raw;
+    for (int b = 0; b < 2; b++) { ring_omega[b] = (double *)q; q += KMC_STAGE * 8; }
+    for (int b = 0; b < 2; b++) { ring_start[b] = (int *)q; q += KMC_STAGE * 4; }
+    for (int b = 0; b < 2; b++) { ring_dest[b] = (int *)q; q += KMC_STAGE * 4; }
+    for (int b = 0; b < 2; b++) { ring_ro[b] = (int *)q; q += (size_t)a.ro_pitch * 4; }
+    uint64_t *full = (uint64_t *)q;
+    q += 16;
+    const size_t per_warp = ((size_t)a.nst_max * 32 * 8 + (size_t)a.n_sites * 4 +
+                             (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4 + 7) / 8 * 8;
+    WarpCtx c;
+    c.lane = lane;
+    c.psum = (double *)(q + per_warp * w);
+    c.lat = (int *)(c.psum + (size_t)a.nst_max * 32);
+    c.occ = (unsigned *)(c.lat + a.n_sites);
+    c.mask0 = c.occ + a.occ_words;
+    c.base = 0; c.p = 0; c.m = 0; c.nst = 0; c.lane_total = 0.0; c.ro = ring_ro[0];
+    c.comp = c.cum = c.lsum = nullptr;
+    c.cidx = c.loff = c.ln = nullptr;
+    KmcState st;
+    memset(&st, 0, sizeof(st));
+    st.phase = KMC_PHASE_HALT;
+    if (active) {
+        st = a.state[r];
+        for (int s = lane; s < a.n_sites; s += 32) c.lat[s] = a.lattice[(int64_t)r * a.n_sites + s];
+        __syncwarp();
+        for (int qq = lane; qq < a.occ_words; qq += 32) {
+            unsigned bits = 0;
+            for (int b = 0; b < 32; b++) {
+                int s = qq * 32 + b;
+                if (s < a.n_sites && c.lat[s] > 0) bits |= 1u << b;
+            }
+            c.occ[qq] = bits;
+        }
+        __syncwarp();
+    }
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // producer (thread 0): item = (frame, stage); a frame without pairs still is one (empty) stage
+    auto issue = [&](int64_t f, int cstage, int b) {
+        const int p = a.counts[f];
+        const int64_t off = f * a.stride + (int64_t)cstage * KMC_STAGE;
+        int64_t e = p > 0 ? a.stride - (int64_t)cstage * KMC_STAGE : 0;   // stays inside the frame's slot
+        if (e > KMC_STAGE) e = KMC_STAGE;
+        uint32_t bytes = (uint32_t)e * 16u + (cstage == 0 ? (uint32_t)a.ro_pitch * 4u : 0u);
+        mbar_expect_tx(&full[b], bytes);
+        if (e > 0) {
+            tma_load_1d(ring_start[b], a.start + off, (uint32_t)e * 4u, &full[b]);
+            tma_load_1d(ring_dest[b], a.dest + off, (uint32_t)e * 4u, &full[b]);
+            tma_load_1d(ring_omega[b], a.omega + off, (uint32_t)e * 8u, &full[b]);
+        }
+        if (cstage == 0)
+            tma_load_1d(ring_ro[f & 1], a.rowoff + f * (int64_t)a.ro_pitch, (uint32_t)a.ro_pitch * 4u, &full[b]);
+    };
+    int64_t pf = 0;   // next item to issue
+    int pc = 0;
+    if (tid == 0 && a.nframes > 0) {
+        issue(0, 0, 0);
+        const int p0 = a.counts[0];
+        const int nst0 = p0 > 0 ? (p0 + KMC_STAGE - 1) / KMC_STAGE : 1;
+        if (++pc >= nst0) { pc = 0; pf = 1; }
+    }
+    unsigned it = 0;
+    for (int64_t f = 0; f < a.nframes; f++) {
+        const int p = a.counts[f];
+        const int nst = p > 0 ? (p + KMC_STAGE - 1) / KMC_STAGE : 1;
+        c.base = f * a.stride;
+        c.p = p;
+        c.nst = nst;
+        c.ro = ring_ro[f & 1];
+        c.lane_total = 0.0;
+        const bool run = active && st.phase != KMC_PHASE_HALT;
+        if (run && a.positions) kmc_observe(a, bx, c, r, f, st);
+        for (int cs = 0; cs < nst; cs++, it++) {
+            if (tid == 0 && pf < a.nframes) {   // prefetch the next item into the other buffer
+                issue(pf, pc, (it + 1) & 1);
+                const int pp = a.counts[pf];
+                const int pn = pp > 0 ? (pp + KMC_STAGE - 1) / KMC_STAGE : 1;
+                if (++pc >= pn) { pc = 0; pf++; }
+            }
+            mbar_wait(&full[it & 1], (it >> 1) & 1);
+            if (run) {
+                const int cnt = min(KMC_STAGE, p - cs * KMC_STAGE);
+                kmc_consume_stage(c, ring_start[it & 1], ring_dest[it & 1], ring_omega[it & 1],
+                                  cs * KMC_STAGE, cnt > 0 ? cnt : 0, cs);
+            }
+            if (run && cs == nst - 1) {
+                __syncwarp();
+                const double rate = warp_sum(c.lane_total);
+                st.site_updates += p;
+                st.frames_seen++;
+                kmc_after_consume(a, c, r, st, rate);
+            }
+            __syncthreads();   // everyone is done with this buffer before it is refilled
+        }
     }
     if (active) {
         __syncwarp();
@@ -853,10 +1149,35 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
     }
     a.occ_words = (k->n_sites + 31) / 32;
     a.mask_words = (int)((stride + 31) / 32) + 1;
-    size_t per_warp = (size_t)a.n_sites * 4 + (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4;
     int rpc = (k->n_replicas + g.sm_count - 1) / g.sm_count;
     if (rpc < 1) rpc = 1;
     if (rpc > 16) rpc = 16;
+    if (k->rng_mode == CMD_RNG_PHILOX && cmd_topo_n_atoms(t) == k->n_sites) {
+        // streaming kernel: TMA-fed shared-memory ring + per-(stage, lane) partial sums
+        const int *d_rowoff;
+        if ((rc = cmd_topo_row_offsets(t, &d_rowoff))) return rc;
+        a.fast = 1;
+        a.rowoff = d_rowoff;
+        a.ro_pitch = cmd_ro_pitch(k->n_sites);
+        a.nst_max = (int)((stride + KMC_STAGE - 1) / KMC_STAGE);
+        if (a.nst_max < 1) a.nst_max = 1;
+        const size_t ring = 2 * (size_t)KMC_STAGE * 16 + 2 * (size_t)a.ro_pitch * 4 + 16;
+        const size_t per_warp = ((size_t)a.nst_max * 32 * 8 + (size_t)a.n_sites * 4 +
+                                 (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4 + 7) / 8 * 8;
+        while (rpc > 1 && ring + per_warp * rpc > 200 * 1024) rpc--;
+        if (ring + per_warp * rpc <= 226 * 1024) {
+            a.replicas_per_cta = rpc;
+            const size_t smem = ring + per_warp * rpc;
+            CMD_CUDA(cudaFuncSetAttribute(k_kmc_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int blocks = (k->n_replicas + rpc - 1) / rpc;
+            k_kmc_stream<<<blocks, rpc * 32, smem, st>>>(k->bx, a);
+            CMD_LAUNCHED();
+            k->frames_total += nframes;
+            return CMD_OK;
+        }
+        a.fast = 0;   // state too large for the ring: the plain kernel below
+    }
+    size_t per_warp = (size_t)a.n_sites * 4 + (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4;
     while (rpc > 1 && per_warp * rpc > 200 * 1024) rpc--;
     if (per_warp * rpc > 226 * 1024)
         return cmd_set_error(CMD_ECAPACITY, "KMC per-replica state (%zu bytes) exceeds shared memory", per_warp);

@@ -39,18 +39,19 @@ struct cmd_topo {
     CellGrid cg;
     int rowcap, cell_batch;
     int4 *d_fxu, *d_sorted;
-    int *d_slot, *d_cell_start, *d_rowcount, *d_rowoff, *d_tmp_j, *d_cap_need;
+    int *d_slot, *d_cell_start, *d_rowcount, *d_rowoff_tmp, *d_tmp_j, *d_cap_need;
     double *d_tmp_d;
     // block results
     int64_t cap_frames, nframes;
     int *d_start, *d_dest, *d_counts, *d_err;
+    int *d_rowoff;   // [frames][n + 1] row index of every frame's list
     double *d_dist, *d_omega, *d_rate_sum;
     uint8_t *d_rebuilt;
     unsigned long long *d_ties;
     // Verlet state carried across blocks
     bool have_last;
     double *d_last, *d_displacement, *d_dr;
-    int *d_carry_start, *d_carry_dest, *d_carry_count;
+    int *d_carry_start, *d_carry_dest, *d_carry_count, *d_carry_rowoff;
     int *d_sched;  // [0] n_rebuild, [1] n_refresh, [2] last head (-1 = carry), then ids
     int *d_rebuild_ids, *d_refresh_ids, *d_head;
     double *d_upload;
@@ -163,7 +164,8 @@ k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RatePara
           const int *__restrict__ carry_count, int *__restrict__ out_start,
           int *__restrict__ out_dest, double *__restrict__ out_dist,
           double *__restrict__ out_omega, int *__restrict__ out_counts,
-          double *__restrict__ out_rate_sum)
+          double *__restrict__ out_rate_sum, const int *__restrict__ carry_rowoff,
+          int *__restrict__ out_rowoff)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if ((int)blockIdx.x >= *n_ids) return;
@@ -179,6 +181,11 @@ k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RatePara
     const int *hs = hd < 0 ? carry_start : out_start + hd * stride;
     const int *hdst = hd < 0 ? carry_dest : out_dest + hd * stride;
     __syncthreads();
+    {   // the list is the head's list: so is its row index
+        const int *hro = hd < 0 ? carry_rowoff : out_rowoff + hd * (int64_t)cmd_ro_pitch(n);
+        int *ro = out_rowoff + f * (int64_t)cmd_ro_pitch(n);
+        for (int k = threadIdx.x; k <= n; k += blockDim.x) ro[k] = hro[k];
+    }
     const int64_t base = f * stride;
     double rsum = 0.0;
     for (int k = threadIdx.x; k < p; k += blockDim.x) {
@@ -207,10 +214,13 @@ k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RatePara
 __global__ void __launch_bounds__(256)
 k_carry(const int *__restrict__ sched, const int *__restrict__ out_start,
         const int *__restrict__ out_dest, const int *__restrict__ out_counts, int64_t stride,
-        int *__restrict__ carry_start, int *__restrict__ carry_dest, int *__restrict__ carry_count)
+        int *__restrict__ carry_start, int *__restrict__ carry_dest, int *__restrict__ carry_count,
+        const int *__restrict__ out_rowoff, int *__restrict__ carry_rowoff, int n)
 {
     int hd = sched[2];
     if (hd < 0) return;  // the head is still the carried list
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= n; k += gridDim.x * blockDim.x)
+        carry_rowoff[k] = out_rowoff[hd * (int64_t)cmd_ro_pitch(n) + k];
     int p = out_counts[hd];
     if (p < 0) p = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < p; k += gridDim.x * blockDim.x) {
@@ -240,6 +250,8 @@ static double exact_sq_threshold(double rc)
 static void topo_free_block(cmd_topo *t)
 {
     cudaFree(t->d_start); cudaFree(t->d_dest); cudaFree(t->d_dist); cudaFree(t->d_omega);
+    cudaFree(t->d_rowoff);
+    t->d_rowoff = nullptr;
     cudaFree(t->d_counts); cudaFree(t->d_rate_sum); cudaFree(t->d_rebuilt); cudaFree(t->d_dr);
     cudaFree(t->d_rebuild_ids); cudaFree(t->d_refresh_ids); cudaFree(t->d_head);
     t->d_start = t->d_dest = t->d_counts = nullptr;
@@ -252,9 +264,9 @@ static void topo_free_block(cmd_topo *t)
 static void cell_free(cmd_topo *t)
 {
     cudaFree(t->d_fxu); cudaFree(t->d_sorted); cudaFree(t->d_slot); cudaFree(t->d_cell_start);
-    cudaFree(t->d_rowcount); cudaFree(t->d_rowoff); cudaFree(t->d_tmp_j); cudaFree(t->d_tmp_d);
+    cudaFree(t->d_rowcount); cudaFree(t->d_rowoff_tmp); cudaFree(t->d_tmp_j); cudaFree(t->d_tmp_d);
     t->d_fxu = t->d_sorted = nullptr;
-    t->d_slot = t->d_cell_start = t->d_rowcount = t->d_rowoff = t->d_tmp_j = nullptr;
+    t->d_slot = t->d_cell_start = t->d_rowcount = t->d_rowoff_tmp = t->d_tmp_j = nullptr;
     t->d_tmp_d = nullptr;
     t->cell_batch = 0;
 }
@@ -266,6 +278,7 @@ extern "C" void cmd_topo_destroy(cmd_topo *t)
     topo_free_block(t);
     cudaFree(t->d_err); cudaFree(t->d_ties); cudaFree(t->d_last); cudaFree(t->d_displacement);
     cudaFree(t->d_carry_start); cudaFree(t->d_carry_dest); cudaFree(t->d_carry_count);
+    cudaFree(t->d_carry_rowoff);
     cudaFree(t->d_sched); cudaFree(t->d_upload); cudaFree(t->d_cap_need);
     cell_free(t);
     free(t);
@@ -435,7 +448,8 @@ static int launch_dense(cmd_topo *t, const double *d_frames, const int *ids, con
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
         k_pairs_dense<K, IM, SP, MT, MB><<<(unsigned)grid, t->threads * SP, smem, st>>>(         \
             t->bx, t->rate, t->fp, d_frames, ids, n_ids, t->n, t->rc, t->t2, stride, hit_cap,    \
-            start, dest, dist, omega, counts, rate_sum, rebuilt, t->d_err, t->d_ties);           \
+            start, dest, dist, omega, counts, rate_sum, rebuilt, start ? t->d_rowoff : nullptr,  \
+            t->d_err, t->d_ties);                                                                \
     } while (0)
 #define DENSE_PICK(SP, MT, MB)                                                                   \
     do {                                                                                         \
@@ -472,7 +486,7 @@ static int cell_reserve(cmd_topo *t, int batch)
     CALLOC(t->d_slot, B * n * 4);
     CALLOC(t->d_cell_start, B * (t->cg.ncell + 1) * 4);
     CALLOC(t->d_rowcount, B * n * 4);
-    CALLOC(t->d_rowoff, B * (n + 1) * 4);
+    CALLOC(t->d_rowoff_tmp, B * (n + 1) * 4);
     CALLOC(t->d_tmp_j, B * n * t->rowcap * 4);
     CALLOC(t->d_tmp_d, B * n * t->rowcap * 8);
 #undef CALLOC
@@ -546,12 +560,13 @@ static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, cons
             continue;   // redo this batch with longer rows
         }
         k_cell_scan<<<batch, 1024, 0, st>>>(ids, n_ids, (int)first, n, stride, t->d_rowcount,
-                                            t->d_rowoff, counts, rebuilt, rate_sum, t->d_err);
+                                            t->d_rowoff_tmp, counts, rebuilt, rate_sum,
+                                            emit ? t->d_rowoff : nullptr, t->d_err);
         CMD_LAUNCHED();
         if (emit) {
             dim3 egrid((unsigned)((n + 255) / 256), (unsigned)batch);
             k_cell_emit<<<egrid, 256, 0, st>>>(t->rate, ids, n_ids, (int)first, n, stride, t->rowcap,
-                                               t->d_rowoff, t->d_tmp_j, t->d_tmp_d, start, dest, dist,
+                                               t->d_rowoff_tmp, t->d_tmp_j, t->d_tmp_d, start, dest, dist,
                                                omega, rate_sum);
             CMD_LAUNCHED();
         }
@@ -634,6 +649,7 @@ static int topo_reserve(cmd_topo *t, int64_t nframes)
     BALLOC(t->d_dist, np * 8);
     BALLOC(t->d_omega, np * 8);
     BALLOC(t->d_counts, (size_t)nframes * 4);
+    BALLOC(t->d_rowoff, (size_t)nframes * cmd_ro_pitch(t->n) * 4);
     BALLOC(t->d_rate_sum, (size_t)nframes * 8);
     BALLOC(t->d_rebuilt, (size_t)nframes);
     if (t->mode == CMD_TOPO_VERLET) {
@@ -677,7 +693,8 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
     if ((rc = topo_reserve(t, nframes))) return rc;
     if (t->mode == CMD_TOPO_VERLET && !t->d_carry_start) {
         if (cudaMalloc((void **)&t->d_carry_start, t->stride * 4) != cudaSuccess ||
-            cudaMalloc((void **)&t->d_carry_dest, t->stride * 4) != cudaSuccess) {
+            cudaMalloc((void **)&t->d_carry_dest, t->stride * 4) != cudaSuccess ||
+            cudaMalloc((void **)&t->d_carry_rowoff, (size_t)(t->n + 1) * 4) != cudaSuccess) {
             cudaGetLastError();
             return cmd_set_error(CMD_ENOMEM, "cudaMalloc failed for the carried pair list");
         }
@@ -718,16 +735,17 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
             k_refresh<false><<<(unsigned)nframes, 256, 0, st>>>(
                 t->bx, t->rate, d_frames, t->d_refresh_ids, t->d_sched + 1, t->d_head, t->n, t->stride,
                 t->d_carry_start, t->d_carry_dest, t->d_carry_count, t->d_start, t->d_dest, t->d_dist,
-                t->d_omega, t->d_counts, t->d_rate_sum);
+                t->d_omega, t->d_counts, t->d_rate_sum, t->d_carry_rowoff, t->d_rowoff);
         else
         k_refresh<true><<<(unsigned)nframes, 256, rsmem, st>>>(
             t->bx, t->rate, d_frames, t->d_refresh_ids, t->d_sched + 1, t->d_head, t->n, t->stride,
             t->d_carry_start, t->d_carry_dest, t->d_carry_count, t->d_start, t->d_dest, t->d_dist,
-            t->d_omega, t->d_counts, t->d_rate_sum);
+            t->d_omega, t->d_counts, t->d_rate_sum, t->d_carry_rowoff, t->d_rowoff);
         CMD_LAUNCHED();
         }
         k_carry<<<8, 256, 0, st>>>(t->d_sched, t->d_start, t->d_dest, t->d_counts, t->stride,
-                                   t->d_carry_start, t->d_carry_dest, t->d_carry_count);
+                                   t->d_carry_start, t->d_carry_dest, t->d_carry_count,
+                                   t->d_rowoff, t->d_carry_rowoff, t->n);
         CMD_LAUNCHED();
         CMD_CUDA(cudaMemcpyAsync(t->d_last, d_frames + (nframes - 1) * (int64_t)t->n * 3,
                                  (size_t)t->n * 24, cudaMemcpyDeviceToDevice, st));
@@ -868,6 +886,15 @@ extern "C" int cmd_topo_device_arrays(const cmd_topo *t, const int **start, cons
     if (counts) *counts = t->d_counts;
     return CMD_OK;
 }
+
+extern "C" int cmd_topo_row_offsets(const cmd_topo *t, const int **d_rowoff)
+{
+    if (!t || t->nframes < 1 || !d_rowoff) return cmd_set_error(CMD_ESTATE, "no block has been built");
+    *d_rowoff = t->d_rowoff;
+    return CMD_OK;
+}
+
+extern "C" int cmd_topo_n_atoms(const cmd_topo *t) { return t ? t->n : -1; }
 
 extern "C" int cmd_topo_positions(const cmd_topo *t, const double **d_frames)
 {

@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(1024, 1)
 k_cell_scan(const int *__restrict__ ids, const int *__restrict__ n_ids, int first, int n,
             int64_t stride, const int *__restrict__ rowcount, int *__restrict__ rowoff,
             int *__restrict__ out_counts, uint8_t *__restrict__ out_rebuilt,
-            double *__restrict__ out_rate_sum, int *__restrict__ err)
+            double *__restrict__ out_rate_sum, int *__restrict__ out_rowoff,
+            int *__restrict__ err)
 {
     __shared__ int scan[40];
     if (n_ids && first + (int)blockIdx.x >= *n_ids) return;
@@ -205,18 +206,23 @@ k_cell_scan(const int *__restrict__ ids, const int *__restrict__ n_ids, int firs
     const int b = blockIdx.x, tid = threadIdx.x;
     const int *rcnt = rowcount + (int64_t)b * n;
     int *ro = rowoff + (int64_t)b * (n + 1);
+    int *ro2 = out_rowoff ? out_rowoff + f * (int64_t)cmd_ro_pitch(n) : nullptr;
     int carry = 0;
     for (int c0 = 0; c0 < n; c0 += blockDim.x) {
         const int c = c0 + tid;
         const int v = c < n ? rcnt[c] : 0;
         const int ex = block_exclusive_scan(v, scan, &scan[33]);
         const int tot = scan[33];
-        if (c < n) ro[c] = carry + ex;
+        if (c < n) {
+            ro[c] = carry + ex;
+            if (ro2) ro2[c] = carry + ex;
+        }
         carry += tot;
         __syncthreads();
     }
     if (tid == 0) {
         ro[n] = carry;
+        if (ro2) ro2[n] = carry;
         out_counts[f] = carry > stride ? -carry : carry;
         if (out_rebuilt) out_rebuilt[f] = 1;
         if (out_rate_sum) out_rate_sum[f] = 0.0;   // k_cell_emit accumulates into it

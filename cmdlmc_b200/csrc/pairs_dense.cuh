@@ -161,7 +161,8 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
               int *__restrict__ out_dest, double *__restrict__ out_dist,
               double *__restrict__ out_omega, int *__restrict__ out_counts,
               double *__restrict__ out_rate_sum, uint8_t *__restrict__ out_rebuilt,
-              int *__restrict__ err, unsigned long long *__restrict__ ties)
+              int *__restrict__ out_rowoff, int *__restrict__ err,
+              unsigned long long *__restrict__ ties)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (n_ids && (int)blockIdx.x >= *n_ids) return;
@@ -352,6 +353,11 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         if (total > stride) atomicMax(err, total);
     }
     if (total > stride) return;
+    if (out_rowoff) {   // row index of the frame's list: row i = [rowoff[i], rowoff[i + 1])
+        int *ro = out_rowoff + f * (int64_t)cmd_ro_pitch(n);
+        for (int k = tid; k < n; k += blockDim.x) ro[k] = s.rowoff[k];
+        if (tid == 0) ro[n] = total;
+    }
 
     // position of (a -> b) = rowoff[a] + #set bits of row a below column b
     const int64_t base = f * stride;

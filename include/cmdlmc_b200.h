@@ -189,6 +189,11 @@ int cmd_topo_get_frame(const cmd_topo *t, int64_t f, int *h_start, int *h_dest, 
 int cmd_topo_device_arrays(const cmd_topo *t, const int **d_start, const int **d_dest,
                            const double **d_dist, const double **d_omega,
                            const int **d_counts);
+/* Row index of the lists of the last block: int32 [nframes][pitch], pitch = n_atoms + 1 rounded
+ * up to a multiple of 4; the pairs that start at site i of frame f are
+ * [rowoff[f][i], rowoff[f][i + 1]) of the frame's arrays. */
+int cmd_topo_row_offsets(const cmd_topo *t, const int **d_rowoff);
+int cmd_topo_n_atoms(const cmd_topo *t);
 /* Device pointer of the frames the last block was built from (float64 [nframes][n_atoms][3]). */
 int cmd_topo_positions(const cmd_topo *t, const double **d_frames);
 /* Tie audit: number of evaluated pairs of the last block whose distance is
