@@ -443,9 +443,20 @@ __device__ __forceinline__ void kmc_consume_stage(WarpCtx &c, const int *s_start
                                                   const double *s_omega, int k0, int cnt, int stage)
 {
     double acc = 0.0;
+    const int full = cnt & ~31;
+    // full groups of 32 pairs: no branch, every load unconditional -> iterations overlap
 #pragma unroll 4
-    for (int i0 = 0; i0 < cnt; i0 += 32) {
+    for (int i0 = 0; i0 < full; i0 += 32) {
         const int k = i0 + c.lane;
+        const int st = s_start[k], de = s_dest[k];
+        const double om = s_omega[k];
+        const bool ok = ((c.occ[st >> 5] >> (st & 31)) & ~(c.occ[de >> 5] >> (de & 31)) & 1u) != 0u;
+        acc += ok ? om : 0.0;
+        const unsigned bits = __ballot_sync(0xffffffffu, ok);
+        if (c.lane == 0) c.mask0[(k0 + i0) >> 5] = bits;
+    }
+    if (full < cnt) {   // ragged tail of the frame (entries behind cnt are not initialised)
+        const int k = full + c.lane;
         bool ok = false;
         if (k < cnt) {
             const int st = s_start[k], de = s_dest[k];
@@ -453,29 +464,26 @@ __device__ __forceinline__ void kmc_consume_stage(WarpCtx &c, const int *s_start
             if (ok) acc += s_omega[k];
         }
         const unsigned bits = __ballot_sync(0xffffffffu, ok);
-        if (c.lane == 0) c.mask0[(k0 + i0) >> 5] = bits;
+        if (c.lane == 0) c.mask0[(k0 + full) >> 5] = bits;
     }
     c.psum[stage * 32 + c.lane] = acc;
     c.lane_total += acc;
 }
 
-// removes transition k of the last consumed frame from the allowed set (bit, partial sum)
-__device__ __forceinline__ void kmc_disallow(const KmcArgs &a, WarpCtx &c, int k)
-{
-    const unsigned bit = 1u << (k & 31);
-    if (c.mask0[k >> 5] & bit) {
-        atomicAnd(&c.mask0[k >> 5], ~bit);
-        atomicAdd(&c.psum[(k >> 10) * 32 + (k & 31)], -__ldg(a.omega + c.base + k));
-    }
-}
-
-__device__ bool kmc_move_fast(const KmcArgs &a, WarpCtx &c, double u, int *o_start, int *o_dest,
-                              int *o_proton, int *o_index, unsigned long long *ties)
+// Selection for the streaming kernel.  The partial sums describe the transitions allowed when the
+// frame was consumed.  A same-frame follow-up event must choose among those that are STILL allowed
+// (Q2: the reference re-filters the filtered arrays, so transitions only ever leave the set).
+// Instead of maintaining the sums, a transition is drawn from the consumed set with probability
+// omega_k / S and redrawn (fresh Philox numbers) when it is no longer allowed -- which leaves
+// exactly the distribution omega_k / S' over the still-allowed ones.  After 24 rejections the
+// exact masked scan over the global arrays (kmc_move) takes over.
+__device__ bool kmc_move_fast(const KmcArgs &a, WarpCtx &c, double u, int r, long long event,
+                              int *o_start, int *o_dest, int *o_proton, int *o_index,
+                              unsigned long long *ties)
 {
     // lane totals -> inclusive scan over lanes; the last value is the total the draw refers to
     double lt = 0.0;
     for (int s = 0; s < c.nst; s++) lt += c.psum[s * 32 + c.lane];
-    lt = fmax(lt, 0.0);   // removals leave rounding residue only
     double inc = lt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -483,76 +491,68 @@ __device__ bool kmc_move_fast(const KmcArgs &a, WarpCtx &c, double u, int *o_sta
         if (c.lane >= o) inc += t;
     }
     const double total = __shfl_sync(0xffffffffu, inc, 31);
-    if (!(total > 0.0)) return false;   // nothing allowed: IndexError upstream
-    const double draw = total * u;
     const unsigned have = __ballot_sync(0xffffffffu, lt > 0.0);
-    if (!have) return false;
-    const unsigned hit = __ballot_sync(0xffffffffu, lt > 0.0 && inc >= draw);
-    const int L = hit ? __ffs(hit) - 1 : 31 - __clz(have);
-    double run = __shfl_sync(0xffffffffu, inc - lt, L);   // rate in front of lane L's pairs
-    // lane L's stages, in order (every lane walks the same values)
-    int sfound = -1;
-    double run_before = run;
-    for (int s = 0; s < c.nst; s++) {
-        const double v = c.psum[s * 32 + L];
-        if (v > 0.0) {
-            sfound = s;
-            run_before = run;
-            if (run + v >= draw) break;
-            run += v;
+    if (!have || !(total > 0.0)) return false;   // nothing was allowed: IndexError upstream
+    for (int attempt = 0; attempt < 24; attempt++) {
+        if (attempt > 0) {
+            uint32_t ctr[4] = {(uint32_t)event, (uint32_t)((uint64_t)event >> 32), (uint32_t)r,
+                               (uint32_t)attempt};
+            philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            u = u53(ctr[0], ctr[1]);
         }
-    }
-    if (sfound < 0) return false;
-    run = run_before;
-    // its <= 32 pairs k = sfound*1024 + i*32 + L, one per lane
-    const int k = sfound * 1024 + c.lane * 32 + L;
-    const bool ok = k < c.p && ((c.mask0[k >> 5] >> L) & 1u);
-    const double om = ok ? __ldg(a.omega + c.base + k) : 0.0;
-    double inc2 = om;
+        const double draw = total * u;
+        const unsigned hit = __ballot_sync(0xffffffffu, lt > 0.0 && inc >= draw);
+        const int L = hit ? __ffs(hit) - 1 : 31 - __clz(have);
+        double run = __shfl_sync(0xffffffffu, inc - lt, L);   // rate in front of lane L's pairs
+        // lane L's stages, in order (every lane walks the same values)
+        int sfound = -1;
+        double run_before = run;
+        for (int s = 0; s < c.nst; s++) {
+            const double v = c.psum[s * 32 + L];
+            if (v > 0.0) {
+                sfound = s;
+                run_before = run;
+                if (run + v >= draw) break;
+                run += v;
+            }
+        }
+        if (sfound < 0) return false;
+        run = run_before;
+        // its <= 32 pairs k = sfound*1024 + i*32 + L, one per lane
+        const int k = sfound * 1024 + c.lane * 32 + L;
+        const bool ok = k < c.p && ((c.mask0[k >> 5] >> L) & 1u);
+        const double om = ok ? __ldg(a.omega + c.base + k) : 0.0;
+        double inc2 = om;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, inc2, o);
-        if (c.lane >= o) inc2 += t;
-    }
-    const unsigned okbits = __ballot_sync(0xffffffffu, ok);
-    if (!okbits) return false;
-    unsigned hit2 = __ballot_sync(0xffffffffu, ok && run + inc2 >= draw);
-    int isel;
-    if (hit2) isel = __ffs(hit2) - 1;
-    else {   // partial sums and the scan round differently: the last allowed pair of the stage
-        isel = 31 - __clz(okbits);
-        if (c.lane == 0) atomicAdd(ties, 1ull);
-    }
-    const int found = sfound * 1024 + isel * 32 + L;
-    const int st = __ldg(a.start + c.base + found), de = __ldg(a.dest + c.base + found);
-    const int proton = c.lat[st];
-    __syncwarp();
-    if (c.lane == 0) {
-        c.lat[de] = proton;
-        c.lat[st] = 0;
-        c.occ[de >> 5] |= 1u << (de & 31);
-        c.occ[st >> 5] &= ~(1u << (st & 31));
-    }
-    __syncwarp();
-    // Same-frame follow-up events see the arrays filtered at consumption, filtered again with the
-    // new lattice (Q2): transitions only ever LEAVE the set -- those starting at st (now empty)
-    // and those ending at de (now occupied).
-    const int r0 = c.ro[st], r1 = c.ro[st + 1];
-    for (int q = r0 + c.lane; q < r1; q += 32) kmc_disallow(a, c, q);
-    __syncwarp();
-    const int d0 = c.ro[de], d1 = c.ro[de + 1];
-    for (int q = d0 + c.lane; q < d1; q += 32) {
-        const int x = __ldg(a.dest + c.base + q);          // neighbour of de; find (x -> de) in row x
-        int lo = c.ro[x], hi = c.ro[x + 1] - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(a.dest + c.base + mid) < de) lo = mid + 1; else hi = mid;
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, inc2, o);
+            if (c.lane >= o) inc2 += t;
         }
-        if (lo < c.ro[x + 1] && __ldg(a.dest + c.base + lo) == de) kmc_disallow(a, c, lo);
+        const unsigned okbits = __ballot_sync(0xffffffffu, ok);
+        if (!okbits) return false;
+        const unsigned hit2 = __ballot_sync(0xffffffffu, ok && run + inc2 >= draw);
+        int isel;
+        if (hit2) isel = __ffs(hit2) - 1;
+        else {   // partial sums and the scan round differently: the last allowed pair of the stage
+            isel = 31 - __clz(okbits);
+            if (c.lane == 0) atomicAdd(ties, 1ull);
+        }
+        const int found = sfound * 1024 + isel * 32 + L;
+        const int st = __ldg(a.start + c.base + found), de = __ldg(a.dest + c.base + found);
+        if (!(occupied(c, st) && !occupied(c, de))) continue;   // left the set since consumption
+        const int proton = c.lat[st];
+        __syncwarp();
+        if (c.lane == 0) {
+            c.lat[de] = proton;
+            c.lat[st] = 0;
+            c.occ[de >> 5] |= 1u << (de & 31);
+            c.occ[st >> 5] &= ~(1u << (st & 31));
+        }
+        __syncwarp();
+        *o_start = st; *o_dest = de; *o_proton = proton; *o_index = found;
+        return true;
     }
-    __syncwarp();
-    *o_start = st; *o_dest = de; *o_proton = proton; *o_index = found;
-    return true;
+    return kmc_move(a, c, u, o_start, o_dest, o_proton, o_index, ties);
 }
 
 // observables on a consumed frame (MDMC.py:198-208 + output.py); the lattice a frame is seen
@@ -633,7 +633,7 @@ __device__ bool kmc_event(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
     }
     int es, ed, ep, ek;
     const bool moved = a.exact ? kmc_move_exact(a, c, u, &es, &ed, &ep, &ek, a.ties)
-                       : a.fast ? kmc_move_fast(a, c, u, &es, &ed, &ep, &ek, a.ties)
+                       : a.fast ? kmc_move_fast(a, c, u, r, st.n_events, &es, &ed, &ep, &ek, a.ties)
                                 : kmc_move(a, c, u, &es, &ed, &ep, &ek, a.ties);
     if (!moved) { st.reason = 2; return false; }
     if (c.lane == 0 && st.log_pos < a.ev_cap) {
@@ -805,29 +805,69 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     } while (!ok);
 }
 
-#define KMC_STAGE 1024   // pairs per ring stage: 4 KB start + 4 KB dest + 8 KB omega
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-// Streaming KMC kernel (Philox mode).  One warp per replica; the replicas of a CTA consume the
-// frames' arrays from a two-stage shared-memory ring filled by TMA bulk copies (thread 0 issues
-// stage i+1 while stage i is consumed).  Per replica-frame the work is one pass over the pairs out
-// of shared memory; events cost O(neighbours) thanks to the per-(stage, lane) partial sums.
-__global__ void __launch_bounds__(512, 1) k_kmc_stream(const __grid_constant__ BoxParams bx,
+#define KMC_STAGE 1024   // pairs per ring stage: 8 KB omega + 4 KB start + 4 KB dest
+#define KMC_NSTG 4       // ring depth: a replica busy with an event may lag three stages
+
+// Streaming KMC kernel (Philox mode).  Warp-specialised: one PRODUCER warp feeds a four-stage
+// shared-memory ring with TMA bulk copies of the frames' (start, dest, omega) arrays; every other
+// warp is one replica consuming the ring (full / empty mbarriers, no CTA-wide barrier in the
+// loop).  Per replica-frame the work is one branch-free pass over the pairs out of shared memory;
+// events cost a few scans thanks to the per-(stage, lane) partial sums.
+__global__ void __launch_bounds__(544, 1) k_kmc_stream(const __grid_constant__ BoxParams bx,
                                                        const __grid_constant__ KmcArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-    const int r = blockIdx.x * a.replicas_per_cta + w;
-    const bool active = r < a.n_replicas;
-    // ring: 2 x (start, dest, omega), 2 x row index, 2 mbarriers; then the per-warp state
-    int *ring_start[2], *ring_dest[2], *ring_ro[2];
-    double *ring_omega[2];
+    const int nrep = a.replicas_per_cta;          // consumer warps; warp `nrep` is the producer
+    int *ring_start[KMC_NSTG], *ring_dest[KMC_NSTG];
+    double *ring_omega[KMC_NSTG];
     unsigned char *q = smem_raw;
-    for (int b = 0; b < 2; b++) { ring_omega[b] = (double *)q; q += KMC_STAGE * 8; }
-    for (int b = 0; b < 2; b++) { ring_start[b] = (int *)q; q += KMC_STAGE * 4; }
-    for (int b = 0; b < 2; b++) { ring_dest[b] = (int *)q; q += KMC_STAGE * 4; }
-    for (int b = 0; b < 2; b++) { ring_ro[b] = (int *)q; q += (size_t)a.ro_pitch * 4; }
-    uint64_t *full = (uint64_t *)q;
-    q += 16;
+    for (int b = 0; b < KMC_NSTG; b++) { ring_omega[b] = (double *)q; q += KMC_STAGE * 8; }
+    for (int b = 0; b < KMC_NSTG; b++) { ring_start[b] = (int *)q; q += KMC_STAGE * 4; }
+    for (int b = 0; b < KMC_NSTG; b++) { ring_dest[b] = (int *)q; q += KMC_STAGE * 4; }
+    uint64_t *full = (uint64_t *)q, *empty = full + KMC_NSTG;
+    q += 2 * KMC_NSTG * 8;
+    if (tid == 0) {
+        for (int b = 0; b < KMC_NSTG; b++) { mbar_init(&full[b], 1); mbar_init(&empty[b], nrep); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (w == nrep) {
+        // ---------------- producer ---------------------------------------------------------------
+        if (lane == 0) {
+            unsigned it = 0;
+            for (int64_t f = 0; f < a.nframes; f++) {
+                const int p = a.counts[f];
+                const int nst = p > 0 ? (p + KMC_STAGE - 1) / KMC_STAGE : 1;
+                for (int cs = 0; cs < nst; cs++, it++) {
+                    const int b = it % KMC_NSTG;
+                    if (it >= KMC_NSTG) mbar_wait(&empty[b], ((it / KMC_NSTG) - 1) & 1);
+                    const int64_t off = f * a.stride + (int64_t)cs * KMC_STAGE;
+                    int64_t e = p > 0 ? a.stride - (int64_t)cs * KMC_STAGE : 0;   // inside the slot
+                    if (e > KMC_STAGE) e = KMC_STAGE;
+                    if (e > 0) {
+                        mbar_expect_tx(&full[b], (uint32_t)e * 16u);
+                        tma_load_1d(ring_start[b], a.start + off, (uint32_t)e * 4u, &full[b]);
+                        tma_load_1d(ring_dest[b], a.dest + off, (uint32_t)e * 4u, &full[b]);
+                        tma_load_1d(ring_omega[b], a.omega + off, (uint32_t)e * 8u, &full[b]);
+                    } else {
+                        mbar_arrive(&full[b]);   // a frame without pairs: an empty stage
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: one replica per warp -------------------------------------------
+    const int r = blockIdx.x * nrep + w;
+    const bool active = r < a.n_replicas;
     const size_t per_warp = ((size_t)a.nst_max * 32 * 8 + (size_t)a.n_sites * 4 +
                              (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4 + 7) / 8 * 8;
     WarpCtx c;
@@ -836,7 +876,7 @@ __global__ void __launch_bounds__(512, 1) k_kmc_stream(const __grid_constant__ B
     c.lat = (int *)(c.psum + (size_t)a.nst_max * 32);
     c.occ = (unsigned *)(c.lat + a.n_sites);
     c.mask0 = c.occ + a.occ_words;
-    c.base = 0; c.p = 0; c.m = 0; c.nst = 0; c.lane_total = 0.0; c.ro = ring_ro[0];
+    c.base = 0; c.p = 0; c.m = 0; c.nst = 0; c.lane_total = 0.0; c.ro = nullptr;
     c.comp = c.cum = c.lsum = nullptr;
     c.cidx = c.loff = c.ln = nullptr;
     KmcState st;
@@ -856,37 +896,6 @@ __global__ void __launch_bounds__(512, 1) k_kmc_stream(const __grid_constant__ B
         }
         __syncwarp();
     }
-    if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // producer (thread 0): item = (frame, stage); a frame without pairs still is one (empty) stage
-    auto issue = [&](int64_t f, int cstage, int b) {
-        const int p = a.counts[f];
-        const int64_t off = f * a.stride + (int64_t)cstage * KMC_STAGE;
-        int64_t e = p > 0 ? a.stride - (int64_t)cstage * KMC_STAGE : 0;   // stays inside the frame's slot
-        if (e > KMC_STAGE) e = KMC_STAGE;
-        uint32_t bytes = (uint32_t)e * 16u + (cstage == 0 ? (uint32_t)a.ro_pitch * 4u : 0u);
-        mbar_expect_tx(&full[b], bytes);
-        if (e > 0) {
-            tma_load_1d(ring_start[b], a.start + off, (uint32_t)e * 4u, &full[b]);
-            tma_load_1d(ring_dest[b], a.dest + off, (uint32_t)e * 4u, &full[b]);
-            tma_load_1d(ring_omega[b], a.omega + off, (uint32_t)e * 8u, &full[b]);
-        }
-        if (cstage == 0)
-            tma_load_1d(ring_ro[f & 1], a.rowoff + f * (int64_t)a.ro_pitch, (uint32_t)a.ro_pitch * 4u, &full[b]);
-    };
-    int64_t pf = 0;   // next item to issue
-    int pc = 0;
-    if (tid == 0 && a.nframes > 0) {
-        issue(0, 0, 0);
-        const int p0 = a.counts[0];
-        const int nst0 = p0 > 0 ? (p0 + KMC_STAGE - 1) / KMC_STAGE : 1;
-        if (++pc >= nst0) { pc = 0; pf = 1; }
-    }
     unsigned it = 0;
     for (int64_t f = 0; f < a.nframes; f++) {
         const int p = a.counts[f];
@@ -894,31 +903,25 @@ __global__ void __launch_bounds__(512, 1) k_kmc_stream(const __grid_constant__ B
         c.base = f * a.stride;
         c.p = p;
         c.nst = nst;
-        c.ro = ring_ro[f & 1];
         c.lane_total = 0.0;
         const bool run = active && st.phase != KMC_PHASE_HALT;
         if (run && a.positions) kmc_observe(a, bx, c, r, f, st);
         for (int cs = 0; cs < nst; cs++, it++) {
-            if (tid == 0 && pf < a.nframes) {   // prefetch the next item into the other buffer
-                issue(pf, pc, (it + 1) & 1);
-                const int pp = a.counts[pf];
-                const int pn = pp > 0 ? (pp + KMC_STAGE - 1) / KMC_STAGE : 1;
-                if (++pc >= pn) { pc = 0; pf++; }
-            }
-            mbar_wait(&full[it & 1], (it >> 1) & 1);
+            const int b = it % KMC_NSTG;
+            mbar_wait(&full[b], (it / KMC_NSTG) & 1);
             if (run) {
                 const int cnt = min(KMC_STAGE, p - cs * KMC_STAGE);
-                kmc_consume_stage(c, ring_start[it & 1], ring_dest[it & 1], ring_omega[it & 1],
-                                  cs * KMC_STAGE, cnt > 0 ? cnt : 0, cs);
+                kmc_consume_stage(c, ring_start[b], ring_dest[b], ring_omega[b], cs * KMC_STAGE,
+                                  cnt > 0 ? cnt : 0, cs);
             }
-            if (run && cs == nst - 1) {
-                __syncwarp();
-                const double rate = warp_sum(c.lane_total);
-                st.site_updates += p;
-                st.frames_seen++;
-                kmc_after_consume(a, c, r, st, rate);
-            }
-            __syncthreads();   // everyone is done with this buffer before it is refilled
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[b]);   // this replica is done with the stage
+        }
+        if (run) {
+            const double rate = warp_sum(c.lane_total);
+            st.site_updates += p;
+            st.frames_seen++;
+            kmc_after_consume(a, c, r, st, rate);
         }
     }
     if (active) {
@@ -1161,7 +1164,7 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
         a.ro_pitch = cmd_ro_pitch(k->n_sites);
         a.nst_max = (int)((stride + KMC_STAGE - 1) / KMC_STAGE);
         if (a.nst_max < 1) a.nst_max = 1;
-        const size_t ring = 2 * (size_t)KMC_STAGE * 16 + 2 * (size_t)a.ro_pitch * 4 + 16;
+        const size_t ring = (size_t)KMC_NSTG * KMC_STAGE * 16 + 2 * KMC_NSTG * 8;
         const size_t per_warp = ((size_t)a.nst_max * 32 * 8 + (size_t)a.n_sites * 4 +
                                  (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4 + 7) / 8 * 8;
         while (rpc > 1 && ring + per_warp * rpc > 200 * 1024) rpc--;
@@ -1170,7 +1173,7 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
             const size_t smem = ring + per_warp * rpc;
             CMD_CUDA(cudaFuncSetAttribute(k_kmc_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int blocks = (k->n_replicas + rpc - 1) / rpc;
-            k_kmc_stream<<<blocks, rpc * 32, smem, st>>>(k->bx, a);
+            k_kmc_stream<<<blocks, (rpc + 1) * 32, smem, st>>>(k->bx, a);   // + the producer warp
             CMD_LAUNCHED();
             k->frames_total += nframes;
             return CMD_OK;
