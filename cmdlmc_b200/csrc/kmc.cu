@@ -37,6 +37,7 @@ struct KmcState {  // one per replica, global memory, persistent across cmd_kmc_
     long long cursor;   // position in the current replay stream
     long long log_pos;  // events logged since the last cmd_kmc_set_event_log
     int phase, reason;  // reason: 1 replay stream exhausted, 2 no allowed transition
+    double u_sel;       // Philox mode: selection uniform drawn together with the time selector
 };
 
 struct cmd_kmc {
@@ -115,6 +116,19 @@ __device__ __forceinline__ double py_mod(double a, double b)
     if (mod != 0) { if ((b < 0) != (mod < 0)) mod += b; }
     else mod = copysign(0.0, b);
     return mod;
+}
+
+// floor(a / b) and a - floor(a / b) * b for finite a >= 0, b > 0 without fmod's division loop: the
+// quotient estimate is corrected with one exact FMA remainder.  Same values as py_floordiv / py_mod
+// (both are the exact floor of the real quotient and the exact remainder).
+__device__ __forceinline__ double floor_div_pos(double a, double b, double *rem)
+{
+    double q = floor(a / b);
+    double r = fma(-q, b, a);
+    if (r < 0.0) { q -= 1.0; r = fma(-q, b, a); }
+    else if (r >= b) { q += 1.0; r = fma(-q, b, a); }
+    *rem = r;
+    return q;
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -439,14 +453,37 @@ __device__ bool kmc_move(const KmcArgs &a, WarpCtx &c, double u, int *o_start, i
 // replicas of the CTA; a lane accumulates the allowed rates of ITS pairs (k mod 32 == lane) per
 // 1024-pair stage without any shuffle.  Selection walks the transitions in (lane, stage, i) order
 // instead of list order -- the probability of picking transition k is omega_k / S either way.
-__device__ __forceinline__ void kmc_consume_stage(WarpCtx &c, const int *s_start, const int *s_dest,
-                                                  const double *s_omega, int k0, int cnt, int stage)
+__device__ __forceinline__ void kmc_consume_stage(WarpCtx &c, const int *__restrict__ s_start,
+                                                  const int *__restrict__ s_dest,
+                                                  const double *__restrict__ s_omega, int k0, int cnt,
+                                                  int stage)
 {
     double acc = 0.0;
     const int full = cnt & ~31;
-    // full groups of 32 pairs: no branch, every load unconditional -> iterations overlap
-#pragma unroll 4
-    for (int i0 = 0; i0 < full; i0 += 32) {
+    int i0 = 0;
+    // 128 pairs per trip, software-pipelined by hand: all loads of the four groups first, then the
+    // occupancy look-ups, then the votes; no branch, one 16-byte store of the four mask words
+    for (; i0 + 128 <= full; i0 += 128) {
+        int st[4], de[4];
+        double om[4];
+        unsigned os[4], od[4], bits[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = i0 + 32 * u + c.lane;
+            st[u] = s_start[k]; de[u] = s_dest[k]; om[u] = s_omega[k];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { os[u] = c.occ[st[u] >> 5]; od[u] = c.occ[de[u] >> 5]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool ok = ((os[u] >> (st[u] & 31)) & ~(od[u] >> (de[u] & 31)) & 1u) != 0u;
+            acc += ok ? om[u] : 0.0;
+            bits[u] = __ballot_sync(0xffffffffu, ok);
+        }
+        if (c.lane == 0)
+            *(uint4 *)(c.mask0 + ((k0 + i0) >> 5)) = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+    }
+    for (; i0 < full; i0 += 32) {
         const int k = i0 + c.lane;
         const int st = s_start[k], de = s_dest[k];
         const double om = s_omega[k];
@@ -627,9 +664,7 @@ __device__ bool kmc_event(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
         if (st.cursor + 1 >= a.n_u) { st.reason = 1; return false; }
         u = a.u[(int64_t)r * a.n_u + st.cursor + 1];
     } else {
-        uint32_t ctr[4] = {(uint32_t)st.n_events, (uint32_t)((uint64_t)st.n_events >> 32), (uint32_t)r, 0u};
-        philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-        u = u53(ctr[2], ctr[3]);
+        u = st.u_sel;   // drawn with the time selector of this event (same Philox counter)
     }
     int es, ed, ep, ek;
     const bool moved = a.exact ? kmc_move_exact(a, c, u, &es, &ed, &ep, &ek, a.ties)
@@ -662,19 +697,28 @@ __device__ void kmc_run_until_frame_needed(const KmcArgs &a, WarpCtx &c, int r, 
             uint32_t ctr[4] = {(uint32_t)st.n_events, (uint32_t)((uint64_t)st.n_events >> 32), (uint32_t)r, 0u};
             philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
             st.time_selector = -log(1 - u53(ctr[0], ctr[1]));         // MDMC.py:148
+            st.u_sel = u53(ctr[2], ctr[3]);                           // MDMC.py:110, same counter
         }
         double t_trial = st.time_selector / st.current_rate;  // Q1: the rate of frame 0, forever
         double x = st.kmc_time + t_trial;
-        if (c.lane == 0) {  // tie audit of the floor-division decision
-            double rm = py_mod(x, a.dt);
-            if (rm < 1e-9 * a.dt || a.dt - rm < 1e-9 * a.dt) atomicAdd(a.ties, 1ull);
+        bool same_frame;
+        double rem_t = 0.0;
+        if (a.fast) {   // kmc_time >= 0, dt > 0: exact floor / remainder without fmod
+            double rem_x;
+            same_frame = floor_div_pos(x, a.dt, &rem_x) == floor_div_pos(st.kmc_time, a.dt, &rem_t);
+        } else {
+            if (c.lane == 0) {  // tie audit of the floor-division decision
+                double rm = py_mod(x, a.dt);
+                if (rm < 1e-9 * a.dt || a.dt - rm < 1e-9 * a.dt) atomicAdd(a.ties, 1ull);
+            }
+            same_frame = py_floordiv(x, a.dt) == py_floordiv(st.kmc_time, a.dt);
         }
-        if (py_floordiv(x, a.dt) == py_floordiv(st.kmc_time, a.dt)) {
+        if (same_frame) {
             st.kmc_time = x;
             st.delta_frame = 0;
             if (!kmc_event(a, c, r, st)) { st.phase = KMC_PHASE_HALT; return; }
         } else {
-            st.delta_t = a.dt - py_mod(st.kmc_time, a.dt);
+            st.delta_t = a.dt - (a.fast ? rem_t : py_mod(st.kmc_time, a.dt));
             st.delta_frame = 1;
             st.current_probsum = st.current_rate * st.delta_t;
             st.phase = KMC_PHASE_SCAN;
@@ -805,13 +849,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     } while (!ok);
 }
 
+// producer flavour: backs off between polls so that it does not eat the issue slots of the
+// replica warp sharing its scheduler
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    for (;;) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     "selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (ok) break;
+        __nanosleep(32);
+    }
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 #define KMC_STAGE 1024   // pairs per ring stage: 8 KB omega + 4 KB start + 4 KB dest
-#define KMC_NSTG 4       // ring depth: a replica busy with an event may lag three stages
+#define KMC_NSTG 8       // ring depth: a replica busy with events may lag seven stages (~ a frame)
 
 // Streaming KMC kernel (Philox mode).  Warp-specialised: one PRODUCER warp feeds a four-stage
 // shared-memory ring with TMA bulk copies of the frames' (start, dest, omega) arrays; every other
@@ -824,12 +884,12 @@ __global__ void __launch_bounds__(544, 1) k_kmc_stream(const __grid_constant__ B
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int nrep = a.replicas_per_cta;          // consumer warps; warp `nrep` is the producer
-    int *ring_start[KMC_NSTG], *ring_dest[KMC_NSTG];
-    double *ring_omega[KMC_NSTG];
-    unsigned char *q = smem_raw;
-    for (int b = 0; b < KMC_NSTG; b++) { ring_omega[b] = (double *)q; q += KMC_STAGE * 8; }
-    for (int b = 0; b < KMC_NSTG; b++) { ring_start[b] = (int *)q; q += KMC_STAGE * 4; }
-    for (int b = 0; b < KMC_NSTG; b++) { ring_dest[b] = (int *)q; q += KMC_STAGE * 4; }
+    // ring stage b: omega at b*8K, start at NSTG*8K + b*4K, dest at NSTG*12K + b*4K (computed from the
+    // shared base every time so that the loads stay LDS, not generic)
+    double *const ring_omega = (double *)smem_raw;
+    int *const ring_start = (int *)(smem_raw + KMC_NSTG * KMC_STAGE * 8);
+    int *const ring_dest = (int *)(smem_raw + KMC_NSTG * KMC_STAGE * 12);
+    unsigned char *q = smem_raw + KMC_NSTG * KMC_STAGE * 16;
     uint64_t *full = (uint64_t *)q, *empty = full + KMC_NSTG;
     q += 2 * KMC_NSTG * 8;
     if (tid == 0) {
@@ -847,15 +907,15 @@ __global__ void __launch_bounds__(544, 1) k_kmc_stream(const __grid_constant__ B
                 const int nst = p > 0 ? (p + KMC_STAGE - 1) / KMC_STAGE : 1;
                 for (int cs = 0; cs < nst; cs++, it++) {
                     const int b = it % KMC_NSTG;
-                    if (it >= KMC_NSTG) mbar_wait(&empty[b], ((it / KMC_NSTG) - 1) & 1);
+                    if (it >= KMC_NSTG) mbar_wait_sleep(&empty[b], ((it / KMC_NSTG) - 1) & 1);
                     const int64_t off = f * a.stride + (int64_t)cs * KMC_STAGE;
                     int64_t e = p > 0 ? a.stride - (int64_t)cs * KMC_STAGE : 0;   // inside the slot
                     if (e > KMC_STAGE) e = KMC_STAGE;
                     if (e > 0) {
                         mbar_expect_tx(&full[b], (uint32_t)e * 16u);
-                        tma_load_1d(ring_start[b], a.start + off, (uint32_t)e * 4u, &full[b]);
-                        tma_load_1d(ring_dest[b], a.dest + off, (uint32_t)e * 4u, &full[b]);
-                        tma_load_1d(ring_omega[b], a.omega + off, (uint32_t)e * 8u, &full[b]);
+                        tma_load_1d(ring_start + b * KMC_STAGE, a.start + off, (uint32_t)e * 4u, &full[b]);
+                        tma_load_1d(ring_dest + b * KMC_STAGE, a.dest + off, (uint32_t)e * 4u, &full[b]);
+                        tma_load_1d(ring_omega + b * KMC_STAGE, a.omega + off, (uint32_t)e * 8u, &full[b]);
                     } else {
                         mbar_arrive(&full[b]);   // a frame without pairs: an empty stage
                     }
@@ -868,14 +928,16 @@ __global__ void __launch_bounds__(544, 1) k_kmc_stream(const __grid_constant__ B
     // ---------------- consumers: one replica per warp -------------------------------------------
     const int r = blockIdx.x * nrep + w;
     const bool active = r < a.n_replicas;
-    const size_t per_warp = ((size_t)a.nst_max * 32 * 8 + (size_t)a.n_sites * 4 +
-                             (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4 + 7) / 8 * 8;
+    // per warp: psum | mask0 (16-byte aligned: written four words at a time) | lattice | occupancy
+    const size_t mask_bytes = ((size_t)a.mask_words * 4 + 15) / 16 * 16;
+    const size_t per_warp = ((size_t)a.nst_max * 32 * 8 + mask_bytes + (size_t)a.n_sites * 4 +
+                             (size_t)a.occ_words * 4 + 15) / 16 * 16;
     WarpCtx c;
     c.lane = lane;
     c.psum = (double *)(q + per_warp * w);
-    c.lat = (int *)(c.psum + (size_t)a.nst_max * 32);
+    c.mask0 = (unsigned *)(c.psum + (size_t)a.nst_max * 32);
+    c.lat = (int *)((unsigned char *)c.mask0 + mask_bytes);
     c.occ = (unsigned *)(c.lat + a.n_sites);
-    c.mask0 = c.occ + a.occ_words;
     c.base = 0; c.p = 0; c.m = 0; c.nst = 0; c.lane_total = 0.0; c.ro = nullptr;
     c.comp = c.cum = c.lsum = nullptr;
     c.cidx = c.loff = c.ln = nullptr;
@@ -911,8 +973,8 @@ __global__ void __launch_bounds__(544, 1) k_kmc_stream(const __grid_constant__ B
             mbar_wait(&full[b], (it / KMC_NSTG) & 1);
             if (run) {
                 const int cnt = min(KMC_STAGE, p - cs * KMC_STAGE);
-                kmc_consume_stage(c, ring_start[b], ring_dest[b], ring_omega[b], cs * KMC_STAGE,
-                                  cnt > 0 ? cnt : 0, cs);
+                kmc_consume_stage(c, ring_start + b * KMC_STAGE, ring_dest + b * KMC_STAGE,
+                                  ring_omega + b * KMC_STAGE, cs * KMC_STAGE, cnt > 0 ? cnt : 0, cs);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[b]);   // this replica is done with the stage
@@ -1165,8 +1227,9 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
         a.nst_max = (int)((stride + KMC_STAGE - 1) / KMC_STAGE);
         if (a.nst_max < 1) a.nst_max = 1;
         const size_t ring = (size_t)KMC_NSTG * KMC_STAGE * 16 + 2 * KMC_NSTG * 8;
-        const size_t per_warp = ((size_t)a.nst_max * 32 * 8 + (size_t)a.n_sites * 4 +
-                                 (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4 + 7) / 8 * 8;
+        const size_t mask_bytes = ((size_t)a.mask_words * 4 + 15) / 16 * 16;
+        const size_t per_warp = ((size_t)a.nst_max * 32 * 8 + mask_bytes + (size_t)a.n_sites * 4 +
+                                 (size_t)a.occ_words * 4 + 15) / 16 * 16;
         while (rpc > 1 && ring + per_warp * rpc > 200 * 1024) rpc--;
         if (ring + per_warp * rpc <= 226 * 1024) {
             a.replicas_per_cta = rpc;
