@@ -45,6 +45,10 @@ UNIT = "pairs/s"
 # algorithmic FP64 cost per unordered O-O pair
 FLOP_ORTHO = 20
 FLOP_GENERAL_REFERENCE = 279      # the reference's 27-image algorithm
+# issue slots of the dense kernel's filter per unordered pair: 3 IADD + 3 I2FP +
+# 3 (ortho) / 6 (triangular general cell) multiply-adds + 3 norm + 1 compare + 1 mask
+FILTER_SLOTS_ORTHO = 14
+FILTER_SLOTS_GENERAL = 17
 
 
 def parse():
@@ -66,15 +70,6 @@ def parse():
 
 def pairs_per_frame(n):
     return n * (n - 1) // 2
-
-
-def flop_per_pair_executed(box_n_images, kind):
-    """FP64 flop the dense kernel's filter issues per unordered pair:
-    ortho 20; general cell 3 sub (pre-wrapped fractional coordinates) + 3 x (2 add rint + 1 sub)
-    + 1 mat-vec (3 mul + 6 fma = 15) + norm (1 mul + 2 fma = 5) + n_img x (3 add + 5 norm + 1 min)."""
-    if kind == 0:
-        return FLOP_ORTHO
-    return 3 + 9 + 15 + 5 + box_n_images * 9
 
 
 # ------------------------------------------------------------------------------ clocks --------
@@ -349,13 +344,15 @@ def run_b200(args):
     value = world * K * B * ppf / (ms_total * 1e-3)
     e2e_value = world * K * B * ppf / (e2e_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (k_pairs_dense), FP64 pipe --------------------------
+    # ---- roofline of the dominant kernel (k_pairs_dense) --------------------------------------
+    # HBM: algorithmic bytes per launch = frames read once (24 B per atom-frame) + every listed
+    # directed pair written once (start i32, dest i32, dist f64, omega f64 = 24 B), DESIGN.md 3.
+    # The kernel is far from that bound: its time goes into instruction issue (17 issue slots per
+    # unordered pair in the FP32/INT filter + the FP64 exact stage of the ~4 % survivors), so the
+    # issue-slot utilisation and the FP64 peak are reported beside it.
     peak_tf = runtime.fp64_peak_tflops(40000)
     n_img = topo.n_images
     kind = 0 if cell.size == 3 else 1
-    flop_exec = flop_per_pair_executed(n_img, kind)
-    flop_ref = FLOP_ORTHO if kind == 0 else FLOP_GENERAL_REFERENCE
-    achieved = B * ppf * flop_exec / (kernel_ms * 1e-3) / 1e12
     out_bytes = float(counts.sum()) * 24.0
     peaks = {}
     try:
@@ -363,18 +360,30 @@ def run_b200(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_gbs = (in_bytes + out_bytes) / (kernel_ms * 1e-3) / 1e9
+    sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    issue_peak = 148 * 4 * sm_mhz * 1e6                     # warp instructions / s
+    slots = FILTER_SLOTS_ORTHO if kind == 0 else FILTER_SLOTS_GENERAL + 7 * n_img
+    filter_issue = B * ppf * slots / 32.0 / (kernel_ms * 1e-3)
+    traffic = None
+    try:   # dram bytes per launch of the same kernel from the committed ncu --set full capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_dense_traffic.json")))
+        traffic = prof["dram_bytes_per_frame"] * B
+    except Exception:
+        pass
     roofline = {
-        "kernel": "k_pairs_dense", "bound": "fp64", "achieved": achieved, "peak": peak_tf,
-        "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
-        "peak_source": "cmd_fp64_peak: DFMA loop on every SM, measured in this run "
-                       "(MEASURED_PEAKS.json has no FP64 figure)",
-        "flop_per_pair_executed": flop_exec, "images_kept": n_img,
-        "flop_per_pair_reference_algorithm": flop_ref,
-        "achieved_reference_equivalent_tflops": B * ppf * flop_ref / (kernel_ms * 1e-3) / 1e12,
+        "kernel": "k_pairs_dense", "bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak,
+        "unit": "GB/s", "frac": hbm_gbs / hbm_peak, "traffic": traffic,
+        "algorithmic_bytes_per_launch": in_bytes + out_bytes,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else
+                       "fallback of B200_PROFILING.md",
         "kernel_ms_per_launch": kernel_ms,
-        "hbm_algorithmic_gbs": (in_bytes + out_bytes) / (kernel_ms * 1e-3) / 1e9,
-        "hbm_peak_gbs": hbm_peak,
-        "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
+        "issue": {"filter_slots_per_pair": slots, "images_kept": n_img,
+                  "filter_warp_instr_per_s": filter_issue, "issue_peak_warp_instr_per_s": issue_peak,
+                  "filter_share_of_issue_peak": filter_issue / issue_peak},
+        "fp64_peak_tflops_measured": peak_tf,
+        "reference_equivalent_tflops": B * ppf * (FLOP_ORTHO if kind == 0 else
+                                                  FLOP_GENERAL_REFERENCE) / (kernel_ms * 1e-3) / 1e12,
     }
 
     line = {
@@ -451,8 +460,12 @@ def run_m2(args, w, box, rate, d_frames, world, dev, dist, barrier):
             "replicas_per_gpu": R, "frames": F, "ms": ms, "events": events,
             "rng": "philox4x32-10", "directed_pairs_per_frame_mean": float(counts.mean()),
             "verlet_rebuilds": int(rebuilt.sum()),
-            "implied_onchip_gbs": rate_su * 16 / 1e9,
-            "hbm_algorithmic_gbs": float(counts.sum()) * 16.0 / (ms * 1e-3) / 1e9}
+            "kernel": "k_kmc_stream",
+            "roofline": {"bound": "smem", "unit": "GB/s", "achieved": rate_su * 16 / 1e9,
+                         "peak": 148 * 128 * 1.965, "frac": rate_su * 16 / 1e9 / (148 * 128 * 1.965),
+                         "note": "16 B of (start, dest, omega) read from the shared-memory ring per "
+                                 "site-update; peak = 148 SMs x 128 B/clk x 1.965 GHz"},
+            "hbm_algorithmic_gbs": float(counts.sum()) * 16.0 * world / (ms * 1e-3) / 1e9}
 
 
 def main():

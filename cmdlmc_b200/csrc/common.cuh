@@ -41,6 +41,9 @@ struct CmdGlobal {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = 0;
+    // second stream for host->device copies that overlap kernels (cmd_topo_build)
+    cudaStream_t copy_stream = 0;
+    cudaEvent_t copy_event[2] = {0, 0};
     int64_t launches = 0;
     // stream-ordered scratch for the host-pointer entry points
     void *scratch[6] = {0, 0, 0, 0, 0, 0};

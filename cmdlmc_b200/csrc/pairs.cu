@@ -437,8 +437,8 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
 
 static int launch_dense(cmd_topo *t, const double *d_frames, const int *ids, const int *n_ids,
                         int64_t grid, int *start, int *dest, double *dist, double *omega,
-                        int *counts, double *rate_sum, uint8_t *rebuilt, int64_t stride,
-                        int hit_cap, size_t smem)
+                        int *counts, double *rate_sum, uint8_t *rebuilt, int *rowoff,
+                        int64_t stride, int hit_cap, size_t smem)
 {
     cudaStream_t st = cmd_global().stream;
     const bool ortho = t->bx.kind == 0;
@@ -448,8 +448,7 @@ static int launch_dense(cmd_topo *t, const double *d_frames, const int *ids, con
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
         k_pairs_dense<K, IM, SP, MT, MB><<<(unsigned)grid, t->threads * SP, smem, st>>>(         \
             t->bx, t->rate, t->fp, d_frames, ids, n_ids, t->n, t->rc, t->t2, stride, hit_cap,    \
-            start, dest, dist, omega, counts, rate_sum, rebuilt, start ? t->d_rowoff : nullptr,  \
-            t->d_err, t->d_ties);                                                                \
+            start, dest, dist, omega, counts, rate_sum, rebuilt, rowoff, t->d_err, t->d_ties);   \
     } while (0)
 #define DENSE_PICK(SP, MT, MB)                                                                   \
     do {                                                                                         \
@@ -507,7 +506,8 @@ static int cell_batch_size(const cmd_topo *t, int64_t want)
 // list.  emit = false stops after the per-frame totals (capacity probe).
 static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, const int *n_ids,
                        int64_t count, int *start, int *dest, double *dist, double *omega,
-                       int *counts, double *rate_sum, uint8_t *rebuilt, int64_t stride, bool emit)
+                       int *counts, double *rate_sum, uint8_t *rebuilt, int *rowoff, int64_t stride,
+                       bool emit)
 {
     cudaStream_t st = cmd_global().stream;
     const bool ortho = t->bx.kind == 0;
@@ -561,7 +561,7 @@ static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, cons
         }
         k_cell_scan<<<batch, 1024, 0, st>>>(ids, n_ids, (int)first, n, stride, t->d_rowcount,
                                             t->d_rowoff_tmp, counts, rebuilt, rate_sum,
-                                            emit ? t->d_rowoff : nullptr, t->d_err);
+                                            emit ? rowoff : nullptr, t->d_err);
         CMD_LAUNCHED();
         if (emit) {
             dim3 egrid((unsigned)((n + 255) / 256), (unsigned)batch);
@@ -588,11 +588,11 @@ static int topo_autosize(cmd_topo *t, const double *d_frame)
     CMD_CUDA(cudaMemsetAsync(t->d_err, 0, sizeof(int), st));
     if (t->n <= 1024 && smem <= 226 * 1024 && t->force_path != 1) {
         rc = launch_dense(t, d_frame, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, d_cnt,
-                          nullptr, nullptr, 0, 0, smem);
+                          nullptr, nullptr, nullptr, 0, 0, smem);
     } else {
         if (t->rowcap < 8) t->rowcap = 40;
         rc = launch_cell(t, d_frame, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, d_cnt,
-                         nullptr, nullptr, (int64_t)1 << 40, false);
+                         nullptr, nullptr, nullptr, (int64_t)1 << 40, false);
     }
     if (rc) return rc;
     int cnt = 0;
@@ -610,13 +610,20 @@ static int topo_autosize(cmd_topo *t, const double *d_frame)
 }
 
 // all-pairs lists of `grid` frames (or of the ids[0 .. *n_ids) frames) by the configured path
+// all-pairs lists of `grid` frames (or of the ids[0 .. *n_ids) frames) by the configured path, into
+// the block arrays.  Frame indices are relative to d_frames; results land at frame f0 + index.
 static int launch_pairs(cmd_topo *t, const double *d_frames, const int *ids, const int *n_ids,
-                        int64_t grid, int *start, int *dest, double *dist, double *omega,
-                        int *counts, double *rate_sum, uint8_t *rebuilt)
+                        int64_t grid, int64_t f0, bool with_rebuilt)
 {
+    int *start = t->d_start + f0 * t->stride, *dest = t->d_dest + f0 * t->stride;
+    double *dist = t->d_dist + f0 * t->stride, *omega = t->d_omega + f0 * t->stride;
+    int *counts = t->d_counts + f0;
+    double *rate_sum = t->d_rate_sum + f0;
+    uint8_t *rebuilt = with_rebuilt ? t->d_rebuilt + f0 : nullptr;
+    int *rowoff = t->d_rowoff + f0 * cmd_ro_pitch(t->n);
     if (t->path == 0)
         return launch_dense(t, d_frames, ids, n_ids, grid, start, dest, dist, omega, counts,
-                            rate_sum, rebuilt, t->stride, t->hit_cap, t->smem_bytes);
+                            rate_sum, rebuilt, rowoff, t->stride, t->hit_cap, t->smem_bytes);
     int64_t count = grid;
     if (n_ids) {   // Verlet: the number of rebuild frames lives on the device
         int h = 0;
@@ -627,7 +634,7 @@ static int launch_pairs(cmd_topo *t, const double *d_frames, const int *ids, con
         if (count <= 0) return CMD_OK;
     }
     return launch_cell(t, d_frames, ids, n_ids, count, start, dest, dist, omega, counts, rate_sum,
-                       rebuilt, t->stride, true);
+                       rebuilt, rowoff, t->stride, true);
 }
 
 static int topo_reserve(cmd_topo *t, int64_t nframes)
@@ -663,6 +670,22 @@ static int topo_reserve(cmd_topo *t, int64_t nframes)
 }
 
 static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes, bool skip);
+
+// capacity check (one 4-byte read-back per block)
+static int topo_check_capacity(cmd_topo *t)
+{
+    cudaStream_t st = cmd_global().stream;
+    int err = 0;
+    CMD_CUDA(cudaMemcpyAsync(&err, t->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
+    if (err > 0) {
+        CMD_CUDA(cudaMemsetAsync(t->d_err, 0, sizeof(int), st));
+        return cmd_set_error(CMD_ECAPACITY, "a frame has %d directed pairs but the per-frame "
+                             "capacity is %lld: re-create the topology with a larger "
+                             "capacity_per_frame", err, (long long)t->stride);
+    }
+    return CMD_OK;
+}
 
 extern "C" int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t nframes)
 {
@@ -702,8 +725,7 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
     t->nframes = skip ? 0 : nframes;
     t->d_frames_last = d_frames;
     if (t->mode == CMD_TOPO_BRUTEFORCE) {
-        rc = launch_pairs(t, d_frames, nullptr, nullptr, nframes, t->d_start, t->d_dest, t->d_dist,
-                          t->d_omega, t->d_counts, t->d_rate_sum, t->d_rebuilt);
+        rc = launch_pairs(t, d_frames, nullptr, nullptr, nframes, 0, true);
         if (rc) return rc;
     } else {
         int blocks = cmd_div_up(nframes * t->n, 256);
@@ -722,13 +744,11 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
             CMD_CUDA(cudaMemcpyAsync(sched, t->d_sched, sizeof(sched), cudaMemcpyDeviceToHost, st));
             CMD_CUDA(cudaStreamSynchronize(st));
             if (sched[0] > 0) {
-                rc = launch_pairs(t, d_frames, t->d_rebuild_ids + sched[0] - 1, nullptr, 1, t->d_start,
-                                  t->d_dest, t->d_dist, t->d_omega, t->d_counts, t->d_rate_sum, nullptr);
+                rc = launch_pairs(t, d_frames, t->d_rebuild_ids + sched[0] - 1, nullptr, 1, 0, false);
                 if (rc) return rc;
             }
         } else {
-        rc = launch_pairs(t, d_frames, t->d_rebuild_ids, t->d_sched, nframes, t->d_start, t->d_dest,
-                          t->d_dist, t->d_omega, t->d_counts, t->d_rate_sum, nullptr);
+        rc = launch_pairs(t, d_frames, t->d_rebuild_ids, t->d_sched, nframes, 0, false);
         if (rc) return rc;
         size_t rsmem = (size_t)t->n * 24;
         if (rsmem > 40 * 1024)
@@ -754,17 +774,7 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
         t->have_last = true;
     }
     t->total_frames += nframes;
-    // capacity check (one 4-byte read-back per block)
-    int err = 0;
-    CMD_CUDA(cudaMemcpyAsync(&err, t->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CMD_CUDA(cudaStreamSynchronize(st));
-    if (err > 0) {
-        CMD_CUDA(cudaMemsetAsync(t->d_err, 0, sizeof(int), st));
-        return cmd_set_error(CMD_ECAPACITY, "a frame has %d directed pairs but the per-frame "
-                             "capacity is %lld: re-create the topology with a larger "
-                             "capacity_per_frame", err, (long long)t->stride);
-    }
-    return CMD_OK;
+    return topo_check_capacity(t);
 }
 
 // host frames -> the topology's staging buffer in HBM (float32 blocks are up-cast on the device)
@@ -797,11 +807,76 @@ static int topo_stage(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_
     return CMD_OK;
 }
 
+// Brute-force blocks from host memory: frames are independent, so the block is cut into chunks and
+// the host->device copy of chunk i+1 (copy stream) overlaps the pair kernel of chunk i.
+static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes)
+{
+    CmdGlobal &g = cmd_global();
+    cudaStream_t st = g.stream;
+    const size_t per_frame = (size_t)t->n * 3;
+    const size_t elems = (size_t)nframes * per_frame;
+    const size_t need = elems * 8 + (dtype_bytes == 4 ? elems * 4 : 0);
+    if (t->upload_bytes < need) {
+        CMD_CUDA(cudaStreamSynchronize(st));
+        cudaFree(t->d_upload);
+        t->d_upload = nullptr;
+        t->upload_bytes = 0;
+        if (cudaMalloc((void **)&t->d_upload, need) != cudaSuccess) {
+            cudaGetLastError();
+            return cmd_set_error(CMD_ENOMEM, "cudaMalloc of %zu staging bytes failed", need);
+        }
+        t->upload_bytes = need;
+    }
+    if (!g.copy_stream) {
+        CMD_CUDA(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) CMD_CUDA(cudaEventCreateWithFlags(&g.copy_event[i], cudaEventDisableTiming));
+    }
+    int64_t chunk = (nframes + 7) / 8;
+    if (chunk < 256) chunk = 256;
+    // the staging buffer may still be read by kernels of the previous block
+    CMD_CUDA(cudaEventRecord(g.copy_event[0], st));
+    CMD_CUDA(cudaStreamWaitEvent(g.copy_stream, g.copy_event[0], 0));
+    float *d32 = (float *)(t->d_upload + elems);
+    int rc;
+    bool sized = t->stride != 0;
+    t->nframes = nframes;
+    t->d_frames_last = t->d_upload;
+    for (int64_t c0 = 0; c0 < nframes; c0 += chunk) {
+        const int64_t cn = nframes - c0 < chunk ? nframes - c0 : chunk;
+        const size_t off = (size_t)c0 * per_frame, ce = (size_t)cn * per_frame;
+        if (dtype_bytes == 8)
+            CMD_CUDA(cudaMemcpyAsync(t->d_upload + off, (const double *)h_frames + off, ce * 8,
+                                     cudaMemcpyHostToDevice, g.copy_stream));
+        else
+            CMD_CUDA(cudaMemcpyAsync(d32 + off, (const float *)h_frames + off, ce * 4,
+                                     cudaMemcpyHostToDevice, g.copy_stream));
+        CMD_CUDA(cudaEventRecord(g.copy_event[1], g.copy_stream));
+        CMD_CUDA(cudaStreamWaitEvent(st, g.copy_event[1], 0));
+        if (dtype_bytes == 4) {
+            int blocks = cmd_div_up(ce, 256);
+            if (blocks > g.sm_count * 16) blocks = g.sm_count * 16;
+            k_upcast_f32<<<blocks, 256, 0, st>>>(d32 + off, t->d_upload + off, (int64_t)ce);
+            CMD_LAUNCHED();
+        }
+        if (!sized) {   // first block ever: probe the capacity on the first frame, then allocate
+            if ((rc = topo_autosize(t, t->d_upload))) return rc;
+            sized = true;
+        }
+        if (c0 == 0 && (rc = topo_reserve(t, nframes))) return rc;
+        if ((rc = launch_pairs(t, t->d_upload + off, nullptr, nullptr, cn, c0, true))) return rc;
+    }
+    t->total_frames += nframes;
+    return topo_check_capacity(t);
+}
+
 extern "C" int cmd_topo_build(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes)
 {
     CMD_REQUIRE_INIT();
     if (!t || !h_frames || nframes < 1 || (dtype_bytes != 4 && dtype_bytes != 8))
         return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (nframes > 0x7fffffff / 2) return cmd_set_error(CMD_EINVAL, "block too large");
+    if (t->mode == CMD_TOPO_BRUTEFORCE && nframes >= 512)
+        return topo_build_pipelined(t, h_frames, dtype_bytes, nframes);
     int rc = topo_stage(t, h_frames, dtype_bytes, nframes);
     if (rc) return rc;
     return cmd_topo_build_dev(t, t->d_upload, nframes);
