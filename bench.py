@@ -247,6 +247,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"     # NCCL logs to stdout: keep it to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     runtime.init(local)
     runtime.use_torch_stream()
