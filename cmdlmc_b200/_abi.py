@@ -75,6 +75,10 @@ SIGNATURES = {
     "cmd_topo_device_arrays": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                          C.POINTER(vp), C.POINTER(vp)]),
     "cmd_topo_tie_count": (C.c_int64, [vp]),
+    "cmd_topo_set_groups": (C.c_int, [vp, ip, C.c_int]),
+    "cmd_topo_apply_angles": (C.c_int, [vp, vp, C.c_int]),
+    "cmd_topo_apply_angles_dev": (C.c_int, [vp, vp]),
+    "cmd_topo_get_frame_angles": (C.c_int, [vp, C.c_int64, dp]),
     "cmd_topo_distance_histogram": (C.c_int, [vp, C.c_double, C.c_double, C.c_int, lp]),
     "cmd_topo_distance_histogram_dev": (C.c_int, [vp, C.c_double, C.c_double, C.c_int, vp]),
     "cmd_kmc_get_event_distances": (C.c_int, [vp, C.c_int, C.c_int64, lp, dp]),

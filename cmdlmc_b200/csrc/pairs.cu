@@ -45,6 +45,13 @@ struct cmd_topo {
     int64_t cap_frames, nframes;
     int *d_start, *d_dest, *d_counts, *d_err;
     int *d_rowoff;   // [frames][n + 1] row index of every frame's list
+    // AngleTopology (topology.py:124-167): angle colvar of the listed pairs
+    int n_extra;
+    int *d_group;      // [n] donor -> index of the extra atom it is bonded to
+    double *d_theta;   // block array [frames * stride]
+    double *d_extra_upload;
+    size_t extra_upload_bytes;
+    bool rate_is_fermi_angle;
     double *d_dist, *d_omega, *d_rate_sum;
     uint8_t *d_rebuilt;
     unsigned long long *d_ties;
@@ -250,8 +257,9 @@ static double exact_sq_threshold(double rc)
 static void topo_free_block(cmd_topo *t)
 {
     cudaFree(t->d_start); cudaFree(t->d_dest); cudaFree(t->d_dist); cudaFree(t->d_omega);
-    cudaFree(t->d_rowoff);
+    cudaFree(t->d_rowoff); cudaFree(t->d_theta);
     t->d_rowoff = nullptr;
+    t->d_theta = nullptr;
     cudaFree(t->d_counts); cudaFree(t->d_rate_sum); cudaFree(t->d_rebuilt); cudaFree(t->d_dr);
     cudaFree(t->d_rebuild_ids); cudaFree(t->d_refresh_ids); cudaFree(t->d_head);
     t->d_start = t->d_dest = t->d_counts = nullptr;
@@ -280,6 +288,7 @@ extern "C" void cmd_topo_destroy(cmd_topo *t)
     cudaFree(t->d_carry_start); cudaFree(t->d_carry_dest); cudaFree(t->d_carry_count);
     cudaFree(t->d_carry_rowoff);
     cudaFree(t->d_sched); cudaFree(t->d_upload); cudaFree(t->d_cap_need);
+    cudaFree(t->d_group); cudaFree(t->d_extra_upload);
     cell_free(t);
     free(t);
 }
@@ -387,13 +396,16 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
     if (!box || !out || n < 1) return cmd_set_error(CMD_EINVAL, "bad argument");
     if (mode != CMD_TOPO_BRUTEFORCE && mode != CMD_TOPO_VERLET)
         return cmd_set_error(CMD_EINVAL, "bad topology mode %d", mode);
-    if (rate_kind < 0 || rate_kind > CMD_RATE_EXP || rate_kind == CMD_RATE_FERMI_ANGLE)
-        return cmd_set_error(CMD_EINVAL, "rate kind %d is not a pure distance function", rate_kind);
+    if (rate_kind < 0 || rate_kind > CMD_RATE_EXP)
+        return cmd_set_error(CMD_EINVAL, "bad rate kind %d", rate_kind);
     if (!(cutoff + buffer >= 0)) return cmd_set_error(CMD_EINVAL, "cutoff + buffer must be >= 0");
     cmd_topo *t = (cmd_topo *)calloc(1, sizeof(cmd_topo));
     if (!t) return cmd_set_error(CMD_ENOMEM, "out of host memory");
     t->bx = box->p;
-    t->rate.kind = rate_kind;
+    // FermiAngle = Fermi masked by the angle colvar: the list kernels evaluate the Fermi part, the
+    // mask is applied by cmd_topo_apply_angles once the angles of the block are known
+    t->rate_is_fermi_angle = rate_kind == CMD_RATE_FERMI_ANGLE;
+    t->rate.kind = t->rate_is_fermi_angle ? CMD_RATE_FERMI : rate_kind;
     if (par) memcpy(t->rate.par, par, sizeof(t->rate.par));
     t->n = n;
     t->cutoff = cutoff;
@@ -975,6 +987,134 @@ extern "C" int cmd_topo_positions(const cmd_topo *t, const double **d_frames)
 {
     if (!t || t->nframes < 1 || !d_frames) return cmd_set_error(CMD_ESTATE, "no block has been built");
     *d_frames = t->d_frames_last;
+    return CMD_OK;
+}
+
+
+// ---- AngleTopology._determine_colvars (topology.py:158-167) --------------------------------------
+// theta[k] = atombox.angle(extra[group[start]], donor[start], donor[dest]) for every listed pair of
+// the block; with a FermiAngle rate omega becomes 0 where theta < theta0
+// (jumprate_generators.py:42-43).  One CTA per frame.
+__global__ void __launch_bounds__(256)
+k_pair_angles(const __grid_constant__ BoxParams bx, const double *__restrict__ donors,
+              const double *__restrict__ extras, const int *__restrict__ group, int n, int n_extra,
+              int64_t stride, const int *__restrict__ counts, const int *__restrict__ start,
+              const int *__restrict__ dest, double *__restrict__ theta, double *__restrict__ omega,
+              double *__restrict__ rate_sum, int mask_rate, double theta0)
+{
+    const int64_t f = blockIdx.x;
+    const int p = counts[f];
+    const double *don = donors + f * (int64_t)n * 3, *ext = extras + f * (int64_t)n_extra * 3;
+    const int64_t base = f * stride;
+    double rsum = 0.0;
+    for (int k = threadIdx.x; k < p; k += blockDim.x) {
+        const int i = start[base + k], j = dest[base + k], g = group[i];
+        const double p1[3] = {ext[3 * g], ext[3 * g + 1], ext[3 * g + 2]};
+        const double p2[3] = {don[3 * i], don[3 * i + 1], don[3 * i + 2]};
+        const double p3[3] = {don[3 * j], don[3 * j + 1], don[3 * j + 2]};
+        const double th = angle_exact(bx, p1, p2, p3);
+        theta[base + k] = th;
+        double om = omega[base + k];
+        if (mask_rate && th < theta0) { om = 0.0; omega[base + k] = 0.0; }
+        rsum += om;
+    }
+    __shared__ double wsum[8];
+    for (int o = 16; o > 0; o >>= 1) rsum += __shfl_down_sync(0xffffffffu, rsum, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = rsum;
+    __syncthreads();
+    if (threadIdx.x == 0 && mask_rate) {
+        double t = 0;
+        for (int w = 0; w < 8; w++) t += wsum[w];
+        rate_sum[f] = t;
+    }
+}
+
+extern "C" int cmd_topo_set_groups(cmd_topo *t, const int *h_group, int n_extra)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || !h_group || n_extra < 1) return cmd_set_error(CMD_EINVAL, "bad argument");
+    for (int i = 0; i < t->n; i++)
+        if (h_group[i] < 0 || h_group[i] >= n_extra)
+            return cmd_set_error(CMD_EINVAL, "donor %d has no extra atom (the reference raises "
+                                             "KeyError there)", i);
+    if (!t->d_group && cudaMalloc((void **)&t->d_group, (size_t)t->n * 4) != cudaSuccess) {
+        cudaGetLastError();
+        return cmd_set_error(CMD_ENOMEM, "cudaMalloc failed for the group map");
+    }
+    cudaStream_t st = cmd_global().stream;
+    CMD_CUDA(cudaMemcpyAsync(t->d_group, h_group, (size_t)t->n * 4, cudaMemcpyHostToDevice, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
+    t->n_extra = n_extra;
+    return CMD_OK;
+}
+
+extern "C" int cmd_topo_apply_angles_dev(cmd_topo *t, const double *d_extra_frames)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || !d_extra_frames) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (t->nframes < 1) return cmd_set_error(CMD_ESTATE, "no block has been built");
+    if (!t->d_group) return cmd_set_error(CMD_ESTATE, "cmd_topo_set_groups has not been called");
+    if (!t->d_theta) {
+        size_t bytes = (size_t)t->cap_frames * t->stride * 8;
+        if (cudaMalloc((void **)&t->d_theta, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return cmd_set_error(CMD_ENOMEM, "cudaMalloc of %zu bytes failed for the angles", bytes);
+        }
+    }
+    k_pair_angles<<<(unsigned)t->nframes, 256, 0, cmd_global().stream>>>(
+        t->bx, t->d_frames_last, d_extra_frames, t->d_group, t->n, t->n_extra, t->stride, t->d_counts,
+        t->d_start, t->d_dest, t->d_theta, t->d_omega, t->d_rate_sum, t->rate_is_fermi_angle ? 1 : 0,
+        t->rate.par[3]);
+    CMD_LAUNCHED();
+    return CMD_OK;
+}
+
+extern "C" int cmd_topo_apply_angles(cmd_topo *t, const void *h_extra_frames, int dtype_bytes)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || !h_extra_frames || (dtype_bytes != 4 && dtype_bytes != 8))
+        return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (t->nframes < 1 || t->n_extra < 1) return cmd_set_error(CMD_ESTATE, "no block / no groups");
+    cudaStream_t st = cmd_global().stream;
+    const size_t elems = (size_t)t->nframes * t->n_extra * 3;
+    const size_t need = elems * 8 + (dtype_bytes == 4 ? elems * 4 : 0);
+    if (t->extra_upload_bytes < need) {
+        CMD_CUDA(cudaStreamSynchronize(st));
+        cudaFree(t->d_extra_upload);
+        t->d_extra_upload = nullptr;
+        t->extra_upload_bytes = 0;
+        if (cudaMalloc((void **)&t->d_extra_upload, need) != cudaSuccess) {
+            cudaGetLastError();
+            return cmd_set_error(CMD_ENOMEM, "cudaMalloc of %zu staging bytes failed", need);
+        }
+        t->extra_upload_bytes = need;
+    }
+    if (dtype_bytes == 8) {
+        CMD_CUDA(cudaMemcpyAsync(t->d_extra_upload, h_extra_frames, elems * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        float *d32 = (float *)(t->d_extra_upload + elems);
+        CMD_CUDA(cudaMemcpyAsync(d32, h_extra_frames, elems * 4, cudaMemcpyHostToDevice, st));
+        int blocks = cmd_div_up(elems, 256);
+        if (blocks > cmd_global().sm_count * 16) blocks = cmd_global().sm_count * 16;
+        k_upcast_f32<<<blocks, 256, 0, st>>>(d32, t->d_extra_upload, (int64_t)elems);
+        CMD_LAUNCHED();
+    }
+    return cmd_topo_apply_angles_dev(t, t->d_extra_upload);
+}
+
+extern "C" int cmd_topo_get_frame_angles(const cmd_topo *t, int64_t f, double *h_theta)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || f < 0 || f >= t->nframes || !h_theta) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (!t->d_theta) return cmd_set_error(CMD_ESTATE, "cmd_topo_apply_angles has not been called");
+    cudaStream_t st = cmd_global().stream;
+    int p = 0;
+    CMD_CUDA(cudaMemcpyAsync(&p, t->d_counts + f, 4, cudaMemcpyDeviceToHost, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
+    if (p > 0) {
+        CMD_CUDA(cudaMemcpyAsync(h_theta, t->d_theta + f * t->stride, (size_t)p * 8, cudaMemcpyDeviceToHost, st));
+        CMD_CUDA(cudaStreamSynchronize(st));
+    }
     return CMD_OK;
 }
 

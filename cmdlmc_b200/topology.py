@@ -30,8 +30,6 @@ class DeviceTopology:
         self.n_atoms = int(n_atoms)
         self.mode = mode
         kind = jumprate.kind if jumprate is not None else 0
-        if kind == 1:  # FermiAngle needs the angle colvar (AngleTopology); rates come later
-            kind = 0
         par = jumprate._par() if jumprate is not None else np.array([0.0, 0.0, 1.0] + [0.0] * 5)
         self._args = (atom_box, n_atoms, cutoff, buffer, mode, kind, par)
         self._handle = C.c_void_p()
@@ -125,6 +123,29 @@ class DeviceTopology:
     def tie_count(self):
         return int(_abi.lib().cmd_topo_tie_count(self._handle))
 
+    def set_groups(self, group, n_extra):
+        """donor index -> index of the extra atom it is bonded to (AngleTopology)."""
+        group = np.ascontiguousarray(group, dtype=np.int32)
+        if group.shape != (self.n_atoms,):
+            raise ValueError("one group entry per donor atom expected")
+        check(_abi.lib().cmd_topo_set_groups(self._handle, ptr(group, C.c_int), int(n_extra)))
+
+    def apply_angles(self, extra_frames):
+        """Angles of the last block's pairs from the extra-atom positions [F, n_extra, 3] of the
+        same frames; masks the rates when the topology was created with a FermiAngle rate."""
+        extra_frames = np.ascontiguousarray(extra_frames)
+        if extra_frames.dtype not in (np.float32, np.float64):
+            extra_frames = extra_frames.astype(np.float64)
+        check(_abi.lib().cmd_topo_apply_angles(self._handle, extra_frames.ctypes.data_as(C.c_void_p),
+                                               extra_frames.dtype.itemsize))
+
+    def get_frame_angles(self, f, count=None):
+        if count is None:
+            count = int(self.frame_info()[0][f])
+        theta = np.empty(count)
+        check(_abi.lib().cmd_topo_get_frame_angles(self._handle, int(f), ptr(theta)))
+        return theta
+
     def positions_ptr(self):
         """Device pointer of the frames the last block was built from."""
         p = C.c_void_p()
@@ -165,6 +186,7 @@ class NeighborTopology:
                  buffer: float = 2.0) -> None:
         self._raw_trajectory = trajectory
         self._cache = deque()
+        self._frame_iter = None
         self.trajectory = trajectory
         self.trajectory_time_step = trajectory.time_step
         self.cutoff = cutoff
@@ -201,8 +223,16 @@ class NeighborTopology:
     def _donor_positions(self, full_frame):
         return np.asarray(full_frame[self.donor_atoms].atom_positions, dtype=float)
 
+    def _frames(self):
+        """The ONE frame stream of this topology: like the reference's
+        cache_last_elements(trajectory) generator (topology.py:43) it is shared by everything that
+        pulls frames, so a frame taken once is not delivered again."""
+        if self._frame_iter is None:
+            self._frame_iter = iter(self.trajectory)
+        return self._frame_iter
+
     def _chunks(self):
-        it = iter(self.trajectory)
+        it = self._frames()
         while True:
             frames = []
             for full_frame in it:
@@ -255,3 +285,80 @@ class NeighborTopology:
 
     def update_time_of_last_jump(self, proton_idx, new_time):
         pass
+
+
+class AngleTopology(NeighborTopology):
+    """This topology class is used to calculate the POO angle as an additional collective variable.
+    Of course, other atom types are possible as well.  In that case, the parameters for donor_atoms
+    and extra_atoms just need to be changed accordingly.  (mdlmc/topo/topology.py:124-167)
+
+                             O -- O
+                            /
+                           P
+    """
+
+    def __init__(self, trajectory, atom_box, *, donor_atoms: str, extra_atoms: str, group_size: int,
+                 cutoff: float = 3.0, buffer: float = 2.0) -> None:
+        super().__init__(trajectory, atom_box, donor_atoms=donor_atoms, cutoff=cutoff, buffer=buffer)
+        self.extra_atoms = extra_atoms
+        self.group_size = group_size
+        self._determine_groups()
+
+    def _determine_groups(self):
+        """Find for each phosphorus atom the closest oxygen atoms (topology.py:142-156): the donor
+        atoms belonging to one group.  Later groups overwrite earlier ones, like the dict upstream."""
+        # upstream this is next(iter(self.trajectory)) on the cached one-shot generator
+        # (topology.py:43,145): the first frame is consumed here, stays in the frame cache, and
+        # the iteration over the topology starts at the second frame
+        first_frame = next(self._frames())
+        self._cache.append(first_frame)
+        distances_PO = self.atombox.length_all_to_all(first_frame[self.extra_atoms].atom_positions,
+                                                      first_frame[self.donor_atoms].atom_positions)
+        closest_Os = np.argsort(distances_PO, axis=1)[:, :self.group_size]
+        self.map_O_to_P = {}
+        for P_index, Os in enumerate(closest_Os):
+            for O_index in Os:
+                self.map_O_to_P[int(O_index)] = P_index
+        self.n_extra = distances_PO.shape[0]
+        n_donor = distances_PO.shape[1]
+        self._group = np.full(n_donor, -1, dtype=np.int32)
+        for o, p in self.map_O_to_P.items():
+            self._group[o] = p
+
+    def _extra_positions(self, full_frame):
+        return np.asarray(full_frame[self.extra_atoms].atom_positions, dtype=float)
+
+    def _determine_colvars(self, start_indices, destination_indices, distances, frame):
+        """Determine here the POO angles (topology.py:158-167), one batched CUDA call."""
+        if len(start_indices) and (self._group[start_indices] < 0).any():
+            raise KeyError(int(start_indices[self._group[start_indices] < 0][0]))
+        p_atoms = self._extra_positions(frame)
+        o_atoms = self._donor_positions(frame)
+        angles = self.atombox.angle(p_atoms[self._group[start_indices]], o_atoms[start_indices],
+                                    o_atoms[destination_indices])
+        return start_indices, destination_indices, distances, np.atleast_1d(angles)
+
+    def device_blocks(self, mode=MODE_VERLET, chunk_size=None):
+        """Block pipeline with the angle colvar (and the FermiAngle mask) applied on the device."""
+        for topo, full_frames, pos in super().device_blocks(mode, chunk_size):
+            if not getattr(topo, "_groups_set", False):
+                topo.set_groups(self._group, self.n_extra)
+                topo._groups_set = True
+            topo.apply_angles(np.stack([self._extra_positions(f) for f in full_frames]))
+            yield topo, full_frames, pos
+
+    def _generate(self, mode):
+        for topo, full_frames, _ in self.device_blocks(mode):
+            counts, _, _ = topo.frame_info()
+            for k, full_frame in enumerate(full_frames):
+                start, dest, dist, _ = topo.get_frame(k, int(counts[k]))
+                self._cache.append(full_frame)
+                yield start, dest, dist, full_frame
+
+    def __iter__(self):
+        for topo, full_frames, _ in self.device_blocks(MODE_VERLET):
+            counts, _, _ = topo.frame_info()
+            for k, full_frame in enumerate(full_frames):
+                start, dest, dist, _ = topo.get_frame(k, int(counts[k]))
+                self._cache.append(full_frame)
+                yield start, dest, dist, topo.get_frame_angles(k, int(counts[k]))

@@ -200,6 +200,17 @@ int cmd_topo_positions(const cmd_topo *t, const double **d_frames);
  * within 1e-11 relative of cutoff+buffer. */
 int64_t cmd_topo_tie_count(const cmd_topo *t);
 
+/* AngleTopology (topology.py:124-167): a second collective variable, the angle
+ * extra[group[start]] - donor[start] - donor[dest] of every listed pair (e.g. P-O...O).
+ * cmd_topo_set_groups: donor -> index of its extra atom (AngleTopology._determine_groups).
+ * cmd_topo_apply_angles: angles of the last block from the extra-atom positions of the same
+ * frames, float64/float32 [nframes][n_extra][3]; with a CMD_RATE_FERMI_ANGLE topology the rates
+ * of pairs with theta < theta0 become 0 (jumprate_generators.py:42-43). */
+int cmd_topo_set_groups(cmd_topo *t, const int *h_group, int n_extra);
+int cmd_topo_apply_angles(cmd_topo *t, const void *h_extra_frames, int dtype_bytes);
+int cmd_topo_apply_angles_dev(cmd_topo *t, const double *d_extra_frames);
+int cmd_topo_get_frame_angles(const cmd_topo *t, int64_t f, double *h_theta);
+
 /* K5 / "jumpstat" (README.md:57-58): histogram of the listed O-O distances of the
  * last block over nbins equal bins of [lo, hi).  Every unordered pair is listed in both
  * directions and counted twice.  Counts are ADDED to the caller's array (int64 on the host,

@@ -15,6 +15,7 @@ Fixtures (all produced by reference code, none by the oracle restatement):
     topology.npz     NeighborTopology.get_topology_bruteforce + topology_verlet_list_generator
     kmc.npz          KMCLattice event traces, consumed uniform stream, observables_output tuples
     fastforward.npz  KMCLattice.fastforward_to_next_jump on constant / sinusoidal rate streams
+    angle.npz        AngleTopology colvars + FermiAngle rates on C1 with its P atoms
 """
 import os
 import sys
@@ -137,6 +138,39 @@ def gen_topology():
     print("topology.npz", len(out), "arrays")
 
 
+def gen_angle():
+    """AngleTopology (topology.py:124-167) + FermiAngle (jumprate_generators.py:37-43) of the
+    REFERENCE on the C1 integration config with its P atoms (tests/integration/mdlmc_run.py:41-62)."""
+    from mdlmc.topo.topology import AngleTopology
+    from mdlmc.LMC.jumprate_generators import FermiAngle
+    w = synth.workload("C1")
+    nfr = 12
+    # AngleTopology._determine_groups pulls the first frame out of the (one-shot) cached
+    # trajectory generator (topology.py:43,145): the iteration starts at trajectory frame 1
+    frames = synth.trajectory(w, nfr + 1, with_extra=True)
+    names = np.array(["O"] * w.n_oxygen + ["P"] * w.n_extra)
+    traj = MockTrajectory(frames, w.time_step, names)
+    top = AngleTopology(traj, make_box(w.cell), donor_atoms="O", extra_atoms="P",
+                        group_size=w.group_size, cutoff=w.cutoff, buffer=w.buffer)
+    rate = FermiAngle(*w.rate_params, np.pi / 2)
+    out = {"nframes": nfr, "group": np.array([top.map_O_to_P[o] for o in range(w.n_oxygen)])}
+    counts, asum, rsum = [], [], []
+    for k, (start, dest, dist, angle) in enumerate(top):
+        if k == 0:
+            out.update(start0=start, dest0=dest, dist0=dist, angle0=angle, rate0=rate(dist, angle))
+        counts.append(len(start))
+        asum.append(angle.sum())
+        rsum.append(rate(dist, angle).sum())
+        if k == nfr - 1:
+            out.update(angle_last=angle, rate_last=rate(dist, angle))
+            break
+    out.update(counts=np.array(counts), angle_sum=np.array(asum), rate_sum=np.array(rsum))
+    assert len(counts) == nfr and "angle_last" in out
+    out["cached_frames_after_init"] = 1   # frame 0 sits in the frame cache
+    np.savez_compressed(os.path.join(GOLD, "angle.npz"), **out)
+    print("angle.npz:", counts[:4], "masked pairs in frame 0:", int((out["rate0"] == 0).sum()))
+
+
 def run_reference_kmc(w, frames, seed, n_events, reset_frequency=None, print_frequency=None):
     """Drives the reference KMCLattice; records events, lattices and (optionally) observables."""
     from mdlmc.topo.topology import NeighborTopology
@@ -250,7 +284,8 @@ def gen_fastforward():
 if __name__ == "__main__":
     ref_import.import_ref_python()
     os.makedirs(GOLD, exist_ok=True)
-    gen_geometry()
-    gen_topology()
-    gen_fastforward()
-    gen_kmc()
+    only = sys.argv[1:]
+    for name, fn in (("geometry", gen_geometry), ("topology", gen_topology),
+                     ("fastforward", gen_fastforward), ("kmc", gen_kmc), ("angle", gen_angle)):
+        if not only or name in only:
+            fn()

@@ -257,3 +257,100 @@ def test_cell_list_random_boxes(orc):
         np.testing.assert_array_equal(col, want[1])
         np.testing.assert_array_equal(dist, want[2])
     assert k == 19
+
+
+def test_c5_water_box_cell_list_vs_oracle(orc):
+    """C5: 32 768 O in a 99.4 A orthorhombic box (cell-list path, 19^3 cells): one frame against
+    the oracle's all-pairs loop (5.4e8 pairs), plus size-independent properties on more frames."""
+    from cmdlmc_b200.topology import DeviceTopology, build_with_retry
+    import cmdlmc_b200 as cm
+    w = synth.workload("C5")
+    frames = synth.trajectory(w, 3)
+    box, obox = make_box(w.cell), orc.OracleBox(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    t = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, 0, rate, cap),
+                         frames)
+    assert t.path == 1
+    counts = t.frame_info()[0]
+    start, dest, dist, omega = t.get_frame(0, int(counts[0]))
+    want = orc.topology_bruteforce(obox, frames[0], w.cutoff, w.buffer)
+    np.testing.assert_array_equal(start, want[0])
+    np.testing.assert_array_equal(dest, want[1])
+    np.testing.assert_array_equal(dist, want[2])
+    for f in (1, 2):
+        s, d, di, om = t.get_frame(f, int(counts[f]))
+        key = s.astype(np.int64) * w.n_oxygen + d
+        assert (np.diff(key) > 0).all() and (di <= w.cutoff + w.buffer).all() and (di > 0).all()
+        rev = np.argsort(d.astype(np.int64) * w.n_oxygen + s, kind="stable")
+        np.testing.assert_array_equal(di[rev], di)          # (j, i) carries the same distance
+    hist = t.distance_histogram(0.0, 5.0, 500)
+    assert hist.sum() == counts.sum()
+
+
+def test_angle_topology_and_fermi_angle_vs_reference(golden):
+    """F1: AngleTopology (P-O...O angle colvar) + FermiAngle against the reference's own run on
+    the C1 integration config with its P atoms (tests/golden/angle.npz)."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.topology import AngleTopology
+    from cmdlmc_b200.trajectory import ArrayTrajectory
+    g = golden("angle")
+    w = synth.workload("C1")
+    nfr = int(g["nframes"])
+    # like upstream, building the groups consumes trajectory frame 0: nfr topologies need nfr + 1
+    frames = synth.trajectory(w, nfr + 1, with_extra=True)
+    names = np.array(["O"] * w.n_oxygen + ["P"] * w.n_extra)
+    box = make_box(w.cell)
+    rate = cm.FermiAngle(*w.rate_params, np.pi / 2)
+
+    def make():
+        top = AngleTopology(ArrayTrajectory(frames, names, time_step=w.time_step), box,
+                            donor_atoms="O", extra_atoms="P", group_size=w.group_size,
+                            cutoff=w.cutoff, buffer=w.buffer)
+        top.chunk_size = 5
+        return top
+    top = make()
+    np.testing.assert_array_equal(top._group, g["group"])
+    assert len(list(top.get_cached_frames())) == int(g["cached_frames_after_init"])
+    # 1. the reference's iteration protocol: (start, dest, dist, angle) per frame
+    k = -1
+    for k, (start, dest, dist, angle) in enumerate(top):
+        assert len(start) == g["counts"][k]
+        assert angle.sum() == pytest.approx(g["angle_sum"][k], rel=1e-12)
+        r = rate(dist, angle)
+        assert r.sum() == pytest.approx(g["rate_sum"][k], rel=1e-10)
+        if k == 0:
+            np.testing.assert_array_equal(start, g["start0"])
+            np.testing.assert_array_equal(dest, g["dest0"])
+            np.testing.assert_allclose(dist, g["dist0"], rtol=1e-12)
+            np.testing.assert_allclose(angle, g["angle0"], rtol=1e-12)
+            np.testing.assert_allclose(r, g["rate0"], rtol=1e-10)
+            assert ((r == 0) == (g["rate0"] == 0)).all() and (r == 0).sum() > 100
+            # the host-level _determine_colvars (one batched angle call) gives the same angles
+            full = next(iter(ArrayTrajectory(frames[1:2], names, time_step=w.time_step)))
+            np.testing.assert_array_equal(top._determine_colvars(start, dest, dist, full)[3], angle)
+    assert k == nfr - 1
+    np.testing.assert_allclose(angle, g["angle_last"], rtol=1e-12)
+    # 2. device pipeline: the fused rates carry the FermiAngle mask
+    top = make()
+    top.attach_jumprate(rate)
+    f = 0
+    for topo, full_frames, _ in top.device_blocks():
+        counts, _, rsum = topo.frame_info()
+        for j in range(len(full_frames)):
+            om = topo.get_frame(j, int(counts[j]))[3]
+            assert om.sum() == pytest.approx(g["rate_sum"][f], rel=1e-10)
+            assert rsum[j] == pytest.approx(g["rate_sum"][f], rel=1e-10)
+            if f == 0:
+                np.testing.assert_allclose(om, g["rate0"], rtol=1e-10)
+            f += 1
+    assert f == nfr
+    # 3. KMC on top of it runs and only uses unmasked transitions
+    from cmdlmc_b200.kmc import KMCLattice
+    np.random.seed(5)
+    frames = synth.trajectory(w, 600, with_extra=True)      # long enough for a few events
+    kmc = KMCLattice(make(), atom_box=box, jumprate_function=rate, lattice_size=w.n_oxygen,
+                     proton_number=w.n_protons, donor_atoms="O", time_step=w.time_step,
+                     extra_atoms="P", chunk_size=128)
+    n = sum(1 for _ in kmc)
+    ev = kmc.event_log
+    assert n > 0 and len(ev["frame"]) > 0

@@ -263,3 +263,30 @@ def test_gsl_stream_helper_matches_oracle_mt(orc):
     raw = lmc.mt19937_u32(5, 10)
     mt = orc.MT19937(5)
     assert [int(x) for x in raw] == [mt.u32() for _ in range(10)]
+
+
+def test_angle_topology_vs_reference(golden, orc):
+    """AngleTopology colvars + FermiAngle (reference run in oracle/make_golden.py gen_angle) vs the
+    oracle restatement: same pair list, angles and masked rates."""
+    g = golden("angle")
+    w = synth.workload("C1")
+    two = synth.trajectory(w, 2, with_extra=True)
+    # groups come from trajectory frame 0, the first yielded topology from frame 1 (the reference
+    # consumes frame 0 in AngleTopology._determine_groups, topology.py:43,145)
+    frames = two[1]
+    oxy, pho = frames[:w.n_oxygen], frames[w.n_oxygen:]
+    obox = orc.OracleBox(w.cell)
+    start, dest, dist = orc.topology_bruteforce(obox, oxy, w.cutoff, w.buffer)
+    np.testing.assert_array_equal(start, g["start0"])
+    np.testing.assert_array_equal(dest, g["dest0"])
+    np.testing.assert_allclose(dist, g["dist0"], rtol=1e-12)
+    d_po = obox.length_all_to_all(two[0][w.n_oxygen:], two[0][:w.n_oxygen])
+    group = np.full(w.n_oxygen, -1)
+    for p_index, os_ in enumerate(np.argsort(d_po, axis=1)[:, :w.group_size]):
+        group[os_] = p_index
+    np.testing.assert_array_equal(group, g["group"])
+    ang = obox.angle(pho[group[start]], oxy[start], oxy[dest])
+    np.testing.assert_allclose(ang, g["angle0"], rtol=1e-12)
+    rate = orc.rates("FermiAngle", tuple(w.rate_params) + (np.pi / 2,), dist, ang)
+    np.testing.assert_allclose(rate, g["rate0"], rtol=1e-10)
+    assert ((rate == 0) == (g["rate0"] == 0)).all()
