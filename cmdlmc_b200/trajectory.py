@@ -120,3 +120,57 @@ class ArrayTrajectory(Trajectory):
         if sel.size != blk.shape[1]:
             blk = blk[:, sel]
         return np.ascontiguousarray(blk, dtype=np.float64)
+
+
+class XYZTrajectory(ArrayTrajectory):
+    """xyz text trajectory with the constructor of the reference's XYZTrajectory
+    (trajectory_parser.py:176-215): the file is read once on the host into a float64 block and
+    then served like any array trajectory (the reference re-parses with np.genfromtxt per frame).
+    `selection` keeps only atoms with that name / those names / those indices."""
+
+    def __init__(self, filename, *, time_step: float, number_of_atoms: int = None,
+                 selection=None, repeat: bool = False) -> None:
+        names, frames = _read_xyz(filename, number_of_atoms)
+        if selection is not None and selection != "None":
+            if isinstance(selection, str):
+                keep = names == selection
+            elif len(selection) and isinstance(selection[0], str):
+                keep = np.isin(names, list(selection))
+            else:
+                keep = np.zeros(names.shape[0], bool)
+                keep[np.asarray(selection, dtype=int)] = True
+            names, frames = names[keep], frames[:, keep]
+        super().__init__(frames, names, time_step=time_step, repeat=repeat)
+        self.filename = filename
+        self.selection_spec = selection
+
+
+def _read_xyz(filename, number_of_atoms=None):
+    """(names [n], positions [frames, n, 3]) of a multi-frame xyz file or open text stream."""
+    if hasattr(filename, "read"):
+        lines = filename.read().splitlines()
+    else:
+        with open(filename, "r") as f:
+            lines = f.read().splitlines()
+    while lines and not lines[-1].strip():
+        lines.pop()
+    n = int(number_of_atoms) if number_of_atoms else int(lines[0].split()[0])
+    per = n + 2
+    if len(lines) < per or len(lines) % per:
+        raise ValueError("xyz file does not hold whole frames of %d atoms" % n)
+    n_frames = len(lines) // per
+    names = np.array([lines[2 + i].split()[0] for i in range(n)])
+    body = [ln for k, ln in enumerate(lines) if k % per >= 2]
+    flat = np.array([ln.split()[1:4] for ln in body], dtype=float)
+    return names, flat.reshape(n_frames, n, 3)
+
+
+class NpzTrajectory(ArrayTrajectory):
+    """Array trajectory from an .npz with `trajectory` [frames, atoms, 3] (float32 or float64, the
+    HDF5 layout of the reference, IO/converters.py:38-43) and `atom_names` [atoms]."""
+
+    def __init__(self, filename: str, *, time_step: float, repeat: bool = False) -> None:
+        with np.load(filename) as z:
+            super().__init__(z["trajectory"], z["atom_names"].astype(str), time_step=time_step,
+                             repeat=repeat)
+        self.filename = filename

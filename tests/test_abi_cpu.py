@@ -60,3 +60,50 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), os.path.join(dirpath, f)
+
+
+def test_compat_shims_and_config_help(tmp_path):
+    """Host logic only (no compute call): the reference's import paths resolve to this package's
+    classes with the reference's constructor signatures, and the driver's INI template lists
+    every class main.py:73-155 can build."""
+    import inspect
+    import io
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from cmdlmc_b200 import compat\n"
+        "done = compat.install()\n"
+        "from mdlmc.cython_exts.LMC.PBCHelper import AtomBoxCubic, AtomBoxMonoclinic\n"
+        "from mdlmc.topo.topology import NeighborTopology, AngleTopology\n"
+        "from mdlmc.LMC.jumprate_generators import Fermi, FermiAngle\n"
+        "from mdlmc.LMC.MDMC import KMCLattice, XYZOutput, ObservablesOutput\n"
+        "from mdlmc.IO.trajectory_parser import Frame, XYZTrajectory\n"
+        "import cmdlmc_b200\n"
+        "assert AtomBoxCubic is cmdlmc_b200.AtomBoxCubic and len(done) == 7\n"
+        "print('ok')\n" % str(__import__('os').path.dirname(__import__('os').path.dirname(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+    from cmdlmc_b200 import kmc, main, topology
+    sig = inspect.signature(kmc.KMCLattice).parameters
+    for key in ("lattice_size", "proton_number", "donor_atoms", "time_step", "extra_atoms"):
+        assert key in sig                       # MDMC.py:34-41
+    sig = inspect.signature(topology.AngleTopology).parameters
+    assert [k for k in sig][:2] == ["trajectory", "atom_box"] and "group_size" in sig
+    buf = io.StringIO()
+    main.config_help(buf)
+    text = buf.getvalue()
+    for word in ("[Trajectory]", "XYZTrajectory", "AtomBoxMonoclinic", "AngleTopology", "FermiAngle",
+                 "KMCLattice", "ObservablesOutput", "reset_frequency"):
+        assert word in text
+    assert main._convert("3", int) == 3 and main._convert("None", float) is None
+    import typing
+    assert main._convert("0.5", typing.Union[int, float]) == 0.5
+    # xyz reader: two frames, selection by name
+    from cmdlmc_b200.trajectory import XYZTrajectory
+    p = tmp_path / "t.xyz"
+    p.write_text("3\n\nO 0 0 0\nH 1 0 0\nO 2 0 0\n3\n\nO 0 1 0\nH 1 1 0\nO 2 1 0\n")
+    t = XYZTrajectory(str(p), time_step=0.5, selection="O")
+    frames = list(t)
+    assert len(frames) == 2 and frames[1].atom_positions.tolist() == [[0, 1, 0], [2, 1, 0]]
+    assert frames[1].time == 0.5 and list(frames[0].atom_names) == ["O", "O"]

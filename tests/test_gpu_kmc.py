@@ -200,3 +200,69 @@ def test_xyz_output_and_errors():
     kmc2 = make_kmc(w2, frames)
     assert list(kmc2) == []
     assert len(kmc2.event_log["time"]) == 0
+
+
+def test_mdmc_driver_end_to_end(tmp_path):
+    """`mdmc config_load file.ini` (cmdlmc_b200.main, sections and keys of mdlmc/main.py:73-155) on
+    an xyz file: same rows as building the objects by hand with the same global seed."""
+    import io
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200 import main
+    from cmdlmc_b200.kmc import KMCLattice, ObservablesOutput
+    from cmdlmc_b200.topology import NeighborTopology
+    from cmdlmc_b200.trajectory import ArrayTrajectory
+    w = synth.workload("C1")
+    nfr = 400
+    frames = synth.trajectory(w, nfr, with_extra=True)
+    names = ["O"] * w.n_oxygen + ["P"] * w.n_extra
+    xyz = tmp_path / "traj.xyz"
+    with open(xyz, "w") as f:
+        for fr in frames:
+            f.write("%d\n\n" % len(names))
+            for nm, p in zip(names, fr):
+                f.write("%s %.17g %.17g %.17g\n" % (nm, p[0], p[1], p[2]))
+    ini = tmp_path / "run.ini"
+    ini.write_text("""
+[Trajectory]
+type = XYZTrajectory
+filename = %s
+time_step = %r
+[AtomBox]
+type = AtomBoxCubic
+periodic_boundaries = [%s]
+[NeighborTopology]
+type = NeighborTopology
+donor_atoms = O
+cutoff = %r
+buffer = %r
+[JumpRate]
+type = Fermi
+a = %r
+b = %r
+c = %r
+[KMCLattice]
+lattice_size = %d
+proton_number = %d
+donor_atoms = O
+time_step = %r
+[Output]
+type = ObservablesOutput
+reset_frequency = 100
+print_frequency = 10
+""" % (xyz, w.time_step, ", ".join(repr(float(x)) for x in w.cell), w.cutoff, w.buffer,
+       w.rate_params[0], w.rate_params[1], w.rate_params[2], w.n_oxygen, w.n_protons, w.time_step))
+    np.random.seed(11)
+    buf = io.StringIO()
+    main.run(str(ini), out=buf)
+    lines = buf.getvalue().strip().splitlines()
+    assert len(lines) > 5
+    np.random.seed(11)
+    box = cm.AtomBoxCubic(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    top = NeighborTopology(ArrayTrajectory(frames, np.array(names), time_step=w.time_step), box,
+                           donor_atoms="O", cutoff=w.cutoff, buffer=w.buffer)
+    kmc = KMCLattice(top, atom_box=box, jumprate_function=rate, lattice_size=w.n_oxygen,
+                     proton_number=w.n_protons, donor_atoms="O", time_step=w.time_step)
+    want = [str(x) for x in ObservablesOutput(kmc, 100, 10)]
+    assert lines == want
+    assert lines[0].startswith("(10, ") and "array([" in lines[0]
