@@ -23,6 +23,7 @@
 
 struct cmd_topo {
     BoxParams bx;
+    BoxParams bx_refresh;   // same box, image set pruned for the refresh radius rc + buffer
     RateParams rate;
     int n;
     double cutoff, buffer, rc;
@@ -60,7 +61,7 @@ struct cmd_topo {
     double *d_last, *d_displacement, *d_dr;
     int *d_carry_start, *d_carry_dest, *d_carry_count, *d_carry_rowoff;
     int *d_sched;  // [0] n_rebuild, [1] n_refresh, [2] last head (-1 = carry), then ids
-    int *d_rebuild_ids, *d_refresh_ids, *d_head;
+    int *d_rebuild_ids, *d_refresh_ids, *d_head, *d_next;
     double *d_upload;
     size_t upload_bytes;
     const double *d_frames_last;  // frames of the last block (device)
@@ -87,6 +88,161 @@ __global__ void __launch_bounds__(256) k_dr(const __grid_constant__ BoxParams bx
             v = length_exact(bx, a, b);
         }
         dr[g] = v;
+    }
+}
+
+
+// ---- parallel rebuild schedule ---------------------------------------------------------------------
+// The rebuild decision looks sequential (displacement accumulates frame after frame), but after a
+// rebuild at frame r the displacement is exactly zero, so the NEXT rebuild frame is a function of r
+// alone.  k_sched_walk evaluates that function for every possible r at once -- one small CTA per
+// start frame walks forward, accumulating in the reference's order (bit-identical sums), until the
+// two largest displacements cross the buffer -- and k_sched_chase then just follows the chain
+// r -> next[r] from the block's start state.  Walks are capped (SCHED_CAP frames); a chain link
+// that hit the cap is walked to its end by the chase kernel itself.
+#define SCHED_THREADS 128
+#define SCHED_CAP 384
+
+// One walk: displacement (shared memory, n doubles, initialised by the caller) += dr[f] for
+// f = first, first+1, ...; returns the first frame whose two largest displacements exceed the
+// buffer, `nframes` if the block ends first, -1 if `cap` frames went by without a crossing.
+__device__ int sched_walk(const double *__restrict__ dr, double *disp, double *red, int n,
+                          int64_t nframes, double buffer, int64_t first, int64_t cap)
+{
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+    for (int64_t f = first; f < nframes; f++) {
+        if (f - first >= cap) return -1;
+        double m1 = -INFINITY, m2 = -INFINITY;
+        for (int a = tid; a < n; a += blockDim.x) {
+            const double v = __dadd_rn(disp[a], dr[f * n + a]);
+            disp[a] = v;
+            if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) m2 = v;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double o1 = __shfl_down_sync(0xffffffffu, m1, o), o2 = __shfl_down_sync(0xffffffffu, m2, o);
+            if (o1 > m1) { m2 = fmax(m1, o2); m1 = o1; } else m2 = fmax(m2, o1);
+        }
+        if (lane == 0) { red[2 * w] = m1; red[2 * w + 1] = m2; }
+        __syncthreads();
+        m1 = red[0]; m2 = red[1];
+        for (int q = 1; q < nw; q++) {
+            const double o1 = red[2 * q], o2 = red[2 * q + 1];
+            if (o1 > m1) { m2 = fmax(m1, o2); m1 = o1; } else m2 = fmax(m2, o1);
+        }
+        __syncthreads();
+        // np.sort(displacement)[-2:] -> (m2, m1); displ_max1 + displ_max2 > buffer (topology.py:101-104)
+        if (n >= 2 && __dadd_rn(m2, m1) > buffer) return (int)f;
+    }
+    return (int)nframes;
+}
+
+// walker w >= 1: the list was rebuilt at frame w - 1, displacement starts at zero, first frame w
+__global__ void __launch_bounds__(SCHED_THREADS)
+k_sched_walk(const double *__restrict__ dr, int n, int64_t nframes, double buffer,
+             int *__restrict__ next)
+{
+    extern __shared__ double sched_smem[];
+    double *disp = sched_smem, *red = sched_smem + n;
+    const int64_t w = (int64_t)blockIdx.x + 1;
+    for (int a = threadIdx.x; a < n; a += blockDim.x) disp[a] = 0.0;
+    __syncthreads();
+    const int r = sched_walk(dr, disp, red, n, nframes, buffer, w, SCHED_CAP);
+    if (threadIdx.x == 0) next[w] = r;
+}
+
+// follows the chain from the block's start state, marks the rebuild frames, leaves the displacement
+// of the block's end in `displacement`
+__global__ void __launch_bounds__(SCHED_THREADS)
+k_sched_chase(const double *__restrict__ dr, double *__restrict__ displacement, int n,
+              int64_t nframes, double buffer, int first_ever, const int *__restrict__ next,
+              uint8_t *__restrict__ rebuilt, int next_smem)
+{
+    extern __shared__ double sched_smem[];
+    double *disp = sched_smem, *red = sched_smem + n;
+    // the chain is pointer chasing: stage next[] in shared memory when it fits (next_smem > 0)
+    int *snext = (int *)(red + 2 * (SCHED_THREADS / 32));
+    if (next_smem)
+        for (int64_t q = threadIdx.x; q <= nframes; q += blockDim.x) snext[q] = q >= 1 ? next[q] : 0;
+    __syncthreads();
+    int64_t cur;      // walker index: 0 = carried displacement from frame 0, w = zero state from w
+    if (first_ever) {   // the very first frame is always built (topology.py:91-93); dr[0] = 0
+        if (threadIdx.x == 0) rebuilt[0] = 1;
+        cur = 1;
+    } else {
+        cur = 0;
+    }
+    for (;;) {
+        int nx;
+        if (cur == 0) {
+            for (int a = threadIdx.x; a < n; a += blockDim.x) disp[a] = displacement[a];
+            __syncthreads();
+            nx = sched_walk(dr, disp, red, n, nframes, buffer, 0, nframes + 1);
+        } else if (cur >= nframes) {
+            nx = (int)nframes;
+        } else {
+            nx = next_smem ? snext[cur] : next[cur];
+            if (nx < 0) {   // the capped walk did not find the crossing: walk it here
+                for (int a = threadIdx.x; a < n; a += blockDim.x) disp[a] = 0.0;
+                __syncthreads();
+                nx = sched_walk(dr, disp, red, n, nframes, buffer, cur, nframes + 1);
+            }
+        }
+        if (nx >= nframes) break;
+        if (threadIdx.x == 0) rebuilt[nx] = 1;
+        cur = nx + 1;
+    }
+    // displacement at the end of the block: the last segment, walked without a crossing
+    __syncthreads();
+    if (cur == 0) {
+        // `disp` already holds carried + all frames of the block (the walk above ran to the end)
+    } else {
+        for (int a = threadIdx.x; a < n; a += blockDim.x) disp[a] = 0.0;
+        __syncthreads();
+        if (cur < nframes) sched_walk(dr, disp, red, n, nframes, INFINITY, cur, nframes + 1);
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < n; a += blockDim.x) displacement[a] = disp[a];
+}
+
+// rebuilt[] flags -> compacted id lists, head frame of every refresh frame, counts
+__global__ void __launch_bounds__(1024, 1)
+k_sched_fill(const uint8_t *__restrict__ rebuilt, int64_t nframes, int *__restrict__ sched,
+             int *__restrict__ rebuild_ids, int *__restrict__ refresh_ids, int *__restrict__ head)
+{
+    __shared__ int scan[40], lastreb[1024];
+    const int tid = threadIdx.x;
+    const int64_t per = (nframes + blockDim.x - 1) / blockDim.x;
+    const int64_t f0 = tid * per, f1 = f0 + per < nframes ? f0 + per : nframes;
+    int cnt = 0, last = -1;
+    for (int64_t f = f0; f < f1; f++)
+        if (rebuilt[f]) { cnt++; last = (int)f; }
+    lastreb[tid] = last;
+    const int ex = block_exclusive_scan(cnt, scan, &scan[33]);
+    const int total = scan[33];
+    // head of the frames in front of this thread's range: last rebuild of an earlier range, else
+    // the list carried from the previous block (sched[2], -1)
+    int hd = sched[2];
+    for (int q = tid - 1; q >= 0; q--)
+        if (lastreb[q] >= 0) { hd = lastreb[q]; break; }
+    int nreb = ex;
+    for (int64_t f = f0; f < f1; f++) {
+        if (rebuilt[f]) {
+            rebuild_ids[nreb++] = (int)f;
+            hd = (int)f;
+            head[f] = (int)f;
+        } else {
+            refresh_ids[f - nreb] = (int)f;   // refresh frames in front of f: f - #rebuilds so far
+            head[f] = hd;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int last_all = sched[2];   // unchanged (the carried list) when the block has no rebuild
+        for (int q = blockDim.x - 1; q >= 0; q--)
+            if (lastreb[q] >= 0) { last_all = lastreb[q]; break; }
+        sched[0] = total;
+        sched[1] = (int)(nframes - total);
+        sched[2] = last_all;
     }
 }
 
@@ -199,7 +355,13 @@ k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RatePara
         int a = hs[k], b = hdst[k];
         double pa[3] = {sp[3 * a], sp[3 * a + 1], sp[3 * a + 2]};
         double pb[3] = {sp[3 * b], sp[3 * b + 1], sp[3 * b + 2]};
-        double dist = length_exact(bx, pa, pb);
+        double dist;
+        if (bx.kind == 0) dist = length_exact(bx, pa, pb);
+        else {   // zero image + the images kept for the refresh radius == the 27-image minimum here
+            double d[3];
+            diff_general_exact(bx, pa, pb, d);
+            dist = sqrt(min_image_norm2_kept(bx, d));
+        }
         double om = rate_eval(rp, dist, 0.0);
         rsum += om;
         out_start[base + k] = a; out_dest[base + k] = b;
@@ -261,11 +423,11 @@ static void topo_free_block(cmd_topo *t)
     t->d_rowoff = nullptr;
     t->d_theta = nullptr;
     cudaFree(t->d_counts); cudaFree(t->d_rate_sum); cudaFree(t->d_rebuilt); cudaFree(t->d_dr);
-    cudaFree(t->d_rebuild_ids); cudaFree(t->d_refresh_ids); cudaFree(t->d_head);
+    cudaFree(t->d_rebuild_ids); cudaFree(t->d_refresh_ids); cudaFree(t->d_head); cudaFree(t->d_next);
     t->d_start = t->d_dest = t->d_counts = nullptr;
     t->d_dist = t->d_omega = t->d_rate_sum = t->d_dr = nullptr;
     t->d_rebuilt = nullptr;
-    t->d_rebuild_ids = t->d_refresh_ids = t->d_head = nullptr;
+    t->d_rebuild_ids = t->d_refresh_ids = t->d_head = t->d_next = nullptr;
     t->cap_frames = 0;
 }
 
@@ -414,6 +576,11 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
     t->t2 = exact_sq_threshold(t->rc);
     // the filter only has to look at the images that can come within rc of the origin
     cmd_box_prune_images(t->bx, t->rc);
+    // Between rebuilds the two largest path lengths sum to <= buffer, so a listed pair (<= rc at
+    // its rebuild) is never farther apart than rc + buffer when it is refreshed: the images that
+    // cannot come within that radius cannot hold the reference's 27-image minimum either.
+    t->bx_refresh = box->p;
+    cmd_box_prune_images(t->bx_refresh, (t->rc + buffer) * (1.0 + 1e-9) + 1e-9);
     topo_filter_params(t);
     topo_cell_grid(t);
     t->mode = mode;
@@ -676,6 +843,7 @@ static int topo_reserve(cmd_topo *t, int64_t nframes)
         BALLOC(t->d_rebuild_ids, (size_t)nframes * 4);
         BALLOC(t->d_refresh_ids, (size_t)nframes * 4);
         BALLOC(t->d_head, (size_t)nframes * 4);
+        BALLOC(t->d_next, ((size_t)nframes + 2) * 4);
     }
     t->cap_frames = nframes;
     return CMD_OK;
@@ -745,12 +913,32 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
         k_dr<<<blocks, 256, 0, st>>>(t->bx, d_frames, t->d_last, t->have_last ? 1 : 0, t->n, nframes,
                                      t->d_dr);
         CMD_LAUNCHED();
-        int sth = (t->n + 31) / 32 * 32;
-        if (sth > 1024) sth = 1024;
-        k_schedule<<<1, sth, 0, st>>>(t->d_dr, t->d_displacement, t->n, nframes, t->buffer,
-                                      t->total_frames == 0 ? 1 : 0, t->d_sched, t->d_rebuild_ids,
-                                      t->d_refresh_ids, t->d_head, t->d_rebuilt);
-        CMD_LAUNCHED();
+        const size_t ssm = ((size_t)t->n + 2 * (SCHED_THREADS / 32)) * 8;
+        if (ssm <= 48 * 1024 && nframes >= 64) {
+            // parallel schedule: next-rebuild function for every start frame, then chain following
+            CMD_CUDA(cudaMemsetAsync(t->d_rebuilt, 0, (size_t)nframes, st));
+            k_sched_walk<<<(unsigned)nframes, SCHED_THREADS, ssm, st>>>(t->d_dr, t->n, nframes, t->buffer,
+                                                                        t->d_next);
+            CMD_LAUNCHED();
+            const size_t nsm = ((size_t)nframes + 2) * 4;
+            const int next_smem = ssm + nsm <= 200 * 1024 ? 1 : 0;
+            const size_t csm = ssm + (next_smem ? nsm : 0);
+            CMD_CUDA(cudaFuncSetAttribute(k_sched_chase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+            k_sched_chase<<<1, SCHED_THREADS, csm, st>>>(t->d_dr, t->d_displacement, t->n, nframes,
+                                                        t->buffer, t->total_frames == 0 ? 1 : 0,
+                                                        t->d_next, t->d_rebuilt, next_smem);
+            CMD_LAUNCHED();
+            k_sched_fill<<<1, 1024, 0, st>>>(t->d_rebuilt, nframes, t->d_sched, t->d_rebuild_ids,
+                                             t->d_refresh_ids, t->d_head);
+            CMD_LAUNCHED();
+        } else {
+            int sth = (t->n + 31) / 32 * 32;
+            if (sth > 1024) sth = 1024;
+            k_schedule<<<1, sth, 0, st>>>(t->d_dr, t->d_displacement, t->n, nframes, t->buffer,
+                                          t->total_frames == 0 ? 1 : 0, t->d_sched, t->d_rebuild_ids,
+                                          t->d_refresh_ids, t->d_head, t->d_rebuilt);
+            CMD_LAUNCHED();
+        }
         if (skip) {
             int sched[3] = {0, 0, -1};
             CMD_CUDA(cudaMemcpyAsync(sched, t->d_sched, sizeof(sched), cudaMemcpyDeviceToHost, st));
@@ -765,12 +953,12 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
         size_t rsmem = (size_t)t->n * 24;
         if (rsmem > 40 * 1024)
             k_refresh<false><<<(unsigned)nframes, 256, 0, st>>>(
-                t->bx, t->rate, d_frames, t->d_refresh_ids, t->d_sched + 1, t->d_head, t->n, t->stride,
+                t->bx_refresh, t->rate, d_frames, t->d_refresh_ids, t->d_sched + 1, t->d_head, t->n, t->stride,
                 t->d_carry_start, t->d_carry_dest, t->d_carry_count, t->d_start, t->d_dest, t->d_dist,
                 t->d_omega, t->d_counts, t->d_rate_sum, t->d_carry_rowoff, t->d_rowoff);
         else
         k_refresh<true><<<(unsigned)nframes, 256, rsmem, st>>>(
-            t->bx, t->rate, d_frames, t->d_refresh_ids, t->d_sched + 1, t->d_head, t->n, t->stride,
+            t->bx_refresh, t->rate, d_frames, t->d_refresh_ids, t->d_sched + 1, t->d_head, t->n, t->stride,
             t->d_carry_start, t->d_carry_dest, t->d_carry_count, t->d_start, t->d_dest, t->d_dist,
             t->d_omega, t->d_counts, t->d_rate_sum, t->d_carry_rowoff, t->d_rowoff);
         CMD_LAUNCHED();
