@@ -159,29 +159,61 @@ def cpu_port_rate(w, seconds, threads=None):
     return nfr * ppf / best, cores, sample, nfr, best
 
 
-def reference_cython_rate(w, frames=2):
-    """The reference's own compiled AtomBox (oracle/_ref): length_all_to_all on a few frames,
-    one core (the reference is single-threaded).  None when oracle/_ref did not travel."""
+def reference_compiled_available():
     try:
-        from oracle import ref_import
-        from cmdlmc_b200 import synth
-        mod = ref_import.import_ref_atombox()
+        from oracle import build_ref
+        return build_ref.is_built()
     except Exception:
-        return None
-    cell = np.asarray(w.cell, dtype=float)
-    box = mod.AtomBoxCubic(cell) if cell.size == 3 else mod.AtomBoxMonoclinic(cell)
-    fr = synth.trajectory(w, frames)
-    t = time.perf_counter()
-    for f in fr:
-        box.length_all_to_all(f, f)
-    dt = time.perf_counter() - t
-    # length_all_to_all evaluates the full n x n table = 2 x the unordered pairs (+ diagonal)
-    return frames * w.n_oxygen * w.n_oxygen / 2.0 / dt
+        return False
+
+
+def reference_compiled_run(w, frames, procs, repeats=1):
+    """The REFERENCE's own compiled AtomBox (oracle/_ref, built from the reference's Cython
+    sources) on `frames` frames of the workload, `procs` worker processes: oracle/ref_bench.py in
+    a child process (it forks workers; this process may hold a CUDA context).  Returns its dict."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--workload", w.name,
+           "--frames", str(int(frames)), "--procs", str(int(procs)), "--repeats", str(int(repeats))]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1800)
+    if out.returncode != 0:
+        raise RuntimeError("oracle/ref_bench.py failed: " + out.stderr[-500:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def reference_compiled_rate(w, seconds):
+    """Bounded sample sized from a one-frame-per-process probe.  (pairs/s, cores, sample text)."""
+    procs = os.cpu_count() or 1
+    probe = reference_compiled_run(w, procs, procs)
+    per_round = max(probe["seconds"], 1e-3)                 # one frame per process
+    k = int(max(1, min(64, seconds / per_round)))
+    r = reference_compiled_run(w, procs * k, procs)
+    sample = ("%d frames of %s (%d O) through the reference's compiled AtomBox.length_all_to_all "
+              "(oracle/_ref, Cython -O3 -ffast-math) + NumPy cutoff and Fermi, %d processes"
+              % (r["frames"], w.name, w.n_oxygen, r["procs"]))
+    return r["pairs_per_s"], r["procs"], sample, r
+
+
+def cpu_baseline_block(w, seconds):
+    """cpu_baseline object: the reference's compiled code when oracle/_ref travelled with the
+    snapshot (kind "reference"), else the oracle's C port (kind "port"); the other one rides
+    along as extra keys."""
+    port_v, port_cores, port_sample, _, _ = cpu_port_rate(w, min(seconds, 8.0))
+    if reference_compiled_available():
+        try:
+            v, cores, sample, _ = reference_compiled_rate(w, seconds)
+            return {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+                    "port_pairs_per_s": port_v, "port_cores": port_cores, "port_sample": port_sample}
+        except Exception as e:   # the checker must never take the bench down
+            note = "oracle/_ref failed: %s" % e
+    else:
+        note = "oracle/_ref not present"
+    return {"value": port_v, "unit": UNIT, "cores": port_cores, "kind": "port",
+            "sample": port_sample, "note": note}
 
 
 def run_reference(args):
-    """Reference arm: the CPU implementation of the same step on the host cores (the oracle's C
-    port with OpenMP; oracle/_ref's Cython AtomBox is timed beside it as `reference_cython`)."""
+    """Reference arm: the CPU implementation of the same step on the host cores -- the reference's
+    own compiled AtomBox (oracle/_ref) when it is present, else the oracle's C port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -191,17 +223,33 @@ def run_reference(args):
     steps, warm = max(1, args.steps), max(0, args.warmup)
     # bounded sample per step so that the whole run ends within a few minutes
     budget = min(args.cpu_seconds, 120.0 / (steps + warm))
-    rate, cores, sample, nfr, _ = cpu_port_rate(w, budget)
-    from oracle import oracle as orc
-    box = orc.OracleBox(w.cell)
-    fr = synth.trajectory(w, nfr)
-    rc = w.cutoff + w.buffer
-    for _ in range(warm):
-        orc.bench_frames(box, fr, rc, w.rate_kind, w.rate_params)
-    t = time.perf_counter()
-    for _ in range(steps):
-        orc.bench_frames(box, fr, rc, w.rate_kind, w.rate_params)
-    dt = time.perf_counter() - t
+    kind = "port"
+    if reference_compiled_available():
+        try:
+            procs = os.cpu_count() or 1
+            probe = reference_compiled_run(w, procs, procs)
+            k = int(max(1, min(64, budget / max(probe["seconds"], 1e-3))))
+            r = reference_compiled_run(w, procs * k, procs, repeats=steps + warm)
+            times = r["seconds_all"][warm:]
+            nfr, cores, dt = r["frames"], r["procs"], float(sum(times))
+            sample = ("%d frames of %s per step through the reference's compiled "
+                      "AtomBox.length_all_to_all (oracle/_ref) + NumPy cutoff and Fermi, "
+                      "%d processes" % (nfr, w.name, cores))
+            kind = "reference"
+        except Exception as e:
+            print("bench.py: oracle/_ref arm failed (%s); using the C port" % e, file=sys.stderr)
+    if kind == "port":
+        _, cores, sample, nfr, _ = cpu_port_rate(w, budget)
+        from oracle import oracle as orc
+        box = orc.OracleBox(w.cell)
+        fr = synth.trajectory(w, nfr)
+        rc = w.cutoff + w.buffer
+        for _ in range(warm):
+            orc.bench_frames(box, fr, rc, w.rate_kind, w.rate_params)
+        t = time.perf_counter()
+        for _ in range(steps):
+            orc.bench_frames(box, fr, rc, w.rate_kind, w.rate_params)
+        dt = time.perf_counter() - t
     value = steps * nfr * ppf / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
@@ -209,9 +257,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "gpu_launches": 0,
         "config": workload_config(w, nfr, "bruteforce", extra={"l2": "n/a (CPU)"}),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample,
-                         "reference_cython_pairs_per_s_1core": reference_cython_rate(w)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -408,10 +455,7 @@ def run_b200(args):
         line["m2"] = run_m2(args, w, box, rate, d_frames, world, dev, dist, barrier)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, sample, _, _ = cpu_port_rate(w, args.cpu_seconds)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": sample,
-                                "reference_cython_pairs_per_s_1core": reference_cython_rate(w)}
+        line["cpu_baseline"] = cpu_baseline_block(w, args.cpu_seconds)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

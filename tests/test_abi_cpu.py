@@ -107,3 +107,24 @@ def test_compat_shims_and_config_help(tmp_path):
     frames = list(t)
     assert len(frames) == 2 and frames[1].atom_positions.tolist() == [[0, 1, 0], [2, 1, 0]]
     assert frames[1].time == 0.5 and list(frames[0].atom_names) == ["O", "O"]
+
+
+def test_reference_arm_prints_one_json_line():
+    """bench.py --impl reference: the CPU arm (the reference's compiled AtomBox from oracle/_ref
+    when present, else the oracle's C port) prints one JSON line with the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference",
+                        "--steps", "1", "--warmup", "0", "--cpu-seconds", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "frames*O-pairs/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}
