@@ -90,6 +90,7 @@ SIGNATURES = {
     "cmd_kmc_create": (C.c_int, [vp, C.c_int, C.c_int, ip, C.c_double, C.c_int, C.c_uint64,
                                  C.POINTER(vp)]),
     "cmd_kmc_destroy": (None, [vp]),
+    "cmd_kmc_set_replica_ids": (C.c_int, [vp, C.c_int, C.c_int]),
     "cmd_kmc_set_replay_stream": (C.c_int, [vp, dp, C.c_int64]),
     "cmd_kmc_set_event_log": (C.c_int, [vp, C.c_int64]),
     "cmd_kmc_set_observables": (C.c_int, [vp, C.c_int, C.c_int]),

@@ -46,6 +46,7 @@ struct cmd_kmc {
     double dt;
     int rng_mode;
     uint64_t seed;
+    int replica_first, replica_step;   // global id of local replica r = first + r * step (Philox)
     int *d_lattice;      // [R][n_sites]
     int *d_lattice0;     // [R][n_sites] autocorrelation reference (output.py:10-11)
     KmcState *d_state;   // [R]
@@ -72,6 +73,7 @@ struct cmd_kmc {
 
 struct KmcArgs {
     int n_sites, n_replicas, rng_mode, replicas_per_cta, mask_words, occ_words;
+    int replica_first, replica_step;
     double dt;
     uint64_t seed;
     int64_t stride, nframes, frames_base, n_u, ev_cap, row_cap;
@@ -532,8 +534,8 @@ __device__ bool kmc_move_fast(const KmcArgs &a, WarpCtx &c, double u, int r, lon
     if (!have || !(total > 0.0)) return false;   // nothing was allowed: IndexError upstream
     for (int attempt = 0; attempt < 24; attempt++) {
         if (attempt > 0) {
-            uint32_t ctr[4] = {(uint32_t)event, (uint32_t)((uint64_t)event >> 32), (uint32_t)r,
-                               (uint32_t)attempt};
+            uint32_t ctr[4] = {(uint32_t)event, (uint32_t)((uint64_t)event >> 32),
+                               (uint32_t)(a.replica_first + r * a.replica_step), (uint32_t)attempt};
             philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
             u = u53(ctr[0], ctr[1]);
         }
@@ -694,7 +696,8 @@ __device__ void kmc_run_until_frame_needed(const KmcArgs &a, WarpCtx &c, int r, 
             // the stream carries -np.log(1 - np.random.random()) as the host evaluated it
             st.time_selector = a.u[(int64_t)r * a.n_u + st.cursor];   // MDMC.py:148
         } else {
-            uint32_t ctr[4] = {(uint32_t)st.n_events, (uint32_t)((uint64_t)st.n_events >> 32), (uint32_t)r, 0u};
+            uint32_t ctr[4] = {(uint32_t)st.n_events, (uint32_t)((uint64_t)st.n_events >> 32),
+                               (uint32_t)(a.replica_first + r * a.replica_step), 0u};
             philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
             st.time_selector = -log(1 - u53(ctr[0], ctr[1]));         // MDMC.py:148
             st.u_sel = u53(ctr[2], ctr[3]);                           // MDMC.py:110, same counter
@@ -1027,6 +1030,8 @@ extern "C" int cmd_kmc_create(const cmd_box *box, int n_sites, int n_replicas, c
     k->dt = dt;
     k->rng_mode = rng_mode;
     k->seed = seed;
+    k->replica_first = 0;
+    k->replica_step = 1;
     cudaStream_t st = cmd_global().stream;
     size_t nl = (size_t)n_replicas * n_sites;
     int rc = CMD_OK;
@@ -1061,6 +1066,14 @@ __global__ void k_kmc_reset_cursor(KmcState *st, int n, int what)
         if (what == 0) st[r].cursor = 0;
         else st[r].log_pos = 0;
     }
+}
+
+extern "C" int cmd_kmc_set_replica_ids(cmd_kmc *k, int first, int step)
+{
+    if (!k || first < 0 || step < 1) return cmd_set_error(CMD_EINVAL, "bad argument");
+    k->replica_first = first;
+    k->replica_step = step;
+    return CMD_OK;
 }
 
 extern "C" int cmd_kmc_get_status(const cmd_kmc *k, int *phase, int *reason, int64_t *cursor)
@@ -1180,6 +1193,7 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
     KmcArgs a;
     memset(&a, 0, sizeof(a));
     a.n_sites = k->n_sites; a.n_replicas = k->n_replicas; a.rng_mode = k->rng_mode;
+    a.replica_first = k->replica_first; a.replica_step = k->replica_step;
     a.dt = k->dt; a.seed = k->seed; a.stride = stride; a.nframes = nframes;
     a.frames_base = k->frames_total; a.n_u = k->n_u; a.ev_cap = k->ev_cap; a.row_cap = k->row_cap;
     a.reset_freq = k->reset_freq; a.print_freq = k->print_freq;

@@ -49,6 +49,11 @@ class DeviceKMC:
                 pass
             self._handle = None
 
+    def set_replica_ids(self, first, step):
+        """Global ids of the local replicas (first + r * step) for the Philox counter: a replica's
+        random stream is the same whatever the number of GPUs sharing the ensemble."""
+        check(_abi.lib().cmd_kmc_set_replica_ids(self._handle, int(first), int(step)))
+
     def set_replay_stream(self, u):
         """u: per replica the uniforms the reference would draw from the legacy RandomState after
         its shuffle (random(), uniform-u, random(), ...).  The even entries are turned into the

@@ -229,6 +229,10 @@ int cmd_topo_distance_histogram_dev(const cmd_topo *t, double lo, double hi, int
 int cmd_kmc_create(const cmd_box *box, int n_sites, int n_replicas, const int *h_lattices,
                    double time_step, int rng_mode, uint64_t seed, cmd_kmc **out);
 void cmd_kmc_destroy(cmd_kmc *k);
+/* Replica sharding across GPUs: local replica r has the GLOBAL id first + r * step, which is what
+ * the Philox counter carries -- a replica's random stream does not depend on how many GPUs share
+ * the ensemble (rank q of G owns the ids q, q + G, ...: first = q, step = G). */
+int cmd_kmc_set_replica_ids(cmd_kmc *k, int first, int step);
 /* Replay stream: h_u float64 [n_replicas][n_per_replica]; consumed strictly alternating per
  * event e: h_u[2e] is the TIME SELECTOR -log(1 - r) of the event's np.random.random() draw r
  * (MDMC.py:148), evaluated by the caller with the reference's own log (NumPy) so that no
