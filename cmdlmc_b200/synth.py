@@ -134,14 +134,17 @@ def trajectory(w, n_frames=None, start=0, dtype=np.float64, amplitude=0.25, nois
     phase = rng.uniform(0, 2 * np.pi, size=base.shape)
     out = np.empty((n_frames,) + base.shape, dtype=dtype)
     block = 4096
-    for b0 in range(0, n_frames, block):
-        b1 = min(n_frames, b0 + block)
-        t = np.arange(start + b0, start + b1, dtype=float)[:, None, None]
+    stop = start + n_frames
+    for blk in range(start // block, (stop + block - 1) // block if n_frames else 0):
+        g0 = blk * block                                   # absolute first frame of the noise block
+        lo, hi = max(start, g0), min(stop, g0 + block)
+        t = np.arange(lo, hi, dtype=float)[:, None, None]
         x = base[None] + amplitude * np.sin(2 * np.pi * t / period[None] + phase[None])
-        # counter-style noise: seeded per block so blocks are reproducible independently
-        nrng = np.random.RandomState((w.seed * 1000003 + (start + b0)) % (2**31 - 1))
-        x += nrng.normal(scale=noise, size=x.shape)
-        out[b0:b1] = x
+        # counter-style noise: one seeded stream per aligned block of 4096 frames, so any frame
+        # range reproduces the same values as the whole trajectory sliced
+        nrng = np.random.RandomState((w.seed * 1000003 + g0) % (2**31 - 1))
+        x += nrng.normal(scale=noise, size=(hi - g0,) + base.shape)[lo - g0:]
+        out[lo - start:hi - start] = x
     return out
 
 
