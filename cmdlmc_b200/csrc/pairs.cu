@@ -621,12 +621,19 @@ static int launch_dense(cmd_topo *t, const double *d_frames, const int *ids, con
 {
     cudaStream_t st = cmd_global().stream;
     const bool ortho = t->bx.kind == 0;
+    // persistent CTAs: as many as are resident at once, each walking its share of the frames
 #define DENSE_LAUNCH(K, IM, SP, MT, MB)                                                          \
     do {                                                                                         \
         CMD_CUDA(cudaFuncSetAttribute(k_pairs_dense<K, IM, SP, MT, MB>,                          \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        k_pairs_dense<K, IM, SP, MT, MB><<<(unsigned)grid, t->threads * SP, smem, st>>>(         \
-            t->bx, t->rate, t->fp, d_frames, ids, n_ids, t->n, t->rc, t->t2, stride, hit_cap,    \
+        int nb_ = 1;                                                                             \
+        CMD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                  \
+            &nb_, k_pairs_dense<K, IM, SP, MT, MB>, t->threads * SP, smem));                     \
+        int64_t pgrid = (int64_t)cmd_global().sm_count * (nb_ > 0 ? nb_ : 1);                    \
+        if (pgrid > grid) pgrid = grid;                                                          \
+        k_pairs_dense<K, IM, SP, MT, MB><<<(unsigned)pgrid, t->threads * SP, smem, st>>>(        \
+            t->bx, t->rate, t->fp, d_frames, ids, n_ids, (int)grid, t->n, t->rc, t->t2, stride,  \
+            hit_cap,                                                                             \
             start, dest, dist, omega, counts, rate_sum, rebuilt, rowoff, t->d_err, t->d_ties);   \
     } while (0)
 #define DENSE_PICK(SP, MT, MB)                                                                   \

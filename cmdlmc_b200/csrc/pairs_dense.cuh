@@ -19,6 +19,7 @@
 //              (start, dest, dist, omega): both directions, row-major, columns ascending.
 #pragma once
 #include "pbc.cuh"
+#include "tma.cuh"
 
 // FP32 side of the filter (host-prepared, cmd_topo_create)
 struct FilterParams {
@@ -29,9 +30,10 @@ struct FilterParams {
 };
 
 struct DenseSmem {
-    double *cx, *cy, *cz;   // [n] Cartesian coordinates of the frame (SoA), phases 1-2
+    double *c;              // [n][3] Cartesian coordinates of the frame as they lie in HBM (the
+                            // next frame is prefetched into this place by TMA), phases 1-2
     int4 *fx;               // [2n + 4] fixed-point fractional coordinates, duplicated (cyclic)
-    unsigned short *wpre;   // [n][W] exclusive popc prefix per mask word (aliases cx..fx, phase 3)
+    unsigned short *wpre;   // [n][W] exclusive popc prefix per mask word (aliases fx, phase 3)
     double *hit_d;          // [hit_cap] distance of a hit, < 0 otherwise
     unsigned *mask;         // [n][W] adjacency bit matrix
     unsigned *hit_ij;       // [hit_cap] (a << 16) | b
@@ -44,7 +46,7 @@ __host__ __device__ inline size_t dense_smem_bytes(int n, int hit_cap)
 {
     int W = (n + 31) / 32;
     size_t b = 0;
-    b += (3 * (size_t)n * 8 + 15) / 16 * 16;  // cx cy cz (padded: fx is read with LDS.128)
+    b += (3 * (size_t)n * 8 + 15) / 16 * 16;  // c (padded: fx is read with LDS.128)
     b += (2 * (size_t)n + 4) * 16;        // fx
     b += (size_t)hit_cap * 8;             // hit_d
     b += 40 * 8;                          // red
@@ -58,18 +60,16 @@ __host__ __device__ inline size_t dense_smem_bytes(int n, int hit_cap)
 __host__ __device__ inline bool dense_use_wpre(int n)
 {
     int W = (n + 31) / 32;
-    return (size_t)n * W * 2 <= 3 * (size_t)n * 8 + (2 * (size_t)n + 4) * 16;
+    return (size_t)n * W * 2 <= (2 * (size_t)n + 4) * 16;
 }
 
 __device__ __forceinline__ DenseSmem dense_carve(unsigned char *base, int n, int hit_cap)
 {
     DenseSmem s;
     int W = (n + 31) / 32;
-    s.cx = (double *)base;
-    s.cy = s.cx + n;
-    s.cz = s.cy + n;
+    s.c = (double *)base;
     s.fx = (int4 *)(base + (3 * (size_t)n * 8 + 15) / 16 * 16);
-    s.wpre = (unsigned short *)base;
+    s.wpre = (unsigned short *)s.fx;
     s.hit_d = (double *)(s.fx + 2 * n + 4);
     s.red = s.hit_d + hit_cap;
     s.mask = (unsigned *)(s.red + 40);
@@ -156,7 +156,8 @@ template <int KIND, bool IMAGES, int SPLIT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ RateParams rp,
               const __grid_constant__ FilterParams fp, const double *__restrict__ frames,
-              const int *__restrict__ ids, const int *__restrict__ n_ids, int n, double rc,
+              const int *__restrict__ ids, const int *__restrict__ n_ids, int n_items, int n,
+              double rc,
               double t2, int64_t stride, int hit_cap, int *__restrict__ out_start,
               int *__restrict__ out_dest, double *__restrict__ out_dist,
               double *__restrict__ out_omega, int *__restrict__ out_counts,
@@ -165,18 +166,36 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
               unsigned long long *__restrict__ ties)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    if (n_ids && (int)blockIdx.x >= *n_ids) return;
-    const int64_t f = ids ? ids[blockIdx.x] : blockIdx.x;
     DenseSmem s = dense_carve(smem_raw, n, hit_cap);
     const int W = (n + 31) / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const double *fr = frames + f * (int64_t)n * 3;
-
-    // stage the frame: contiguous, coalesced read of 3n doubles, de-interleaved into SoA
-    for (int k = tid; k < 3 * n; k += blockDim.x) {
-        double v = __ldg(fr + k);
-        int a = k / 3, c = k - 3 * a;
-        (c == 0 ? s.cx : c == 1 ? s.cy : s.cz)[a] = v;
+    const int total_items = n_ids ? *n_ids : n_items;
+    // Persistent CTA: frames item = blockIdx.x, + gridDim.x, ...  The coordinates of a frame are one
+    // contiguous 24n-byte run in HBM; TMA (cp.async.bulk) drops the NEXT frame into s.c while
+    // phase 3 of the current one runs, so a frame never waits for global memory.  (Bulk copies
+    // need 16-byte granules: an odd atom count falls back to plain loads.)
+    uint64_t *bar = (uint64_t *)(s.red + 36);
+    const bool use_tma = (n & 1) == 0 && (((size_t)frames) & 15) == 0;
+    if (tid == 0 && use_tma) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto prefetch = [&](int item) {
+        const int64_t fn = ids ? ids[item] : item;
+        mbar_expect_tx(bar, (uint32_t)n * 24u);
+        tma_load_1d(s.c, frames + fn * (int64_t)n * 3, (uint32_t)n * 24u, bar);
+    };
+    if (use_tma && tid == 0 && (int)blockIdx.x < total_items) prefetch(blockIdx.x);
+    unsigned tma_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const int64_t f = ids ? ids[item] : item;
+    if (use_tma) {
+        mbar_wait(bar, tma_phase & 1u);
+        tma_phase++;
+    } else {
+        const double *fr = frames + f * (int64_t)n * 3;
+        for (int k = tid; k < 3 * n; k += blockDim.x) s.c[k] = __ldg(fr + k);
     }
     for (int k = tid; k < n * W; k += blockDim.x) s.mask[k] = 0u;
     if (tid == 0) { s.misc[0] = 0; s.misc[1] = 0; }
@@ -184,7 +203,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
     // fractional coordinates in 2^-32 fixed point; the low 32 bits of the rounded product ARE the
     // coordinate modulo one cell vector.  Stored twice so that the cyclic walk needs no modulo.
     for (int a = tid; a < n; a += blockDim.x) {
-        const double x = s.cx[a], y = s.cy[a], z = s.cz[a];
+        const double x = s.c[3 * a], y = s.c[3 * a + 1], z = s.c[3 * a + 2];
         int q[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
@@ -276,19 +295,17 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
     }
     __syncthreads();
     const int ncand = s.misc[0];
-    if (ncand > hit_cap) {  // capacity probe / overflow: report the (upper bound of the) need
-        if (tid == 0) {
-            out_counts[f] = -2 * ncand;
-            if (out_rebuilt) out_rebuilt[f] = 1;
-            atomicMax(err, 2 * ncand);
-        }
-        return;
+    const bool overflow = ncand > hit_cap;
+    if (overflow && tid == 0) {  // capacity probe / overflow: report the (upper bound of the) need
+        out_counts[f] = -2 * ncand;
+        if (out_rebuilt) out_rebuilt[f] = 1;
+        atomicMax(err, 2 * ncand);
     }
 
     // ---- phase 2: exact evaluation of the candidates ----------------------------------------
     // two candidates per trip: independent FP64 chains for the scheduler to interleave
     unsigned long long my_ties = 0;
-    for (int c0 = tid; c0 < ncand; c0 += 2 * blockDim.x) {
+    for (int c0 = tid; c0 < (overflow ? 0 : ncand); c0 += 2 * blockDim.x) {
         const int c1 = c0 + blockDim.x;
         const bool two = c1 < ncand;
         const unsigned ij[2] = {s.hit_ij[c0], s.hit_ij[two ? c1 : c0]};
@@ -296,7 +313,8 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
 #pragma unroll
         for (int q = 0; q < 2; q++) {
             const int a = ij[q] >> 16, b = ij[q] & 0xffff;
-            const double pa[3] = {s.cx[a], s.cy[a], s.cz[a]}, pb[3] = {s.cx[b], s.cy[b], s.cz[b]};
+            const double pa[3] = {s.c[3 * a], s.c[3 * a + 1], s.c[3 * a + 2]};
+            const double pb[3] = {s.c[3 * b], s.c[3 * b + 1], s.c[3 * b + 2]};
             double d[3];
             if (KIND == 0) {
                 // reference: length(frame[hi], frame[lo]) (topology.py:62-66); the arithmetic is
@@ -325,9 +343,12 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
     }
     if (my_ties) atomicAdd(ties, my_ties);
     __syncthreads();
+    // the coordinates are dead from here on: bring in the next frame of this CTA
+    if (use_tma && tid == 0 && item + (int)gridDim.x < total_items) prefetch(item + gridDim.x);
 
     // ---- phase 3: row counts -> exclusive offsets (LIL->COO order is row-major), write-out ---
-    const bool use_wpre = dense_use_wpre(n);   // the coordinates are dead: reuse them
+    if (!overflow) {
+    const bool use_wpre = dense_use_wpre(n);   // the fixed-point coordinates are dead: reuse them
     int cnt = 0, c0 = 0;
 #pragma unroll
     for (int q = 0; q < 2; q++) {
@@ -352,7 +373,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         if (out_rebuilt) out_rebuilt[f] = 1;
         if (total > stride) atomicMax(err, total);
     }
-    if (total > stride) return;
+    if (total <= stride) {
     if (out_rowoff) {   // row index of the frame's list: row i = [rowoff[i], rowoff[i + 1])
         int *ro = out_rowoff + f * (int64_t)cmd_ro_pitch(n);
         for (int k = tid; k < n; k += blockDim.x) ro[k] = s.rowoff[k];
@@ -401,4 +422,8 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
             out_rate_sum[f] = 2.0 * t;
         }
     }
+    }   // total <= stride
+    }   // !overflow
+    __syncthreads();   // phase 3 is done with the masks / hit lists before the next frame resets them
+    }   // frames of this CTA
 }
