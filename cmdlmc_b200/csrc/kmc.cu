@@ -93,7 +93,7 @@ struct KmcArgs {
     int fast, ro_pitch, nst_max;
     const int *rowoff;
     // exact-replay scratch, one slice per replica (see kmc_consume_exact)
-    int exact;
+    int exact, x_smem;   // x_smem: the scratch of the replica lives in shared memory
     int64_t x_cap, x_leaves;
     double *x_comp, *x_cum, *x_lsum;
     int *x_cidx, *x_loff, *x_ln;
@@ -289,22 +289,34 @@ __device__ double kmc_consume_exact(const KmcArgs &a, WarpCtx &c, int64_t f)
     c.base = base;
     c.p = p;
     int m = 0;
-    for (int k0 = 0; k0 < p; k0 += 32) {
-        int k = k0 + c.lane;
-        bool ok = false;
-        double om = 0.0;
-        if (k < p) {
-            int st = __ldg(a.start + base + k), de = __ldg(a.dest + base + k);
-            ok = occupied(c, st) && !occupied(c, de);
-            if (ok) om = __ldg(a.omega + base + k);
+    // 128 pairs per trip: all loads of the four groups are issued before anything depends on them
+    // (a verification run has one warp per SM and nothing else to hide the latency behind)
+    for (int k0 = 0; k0 < p; k0 += 128) {
+        int st[4], de[4];
+        double om[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = k0 + 32 * u + c.lane;
+            st[u] = k < p ? __ldg(a.start + base + k) : 0;
+            de[u] = k < p ? __ldg(a.dest + base + k) : 0;
+            om[u] = k < p ? __ldg(a.omega + base + k) : 0.0;
         }
-        unsigned bits = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            int e = m + __popc(bits & ((1u << c.lane) - 1u));
-            c.comp[e] = om;
-            c.cidx[e] = k;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = k0 + 32 * u + c.lane;
+            ok[u] = k < p && occupied(c, st[u]) && !occupied(c, de[u]);
         }
-        m += __popc(bits);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned bits = __ballot_sync(0xffffffffu, ok[u]);
+            if (ok[u]) {
+                const int e = m + __popc(bits & ((1u << c.lane) - 1u));
+                c.comp[e] = om[u];
+                c.cidx[e] = k0 + 32 * u + c.lane;
+            }
+            m += __popc(bits);
+        }
     }
     __syncwarp();
     c.m = m;
@@ -320,29 +332,46 @@ __device__ bool kmc_move_exact(const KmcArgs &a, WarpCtx &c, double u, int *o_st
 {
     const int m = c.m;
     const int64_t base = c.base;
-    double cum = 0.0;
     bool any = false;
-    for (int e0 = 0; e0 < m; e0 += 32) {
-        int e = e0 + c.lane;
-        double om = 0.0;
-        bool ok = false;
-        if (e < m) {
-            int k = c.cidx[e];
-            int st = __ldg(a.start + base + k), de = __ldg(a.dest + base + k);
-            ok = occupied(c, st) && !occupied(c, de);
-            if (ok) om = c.comp[e];
-        }
-        unsigned okbits = __ballot_sync(0xffffffffu, ok);
-        any |= okbits != 0u;
-        double mine = 0.0;
+    // 1. re-mask in parallel: cum[e] <- the rate if transition e is still allowed, else +0.0 (adding
+    //    +0.0 leaves a running sum unchanged, like the entry being absent from np.cumsum's input)
+    for (int e0 = 0; e0 < m; e0 += 128) {
+        int st[4], de[4];
 #pragma unroll
-        for (int i = 0; i < 32; i++) {  // sequential running sum, formed redundantly by every lane
-            cum = __dadd_rn(cum, __shfl_sync(0xffffffffu, om, i));   // + 0.0 leaves cum unchanged
-            if (i == c.lane) mine = cum;
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + 32 * u + c.lane;
+            const int k = e < m ? c.cidx[e] : 0;
+            st[u] = e < m ? __ldg(a.start + base + k) : 0;
+            de[u] = e < m ? __ldg(a.dest + base + k) : 0;
         }
-        if (e < m) c.cum[e] = mine;
-        if (c.lane == 0) c.mask0[e0 >> 5] = okbits;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + 32 * u + c.lane;
+            const bool ok = e < m && occupied(c, st[u]) && !occupied(c, de[u]);
+            if (e < m) c.cum[e] = ok ? c.comp[e] : 0.0;
+            const unsigned okbits = __ballot_sync(0xffffffffu, ok);
+            any |= okbits != 0u;
+            if (c.lane == 0 && e0 + 32 * u < m) c.mask0[(e0 >> 5) + u] = okbits;
+        }
     }
+    __syncwarp();
+    // 2. np.cumsum: strictly sequential additions, one lane, eight values per trip so that only
+    //    the additions themselves are on the dependency chain
+    double cum = 0.0;
+    if (c.lane == 0) {
+        int e = 0;
+        for (; e + 8 <= m; e += 8) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = c.cum[e + q];
+#pragma unroll
+            for (int q = 0; q < 8; q++) { cum = __dadd_rn(cum, v[q]); v[q] = cum; }
+#pragma unroll
+            for (int q = 0; q < 8; q++) c.cum[e + q] = v[q];
+        }
+        for (; e < m; e++) { cum = __dadd_rn(cum, c.cum[e]); c.cum[e] = cum; }
+    }
+    cum = __shfl_sync(0xffffffffu, cum, 0);
     __syncwarp();
     if (!any) return false;  // empty cumsum: IndexError upstream
     const double total = cum;
@@ -778,12 +807,22 @@ __global__ void __launch_bounds__(512, 1) k_kmc_advance(const __grid_constant__ 
     c.comp = c.cum = c.lsum = nullptr;
     c.cidx = c.loff = c.ln = nullptr;
     if (a.exact && active) {
-        c.comp = a.x_comp + (int64_t)r * a.x_cap;
-        c.cum = a.x_cum + (int64_t)r * a.x_cap;
-        c.cidx = a.x_cidx + (int64_t)r * a.x_cap;
-        c.lsum = a.x_lsum + (int64_t)r * a.x_leaves;
-        c.loff = a.x_loff + (int64_t)r * a.x_leaves;
-        c.ln = a.x_ln + (int64_t)r * a.x_leaves;
+        if (a.x_smem) {   // one replica per CTA: comp | cum | lsum | cidx | loff | ln behind the state
+            unsigned char *x = smem_raw + ((per_warp * a.replicas_per_cta + 15) / 16) * 16;
+            c.comp = (double *)x;
+            c.cum = c.comp + a.x_cap;
+            c.lsum = c.cum + a.x_cap;
+            c.cidx = (int *)(c.lsum + a.x_leaves);
+            c.loff = c.cidx + a.x_cap;
+            c.ln = c.loff + a.x_leaves;
+        } else {
+            c.comp = a.x_comp + (int64_t)r * a.x_cap;
+            c.cum = a.x_cum + (int64_t)r * a.x_cap;
+            c.cidx = a.x_cidx + (int64_t)r * a.x_cap;
+            c.lsum = a.x_lsum + (int64_t)r * a.x_leaves;
+            c.loff = a.x_loff + (int64_t)r * a.x_leaves;
+            c.ln = a.x_ln + (int64_t)r * a.x_leaves;
+        }
     }
     KmcState st;
     memset(&st, 0, sizeof(st));
@@ -1210,6 +1249,14 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
         return cmd_set_error(CMD_ECAPACITY, "KMC per-replica state (%zu bytes) exceeds shared memory", per_warp);
     a.replicas_per_cta = rpc;
     size_t smem = per_warp * rpc;
+    if (a.exact && rpc == 1) {   // few replicas (verification runs, `mdmc`): scratch in shared memory
+        const size_t xbytes = (size_t)a.x_cap * 20 + (size_t)a.x_leaves * 16;
+        const size_t xoff = ((per_warp + 15) / 16) * 16;
+        if (xoff + xbytes <= 226 * 1024) {
+            a.x_smem = 1;
+            smem = xoff + xbytes;
+        }
+    }
     CMD_CUDA(cudaFuncSetAttribute(k_kmc_advance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (k->n_replicas + rpc - 1) / rpc;
     k_kmc_advance<<<blocks, rpc * 32, smem, st>>>(k->bx, a);
