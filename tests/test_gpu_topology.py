@@ -354,3 +354,55 @@ def test_angle_topology_and_fermi_angle_vs_reference(golden):
     n = sum(1 for _ in kmc)
     ev = kmc.event_log
     assert n > 0 and len(ev["frame"]) > 0
+
+
+def test_full_size_c2_trajectory_properties():
+    """BASELINE.json config 2 at its full size (100 000 frames, float32 storage like the HDF5
+    path) through the Verlet pipeline in blocks: size-independent properties of the reference
+    (tests/topo/test_topology.py:68-101: a Verlet list restricted to cutoff+buffer equals the
+    brute-force list) on sampled frames, list symmetry / order on every sampled frame, and
+    conservation laws over the whole run."""
+    from cmdlmc_b200.topology import DeviceTopology, MODE_BRUTEFORCE, MODE_VERLET, build_with_retry
+    import cmdlmc_b200 as cm
+    w = synth.workload("C2")
+    total, block = 100000, 20000
+    box = make_box(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    verlet = bf = None
+    rng = np.random.RandomState(0)
+    n_rebuilds = n_pairs = 0
+    for b0 in range(0, total, block):
+        fr32 = synth.trajectory(w, block, start=b0, dtype=np.float32)
+        if verlet is None:
+            verlet = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer,
+                                                                 MODE_VERLET, rate, cap), fr32)
+        else:
+            verlet.build(fr32)
+        counts, rebuilt, rsum = verlet.frame_info()
+        assert (counts > 0).all() and (counts % 2 == 0).all() and np.isfinite(rsum).all()
+        n_rebuilds += int(rebuilt.sum())
+        n_pairs += int(counts.sum())
+        sample = np.sort(rng.choice(block, 6, replace=False))
+        sub = np.ascontiguousarray(fr32[sample])
+        if bf is None:
+            bf = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer,
+                                                             MODE_BRUTEFORCE, rate, cap), sub)
+        else:
+            bf.build(sub)
+        bcounts = bf.frame_info()[0]
+        for j, f in enumerate(sample):
+            s, d, dist, om = verlet.get_frame(int(f), int(counts[f]))
+            key = s.astype(np.int64) * w.n_oxygen + d
+            assert (np.diff(key) > 0).all()                          # row-major, columns ascending
+            order = np.argsort(d.astype(np.int64) * w.n_oxygen + s, kind="stable")
+            np.testing.assert_array_equal(dist[order], dist)         # (j, i) mirrors (i, j) bitwise
+            bs, bd, bdist, bom = bf.get_frame(j, int(bcounts[j]))
+            # the buffer guarantees that every pair within `cutoff` is on the Verlet list
+            keep, bkeep = dist <= w.cutoff, bdist <= w.cutoff
+            assert keep.sum() > 100
+            np.testing.assert_array_equal(s[keep], bs[bkeep])
+            np.testing.assert_array_equal(d[keep], bd[bkeep])
+            np.testing.assert_array_equal(dist[keep], bdist[bkeep])  # refresh == rebuild, bit for bit
+            np.testing.assert_array_equal(om[keep], bom[bkeep])
+    assert 0.01 * total < n_rebuilds < 0.1 * total
+    assert n_pairs > 6000 * total
