@@ -75,6 +75,9 @@ SIGNATURES = {
     "cmd_topo_device_arrays": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                          C.POINTER(vp), C.POINTER(vp)]),
     "cmd_topo_tie_count": (C.c_int64, [vp]),
+    "cmd_topo_nearest": (C.c_int, [vp, C.c_int]),
+    "cmd_topo_near_arrays": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), lp]),
+    "cmd_topo_get_frame_nearest": (C.c_int, [vp, C.c_int64, ip, dp]),
     "cmd_topo_set_groups": (C.c_int, [vp, ip, C.c_int]),
     "cmd_topo_apply_angles": (C.c_int, [vp, vp, C.c_int]),
     "cmd_topo_apply_angles_dev": (C.c_int, [vp, vp]),
@@ -91,6 +94,9 @@ SIGNATURES = {
                                  C.POINTER(vp)]),
     "cmd_kmc_destroy": (None, [vp]),
     "cmd_kmc_set_replica_ids": (C.c_int, [vp, C.c_int, C.c_int]),
+    "cmd_kmc_set_hydronium": (C.c_int, [vp, C.c_int, dp, C.c_int, dp, dp, dp, C.c_int, C.c_double,
+                                        C.c_double]),
+    "cmd_kmc_get_last_jump_times": (C.c_int, [vp, dp]),
     "cmd_kmc_set_replay_stream": (C.c_int, [vp, dp, C.c_int64]),
     "cmd_kmc_set_event_log": (C.c_int, [vp, C.c_int64]),
     "cmd_kmc_set_observables": (C.c_int, [vp, C.c_int, C.c_int]),

@@ -12,7 +12,9 @@ MODULES = {
     "mdlmc.cython_exts.LMC.PBCHelper": ("atombox", ["AtomBox", "AtomBoxCubic", "AtomBoxMonoclinic",
                                                     "AtomBoxWater", "AtomBoxWaterLinearConversion",
                                                     "AtomBoxWaterRampConversion"]),
-    "mdlmc.topo.topology": ("topology", ["NeighborTopology", "AngleTopology"]),
+    "mdlmc.topo.topology": ("topology", ["NeighborTopology", "AngleTopology", "HydroniumTopology",
+                                         "DistanceTransformation", "ReLUTransformation",
+                                         "InterpolatedTransformation", "DistanceInterpolator"]),
     "mdlmc.LMC.jumprate_generators": ("jumprate", ["JumpRate", "Fermi", "FermiAngle"]),
     "mdlmc.LMC.MDMC": ("kmc", ["KMCLattice", "Output", "XYZOutput", "ObservablesOutput"]),
     "mdlmc.LMC.output": ("output", ["CovalentAutocorrelation", "MeanSquareDisplacement"]),

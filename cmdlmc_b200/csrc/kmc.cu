@@ -41,6 +41,19 @@ struct KmcState {  // one per replica, global memory, persistent across cmd_kmc_
     double u_sel;       // Philox mode: selection uniform drawn together with the time selector
 };
 
+// HydroniumTopology colvars inside the KMC (topology.py:213-232,260-353): the distance of a
+// transition is rescaled depending on how long its proton has been sitting on the start site
+struct HydParams {
+    int on;
+    RateParams rate;     // jump rate evaluated on the rescaled distance
+    int tkind;           // 0 none, 1 ReLUTransformation, 2 InterpolatedTransformation
+    double tpar[5];      // ReLU: a, b, d0, left_bound, right_bound
+    const double *tx, *ty;   // interpolation table (device)
+    int nt;
+    double relax;        // DistanceInterpolator.relaxation_time; <= 0: no interpolator
+    double frame_dt;     // trajectory time step: frame.time = frame_number * frame_dt
+};
+
 struct cmd_kmc {
     BoxParams bx;
     int n_sites, n_replicas, n_protons_max;
@@ -67,6 +80,9 @@ struct cmd_kmc {
     double *d_disp;      // [R][n_sites][3]
     unsigned long long *d_ties;
     int64_t frames_total;
+    HydParams hyd;
+    double *d_tlast;     // [R][n_sites] time of the last jump per proton label - 1 (-1: never)
+    double *d_tx, *d_ty;
     // exact-replay scratch (per replica): the compacted allowed list of the last consumed frame
     void *d_exact;
     size_t exact_bytes;
@@ -89,6 +105,8 @@ struct KmcArgs {
     double *ev_dist;
     double *rows, *snapshot, *disp;
     unsigned long long *ties;
+    HydParams hyd;
+    double *tlast;
     // streaming (Philox) kernel: row index of the block's lists, smem ring geometry
     int fast, ro_pitch, nst_max;
     const int *rowoff;
@@ -159,9 +177,51 @@ struct WarpCtx {
     const int *ro;
     double lane_total;
     int nst;
+    double *tlast;       // hydronium: [n_sites] last jump time per proton label - 1 (shared memory)
+    double t_frame;      // hydronium: frame.time of the frame being consumed
 };
 
 __device__ __forceinline__ bool occupied(const WarpCtx &c, int s) { return (c.occ[s >> 5] >> (s & 31)) & 1u; }
+
+
+// ---- HydroniumTopology: rescaled distance of one transition --------------------------------------
+// ReLUTransformation.__call__ (topology.py:286-290), InterpolatedTransformation.__call__ (:328-333,
+// scipy interp1d kind="linear": slope * (x - x_lo) + y_lo), DistanceInterpolator.__call__ (:349-353)
+// and transform_distances (:213-232), in NumPy's operation order without FMA contraction.
+__device__ __forceinline__ double hyd_transform(const HydParams &h, double d)
+{
+    if (h.tkind == 1) {
+        if (d <= h.tpar[3] || h.tpar[4] <= d) return d;
+        return d < h.tpar[2] ? h.tpar[1] : __dadd_rn(__dmul_rn(h.tpar[0], __dadd_rn(d, -h.tpar[2])), h.tpar[1]);
+    }
+    if (h.tkind == 2) {
+        const double x_min = h.tx[0], x_max = h.tx[h.nt - 1];
+        if (!(x_min <= d && d <= x_max)) return d < x_min ? h.ty[0] : d;
+        // np.searchsorted(x, d) (side='left'), clipped to [1, n - 1]
+        int lo = 0, hi = h.nt;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (h.tx[mid] < d) lo = mid + 1; else hi = mid; }
+        int idx = lo < 1 ? 1 : (lo > h.nt - 1 ? h.nt - 1 : lo);
+        const double x_lo = h.tx[idx - 1], x_hi = h.tx[idx], y_lo = h.ty[idx - 1], y_hi = h.ty[idx];
+        const double slope = __ddiv_rn(__dadd_rn(y_hi, -y_lo), __dadd_rn(x_hi, -x_lo));
+        const double y = __dadd_rn(__dmul_rn(slope, __dadd_rn(d, -x_lo)), y_lo);
+        return y < x_min ? h.ty[0] : y;
+    }
+    return d;
+}
+
+__device__ __forceinline__ double hyd_rate(const HydParams &h, const WarpCtx &c, int start, double d)
+{
+    const int proton = c.lat[start];
+    const double tl = c.tlast[proton - 1];
+    const double relaxed = hyd_transform(h, d);
+    double dd = relaxed;
+    if (h.relax > 0.0) {
+        const double res = tl >= 0.0 ? __dadd_rn(c.t_frame, -tl) : INFINITY;
+        const double ratio = fmin(__ddiv_rn(res, h.relax), 1.0);
+        dd = __dadd_rn(__dmul_rn(__dadd_rn(1.0, -ratio), d), __dmul_rn(ratio, relaxed));
+    }
+    return rate_eval(h.rate, dd, 0.0);
+}
 
 // jumprate_generator + np.sum (MDMC.py:229-238, :85): total rate of the allowed transitions of
 // frame f for this replica; records the allowed mask (remember_last_element, MDMC.py:83-84)
@@ -300,12 +360,14 @@ __device__ double kmc_consume_exact(const KmcArgs &a, WarpCtx &c, int64_t f)
             const int k = k0 + 32 * u + c.lane;
             st[u] = k < p ? __ldg(a.start + base + k) : 0;
             de[u] = k < p ? __ldg(a.dest + base + k) : 0;
-            om[u] = k < p ? __ldg(a.omega + base + k) : 0.0;
+            om[u] = k < p ? __ldg((a.hyd.on ? a.dist : a.omega) + base + k) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int k = k0 + 32 * u + c.lane;
             ok[u] = k < p && occupied(c, st[u]) && !occupied(c, de[u]);
+            // hydronium: the rate depends on this replica's lattice and jump times
+            if (a.hyd.on && ok[u]) om[u] = hyd_rate(a.hyd, c, st[u], om[u]);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -703,6 +765,8 @@ __device__ bool kmc_event(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
                        : a.fast ? kmc_move_fast(a, c, u, r, st.n_events, &es, &ed, &ep, &ek, a.ties)
                                 : kmc_move(a, c, u, &es, &ed, &ep, &ek, a.ties);
     if (!moved) { st.reason = 2; return false; }
+    if (a.hyd.on && c.lane == 0) c.tlast[ep - 1] = st.kmc_time;   // update_time_of_last_jump (MDMC.py:99)
+    __syncwarp();
     if (c.lane == 0 && st.log_pos < a.ev_cap) {
         int64_t q = (int64_t)r * a.ev_cap + st.log_pos;
         a.ev_frame[q] = st.sweep;
@@ -795,12 +859,15 @@ __global__ void __launch_bounds__(512, 1) k_kmc_advance(const __grid_constant__ 
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * a.replicas_per_cta + w;
     const bool active = r < a.n_replicas;
-    const size_t per_warp = (size_t)a.n_sites * 4 + (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4;
+    const size_t base_bytes = ((size_t)a.n_sites * 4 + (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4 + 7) / 8 * 8;
+    const size_t per_warp = base_bytes + (a.hyd.on ? (size_t)a.n_sites * 8 : 0);
     WarpCtx c;
     c.lane = lane;
     c.lat = (int *)(smem_raw + per_warp * w);
     c.occ = (unsigned *)(c.lat + a.n_sites);
     c.mask0 = c.occ + a.occ_words;
+    c.tlast = (double *)(smem_raw + per_warp * w + base_bytes);
+    c.t_frame = 0.0;
     c.base = 0;
     c.p = 0;
     c.m = 0;
@@ -830,6 +897,8 @@ __global__ void __launch_bounds__(512, 1) k_kmc_advance(const __grid_constant__ 
     if (active) {
         st = a.state[r];
         for (int s = lane; s < a.n_sites; s += 32) c.lat[s] = a.lattice[(int64_t)r * a.n_sites + s];
+        if (a.hyd.on)
+            for (int s = lane; s < a.n_sites; s += 32) c.tlast[s] = a.tlast[(int64_t)r * a.n_sites + s];
         __syncwarp();
         for (int q = lane; q < a.occ_words; q += 32) {
             unsigned bits = 0;
@@ -844,6 +913,7 @@ __global__ void __launch_bounds__(512, 1) k_kmc_advance(const __grid_constant__ 
     for (int64_t f = 0; f < a.nframes; f++) {
         if (active && st.phase != KMC_PHASE_HALT) {
             if (a.positions) kmc_observe(a, bx, c, r, f, st);
+            c.t_frame = __dmul_rn((double)(a.frames_base + f), a.hyd.frame_dt);   // frame.time
             double rate = a.exact ? kmc_consume_exact(a, c, f) : kmc_consume(a, c, f);
             st.site_updates += c.p;
             st.frames_seen++;
@@ -854,6 +924,8 @@ __global__ void __launch_bounds__(512, 1) k_kmc_advance(const __grid_constant__ 
     if (active) {
         __syncwarp();
         for (int s = lane; s < a.n_sites; s += 32) a.lattice[(int64_t)r * a.n_sites + s] = c.lat[s];
+        if (a.hyd.on)
+            for (int s = lane; s < a.n_sites; s += 32) a.tlast[(int64_t)r * a.n_sites + s] = c.tlast[s];
         if (lane == 0) a.state[r] = st;
     }
 }
@@ -990,7 +1062,7 @@ extern "C" void cmd_kmc_destroy(cmd_kmc *k)
     cudaFree(k->d_lattice); cudaFree(k->d_lattice0); cudaFree(k->d_state); cudaFree(k->d_u);
     cudaFree(k->d_ev_frame); cudaFree(k->d_ev_time); cudaFree(k->d_ev_start); cudaFree(k->d_ev_dest);
     cudaFree(k->d_ev_proton); cudaFree(k->d_ev_dist); cudaFree(k->d_rows); cudaFree(k->d_snapshot); cudaFree(k->d_disp);
-    cudaFree(k->d_ties); cudaFree(k->d_exact);
+    cudaFree(k->d_ties); cudaFree(k->d_exact); cudaFree(k->d_tlast); cudaFree(k->d_tx); cudaFree(k->d_ty);
     free(k);
 }
 
@@ -1052,6 +1124,62 @@ __global__ void k_kmc_reset_cursor(KmcState *st, int n, int what)
         if (what == 0) st[r].cursor = 0;
         else st[r].log_pos = 0;
     }
+}
+
+__global__ void k_fill_double(double *p, int64_t n, double v)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+extern "C" int cmd_kmc_set_hydronium(cmd_kmc *k, int rate_kind, const double rate_par[CMD_RATE_NPAR],
+                                     int transform_kind, const double tpar[5], const double *h_table_x,
+                                     const double *h_table_y, int n_table, double relaxation_time,
+                                     double frame_time_step)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || !rate_par || rate_kind < 0 || rate_kind > CMD_RATE_EXP || rate_kind == CMD_RATE_FERMI_ANGLE ||
+        transform_kind < 0 || transform_kind > 2)
+        return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (transform_kind == 1 && !tpar) return cmd_set_error(CMD_EINVAL, "ReLU parameters missing");
+    if (transform_kind == 2 && (!h_table_x || !h_table_y || n_table < 2))
+        return cmd_set_error(CMD_EINVAL, "interpolation table needs at least two points");
+    if (k->frames_total > 0) return cmd_set_error(CMD_ESTATE, "set the hydronium mode before the first advance");
+    cudaStream_t st = cmd_global().stream;
+    HydParams &h = k->hyd;
+    memset(&h, 0, sizeof(h));
+    h.on = 1;
+    h.rate.kind = rate_kind;
+    memcpy(h.rate.par, rate_par, sizeof(h.rate.par));
+    h.tkind = transform_kind;
+    if (tpar) memcpy(h.tpar, tpar, sizeof(h.tpar));
+    h.relax = relaxation_time;
+    h.frame_dt = frame_time_step;
+    if (transform_kind == 2) {
+        cudaFree(k->d_tx); cudaFree(k->d_ty);
+        k->d_tx = k->d_ty = nullptr;
+        KALLOC(k->d_tx, (size_t)n_table * 8);
+        KALLOC(k->d_ty, (size_t)n_table * 8);
+        CMD_CUDA(cudaMemcpyAsync(k->d_tx, h_table_x, (size_t)n_table * 8, cudaMemcpyHostToDevice, st));
+        CMD_CUDA(cudaMemcpyAsync(k->d_ty, h_table_y, (size_t)n_table * 8, cudaMemcpyHostToDevice, st));
+        h.tx = k->d_tx; h.ty = k->d_ty; h.nt = n_table;
+    }
+    if (!k->d_tlast) KALLOC(k->d_tlast, (size_t)k->n_replicas * k->n_sites * 8);
+    // _time_of_last_jump_vec = -1 for every proton (topology.py:209)
+    k_fill_double<<<64, 256, 0, st>>>(k->d_tlast, (int64_t)k->n_replicas * k->n_sites, -1.0);
+    CMD_LAUNCHED();
+    CMD_CUDA(cudaStreamSynchronize(st));
+    return CMD_OK;
+}
+
+extern "C" int cmd_kmc_get_last_jump_times(const cmd_kmc *k, double *h_tlast)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || !h_tlast || !k->d_tlast) return cmd_set_error(CMD_ESTATE, "hydronium mode is not enabled");
+    cudaStream_t st = cmd_global().stream;
+    CMD_CUDA(cudaMemcpyAsync(h_tlast, k->d_tlast, (size_t)k->n_replicas * k->n_sites * 8, cudaMemcpyDeviceToHost, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
+    return CMD_OK;
 }
 
 extern "C" int cmd_kmc_set_replica_ids(cmd_kmc *k, int first, int step)
@@ -1159,6 +1287,12 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
     CmdGlobal &g = cmd_global();
     cudaStream_t st = g.stream;
     int64_t nframes = cmd_topo_nframes(t), stride = cmd_topo_stride(t);
+    if (k->hyd.on) {
+        // HydroniumTopology: the transitions of a frame are the k nearest listed neighbours of every
+        // site (cmd_topo_nearest); their rates are evaluated per replica inside the kernel
+        if ((rc = cmd_topo_near_arrays(t, &d_start, &d_dest, &d_dist, &d_counts, &stride))) return rc;
+        d_omega = d_dist;
+    }
     // observable rows: grow to hold this block's prints
     if (obs) {
         int64_t need = (k->frames_total + nframes) / k->print_freq + 2;
@@ -1189,7 +1323,10 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
     a.ev_frame = k->d_ev_frame; a.ev_time = k->d_ev_time; a.ev_start = k->d_ev_start;
     a.ev_dest = k->d_ev_dest; a.ev_proton = k->d_ev_proton; a.ev_dist = k->d_ev_dist;
     a.rows = k->d_rows; a.snapshot = k->d_snapshot; a.disp = k->d_disp; a.ties = k->d_ties;
-    a.exact = k->rng_mode == CMD_RNG_REPLAY ? 1 : 0;
+    a.hyd = k->hyd;
+    a.tlast = k->d_tlast;
+    // reference-order arithmetic in replay mode -- and for hydronium runs in either RNG mode
+    a.exact = (k->rng_mode == CMD_RNG_REPLAY || k->hyd.on) ? 1 : 0;
     if (a.exact) {
         // per replica: comp f64[cap], cum f64[cap], lsum f64[leaves], cidx i32[cap],
         // loff i32[leaves], ln i32[leaves]
@@ -1217,7 +1354,7 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
     int rpc = (k->n_replicas + g.sm_count - 1) / g.sm_count;
     if (rpc < 1) rpc = 1;
     if (rpc > 16) rpc = 16;
-    if (k->rng_mode == CMD_RNG_PHILOX && cmd_topo_n_atoms(t) == k->n_sites) {
+    if (k->rng_mode == CMD_RNG_PHILOX && !k->hyd.on && cmd_topo_n_atoms(t) == k->n_sites) {
         // streaming kernel: TMA-fed shared-memory ring + per-(stage, lane) partial sums
         const int *d_rowoff;
         if ((rc = cmd_topo_row_offsets(t, &d_rowoff))) return rc;
@@ -1243,7 +1380,8 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
         }
         a.fast = 0;   // state too large for the ring: the plain kernel below
     }
-    size_t per_warp = (size_t)a.n_sites * 4 + (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4;
+    size_t per_warp = ((size_t)a.n_sites * 4 + (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4 + 7) / 8 * 8 +
+                      (k->hyd.on ? (size_t)a.n_sites * 8 : 0);
     while (rpc > 1 && per_warp * rpc > 200 * 1024) rpc--;
     if (per_warp * rpc > 226 * 1024)
         return cmd_set_error(CMD_ECAPACITY, "KMC per-replica state (%zu bytes) exceeds shared memory", per_warp);

@@ -53,6 +53,11 @@ struct cmd_topo {
     double *d_extra_upload;
     size_t extra_upload_bytes;
     bool rate_is_fermi_angle;
+    // HydroniumTopology (topology.py:234-253): per site the k nearest listed neighbours
+    int near_k;
+    int64_t near_stride;
+    int *d_near_start, *d_near_dest, *d_near_counts;
+    double *d_near_dist;
     double *d_dist, *d_omega, *d_rate_sum;
     uint8_t *d_rebuilt;
     unsigned long long *d_ties;
@@ -420,8 +425,11 @@ static void topo_free_block(cmd_topo *t)
 {
     cudaFree(t->d_start); cudaFree(t->d_dest); cudaFree(t->d_dist); cudaFree(t->d_omega);
     cudaFree(t->d_rowoff); cudaFree(t->d_theta);
+    cudaFree(t->d_near_start); cudaFree(t->d_near_dest); cudaFree(t->d_near_counts); cudaFree(t->d_near_dist);
     t->d_rowoff = nullptr;
     t->d_theta = nullptr;
+    t->d_near_start = t->d_near_dest = t->d_near_counts = nullptr;
+    t->d_near_dist = nullptr;
     cudaFree(t->d_counts); cudaFree(t->d_rate_sum); cudaFree(t->d_rebuilt); cudaFree(t->d_dr);
     cudaFree(t->d_rebuild_ids); cudaFree(t->d_refresh_ids); cudaFree(t->d_head); cudaFree(t->d_next);
     t->d_start = t->d_dest = t->d_counts = nullptr;
@@ -1310,6 +1318,117 @@ extern "C" int cmd_topo_get_frame_angles(const cmd_topo *t, int64_t f, double *h
         CMD_CUDA(cudaMemcpyAsync(h_theta, t->d_theta + f * t->stride, (size_t)p * 8, cudaMemcpyDeviceToHost, st));
         CMD_CUDA(cudaStreamSynchronize(st));
     }
+    return CMD_OK;
+}
+
+
+// ---- HydroniumTopology._determine_colvars, lattice-independent part (topology.py:234-249) ----------
+// Per frame and site: the k listed neighbours with the smallest distance, ascending (np.argsort of
+// the row's distances; equal distances keep list order).  One warp per (frame, site).  Output in
+// the layout of a pair list -- entry e = site * k + q: start = site, dest, dist -- so the KMC kernels
+// read it like any other list (stride = near_stride, count = n * k).
+__global__ void __launch_bounds__(256)
+k_nearest(const int *__restrict__ counts, const int *__restrict__ rowoff, int ro_pitch,
+          const int *__restrict__ dest, const double *__restrict__ dist, int64_t stride, int n, int k,
+          int64_t nframes, int64_t near_stride, int *__restrict__ ns, int *__restrict__ nd,
+          double *__restrict__ ndist, int *__restrict__ ncounts, int *__restrict__ err)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wglobal = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (wglobal >= nframes * n) return;
+    const int64_t f = wglobal / n;
+    const int s = (int)(wglobal - f * n);
+    const int *ro = rowoff + f * ro_pitch;
+    const int r0 = ro[s], r1 = ro[s + 1];
+    const int64_t base = f * stride, obase = f * near_stride + (int64_t)s * k;
+    if (s == 0 && lane == 0) ncounts[f] = n * k;
+    if (r1 - r0 < k) {   // the reference fails here (ValueError, topology.py:250)
+        if (lane == 0) atomicMax(err, s + 1);
+        for (int q = lane; q < k; q += 32) { ns[obase + q] = s; nd[obase + q] = s; ndist[obase + q] = INFINITY; }
+        return;
+    }
+    unsigned long long taken = 0ull;   // entries of the row already emitted (rows hold < 64 * 32)
+    for (int q = 0; q < k; q++) {
+        double best = INFINITY;
+        int bi = 0x7fffffff;
+        for (int e = r0 + lane; e < r1; e += 32) {
+            const int slot = (e - r0) >> 5;
+            if (slot < 64 && ((taken >> slot) & 1ull)) continue;
+            const double d = __ldg(dist + base + e);
+            if (d < best || (d == best && e < bi)) { best = d; bi = e; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (((bi - r0) & 31) == lane) taken |= 1ull << ((bi - r0) >> 5);
+        if (lane == 0) { ns[obase + q] = s; nd[obase + q] = __ldg(dest + base + bi); ndist[obase + q] = best; }
+    }
+}
+
+extern "C" int cmd_topo_nearest(cmd_topo *t, int k)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || k < 1 || k > 16) return cmd_set_error(CMD_EINVAL, "bad argument (1 <= k <= 16)");
+    if (t->nframes < 1) return cmd_set_error(CMD_ESTATE, "no block has been built");
+    cudaStream_t st = cmd_global().stream;
+    const int64_t ns = ((int64_t)t->n * k + 63) / 64 * 64;
+    if (!t->d_near_dest || t->near_k != k) {
+        CMD_CUDA(cudaStreamSynchronize(st));
+        cudaFree(t->d_near_start); cudaFree(t->d_near_dest); cudaFree(t->d_near_counts); cudaFree(t->d_near_dist);
+        t->d_near_start = t->d_near_dest = t->d_near_counts = nullptr;
+        t->d_near_dist = nullptr;
+        const size_t np = (size_t)t->cap_frames * ns;
+        if (cudaMalloc((void **)&t->d_near_start, np * 4) != cudaSuccess ||
+            cudaMalloc((void **)&t->d_near_dest, np * 4) != cudaSuccess ||
+            cudaMalloc((void **)&t->d_near_dist, np * 8) != cudaSuccess ||
+            cudaMalloc((void **)&t->d_near_counts, (size_t)t->cap_frames * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return cmd_set_error(CMD_ENOMEM, "cudaMalloc failed for the nearest-neighbour arrays");
+        }
+        t->near_k = k;
+        t->near_stride = ns;
+    }
+    const int64_t warps = t->nframes * t->n;
+    k_nearest<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+        t->d_counts, t->d_rowoff, cmd_ro_pitch(t->n), t->d_dest, t->d_dist, t->stride, t->n, k, t->nframes,
+        t->near_stride, t->d_near_start, t->d_near_dest, t->d_near_dist, t->d_near_counts, t->d_err);
+    CMD_LAUNCHED();
+    int err = 0;
+    CMD_CUDA(cudaMemcpyAsync(&err, t->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
+    if (err > 0) {
+        CMD_CUDA(cudaMemsetAsync(t->d_err, 0, sizeof(int), st));
+        return cmd_set_error(CMD_EINVAL, "site %d has fewer than %d listed neighbours (the reference "
+                             "raises ValueError there, topology.py:250)", err - 1, k);
+    }
+    return CMD_OK;
+}
+
+extern "C" int cmd_topo_near_arrays(const cmd_topo *t, const int **d_start, const int **d_dest,
+                                    const double **d_dist, const int **d_counts, int64_t *stride)
+{
+    if (!t || !t->d_near_dest || t->nframes < 1)
+        return cmd_set_error(CMD_ESTATE, "cmd_topo_nearest has not been called for this block");
+    if (d_start) *d_start = t->d_near_start;
+    if (d_dest) *d_dest = t->d_near_dest;
+    if (d_dist) *d_dist = t->d_near_dist;
+    if (d_counts) *d_counts = t->d_near_counts;
+    if (stride) *stride = t->near_stride;
+    return CMD_OK;
+}
+
+extern "C" int cmd_topo_get_frame_nearest(const cmd_topo *t, int64_t f, int *h_dest, double *h_dist)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || f < 0 || f >= t->nframes) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (!t->d_near_dest) return cmd_set_error(CMD_ESTATE, "cmd_topo_nearest has not been called");
+    cudaStream_t st = cmd_global().stream;
+    const size_t cnt = (size_t)t->n * t->near_k;
+    if (h_dest) CMD_CUDA(cudaMemcpyAsync(h_dest, t->d_near_dest + f * t->near_stride, cnt * 4, cudaMemcpyDeviceToHost, st));
+    if (h_dist) CMD_CUDA(cudaMemcpyAsync(h_dist, t->d_near_dist + f * t->near_stride, cnt * 8, cudaMemcpyDeviceToHost, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
     return CMD_OK;
 }
 

@@ -54,6 +54,22 @@ class DeviceKMC:
         random stream is the same whatever the number of GPUs sharing the ensemble."""
         check(_abi.lib().cmd_kmc_set_replica_ids(self._handle, int(first), int(step)))
 
+    def set_hydronium(self, jumprate, *, kind, tpar, table_x, table_y, relaxation_time,
+                      frame_time_step):
+        """HydroniumTopology mode: per-replica distance rescaling + rate inside the KMC kernel."""
+        tx = np.ascontiguousarray(table_x, dtype=float) if table_x is not None else None
+        ty = np.ascontiguousarray(table_y, dtype=float) if table_y is not None else None
+        check(_abi.lib().cmd_kmc_set_hydronium(
+            self._handle, int(jumprate.kind), ptr(jumprate._par()), int(kind),
+            ptr(np.ascontiguousarray(tpar, dtype=float)), ptr(tx) if tx is not None else None,
+            ptr(ty) if ty is not None else None, 0 if tx is None else tx.size,
+            float(relaxation_time), float(frame_time_step)))
+
+    def last_jump_times(self):
+        out = np.zeros((self.n_replicas, self.n_sites))
+        check(_abi.lib().cmd_kmc_get_last_jump_times(self._handle, ptr(out)))
+        return out
+
     def set_replay_stream(self, u):
         """u: per replica the uniforms the reference would draw from the legacy RandomState after
         its shuffle (random(), uniform-u, random(), ...).  The even entries are turned into the
@@ -192,6 +208,8 @@ class KMCLattice:
         self._device = dev
         if observables:
             dev.set_observables(*observables)
+        if hasattr(self.topology, "hydronium_parameters"):
+            dev.set_hydronium(self._jumprate_function, **self.topology.hydronium_parameters())
         first = 0
         for topo, full_frames, _ in self.topology.device_blocks(MODE_VERLET, self._chunk_size):
             nfr = len(full_frames)

@@ -23,7 +23,12 @@ SECTIONS = {
     "Trajectory": {"XYZTrajectory": trajectory.XYZTrajectory, "NpzTrajectory": trajectory.NpzTrajectory},
     "AtomBox": {"AtomBoxCubic": atombox.AtomBoxCubic, "AtomBoxMonoclinic": atombox.AtomBoxMonoclinic},
     "NeighborTopology": {"NeighborTopology": topology.NeighborTopology,
-                         "AngleTopology": topology.AngleTopology},
+                         "AngleTopology": topology.AngleTopology,
+                         "HydroniumTopology": topology.HydroniumTopology},
+    "DistanceTransformation": {"ReLUTransformation": topology.ReLUTransformation,
+                               "InterpolatedTransformation":
+                                   topology.InterpolatedTransformation.from_file},
+    "DistanceInterpolator": {"DistanceInterpolator": topology.DistanceInterpolator},
     "JumpRate": {"Fermi": jumprate.Fermi, "FermiAngle": jumprate.FermiAngle,
                  "ActivationEnergy": jumprate.ActivationEnergy, "Exponential": jumprate.Exponential},
     "KMCLattice": {"KMCLattice": kmc.KMCLattice},
@@ -90,7 +95,14 @@ def run(configfile, out=sys.stdout):
     box_opts = dict(cp["AtomBox"])
     pbc = np.array([float(x) for x in box_opts["periodic_boundaries"].strip("[]()").split(",")])
     box = SECTIONS["AtomBox"][box_opts["type"]](pbc)
-    topo = build_section(cp, "NeighborTopology", traj, box)
+    extra = {}
+    if cp["NeighborTopology"].get("type") == "HydroniumTopology":   # main.py:89-127 upstream
+        if "DistanceTransformation" not in cp:
+            raise NameError("Distance Transformation needs to be specified!")
+        extra["distance_transformation_function"] = build_section(cp, "DistanceTransformation")
+        extra["distance_interpolator"] = (build_section(cp, "DistanceInterpolator")
+                                          if "DistanceInterpolator" in cp else None)
+    topo = build_section(cp, "NeighborTopology", traj, box, **extra)
     rate = build_section(cp, "JumpRate")
     lattice = build_section(cp, "KMCLattice", topo, jumprate_function=rate, atom_box=box)
     output = build_section(cp, "Output", lattice)

@@ -362,3 +362,163 @@ class AngleTopology(NeighborTopology):
                 start, dest, dist, _ = topo.get_frame(k, int(counts[k]))
                 self._cache.append(full_frame)
                 yield start, dest, dist, topo.get_frame_angles(k, int(counts[k]))
+
+
+class DistanceTransformation:
+    """If a topology which supports a transformation of the donor-acceptor distances is chosen
+    (for example HydroniumTopology), this class specifies how the donor-acceptor distances are
+    rescaled.  (mdlmc/topo/topology.py:260-270)"""
+    __show_in_config__ = True
+    transform_kind = 0
+
+    def __call__(self, distances):
+        return distances
+
+    def device_parameters(self):
+        """(kind, tpar[5], table_x, table_y) for cmd_kmc_set_hydronium."""
+        return 0, np.zeros(5), None, None
+
+
+class ReLUTransformation(DistanceTransformation):
+    """Rectified Linear Unit transformation (topology.py:273-291): a constant b below d0, the line
+    a (d - d0) + b above it, identity outside (left_bound, right_bound)."""
+    transform_kind = 1
+
+    def __init__(self, a: float, b: float, d0: float, left_bound: float, right_bound: float) -> None:
+        self.a, self.b, self.d0 = a, b, d0
+        self.left_bound, self.right_bound = left_bound, right_bound
+
+    def __call__(self, distances):
+        distances = np.asarray(distances, dtype=float)
+        rescaled = np.where(distances < self.d0, self.b, self.a * (distances - self.d0) + self.b)
+        mask = (distances <= self.left_bound) | (self.right_bound <= distances)
+        rescaled[mask] = distances[mask]
+        return rescaled
+
+    def device_parameters(self):
+        return 1, np.array([self.a, self.b, self.d0, self.left_bound, self.right_bound], float), None, None
+
+
+class InterpolatedTransformation(DistanceTransformation):
+    """Transform O-O distances by linear interpolation in a table (topology.py:294-334; scipy's
+    interp1d(kind="linear") upstream: slope * (x - x_lo) + y_lo)."""
+    __show_signature_of__ = "from_file"
+    transform_kind = 2
+
+    def __init__(self, dist_array, conversion_array):
+        self.x = np.ascontiguousarray(dist_array, dtype=float)
+        self.y = np.ascontiguousarray(conversion_array, dtype=float)
+        if self.x.ndim != 1 or self.x.shape != self.y.shape or self.x.size < 2:
+            raise ValueError("dist_array and conversion_array must be 1-d arrays of equal length >= 2")
+        self.x_min, self.x_max = self.x[0], self.x[-1]
+        self.y_min = self.y[0]
+
+    @classmethod
+    def from_file(cls, dist_array_filename: str, conversion_array_filename: str):
+        return cls(np.load(dist_array_filename), np.load(conversion_array_filename))
+
+    def _interp(self, d):
+        idx = np.clip(np.searchsorted(self.x, d), 1, self.x.size - 1)
+        lo, hi = idx - 1, idx
+        slope = (self.y[hi] - self.y[lo]) / (self.x[hi] - self.x[lo])
+        return slope * (d - self.x[lo]) + self.y[lo]
+
+    def __call__(self, distances):
+        distances = np.asarray(distances, dtype=float)
+        inside = (self.x_min <= distances) & (distances <= self.x_max)
+        rescaled = np.copy(distances)
+        rescaled[inside] = self._interp(rescaled[inside])
+        rescaled[rescaled < self.x_min] = self.y_min
+        return rescaled
+
+    def device_parameters(self):
+        return 2, np.zeros(5), self.x, self.y
+
+
+class DistanceInterpolator:
+    """Interpolates linearly in time between neutral and relaxed donor-acceptor distances
+    (topology.py:337-353)."""
+    __show_in_config__ = True
+
+    def __init__(self, relaxation_time: float):
+        self.relaxation_time = relaxation_time
+
+    def __call__(self, residence_time, distance_neutral, distance_relaxed):
+        ratio = np.minimum(np.asarray(residence_time) / self.relaxation_time, 1)[:, None]
+        return (1 - ratio) * distance_neutral + ratio * distance_relaxed
+
+
+class HydroniumTopology(NeighborTopology):
+    """Mimics the neighbor topology of a H3O+ ion in water by only defining connections to the
+    closest oxygen neighbors (mdlmc/topo/topology.py:170-257): per site the four nearest listed
+    neighbours, distances rescaled by a DistanceTransformation and relaxed with the residence
+    time of the proton sitting on the site.
+
+    In the device pipeline the lattice-independent part (nearest neighbours per site and frame)
+    is computed with the lists (cmd_topo_nearest) and the per-replica rescaling + rate inside the
+    KMC kernel (cmd_kmc_set_hydronium); `_determine_colvars` is the host-level mirror."""
+    __no_config_parameter__ = ["trajectory", "atom_box", "distance_transformation_function",
+                               "distance_interpolator"]
+    n_nearest = 4
+
+    def __init__(self, trajectory, atom_box, *, donor_atoms: str, cutoff: float, buffer: float = 0.0,
+                 distance_transformation_function: "DistanceTransformation" = None,
+                 distance_interpolator: "DistanceInterpolator" = None) -> None:
+        super().__init__(trajectory, atom_box, donor_atoms=donor_atoms, cutoff=cutoff, buffer=buffer)
+        self._time_of_last_jump_vec = None
+        self._distance_transformation_function = distance_transformation_function or DistanceTransformation()
+        self._distance_interpolator = distance_interpolator
+        self._lattice = None
+
+    def take_lattice_reference(self, lattice):
+        """Stores a read-only view of KMCLattice's lattice (topology.py:201-211)."""
+        self._lattice = lattice.view()
+        self._lattice.flags.writeable = False
+        self._proton_number = int((lattice != 0).sum())
+        self._time_of_last_jump_vec = -np.ones(self._proton_number)
+
+    def hydronium_parameters(self):
+        """What cmd_kmc_set_hydronium needs besides the rate: transformation and relaxation time."""
+        kind, tpar, tx, ty = self._distance_transformation_function.device_parameters()
+        relax = self._distance_interpolator.relaxation_time if self._distance_interpolator else 0.0
+        return dict(kind=kind, tpar=tpar, table_x=tx, table_y=ty, relaxation_time=float(relax),
+                    frame_time_step=float(self.trajectory_time_step))
+
+    def transform_distances(self, occupied_indices, distances, time):
+        occupied_indices = np.unique(occupied_indices)
+        proton_indices = self._lattice[occupied_indices]
+        last_jump_times = self._time_of_last_jump_vec[proton_indices - 1]
+        residence_times = np.where(last_jump_times >= 0, time - last_jump_times, np.inf)
+        rescaled = self._distance_transformation_function(distances)
+        if self._distance_interpolator is None:
+            return rescaled
+        return self._distance_interpolator(residence_times, distances, rescaled)
+
+    def _determine_colvars(self, start_indices, destination_indices, distances, frame):
+        """Per site the n_nearest listed neighbours, ascending by distance (topology.py:234-253)."""
+        n_atoms = self.n_nearest
+        donor_nr = len(self._lattice)
+        order = np.lexsort((distances, start_indices))
+        s_sorted, d_sorted, dist_sorted = start_indices[order], destination_indices[order], distances[order]
+        first = np.searchsorted(s_sorted, np.arange(donor_nr))
+        counts = np.bincount(start_indices, minlength=donor_nr)
+        if (counts < n_atoms).any():
+            raise ValueError("site %d has fewer than %d listed neighbours (topology.py:250)"
+                             % (int(np.argmax(counts < n_atoms)), n_atoms))
+        take = first[:, None] + np.arange(n_atoms)[None, :]
+        new_start = np.repeat(np.arange(donor_nr), n_atoms).reshape(donor_nr, n_atoms)
+        new_dest = d_sorted[take]
+        new_dist = self.transform_distances(new_start, dist_sorted[take], frame.time)
+        return new_start.flatten(), new_dest.flatten(), new_dist.flatten()
+
+    def device_blocks(self, mode=MODE_VERLET, chunk_size=None):
+        for topo, full_frames, pos in super().device_blocks(mode, chunk_size):
+            check(_abi.lib().cmd_topo_nearest(topo.handle, self.n_nearest))
+            yield topo, full_frames, pos
+
+    def __iter__(self):
+        for start, dest, dist, frame in self.topology_verlet_list_generator():
+            yield self._determine_colvars(start, dest, dist, frame)
+
+    def update_time_of_last_jump(self, proton_idx, new_time):
+        self._time_of_last_jump_vec[proton_idx - 1] = new_time

@@ -211,6 +211,14 @@ int cmd_topo_apply_angles(cmd_topo *t, const void *h_extra_frames, int dtype_byt
 int cmd_topo_apply_angles_dev(cmd_topo *t, const double *d_extra_frames);
 int cmd_topo_get_frame_angles(const cmd_topo *t, int64_t f, double *h_theta);
 
+/* HydroniumTopology (topology.py:170-257), lattice-independent part: per site of every frame of
+ * the last block the k listed neighbours with the smallest distance, ascending (k = 4 upstream).
+ * Fails when a site has fewer than k listed neighbours, like the reference (topology.py:250). */
+int cmd_topo_nearest(cmd_topo *t, int k);
+int cmd_topo_near_arrays(const cmd_topo *t, const int **d_start, const int **d_dest,
+                         const double **d_dist, const int **d_counts, int64_t *stride);
+int cmd_topo_get_frame_nearest(const cmd_topo *t, int64_t f, int *h_dest, double *h_dist);
+
 /* K5 / "jumpstat" (README.md:57-58): histogram of the listed O-O distances of the
  * last block over nbins equal bins of [lo, hi).  Every unordered pair is listed in both
  * directions and counted twice.  Counts are ADDED to the caller's array (int64 on the host,
@@ -233,6 +241,23 @@ void cmd_kmc_destroy(cmd_kmc *k);
  * the Philox counter carries -- a replica's random stream does not depend on how many GPUs share
  * the ensemble (rank q of G owns the ids q, q + G, ...: first = q, step = G). */
 int cmd_kmc_set_replica_ids(cmd_kmc *k, int first, int step);
+/* HydroniumTopology mode (topology.py:170-257): the transitions of a frame are the k nearest listed
+ * neighbours of every site (cmd_topo_nearest must have run on the block), and the distance d of a
+ * transition is rescaled per replica before the rate is evaluated:
+ *   d_relaxed = T(d)   T: CMD_TRANSFORM_RELU (ReLUTransformation, tpar = a, b, d0, left, right) or
+ *                         CMD_TRANSFORM_TABLE (InterpolatedTransformation, linear table x -> y)
+ *   d' = (1 - r) d + r d_relaxed,  r = min((frame.time - t_last_jump[proton]) / relaxation_time, 1)
+ *        (DistanceInterpolator; relaxation_time <= 0: r = 1; a proton that never jumped: r = 1)
+ *   omega = rate(d').  Must be called before the first cmd_kmc_advance. */
+#define CMD_TRANSFORM_NONE 0
+#define CMD_TRANSFORM_RELU 1
+#define CMD_TRANSFORM_TABLE 2
+int cmd_kmc_set_hydronium(cmd_kmc *k, int rate_kind, const double h_rate_par[CMD_RATE_NPAR],
+                          int transform_kind, const double h_tpar[5], const double *h_table_x,
+                          const double *h_table_y, int n_table, double relaxation_time,
+                          double frame_time_step);
+/* float64 [n_replicas][n_sites]: time of the last jump of proton (label - 1); -1 = never. */
+int cmd_kmc_get_last_jump_times(const cmd_kmc *k, double *h_tlast);
 /* Replay stream: h_u float64 [n_replicas][n_per_replica]; consumed strictly alternating per
  * event e: h_u[2e] is the TIME SELECTOR -log(1 - r) of the event's np.random.random() draw r
  * (MDMC.py:148), evaluated by the caller with the reference's own log (NumPy) so that no

@@ -171,15 +171,19 @@ def gen_angle():
     print("angle.npz:", counts[:4], "masked pairs in frame 0:", int((out["rate0"] == 0).sum()))
 
 
-def run_reference_kmc(w, frames, seed, n_events, reset_frequency=None, print_frequency=None):
+def run_reference_kmc(w, frames, seed, n_events, reset_frequency=None, print_frequency=None,
+                      make_topology=None):
     """Drives the reference KMCLattice; records events, lattices and (optionally) observables."""
     from mdlmc.topo.topology import NeighborTopology
     from mdlmc.LMC.MDMC import KMCLattice
     from mdlmc.LMC.jumprate_generators import Fermi
     box = make_box(w.cell)
     names = np.array(["O"] * w.n_oxygen)
-    topo = NeighborTopology(MockTrajectory(frames, w.time_step, names), box, donor_atoms="O",
-                            cutoff=w.cutoff, buffer=w.buffer)
+    if make_topology is not None:
+        topo = make_topology(MockTrajectory(frames, w.time_step, names), box)
+    else:
+        topo = NeighborTopology(MockTrajectory(frames, w.time_step, names), box, donor_atoms="O",
+                                cutoff=w.cutoff, buffer=w.buffer)
     np.random.seed(seed)
     kmc = KMCLattice(topo, atom_box=box, jumprate_function=Fermi(*w.rate_params),
                      lattice_size=w.n_oxygen, proton_number=w.n_protons, donor_atoms="O",
@@ -236,6 +240,59 @@ def run_reference_kmc(w, frames, seed, n_events, reset_frequency=None, print_fre
                 lattice_final=kmc.lattice.copy())
 
 
+HYD_RELU = dict(a=0.9, b=2.35, d0=2.5, left_bound=2.2, right_bound=3.2)
+HYD_RELAX = 6.0
+HYD_PROTONS = 24
+HYD_FERMI = (0.3, 2.45, 0.12)
+
+
+def gen_hydronium():
+    """HydroniumTopology (topology.py:170-257) with ReLUTransformation + DistanceInterpolator and
+    with an InterpolatedTransformation, driven by the reference KMCLattice on C2-sized frames:
+    event traces (rates depend on the residence time of every proton since its last jump)."""
+    import copy
+    from mdlmc.topo.topology import (HydroniumTopology, ReLUTransformation, DistanceInterpolator,
+                                     InterpolatedTransformation)
+    out = {}
+    w = copy.deepcopy(synth.workload("C2"))
+    w.n_protons = HYD_PROTONS
+    w.rate_params = HYD_FERMI
+    nfr = 150
+    frames = synth.trajectory(w, nfr)
+    xs = np.linspace(2.0, 3.4, 15)
+    ys = 2.3 + 0.8 * (xs - 2.0) ** 1.5
+    out["interp_x"], out["interp_y"] = xs, ys
+    variants = {
+        "relu": lambda traj, box: HydroniumTopology(
+            traj, box, donor_atoms="O", cutoff=w.cutoff, buffer=w.buffer,
+            distance_transformation_function=ReLUTransformation(**HYD_RELU),
+            distance_interpolator=DistanceInterpolator(HYD_RELAX)),
+        "interp": lambda traj, box: HydroniumTopology(
+            traj, box, donor_atoms="O", cutoff=w.cutoff, buffer=w.buffer,
+            distance_transformation_function=InterpolatedTransformation(xs, ys),
+            distance_interpolator=None),
+    }
+    for name, mk in variants.items():
+        res = run_reference_kmc(w, frames, 31, n_events=10 ** 9, make_topology=mk)
+        for k, v in res.items():
+            out["%s_%s" % (name, k)] = v
+        print("hydronium", name, "events:", len(res["ev_start"]))
+    # colvars of one frame for a fixed lattice / jump-time state (host-level parity)
+    box = make_box(w.cell)
+    names = np.array(["O"] * w.n_oxygen)
+    top = variants["relu"](MockTrajectory(frames[:3], w.time_step, names), box)
+    lattice = np.zeros(w.n_oxygen, np.int32)
+    lattice[::17][:HYD_PROTONS] = np.arange(1, HYD_PROTONS + 1)
+    top.take_lattice_reference(lattice)
+    top._time_of_last_jump_vec[::2] = np.linspace(0.0, 0.7, len(top._time_of_last_jump_vec[::2]))
+    cols = list(top)
+    out["colvar_lattice"] = lattice
+    out["colvar_tlast"] = top._time_of_last_jump_vec.copy()
+    for k, (s, d, dist) in enumerate(cols):
+        out["colvar%d_start" % k], out["colvar%d_dest" % k], out["colvar%d_dist" % k] = s, d, dist
+    np.savez_compressed(os.path.join(GOLD, "hydronium.npz"), **out)
+
+
 def gen_kmc():
     out = {}
     for cfg, nfr, seed in (("C1", 400, 11), ("C2", 60, 12)):
@@ -286,6 +343,7 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     only = sys.argv[1:]
     for name, fn in (("geometry", gen_geometry), ("topology", gen_topology),
-                     ("fastforward", gen_fastforward), ("kmc", gen_kmc), ("angle", gen_angle)):
+                     ("fastforward", gen_fastforward), ("kmc", gen_kmc), ("angle", gen_angle),
+                     ("hydronium", gen_hydronium)):
         if not only or name in only:
             fn()

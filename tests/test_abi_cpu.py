@@ -128,3 +128,28 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
+
+
+def test_distance_transformations_host_mirrors():
+    """ReLUTransformation / InterpolatedTransformation / DistanceInterpolator host classes
+    (topology.py:273-353): known answers and scipy's interp1d, which the reference uses."""
+    import numpy as np
+    from scipy.interpolate import interp1d
+    from cmdlmc_b200.topology import (DistanceInterpolator, InterpolatedTransformation,
+                                      ReLUTransformation)
+    relu = ReLUTransformation(a=0.9, b=2.35, d0=2.5, left_bound=2.2, right_bound=3.2)
+    d = np.array([2.0, 2.2, 2.3, 2.5, 2.8, 3.2, 3.5])
+    np.testing.assert_array_equal(relu(d), [2.0, 2.2, 2.35, 0.9 * 0.0 + 2.35, 0.9 * (2.8 - 2.5) + 2.35, 3.2, 3.5])
+    xs = np.linspace(2.0, 3.4, 15)
+    ys = 2.3 + 0.8 * (xs - 2.0) ** 1.5
+    it = InterpolatedTransformation(xs, ys)
+    q = np.array([1.5, 2.0, 2.05, 2.77, 3.4, 3.9])
+    ref = interp1d(xs, ys, kind="linear")
+    want = q.copy()
+    inside = (xs[0] <= q) & (q <= xs[-1])
+    want[inside] = ref(q[inside])
+    want[want < xs[0]] = ys[0]
+    np.testing.assert_array_equal(it(q), want)
+    ip = DistanceInterpolator(4.0)
+    out = ip(np.array([0.0, 2.0, np.inf]), np.full((3, 2), 3.0), np.full((3, 2), 2.0))
+    np.testing.assert_array_equal(out, [[3.0, 3.0], [2.5, 2.5], [2.0, 2.0]])
