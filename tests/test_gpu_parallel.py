@@ -148,3 +148,26 @@ def test_replica_sharded_ensemble_is_world_size_invariant():
         np.testing.assert_allclose(merged["mean"], one["observables"]["mean"], rtol=1e-13)
         assert sum(p["jump_hist"].sum() for p in parts) == one["events"]
         np.testing.assert_array_equal(sum(p["jump_hist"] for p in parts), one["jump_hist"])
+
+
+def test_jumpstat_probability_follows_the_rate():
+    """jumpstat: jumps per listed pair-frame per distance bin.  A pair can only carry a jump when its
+    start site is occupied and its destination empty; with protons spread uniformly that factor is
+    the same in every bin, so p(d) / Fermi(d) must be flat over the bins with enough jumps."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.jumpstat import jump_statistics
+    w = synth.workload("C4")
+    nfr = 400
+    frames = synth.trajectory(w, nfr)
+    box = make_box(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    st = jump_statistics(box, lambda a, b: frames[a:b], nfr, n_sites=w.n_oxygen, n_protons=w.n_protons,
+                         cutoff=w.cutoff, buffer=w.buffer, jumprate=rate, time_step=w.time_step,
+                         n_replicas=96, seed=2, nbins=50, chunk=200)
+    assert st["jumps"].sum() == st["events"] > 20000
+    ok = st["jumps"] > 400
+    assert ok.sum() >= 4
+    ratio = st["probability"][ok] / rate(st["centers"][ok])
+    # statistical error per bin < 5 %, bin-centre approximation of the steep Fermi function ~10 %
+    assert ratio.max() / ratio.min() < 1.5, ratio
+    assert (st["probability"][st["centers"] > 3.5] < 1e-6).all()
