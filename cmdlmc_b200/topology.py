@@ -494,22 +494,15 @@ class HydroniumTopology(NeighborTopology):
             return rescaled
         return self._distance_interpolator(residence_times, distances, rescaled)
 
-    def _determine_colvars(self, start_indices, destination_indices, distances, frame):
-        """Per site the n_nearest listed neighbours, ascending by distance (topology.py:234-253)."""
-        n_atoms = self.n_nearest
+    def _colvars_from_nearest(self, near_dest, near_dist, frame):
+        """(start, dest, rescaled distance) of one frame from the device's nearest-neighbour arrays
+        (topology.py:234-253): the selection ran in k_nearest, the user's transformation /
+        interpolator objects are applied here like upstream."""
         donor_nr = len(self._lattice)
-        order = np.lexsort((distances, start_indices))
-        s_sorted, d_sorted, dist_sorted = start_indices[order], destination_indices[order], distances[order]
-        first = np.searchsorted(s_sorted, np.arange(donor_nr))
-        counts = np.bincount(start_indices, minlength=donor_nr)
-        if (counts < n_atoms).any():
-            raise ValueError("site %d has fewer than %d listed neighbours (topology.py:250)"
-                             % (int(np.argmax(counts < n_atoms)), n_atoms))
-        take = first[:, None] + np.arange(n_atoms)[None, :]
+        n_atoms = self.n_nearest
         new_start = np.repeat(np.arange(donor_nr), n_atoms).reshape(donor_nr, n_atoms)
-        new_dest = d_sorted[take]
-        new_dist = self.transform_distances(new_start, dist_sorted[take], frame.time)
-        return new_start.flatten(), new_dest.flatten(), new_dist.flatten()
+        new_dist = self.transform_distances(new_start, near_dist.reshape(donor_nr, n_atoms), frame.time)
+        return new_start.flatten(), near_dest.astype(int), new_dist.flatten()
 
     def device_blocks(self, mode=MODE_VERLET, chunk_size=None):
         for topo, full_frames, pos in super().device_blocks(mode, chunk_size):
@@ -517,8 +510,15 @@ class HydroniumTopology(NeighborTopology):
             yield topo, full_frames, pos
 
     def __iter__(self):
-        for start, dest, dist, frame in self.topology_verlet_list_generator():
-            yield self._determine_colvars(start, dest, dist, frame)
+        if self._lattice is None:
+            raise RuntimeError("take_lattice_reference has not been called (KMCLattice does it)")
+        for topo, full_frames, _ in self.device_blocks(MODE_VERLET):
+            for k, full_frame in enumerate(full_frames):
+                dest = np.zeros(self.n_nearest * len(self._lattice), np.int32)
+                dist = np.zeros(self.n_nearest * len(self._lattice))
+                check(_abi.lib().cmd_topo_get_frame_nearest(topo.handle, k, ptr(dest, C.c_int), ptr(dist)))
+                self._cache.append(full_frame)
+                yield self._colvars_from_nearest(dest, dist, full_frame)
 
     def update_time_of_last_jump(self, proton_idx, new_time):
         self._time_of_last_jump_vec[proton_idx - 1] = new_time
