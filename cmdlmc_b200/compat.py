@@ -18,7 +18,8 @@ MODULES = {
     "mdlmc.LMC.jumprate_generators": ("jumprate", ["JumpRate", "Fermi", "FermiAngle"]),
     "mdlmc.LMC.MDMC": ("kmc", ["KMCLattice", "Output", "XYZOutput", "ObservablesOutput"]),
     "mdlmc.LMC.output": ("output", ["CovalentAutocorrelation", "MeanSquareDisplacement"]),
-    "mdlmc.IO.trajectory_parser": ("trajectory", ["Frame", "Trajectory", "XYZTrajectory"]),
+    "mdlmc.IO.trajectory_parser": ("trajectory", ["Frame", "Trajectory", "XYZTrajectory",
+                                                  "HDF5Trajectory"]),
     "mdlmc.main": ("main", ["main"]),
 }
 

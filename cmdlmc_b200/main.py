@@ -20,7 +20,8 @@ from . import atombox, jumprate, kmc, topology, trajectory
 
 SECTIONS = {
     # section -> (registry of `type` values, positional objects it is built from)
-    "Trajectory": {"XYZTrajectory": trajectory.XYZTrajectory, "NpzTrajectory": trajectory.NpzTrajectory},
+    "Trajectory": {"XYZTrajectory": trajectory.XYZTrajectory, "NpzTrajectory": trajectory.NpzTrajectory,
+                   "HDF5Trajectory": trajectory.HDF5Trajectory},
     "AtomBox": {"AtomBoxCubic": atombox.AtomBoxCubic, "AtomBoxMonoclinic": atombox.AtomBoxMonoclinic},
     "NeighborTopology": {"NeighborTopology": topology.NeighborTopology,
                          "AngleTopology": topology.AngleTopology,

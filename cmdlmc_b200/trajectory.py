@@ -174,3 +174,23 @@ class NpzTrajectory(ArrayTrajectory):
             super().__init__(z["trajectory"], z["atom_names"].astype(str), time_step=time_step,
                              repeat=repeat)
         self.filename = filename
+
+
+class HDF5Trajectory(ArrayTrajectory):
+    """HDF5 trajectory with the reference's layout (IO/converters.py:38-43: dataset `trajectory`
+    float32 [frames, atoms, 3], `atom_names`) and constructor (trajectory_parser.py:290-311).  Needs
+    h5py, which this image does not ship: the class exists so that reference drivers import, and
+    works wherever h5py does.  The float32 block goes to the GPU as it is (up-cast on the device)."""
+
+    def __init__(self, filename: str, time_step: float, selection=None, repeat: bool = False,
+                 chunk_size: int = 1000) -> None:
+        try:
+            import h5py
+        except ImportError as e:   # pragma: no cover - h5py is absent from the build image
+            raise ImportError("HDF5Trajectory needs h5py; use NpzTrajectory / XYZTrajectory") from e
+        with h5py.File(filename, "r") as f:
+            names = f["atom_names"][:].astype("<U2")
+            positions = f["trajectory"][:]
+        super().__init__(positions, names, time_step=time_step, repeat=repeat)
+        self.filename = filename
+        self._chunk_size = chunk_size
