@@ -20,6 +20,51 @@ MODE_BRUTEFORCE = 0
 MODE_VERLET = 1
 
 
+class _ArrayFrames:
+    """Frame stream of an array-backed trajectory with a visible cursor, so that whole blocks can be
+    taken by slicing instead of frame by frame (same one-shot semantics as a generator)."""
+
+    def __init__(self, traj):
+        self.traj = traj
+        self.pos = 0
+
+    def __iter__(self):
+        return self
+
+    def frame(self, k):
+        from .trajectory import Frame
+        t = self.traj
+        return Frame(t.atom_names, np.asarray(t.positions[k % len(t)], dtype=float), time=k * t.time_step)
+
+    def __next__(self):
+        if self.pos >= len(self.traj) and not self.traj.repeat:
+            raise StopIteration
+        k = self.pos
+        self.pos += 1
+        return self.frame(k)
+
+
+class _LazyFrames:
+    """Frames [k0, k1) of an array trajectory, materialised only when somebody looks at them."""
+
+    def __init__(self, stream, k0, k1):
+        self.stream, self.k0, self.k1 = stream, k0, k1
+
+    def __len__(self):
+        return self.k1 - self.k0
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return self.stream.frame(self.k0 + i)
+
+    def __iter__(self):
+        for k in range(self.k0, self.k1):
+            yield self.stream.frame(k)
+
+
 class DeviceTopology:
     """Thin owner of a `cmd_topo` handle: neighbour lists + rates of a block of frames in HBM."""
 
@@ -228,11 +273,21 @@ class NeighborTopology:
         cache_last_elements(trajectory) generator (topology.py:43) it is shared by everything that
         pulls frames, so a frame taken once is not delivered again."""
         if self._frame_iter is None:
-            self._frame_iter = iter(self.trajectory)
+            from .trajectory import ArrayTrajectory
+            if isinstance(self.trajectory, ArrayTrajectory):
+                self._frame_iter = _ArrayFrames(self.trajectory)
+            else:
+                self._frame_iter = iter(self.trajectory)
         return self._frame_iter
 
     def _chunks(self):
         it = self._frames()
+        if isinstance(it, _ArrayFrames) and not it.traj.repeat:
+            while it.pos < len(it.traj):
+                k0, k1 = it.pos, min(len(it.traj), it.pos + self.chunk_size)
+                it.pos = k1
+                yield _LazyFrames(it, k0, k1)
+            return
         while True:
             frames = []
             for full_frame in it:
@@ -252,7 +307,10 @@ class NeighborTopology:
             self.chunk_size = int(chunk_size)
         topo = None
         for full_frames in self._chunks():
-            pos = np.stack([self._donor_positions(f) for f in full_frames])
+            if isinstance(full_frames, _LazyFrames):   # array trajectory: one slice, no Frame objects
+                pos = self.trajectory.block(self.donor_atoms, full_frames.k0, full_frames.k1)
+            else:
+                pos = np.stack([self._donor_positions(f) for f in full_frames])
             if topo is None:
                 topo = build_with_retry(
                     lambda cap: DeviceTopology(self.atombox, pos.shape[1], self.cutoff,
@@ -344,7 +402,11 @@ class AngleTopology(NeighborTopology):
             if not getattr(topo, "_groups_set", False):
                 topo.set_groups(self._group, self.n_extra)
                 topo._groups_set = True
-            topo.apply_angles(np.stack([self._extra_positions(f) for f in full_frames]))
+            if isinstance(full_frames, _LazyFrames):
+                extra = self.trajectory.block(self.extra_atoms, full_frames.k0, full_frames.k1)
+            else:
+                extra = np.stack([self._extra_positions(f) for f in full_frames])
+            topo.apply_angles(extra)
             yield topo, full_frames, pos
 
     def _generate(self, mode):
