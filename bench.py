@@ -300,6 +300,7 @@ def run_b200(args):
     runtime.init(local)
     runtime.use_torch_stream()
     dev = torch.device("cuda", local)
+    numa_node = runtime.bind_to_gpu_numa_node(local) if world > 1 else None
 
     w = synth.workload(args.workload)
     n, B = w.n_oxygen, args.frames_per_step
@@ -446,7 +447,8 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": B * 13 + 4, "ms_per_step": e2e_ms / K,
-                "api": "cmd_topo_build(host f64 frames) + cmd_topo_frame_info"},
+                "api": "cmd_topo_build(host f64 frames) + cmd_topo_frame_info",
+                "numa_node_bound": numa_node},
         "roofline": roofline, "clocks": clocks,
     }
 
