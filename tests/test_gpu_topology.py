@@ -406,3 +406,63 @@ def test_full_size_c2_trajectory_properties():
             np.testing.assert_array_equal(om[keep], bom[bkeep])
     assert 0.01 * total < n_rebuilds < 0.1 * total
     assert n_pairs > 6000 * total
+
+
+def test_randomised_sweep_vs_oracle(orc):
+    """Seeded sweep over cell shapes (incl. strongly skewed cells that keep periodic images in the
+    filter), atom counts (odd / even / tiny / beyond one warp), radii (up to half the smallest
+    height) and both search paths: every list must equal the oracle's, bit for bit; then Verlet
+    runs with random block sizes against the oracle's generator."""
+    from cmdlmc_b200.topology import DeviceTopology, NeighborTopology, build_with_retry
+    import cmdlmc_b200 as cm
+    rng = np.random.RandomState(2024)
+    n_images_seen = set()
+    for case in range(40):
+        if case % 3 == 0:
+            cell = rng.uniform(7.0, 16.0, size=3)
+            hm = np.diag(cell)
+        else:
+            hm = np.diag(rng.uniform(8.0, 15.0, size=3))
+            hm[1, 0], hm[2, 0], hm[2, 1] = rng.uniform(-0.45, 0.45, size=3) * np.array([hm[0, 0], hm[0, 0], hm[1, 1]])
+            if case % 3 == 2:
+                hm[0, 1], hm[0, 2], hm[1, 2] = rng.uniform(-1.5, 1.5, size=3)
+            cell = hm.ravel()
+        box, obox = make_box(cell), orc.OracleBox(cell)
+        heights = 1.0 / np.linalg.norm(np.linalg.inv(hm.T), axis=1)
+        rc = float(rng.uniform(0.15, 0.5) * heights.min())
+        if case % 4 == 1:       # radius beyond half the smallest height: periodic images matter
+            rc = float(rng.uniform(0.55, 0.95) * heights.min())
+        n = int(rng.choice([1, 2, 3, 5, 31, 32, 33, 64, 97, 200, 333]))
+        if case % 4 == 1:
+            n = min(n, 97)      # nearly every pair is listed at such radii: keep the lists small
+        p = rng.uniform(-0.6, 1.6, size=(n, 3)) @ hm
+        if n > 3 and case % 5 == 0:
+            p[1] = p[0]                                   # coincident pair: dropped (sparse zero)
+        cutoff, buffer = 0.7 * rc, 0.3 * rc
+        want = orc.topology_bruteforce(obox, p, cutoff, buffer)
+        for path in (0, 1):
+            t = build_with_retry(lambda cap: DeviceTopology(box, n, cutoff, buffer, 0, None, cap,
+                                                            path=path), p[None])
+            n_images_seen.add(t.n_images)
+            c = t.frame_info()[0]
+            got = t.get_frame(0, int(c[0]))
+            np.testing.assert_array_equal(got[0], want[0], err_msg="case %d path %d" % (case, path))
+            np.testing.assert_array_equal(got[1], want[1])
+            np.testing.assert_array_equal(got[2], want[2])
+    assert max(n_images_seen) > 0          # some cells needed periodic images in the filter
+    # Verlet with random chunking on a random walk in a skewed cell
+    hm = np.array([[11.0, 0, 0], [3.0, 10.0, 0], [-2.0, 4.0, 12.0]])
+    box, obox = make_box(hm.ravel()), orc.OracleBox(hm.ravel())
+    n, nfr = 150, 90
+    pos0 = rng.uniform(0, 1, size=(n, 3)) @ hm
+    frames = pos0[None] + np.cumsum(rng.normal(scale=0.06, size=(nfr, n, 3)), axis=0)
+    top = NeighborTopology(make_traj(frames), box, donor_atoms="O", cutoff=2.5, buffer=0.8)
+    top.chunk_size = 13
+    gen = orc.verlet_generator(obox, frames, 2.5, 0.8)
+    n_reb = 0
+    for (row, col, dist, _), want in zip(top.topology_verlet_list_generator(), gen):
+        np.testing.assert_array_equal(row, want[0])
+        np.testing.assert_array_equal(col, want[1])
+        np.testing.assert_array_equal(dist, want[2])
+        n_reb += bool(want[3])
+    assert 2 < n_reb < nfr
