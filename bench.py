@@ -525,6 +525,31 @@ def run_m2(args, w, box, rate, d_frames, world, dev, dist, barrier):
             updates = int(st["site_updates"].sum())
             events = int(st["n_events"].sum())
     ms = float(np.mean(times))
+    # legacy LMC sweep (row A14): one sweep = P attempts per frame and replica, Philox
+    from cmdlmc_b200.lmc import DeviceLMC
+    lmc_times, lmc_attempts, lmc_jumps = [], 0, 0
+    for it in range(3):
+        lmc = DeviceLMC(lattices, RNG_PHILOX, seed=21 + it)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        lmc.advance(topo, w.time_step, 1)
+        b.record()
+        barrier()
+        if it > 0:
+            lmc_times.append(a.elapsed_time(b))
+            ls = lmc.state()
+            lmc_attempts, lmc_jumps = int(ls["attempts"].sum()), int(ls["jumps"].sum())
+    lmc_ms = float(np.mean(lmc_times))
+    tl = torch.tensor([lmc_ms], dtype=torch.float64, device=dev)
+    tot_l = torch.tensor([float(lmc_attempts), float(lmc_jumps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_l)
+    lmc_block = {"metric": "LMC site-updates/s (jump attempts)", "kernel": "k_lmc_sweep",
+                 "value": float(tot_l[0].item()) / (float(tl.item()) * 1e-3), "unit": "attempts/s",
+                 "ms": float(tl.item()), "jumps": float(tot_l[1].item()), "sweeps_per_frame": 1,
+                 "rng": "philox4x32-10", "parity": "unpinned upstream (engine not in the reference tree)"}
     tm = torch.tensor([ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(updates), float(events)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -536,7 +561,7 @@ def run_m2(args, w, box, rate, d_frames, world, dev, dist, barrier):
     return {"metric": "KMC site-updates/s", "value": rate_su, "unit": "site-updates/s",
             "replicas_per_gpu": R, "frames": F, "ms": ms, "events": events,
             "rng": "philox4x32-10", "directed_pairs_per_frame_mean": float(counts.mean()),
-            "verlet_rebuilds": int(rebuilt.sum()), "verlet_pipeline": verlet,
+            "verlet_rebuilds": int(rebuilt.sum()), "verlet_pipeline": verlet, "lmc_sweep": lmc_block,
             "kernel": "k_kmc_stream",
             "roofline": {"bound": "smem", "unit": "GB/s", "achieved": rate_su * 16 / 1e9,
                          "peak": 148 * 128 * 1.965, "frac": rate_su * 16 / 1e9 / (148 * 128 * 1.965),

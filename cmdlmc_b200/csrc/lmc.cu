@@ -16,12 +16,14 @@
 //   replay mode  pick / u come from host-pregenerated streams (e.g. a GSL-style MT19937
 //                gsl_rng_uniform_int / gsl_rng_uniform sequence): occupancy trajectories are
 //                bit-identical to the CPU restatement on the same streams;
-//   Philox mode  Philox4x32-10, counter = (attempt, sweep, replica), key = seed.
+//   Philox mode  Philox4x32-10, counter = (attempt pair, sweep, replica), key = seed; one call
+//                yields the pick and a 32-bit acceptance uniform for two attempts.
 #include <math.h>
 #include <stdlib.h>
 
 #include "pbc.cuh"
 #include "philox.cuh"
+#include "tma.cuh"
 
 struct cmd_lmc {
     int n_sites, n_replicas, rng_mode;
@@ -48,15 +50,99 @@ struct LmcArgs {
     const double *acc;
     unsigned long long *jumpmatrix;
     int *halt;
+    int resident;        // the frame's arrays are staged in shared memory (TMA) for all replicas
+    int64_t buf_pairs;   // capacity of that stage, a multiple of 64 pairs
 };
+
+// One sweep-block of the frame for one replica (warp): `p` attempts against `lat`.
+// RES = true: start / dest / omega point into shared memory (the frame was staged by TMA).
+template <bool RES>
+__device__ __forceinline__ void lmc_frame(const LmcArgs &a, int r, int lane, int *lat, int p,
+                                          const int *__restrict__ fstart, const int *__restrict__ fdest,
+                                          const double *__restrict__ fomega, long long &jumps,
+                                          long long &attempts, long long &cursor, long long &sweeps,
+                                          bool &halted)
+{
+    for (int sw = 0; sw < a.sweeps_per_frame && !halted; sw++) {
+        if (a.rng_mode == CMD_RNG_REPLAY && cursor + p > a.n_stream) {
+            halted = true;   // not enough pregenerated numbers for a whole sweep
+            break;
+        }
+        // 128 attempts per trip: the four groups draw their numbers and gather their pairs first
+        // (independent chains), then commit in attempt order group by group
+        for (int a0 = 0; a0 < p; a0 += 128) {
+            int si[4], di[4];
+            bool cand[4];
+            uint32_t rnd[2][4];
+            if (a.rng_mode != CMD_RNG_REPLAY) {
+                // one Philox call serves two attempts: (pick, 32-bit acceptance uniform) each
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    rnd[h][0] = (uint32_t)(a0 + 64 * h + lane); rnd[h][1] = (uint32_t)sweeps;
+                    rnd[h][2] = (uint32_t)r; rnd[h][3] = (uint32_t)((uint64_t)sweeps >> 32);
+                    philox4x32_10(rnd[h], (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const int at = a0 + 32 * g + lane;
+                const bool valid = at < p;
+                int k = 0;
+                double u = 2.0;
+                if (valid) {
+                    if (a.rng_mode == CMD_RNG_REPLAY) {
+                        k = a.pick[(int64_t)r * a.n_stream + cursor + at];
+                        u = a.acc[(int64_t)r * a.n_stream + cursor + at];
+                    } else {
+                        k = (int)__umulhi(rnd[g >> 1][2 * (g & 1)], (uint32_t)p);
+                        u = ((double)rnd[g >> 1][2 * (g & 1) + 1] + 0.5) * 2.3283064365386963e-10;
+                    }
+                }
+                const bool inrange = valid && k >= 0 && k < p;
+                si[g] = inrange ? (RES ? fstart[k] : __ldg(fstart + k)) : 0;
+                di[g] = inrange ? (RES ? fdest[k] : __ldg(fdest + k)) : 0;
+                const double om = inrange ? (RES ? fomega[k] : __ldg(fomega + k)) : 0.0;
+                // acceptance against the probability does not depend on the lattice
+                cand[g] = inrange && u < __dmul_rn(om, a.prob_scale);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                unsigned pending = __ballot_sync(0xffffffffu, cand[g]);
+                while (pending) {
+                    const bool ok = ((pending >> lane) & 1u) && lat[si[g]] != 0 && lat[di[g]] == 0;
+                    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                    if (!bal) break;
+                    const int l = __ffs(bal) - 1;
+                    if (lane == l) {
+                        lat[di[g]] = lat[si[g]];
+                        lat[si[g]] = 0;
+                        if (a.jumpmatrix)
+                            atomicAdd(a.jumpmatrix + (int64_t)si[g] * a.n_sites + di[g], 1ull);
+                    }
+                    jumps++;
+                    pending &= l == 31 ? 0u : ~((2u << l) - 1u);   // attempts behind the hop
+                    __syncwarp();
+                }
+            }
+        }
+        attempts += p;
+        cursor += p;
+        sweeps++;
+    }
+}
 
 __global__ void __launch_bounds__(512, 1) k_lmc_sweep(const __grid_constant__ LmcArgs a)
 {
-    extern __shared__ int lmc_smem[];
+    extern __shared__ __align__(16) unsigned char lmc_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * a.replicas_per_cta + w;
     const bool active = r < a.n_replicas;
-    int *lat = lmc_smem + (size_t)w * a.n_sites;
+    // resident mode: [omega f64 | start i32 | dest i32] of one frame, one mbarrier, the lattices
+    double *s_omega = (double *)lmc_smem;
+    int *s_start = (int *)(s_omega + (a.resident ? a.buf_pairs : 0));
+    int *s_dest = s_start + (a.resident ? a.buf_pairs : 0);
+    uint64_t *bar = (uint64_t *)(s_dest + (a.resident ? a.buf_pairs : 0));
+    int *lat = (int *)(bar + (a.resident ? 2 : 0)) + (size_t)w * a.n_sites;
     long long jumps = 0, attempts = 0, cursor = 0, sweeps = 0;
     bool halted = false;
     if (active) {
@@ -65,60 +151,34 @@ __global__ void __launch_bounds__(512, 1) k_lmc_sweep(const __grid_constant__ Lm
         halted = a.halt[r] != 0;
         __syncwarp();
     }
+    if (a.resident && threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned nload = 0;   // completed TMA stages: the mbarrier phase
     for (int64_t f = 0; f < a.nframes; f++) {
         const int p = a.counts[f];
         const int64_t base = f * a.stride;
-        if (active && !halted && p > 0) {
-            for (int sw = 0; sw < a.sweeps_per_frame && !halted; sw++) {
-                if (a.rng_mode == CMD_RNG_REPLAY && cursor + p > a.n_stream) {
-                    halted = true;   // not enough pregenerated numbers for a whole sweep
-                    break;
-                }
-                for (int a0 = 0; a0 < p; a0 += 32) {
-                    const int at = a0 + lane;
-                    const bool valid = at < p;
-                    int k = 0;
-                    double u = 2.0;
-                    if (valid) {
-                        if (a.rng_mode == CMD_RNG_REPLAY) {
-                            k = a.pick[(int64_t)r * a.n_stream + cursor + at];
-                            u = a.acc[(int64_t)r * a.n_stream + cursor + at];
-                        } else {
-                            uint32_t c[4] = {(uint32_t)at, (uint32_t)sweeps,
-                                             (uint32_t)r, (uint32_t)((uint64_t)sweeps >> 32)};
-                            philox4x32_10(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-                            k = (int)__umulhi(c[0], (uint32_t)p);
-                            u = u53(c[1], c[2]);
-                        }
-                    }
-                    const bool inrange = valid && k >= 0 && k < p;
-                    const int si = inrange ? __ldg(a.start + base + k) : 0;
-                    const int di = inrange ? __ldg(a.dest + base + k) : 0;
-                    // acceptance against the probability does not depend on the lattice
-                    bool cand = inrange && u < __dmul_rn(__ldg(a.omega + base + k), a.prob_scale);
-                    unsigned pending = __ballot_sync(0xffffffffu, cand);
-                    while (pending) {
-                        const bool ok = ((pending >> lane) & 1u) && lat[si] != 0 && lat[di] == 0;
-                        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-                        if (!bal) break;
-                        const int l = __ffs(bal) - 1;
-                        if (lane == l) {
-                            lat[di] = lat[si];
-                            lat[si] = 0;
-                            if (a.jumpmatrix)
-                                atomicAdd(a.jumpmatrix + (int64_t)si * a.n_sites + di, 1ull);
-                        }
-                        jumps++;
-                        pending &= l == 31 ? 0u : ~((2u << l) - 1u);   // attempts behind the hop
-                        __syncwarp();
-                    }
-                }
-                attempts += p;
-                cursor += p;
-                sweeps++;
+        if (a.resident) {
+            // the picks of a sweep are random: the whole frame has to be on chip.  One thread
+            // issues three TMA bulk copies, every replica of the CTA then gathers from shared memory
+            if (threadIdx.x == 0 && p > 0) {
+                const uint32_t e = (uint32_t)((p + 63) / 64 * 64);
+                mbar_expect_tx(bar, e * 16u);
+                tma_load_1d(s_omega, a.omega + base, e * 8u, bar);
+                tma_load_1d(s_start, a.start + base, e * 4u, bar);
+                tma_load_1d(s_dest, a.dest + base, e * 4u, bar);
             }
+            if (p > 0) { mbar_wait(bar, nload & 1u); nload++; }
+            if (active && !halted && p > 0)
+                lmc_frame<true>(a, r, lane, lat, p, s_start, s_dest, s_omega, jumps, attempts, cursor,
+                                sweeps, halted);
+        } else if (active && !halted && p > 0) {
+            lmc_frame<false>(a, r, lane, lat, p, a.start + base, a.dest + base, a.omega + base, jumps,
+                             attempts, cursor, sweeps, halted);
         }
-        __syncthreads();   // replicas of a CTA stay on the same frame (L1 reuse of its arrays)
+        __syncthreads();   // every replica is done with the frame before it is replaced
     }
     if (active) {
         __syncwarp();
@@ -246,8 +306,27 @@ extern "C" int cmd_lmc_advance(cmd_lmc *k, const cmd_topo *t, double prob_scale,
     if (rpc < 1) rpc = 1;
     if (rpc > 16) rpc = 16;
     while (rpc > 1 && per_warp * rpc > 200 * 1024) rpc--;
-    a.replicas_per_cta = rpc;
+    // resident mode: the largest frame of the block (16 B per pair) next to the lattices
+    int maxp = 0;
+    {
+        int64_t nf = a.nframes;
+        int *hc = (int *)malloc((size_t)nf * sizeof(int));
+        if (!hc) return cmd_set_error(CMD_ENOMEM, "out of host memory");
+        cudaError_t e = cudaMemcpyAsync(hc, d_counts, (size_t)nf * 4, cudaMemcpyDeviceToHost, g.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+        for (int64_t f = 0; e == cudaSuccess && f < nf; f++) if (hc[f] > maxp) maxp = hc[f];
+        free(hc);
+        CMD_CUDA(e);
+    }
+    a.buf_pairs = ((int64_t)maxp + 63) / 64 * 64;
+    if (a.buf_pairs > a.stride) a.buf_pairs = a.stride;
+    a.resident = 0;
     size_t smem = per_warp * rpc;
+    if (a.buf_pairs > 0 && (size_t)a.buf_pairs * 16 + 16 + per_warp * rpc <= 220 * 1024) {
+        a.resident = 1;
+        smem = (size_t)a.buf_pairs * 16 + 16 + per_warp * rpc;
+    }
+    a.replicas_per_cta = rpc;
     CMD_CUDA(cudaFuncSetAttribute(k_lmc_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (k->n_replicas + rpc - 1) / rpc;
     k_lmc_sweep<<<blocks, rpc * 32, smem, g.stream>>>(a);
