@@ -97,6 +97,8 @@ SIGNATURES = {
     "cmd_kmc_set_hydronium": (C.c_int, [vp, C.c_int, dp, C.c_int, dp, dp, dp, C.c_int, C.c_double,
                                         C.c_double]),
     "cmd_kmc_get_last_jump_times": (C.c_int, [vp, dp]),
+    "cmd_kmc_enable_occupancy": (C.c_int, [vp]),
+    "cmd_kmc_get_occupancy": (C.c_int, [vp, lp, lp]),
     "cmd_kmc_set_replay_stream": (C.c_int, [vp, dp, C.c_int64]),
     "cmd_kmc_set_event_log": (C.c_int, [vp, C.c_int64]),
     "cmd_kmc_set_observables": (C.c_int, [vp, C.c_int, C.c_int]),

@@ -82,6 +82,9 @@ struct cmd_kmc {
     int64_t frames_total;
     HydParams hyd;
     double *d_tlast;     // [R][n_sites] time of the last jump per proton label - 1 (-1: never)
+    // occupancy histogram: frames a site was seen occupied, kept as (closed intervals, open since)
+    unsigned int *d_occ_count;   // [R][n_sites]
+    int *d_occ_since;            // [R][n_sites] consumed-frame count at which the site was filled
     double *d_tx, *d_ty;
     // exact-replay scratch (per replica): the compacted allowed list of the last consumed frame
     void *d_exact;
@@ -107,6 +110,8 @@ struct KmcArgs {
     unsigned long long *ties;
     HydParams hyd;
     double *tlast;
+    unsigned int *occ_count;
+    int *occ_since;
     // streaming (Philox) kernel: row index of the block's lists, smem ring geometry
     int fast, ro_pitch, nst_max;
     const int *rowoff;
@@ -766,6 +771,13 @@ __device__ bool kmc_event(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
                                 : kmc_move(a, c, u, &es, &ed, &ep, &ek, a.ties);
     if (!moved) { st.reason = 2; return false; }
     if (a.hyd.on && c.lane == 0) c.tlast[ep - 1] = st.kmc_time;   // update_time_of_last_jump (MDMC.py:99)
+    if (a.occ_count && c.lane == 0) {
+        // occupancy histogram: the frames consumed so far saw `es` occupied since occ_since[es]; the
+        // following ones see `ed` occupied
+        const int64_t o = (int64_t)r * a.n_sites;
+        a.occ_count[o + es] += (unsigned int)(st.frames_seen - a.occ_since[o + es]);
+        a.occ_since[o + ed] = (int)st.frames_seen;
+    }
     __syncwarp();
     if (c.lane == 0 && st.log_pos < a.ev_cap) {
         int64_t q = (int64_t)r * a.ev_cap + st.log_pos;
@@ -1063,6 +1075,7 @@ extern "C" void cmd_kmc_destroy(cmd_kmc *k)
     cudaFree(k->d_ev_frame); cudaFree(k->d_ev_time); cudaFree(k->d_ev_start); cudaFree(k->d_ev_dest);
     cudaFree(k->d_ev_proton); cudaFree(k->d_ev_dist); cudaFree(k->d_rows); cudaFree(k->d_snapshot); cudaFree(k->d_disp);
     cudaFree(k->d_ties); cudaFree(k->d_exact); cudaFree(k->d_tlast); cudaFree(k->d_tx); cudaFree(k->d_ty);
+    cudaFree(k->d_occ_count); cudaFree(k->d_occ_since);
     free(k);
 }
 
@@ -1179,6 +1192,59 @@ extern "C" int cmd_kmc_get_last_jump_times(const cmd_kmc *k, double *h_tlast)
     cudaStream_t st = cmd_global().stream;
     CMD_CUDA(cudaMemcpyAsync(h_tlast, k->d_tlast, (size_t)k->n_replicas * k->n_sites * 8, cudaMemcpyDeviceToHost, st));
     CMD_CUDA(cudaStreamSynchronize(st));
+    return CMD_OK;
+}
+
+extern "C" int cmd_kmc_enable_occupancy(cmd_kmc *k)
+{
+    CMD_REQUIRE_INIT();
+    if (!k) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (k->frames_total > 0) return cmd_set_error(CMD_ESTATE, "enable the occupancy histogram before the first advance");
+    if (!k->d_occ_count) {
+        const size_t n = (size_t)k->n_replicas * k->n_sites;
+        KALLOC(k->d_occ_count, n * 4);
+        KALLOC(k->d_occ_since, n * 4);
+        CMD_CUDA(cudaMemsetAsync(k->d_occ_count, 0, n * 4, cmd_global().stream));
+        CMD_CUDA(cudaMemsetAsync(k->d_occ_since, 0, n * 4, cmd_global().stream));
+    }
+    return CMD_OK;
+}
+
+// counts[s] = number of (replica, consumed frame) pairs that saw site s occupied
+extern "C" int cmd_kmc_get_occupancy(const cmd_kmc *k, int64_t *h_counts, int64_t *h_replica_frames)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || !h_counts) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (!k->d_occ_count) return cmd_set_error(CMD_ESTATE, "the occupancy histogram is not enabled");
+    cudaStream_t st = cmd_global().stream;
+    const size_t R = (size_t)k->n_replicas, n = (size_t)k->n_sites;
+    unsigned int *cnt = (unsigned int *)malloc(R * n * 4);
+    int *since = (int *)malloc(R * n * 4), *lat = (int *)malloc(R * n * 4);
+    KmcState *hs = (KmcState *)malloc(R * sizeof(KmcState));
+    if (!cnt || !since || !lat || !hs) {
+        free(cnt); free(since); free(lat); free(hs);
+        return cmd_set_error(CMD_ENOMEM, "out of host memory");
+    }
+    cudaError_t e = cudaMemcpyAsync(cnt, k->d_occ_count, R * n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(since, k->d_occ_since, R * n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lat, k->d_lattice, R * n * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hs, k->d_state, R * sizeof(KmcState), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) {
+        int64_t frames = 0;
+        for (size_t s = 0; s < n; s++) h_counts[s] = 0;
+        for (size_t r = 0; r < R; r++) {
+            frames += hs[r].frames_seen;
+            for (size_t s = 0; s < n; s++) {
+                int64_t c = cnt[r * n + s];
+                if (lat[r * n + s] > 0) c += hs[r].frames_seen - since[r * n + s];   // still open
+                h_counts[s] += c;
+            }
+        }
+        if (h_replica_frames) *h_replica_frames = frames;
+    }
+    free(cnt); free(since); free(lat); free(hs);
+    CMD_CUDA(e);
     return CMD_OK;
 }
 
@@ -1325,6 +1391,8 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
     a.rows = k->d_rows; a.snapshot = k->d_snapshot; a.disp = k->d_disp; a.ties = k->d_ties;
     a.hyd = k->hyd;
     a.tlast = k->d_tlast;
+    a.occ_count = k->d_occ_count;
+    a.occ_since = k->d_occ_since;
     // reference-order arithmetic in replay mode -- and for hydronium runs in either RNG mode
     a.exact = (k->rng_mode == CMD_RNG_REPLAY || k->hyd.on) ? 1 : 0;
     if (a.exact) {

@@ -48,6 +48,7 @@ def run_kmc_ensemble(atom_box, frames_source, n_frames, *, n_sites, n_protons, c
         kmc.set_replica_ids(rank, world)
         if observe:
             kmc.set_observables(reset_frequency, print_frequency)
+        kmc.enable_occupancy()
         if histogram:
             kmc.set_event_log(64 * n_frames + 64)
     pair_hist = np.zeros(histogram[2], np.int64) if histogram else None
@@ -63,13 +64,17 @@ def run_kmc_ensemble(atom_box, frames_source, n_frames, *, n_sites, n_protons, c
         pos = hi
     local = {"replica_ids": ids}
     stats = {"events": np.zeros(1, np.int64), "site_updates": np.zeros(1, np.int64),
-             "replicas": np.array([len(ids)], np.int64)}
+             "replicas": np.array([len(ids)], np.int64), "occupancy": np.zeros(n_sites, np.int64),
+             "replica_frames": np.zeros(1, np.int64)}
     rows = []
     if kmc is not None:
         st = kmc.state()
         local.update(lattices=st["lattices"], n_events=st["n_events"], time=st["time"])
         stats["events"][0] = st["n_events"].sum()
         stats["site_updates"][0] = st["site_updates"].sum()
+        occ, rf = kmc.occupancy()
+        stats["occupancy"][:] = occ
+        stats["replica_frames"][0] = rf
         if observe:
             rows = [kmc.observables(k) for k in range(len(ids))]
             local["observables"] = rows
@@ -81,7 +86,10 @@ def run_kmc_ensemble(atom_box, frames_source, n_frames, *, n_sites, n_protons, c
         stats["pair_hist"] = pair_hist if rank == 0 else np.zeros_like(pair_hist)
     tot = parallel.allreduce_sum(stats) if reduce else stats
     out = {"local": local, "n_replicas": int(tot["replicas"][0]), "events": int(tot["events"][0]),
-           "site_updates": int(tot["site_updates"][0])}
+           "site_updates": int(tot["site_updates"][0]),
+           # fraction of (replica, frame) pairs in which a site carried a proton
+           "occupancy": tot["occupancy"] / max(int(tot["replica_frames"][0]), 1),
+           "occupancy_counts": tot["occupancy"], "replica_frames": int(tot["replica_frames"][0])}
     if histogram:
         out["jump_hist"], out["pair_hist"] = tot["jump_hist"], tot["pair_hist"]
     if observe:

@@ -70,6 +70,17 @@ class DeviceKMC:
         check(_abi.lib().cmd_kmc_get_last_jump_times(self._handle, ptr(out)))
         return out
 
+    def enable_occupancy(self):
+        check(_abi.lib().cmd_kmc_enable_occupancy(self._handle))
+
+    def occupancy(self):
+        """(counts int64[n_sites], replica_frames): how many (replica, consumed frame) pairs saw
+        each site occupied, and the number of such pairs in total."""
+        counts = np.zeros(self.n_sites, np.int64)
+        frames = C.c_int64(0)
+        check(_abi.lib().cmd_kmc_get_occupancy(self._handle, ptr(counts, C.c_int64), C.byref(frames)))
+        return counts, frames.value
+
     def set_replay_stream(self, u):
         """u: per replica the uniforms the reference would draw from the legacy RandomState after
         its shuffle (random(), uniform-u, random(), ...).  The even entries are turned into the

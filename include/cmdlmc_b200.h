@@ -258,6 +258,11 @@ int cmd_kmc_set_hydronium(cmd_kmc *k, int rate_kind, const double h_rate_par[CMD
                           double frame_time_step);
 /* float64 [n_replicas][n_sites]: time of the last jump of proton (label - 1); -1 = never. */
 int cmd_kmc_get_last_jump_times(const cmd_kmc *k, double *h_tlast);
+/* Occupancy histogram (one of the statistics north_star reduces across GPUs): h_counts[s] = number
+ * of (replica, consumed frame) pairs that saw site s occupied; *h_replica_frames = sum over
+ * replicas of the frames consumed (the normalisation).  Enable before the first advance. */
+int cmd_kmc_enable_occupancy(cmd_kmc *k);
+int cmd_kmc_get_occupancy(const cmd_kmc *k, int64_t *h_counts, int64_t *h_replica_frames);
 /* Replay stream: h_u float64 [n_replicas][n_per_replica]; consumed strictly alternating per
  * event e: h_u[2e] is the TIME SELECTOR -log(1 - r) of the event's np.random.random() draw r
  * (MDMC.py:148), evaluated by the caller with the reference's own log (NumPy) so that no

@@ -43,7 +43,8 @@ def main(out_path):
     if rank == 0:
         json.dump({"world": world, "hist": tot["hist"].tolist(), "pairs": int(tot["pairs"][0]),
                    "events": ens["events"], "jump_hist": ens["jump_hist"].tolist(),
-                   "n_replicas": ens["n_replicas"], "msd_mean": ens["observables"]["mean"].tolist(),
+                   "n_replicas": ens["n_replicas"], "occupancy": ens["occupancy_counts"].tolist(),
+                   "msd_mean": ens["observables"]["mean"].tolist(),
                    "msd_sem": ens["observables"]["sem"].tolist()}, open(out_path, "w"))
     dist.barrier()
     dist.destroy_process_group()

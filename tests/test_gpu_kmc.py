@@ -266,3 +266,40 @@ print_frequency = 10
     want = [str(x) for x in ObservablesOutput(kmc, 100, 10)]
     assert lines == want
     assert lines[0].startswith("(10, ") and "array([" in lines[0]
+
+
+@pytest.mark.parametrize("rng_mode", ["replay", "philox"])
+def test_occupancy_histogram_matches_event_log(orc, rng_mode):
+    """Occupancy histogram (frames a site was seen occupied) == the same quantity rebuilt from the
+    event log, and sums to protons x frames."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.kmc import DeviceKMC, RNG_PHILOX, RNG_REPLAY
+    from cmdlmc_b200.topology import DeviceTopology, MODE_VERLET, build_with_retry
+    w = synth.workload("C1")
+    nfr, R = 500, 3
+    frames = synth.trajectory(w, nfr)
+    box = make_box(w.cell)
+    topo = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer,
+                                                       MODE_VERLET, cm.Fermi(*w.rate_params), cap), frames)
+    lat0 = np.stack([synth.initial_lattice(w.n_oxygen, w.n_protons, 70 + r)[0] for r in range(R)])
+    kmc = DeviceKMC(box, lat0, w.time_step, RNG_REPLAY if rng_mode == "replay" else RNG_PHILOX, seed=4)
+    kmc.enable_occupancy()
+    kmc.set_event_log(20000)
+    if rng_mode == "replay":
+        kmc.set_replay_stream(np.random.RandomState(8).random_sample((R, 40000)))
+    kmc.advance(topo)
+    counts, replica_frames = kmc.occupancy()
+    st = kmc.state()
+    assert replica_frames == R * nfr and counts.sum() == w.n_protons * R * nfr
+    want = np.zeros(w.n_oxygen, np.int64)
+    for r in range(R):
+        ev = kmc.events(r)
+        assert len(ev["frame"]) == st["n_events"][r] > 5
+        occ = lat0[r] > 0
+        prev = 0
+        for f, s, d in zip(ev["frame"], ev["start"], ev["dest"]):
+            want[occ] += int(f) + 1 - prev
+            prev = int(f) + 1
+            occ[s], occ[d] = False, True
+        want[occ] += nfr - prev
+    np.testing.assert_array_equal(counts, want)

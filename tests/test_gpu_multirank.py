@@ -45,5 +45,6 @@ def test_two_ranks_nccl_equal_one_process(tmp_path):
                            print_frequency=20, chunk=64, histogram=(0.0, 5.0, 50), rank=0, world=1)
     assert got["events"] == one["events"] and got["n_replicas"] == R
     np.testing.assert_array_equal(got["jump_hist"], one["jump_hist"])
+    np.testing.assert_array_equal(got["occupancy"], one["occupancy_counts"])
     np.testing.assert_allclose(got["msd_mean"], one["observables"]["mean"], rtol=1e-12)
     np.testing.assert_allclose(got["msd_sem"], one["observables"]["sem"], rtol=1e-9)

@@ -130,6 +130,8 @@ def test_replica_sharded_ensemble_is_world_size_invariant():
     assert one["n_replicas"] == R and one["events"] > R
     assert one["jump_hist"].sum() == one["events"]
     assert one["pair_hist"].sum() > 0 and one["observables"]["n"] == R
+    assert one["replica_frames"] == R * nfr
+    assert one["occupancy_counts"].sum() == w.n_protons * R * nfr        # protons are conserved
     for world in (2, 3):
         parts = [run_kmc_ensemble(box, lambda a, b: frames[a:b], nfr, rank=q, world=world,
                                   reduce=False, **kw) for q in range(world)]
@@ -148,6 +150,7 @@ def test_replica_sharded_ensemble_is_world_size_invariant():
         np.testing.assert_allclose(merged["mean"], one["observables"]["mean"], rtol=1e-13)
         assert sum(p["jump_hist"].sum() for p in parts) == one["events"]
         np.testing.assert_array_equal(sum(p["jump_hist"] for p in parts), one["jump_hist"])
+        np.testing.assert_array_equal(sum(p["occupancy_counts"] for p in parts), one["occupancy_counts"])
 
 
 def test_jumpstat_probability_follows_the_rate():
