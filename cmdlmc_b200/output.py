@@ -54,3 +54,31 @@ class MeanSquareDisplacement:
 
     def msd(self):
         return np.sum(self.displacement ** 2, axis=0) / self.displacement.shape[0]
+
+
+def diffusion_coefficient(rows, reset_frequency, fit_start=0):
+    """Interval averaging of printed observables, the job of mdlmc/LMC/average_MC_out.py
+    (`avg` :115-125, `get_slope` :149-205, its default branch): the rows (frame, time, msd_x,
+    msd_y, msd_z, autocorr) are cut into the intervals between MSD resets, a line m t + y0 is
+    fitted to the summed MSD of every interval from `fit_start` on, and D = mean(m) / 6 with the
+    standard deviation of the slopes as its error.  Host-side post-processing of a few rows."""
+    rows = np.asarray(rows, dtype=float)
+    if rows.ndim != 2 or rows.shape[1] < 5:
+        raise ValueError("rows must be [n, >= 5]: frame, time, msd_x, msd_y, msd_z, ...")
+    interval = (rows[:, 0] // reset_frequency).astype(np.int64)
+    slopes, offsets = [], []
+    for k in np.unique(interval):
+        part = rows[interval == k][fit_start:]
+        if len(part) < 2:
+            continue
+        t = part[:, 1] - part[0, 1]
+        y = part[:, 2:5].sum(axis=1)
+        m, y0 = np.polyfit(t, y, 1)
+        slopes.append(m)
+        offsets.append(y0)
+    if not slopes:
+        raise ValueError("no interval holds two or more rows")
+    slopes = np.asarray(slopes)
+    return dict(slope=float(slopes.mean()), slope_err=float(slopes.std()),
+                diffusion_coefficient=float(slopes.mean() / 6), error=float(slopes.std() / 6),
+                intervals=len(slopes), offset=float(np.mean(offsets)))

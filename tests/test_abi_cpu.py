@@ -153,3 +153,19 @@ def test_distance_transformations_host_mirrors():
     ip = DistanceInterpolator(4.0)
     out = ip(np.array([0.0, 2.0, np.inf]), np.full((3, 2), 3.0), np.full((3, 2), 2.0))
     np.testing.assert_array_equal(out, [[3.0, 3.0], [2.5, 2.5], [2.0, 2.0]])
+
+
+def test_diffusion_coefficient_from_rows():
+    """average_MC_out.get_slope equivalent: D = slope / 6 of the summed MSD per reset interval."""
+    import numpy as np
+    from cmdlmc_b200.output import diffusion_coefficient
+    rng = np.random.RandomState(1)
+    rows = []
+    for frame in range(10, 3001, 10):
+        t = frame * 0.5
+        t_in = (frame % 1000) * 0.5
+        msd = np.array([0.2, 0.3, 0.1]) * t_in + rng.normal(scale=1e-3, size=3)
+        rows.append([frame, t, *msd, 40])
+    r = diffusion_coefficient(rows, reset_frequency=1000)
+    assert r["intervals"] == 4 or r["intervals"] == 3
+    assert abs(r["slope"] - 0.6) < 5e-3 and abs(r["diffusion_coefficient"] - 0.1) < 1e-3
