@@ -303,3 +303,40 @@ def test_occupancy_histogram_matches_event_log(orc, rng_mode):
             occ[s], occ[d] = False, True
         want[occ] += nfr - prev
     np.testing.assert_array_equal(counts, want)
+
+
+def test_replay_many_replicas_equals_single_replica_runs():
+    """More replay replicas than SMs (several warps per CTA, exact scratch in global memory) must
+    give, replica by replica, what a one-replica run (scratch in shared memory) gives."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.kmc import DeviceKMC, RNG_REPLAY
+    from cmdlmc_b200.topology import DeviceTopology, MODE_VERLET, build_with_retry
+    w = synth.workload("C1")
+    nfr, R = 120, 320
+    frames = synth.trajectory(w, nfr)
+    box = make_box(w.cell)
+    topo = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer,
+                                                       MODE_VERLET, cm.Fermi(*w.rate_params), cap), frames)
+    lat0 = np.stack([synth.initial_lattice(w.n_oxygen, w.n_protons, 500 + (r % 7))[0] for r in range(R)])
+    u = np.stack([np.random.RandomState(900 + (r % 5)).random_sample(4000) for r in range(R)])
+    big = DeviceKMC(box, lat0, w.time_step, RNG_REPLAY)
+    big.set_replay_stream(u)
+    big.set_event_log(2000)
+    big.advance(topo)
+    st = big.state()
+    assert (st["n_events"] > 10).all()
+    for r in (0, 1, 150, 319):
+        one = DeviceKMC(box, lat0[r:r + 1], w.time_step, RNG_REPLAY)
+        one.set_replay_stream(u[r:r + 1])
+        one.set_event_log(2000)
+        one.advance(topo)
+        s1 = one.state()
+        np.testing.assert_array_equal(s1["lattices"][0], st["lattices"][r])
+        assert s1["time"][0] == st["time"][r] and s1["n_events"][0] == st["n_events"][r]
+        e1, eb = one.events(0), big.events(r)
+        for key in ("frame", "start", "dest", "proton", "time"):
+            np.testing.assert_array_equal(e1[key], eb[key])
+    # replicas with the same lattice and stream are identical
+    same = [r for r in range(R) if r % 35 == 3]
+    for r in same[1:]:
+        np.testing.assert_array_equal(st["lattices"][r], st["lattices"][same[0]])
