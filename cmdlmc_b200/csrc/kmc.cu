@@ -39,6 +39,7 @@ struct KmcState {  // one per replica, global memory, persistent across cmd_kmc_
     long long log_pos;  // events logged since the last cmd_kmc_set_event_log
     int phase, reason;  // reason: 1 replay stream exhausted, 2 no allowed transition
     double u_sel;       // Philox mode: selection uniform drawn together with the time selector
+    long long ev_resolved;  // logged events whose jump distance has been filled in (k_resolve_ev_dist)
 };
 
 // HydroniumTopology colvars inside the KMC (topology.py:213-232,260-353): the distance of a
@@ -89,6 +90,8 @@ struct cmd_kmc {
     // exact-replay scratch (per replica): the compacted allowed list of the last consumed frame
     void *d_exact;
     size_t exact_bytes;
+    int solo_enabled;    // CMDLMC_B200_KMC_SOLO=0 keeps few-replica runs on the warp-per-replica kernel
+    double sel_margin;   // CMDLMC_B200_KMC_SELECT_MARGIN scales the solo kernel's selection margin
 };
 
 struct KmcArgs {
@@ -116,6 +119,7 @@ struct KmcArgs {
     int fast, ro_pitch, nst_max;
     const int *rowoff;
     // exact-replay scratch, one slice per replica (see kmc_consume_exact)
+    double sel_margin;   // solo kernel: relative safety margin of the parallel selection
     int exact, x_smem;   // x_smem: the scratch of the replica lives in shared memory
     int64_t x_cap, x_leaves;
     double *x_comp, *x_cum, *x_lsum;
@@ -184,7 +188,64 @@ struct WarpCtx {
     int nst;
     double *tlast;       // hydronium: [n_sites] last jump time per proton label - 1 (shared memory)
     double t_frame;      // hydronium: frame.time of the frame being consumed
+    // solo kernel (one CTA per replica): the state machine runs on the first warp, the other warps
+    // join it for the per-frame and per-event array work; `leader` is the one thread with side
+    // effects (lane 0 of the replica's warp in every kernel)
+    bool solo, leader;
+    int tid, nthr;
+    unsigned *kbits;     // [mask_words] allowed bits of the last consumed frame in list order
+    int *wpre;           // [mask_words] exclusive popc prefix of kbits
+    int *si;             // [64] ints: results / warp totals
+    double *sd;          // [64] doubles: results / warp totals
+    unsigned *cpair;     // [x_cap] (start << 16) | dest of the compacted transitions
+    unsigned *praw;      // [x_cap] the same for every pair of the frame, list order (staging)
+    double *lsum2;       // second value buffer of the tree combine
+    int *loff2, *ln2;    // second node buffer of the tree walk
+    unsigned *tflags;    // [SOLO_LEVELS][tlw] "node was split" bits per tree level
+    int *tcnt;           // [SOLO_LEVELS + 1] nodes per level, [SOLO_LEVELS + 1] = number of levels
+    int tlw;
+    // replay stream look-ahead: (uc0, uc1) = stream[uc_pos, uc_pos + 1], (un0, un1) the next pair
+    double uc0, uc1, un0, un1;
+    long long uc_pos;
+    int scan_par;        // solo scans alternate between two sets of warp-total slots
+    int p_next;          // pair count of the next frame, requested a frame ahead (-1: none)
+#ifdef SOLO_PROFILE
+    long long prof[16], prof_t;
+#endif
 };
+
+#define SOLO_LEVELS 20
+
+// -DSOLO_PROFILE: cycle counters of the first thread per phase, added to ties[2 + i] (tools only)
+#ifdef SOLO_PROFILE
+#define SOLO_T(i) do { const long long t_ = clock64(); if (c.tid == 0) c.prof[i] += t_ - c.prof_t; c.prof_t = t_; } while (0)
+#else
+#define SOLO_T(i) do { } while (0)
+#endif
+
+__host__ __device__ inline size_t solo_scratch_bytes(int64_t cap, int64_t leaves)
+{
+    const size_t lw = (size_t)(leaves + 31) / 32;
+    size_t b = (size_t)cap * 24 + (size_t)leaves * 32 + (size_t)SOLO_LEVELS * lw * 4 + (SOLO_LEVELS + 4) * 4;
+    return (b + 15) / 16 * 16;
+}
+
+// replay stream values of the event at `cursor`; the following event's pair is requested at the
+// same time, so that its latency hides behind this event's work
+__device__ __forceinline__ void replay_fetch(const KmcArgs &a, WarpCtx &c, int r, long long cursor)
+{
+    if (c.uc_pos == cursor) return;
+    const double *u = a.u + (int64_t)r * a.n_u;
+    if (c.uc_pos + 2 == cursor) { c.uc0 = c.un0; c.uc1 = c.un1; }
+    else {
+        c.uc0 = cursor < a.n_u ? u[cursor] : 0.0;
+        c.uc1 = cursor + 1 < a.n_u ? u[cursor + 1] : 0.0;
+    }
+    c.uc_pos = cursor;
+    c.un0 = cursor + 2 < a.n_u ? u[cursor + 2] : 0.0;
+    c.un1 = cursor + 3 < a.n_u ? u[cursor + 3] : 0.0;
+}
+
 
 __device__ __forceinline__ bool occupied(const WarpCtx &c, int s) { return (c.occ[s >> 5] >> (s & 31)) & 1u; }
 
@@ -252,6 +313,61 @@ __device__ double kmc_consume(const KmcArgs &a, WarpCtx &c, int64_t f)
     return warp_sum(s);
 }
 
+// leaves of NumPy's pairwise recursion over m elements, left to right: (offset, length <= 128)
+__device__ int np_sum_leaves(int m, int *loff, int *ln)
+{
+    int nleaf = 0;
+    int so[40], sn[40], sp = 1;
+    so[0] = 0; sn[0] = m;
+    while (sp) {
+        --sp;
+        int off = so[sp], n = sn[sp];
+        if (n <= 128) { loff[nleaf] = off; ln[nleaf] = n; nleaf++; }
+        else {
+            int n2 = n / 2;
+            n2 -= n2 % 8;
+            so[sp] = off + n2; sn[sp] = n - n2; sp++;   // right half below, left half on top
+            so[sp] = off; sn[sp] = n2; sp++;
+        }
+    }
+    return nleaf;
+}
+
+// the leaf sums combined along the same recursion tree: pairwise(left) + pairwise(right)
+__device__ double np_sum_combine(int m, const double *lsum)
+{
+    double ret = 0.0;
+    double val[40];
+    int sn[40], sp = 1, li = 0;
+    signed char ph[40];
+    bool have = false;
+    sn[0] = m; ph[0] = 0;
+    while (sp > 0) {
+        const int t = sp - 1;
+        if (have) {
+            if (ph[t] == 1) {  // left value arrived: descend into the right half
+                val[t] = ret; ph[t] = 2; have = false;
+                int n = sn[t], n2 = n / 2;
+                n2 -= n2 % 8;
+                sn[sp] = n - n2; ph[sp] = 0; sp++;
+            } else {
+                ret = __dadd_rn(val[t], ret);
+                sp--;
+            }
+        } else {
+            int n = sn[t];
+            if (n <= 128) { ret = lsum[li++]; have = true; sp--; }
+            else {
+                ph[t] = 1;
+                int n2 = n / 2;
+                n2 -= n2 % 8;
+                sn[sp] = n2; ph[sp] = 0; sp++;
+            }
+        }
+    }
+    return ret;
+}
+
 // ---- exact-replay arithmetic ------------------------------------------------------------------
 // The reference's time stepping feeds rounding noise back into kmc_time with gain S_0/S_t per
 // event (quirk Q1: the partial-frame interval always uses the total rate of frame 0), so a replay
@@ -270,21 +386,7 @@ __device__ double np_sum_warp(WarpCtx &c, int m)
     }
     // 1. leaves of the recursion, left to right (lane 0)
     int nleaf = 0;
-    if (c.lane == 0) {
-        int so[40], sn[40], sp = 1;
-        so[0] = 0; sn[0] = m;
-        while (sp) {
-            --sp;
-            int off = so[sp], n = sn[sp];
-            if (n <= 128) { c.loff[nleaf] = off; c.ln[nleaf] = n; nleaf++; }
-            else {
-                int n2 = n / 2;
-                n2 -= n2 % 8;
-                so[sp] = off + n2; sn[sp] = n - n2; sp++;   // right half below, left half on top
-                so[sp] = off; sn[sp] = n2; sp++;
-            }
-        }
-    }
+    if (c.lane == 0) nleaf = np_sum_leaves(m, c.loff, c.ln);
     nleaf = __shfl_sync(0xffffffffu, nleaf, 0);
     __syncwarp();
     // 2. leaf sums: 8 lanes = the 8 accumulators of one leaf, 4 leaves per pass
@@ -312,36 +414,7 @@ __device__ double np_sum_warp(WarpCtx &c, int m)
     __syncwarp();
     // 3. combine the leaves along the recursion tree (lane 0)
     double ret = 0.0;
-    if (c.lane == 0) {
-        double val[40];
-        int sn[40], sp = 1, li = 0;
-        signed char ph[40];
-        bool have = false;
-        sn[0] = m; ph[0] = 0;
-        while (sp > 0) {
-            const int t = sp - 1;
-            if (have) {
-                if (ph[t] == 1) {  // left value arrived: descend into the right half
-                    val[t] = ret; ph[t] = 2; have = false;
-                    int n = sn[t], n2 = n / 2;
-                    n2 -= n2 % 8;
-                    sn[sp] = n - n2; ph[sp] = 0; sp++;
-                } else {
-                    ret = __dadd_rn(val[t], ret);
-                    sp--;
-                }
-            } else {
-                int n = sn[t];
-                if (n <= 128) { ret = c.lsum[li++]; have = true; sp--; }
-                else {
-                    ph[t] = 1;
-                    int n2 = n / 2;
-                    n2 -= n2 % 8;
-                    sn[sp] = n2; ph[sp] = 0; sp++;
-                }
-            }
-        }
-    }
+    if (c.lane == 0) ret = np_sum_combine(m, c.lsum);
     return __shfl_sync(0xffffffffu, ret, 0);
 }
 
@@ -691,6 +764,416 @@ __device__ bool kmc_move_fast(const KmcArgs &a, WarpCtx &c, double u, int r, lon
     return kmc_move(a, c, u, o_start, o_dest, o_proton, o_index, ties);
 }
 
+
+// ---- solo mode: ONE CTA PER REPLICA (exact arithmetic, few replicas: `mdmc`, verification runs) ---
+// A single replica is sequential in time, so the only parallelism is inside a frame.  The first
+// warp runs the scalar state machine (kmc_after_consume / kmc_run_until_frame_needed, as in the
+// warp-per-replica kernels); all warps share the array work of a frame (solo_consume) and of an
+// event (solo_move), the helper warps waiting in solo_helpers for the first warp's requests.
+//   consume  allowed bits in list order -> popc prefix -> compaction (the arrays jumprate_generator
+//            yields, MDMC.py:229-238) -> np.sum's pairwise tree with one 8-lane group per leaf
+//   move     np.cumsum is strictly sequential in the reference, but move_proton (MDMC.py:101-119)
+//            only uses the INDEX searchsorted returns.  The index is decided on a parallel prefix
+//            sum whenever the draw is further than the worst-case rounding distance between any
+//            two summation orders from the interval's ends (margin = sel_margin * m * S, with
+//            sel_margin = 2^-50 against a bound of 2 m 2^-53 S per order); otherwise -- once in
+//            ~1e8 events -- the leader repeats the reference's sequential sum (counted in
+//            cmd_kmc_selection_fallbacks).  The decision is the reference's either way.
+
+// exclusive CTA-wide scans (one barrier; the warp-total slots alternate between two sets); every
+// thread obtains the same total
+__device__ __forceinline__ int solo_scan_int(WarpCtx &c, int v, int *total)
+{
+    const int wid = c.tid >> 5, nw = c.nthr >> 5;
+    int *slot = c.si + 16 + 16 * (c.scan_par & 1);
+    c.scan_par++;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (c.lane >= o) inc += t;
+    }
+    if (c.lane == 31) slot[wid] = inc;
+    __syncthreads();
+    const int x = c.lane < nw ? slot[c.lane] : 0;
+    int winc = x;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (c.lane >= o) winc += t;
+    }
+    *total = __shfl_sync(0xffffffffu, winc, 15);
+    return __shfl_sync(0xffffffffu, winc - x, wid) + inc - v;
+}
+
+__device__ __forceinline__ double solo_scan_double(WarpCtx &c, double v, double *total)
+{
+    const int wid = c.tid >> 5, nw = c.nthr >> 5;
+    double *slot = c.sd + 16 + 16 * (c.scan_par & 1);
+    c.scan_par++;
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (c.lane >= o) inc += t;
+    }
+    double excl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (c.lane == 0) excl = 0.0;
+    if (c.lane == 31) slot[wid] = inc;
+    __syncthreads();
+    const double x = c.lane < nw ? slot[c.lane] : 0.0;
+    double winc = x;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (c.lane >= o) winc += t;
+    }
+    *total = __shfl_sync(0xffffffffu, winc, 15);
+    return __shfl_sync(0xffffffffu, winc - x, wid) + excl;
+}
+
+// np.sum's recursion tree over m elements, built breadth first by ONE WARP: a node (offset, n)
+// with n > 128 splits into (offset, n2) and (offset + n2, n - n2), n2 = n / 2 rounded down to a
+// multiple of 8 (NumPy's pairwise_sum).  Level l keeps its "was split" bits in tflags[l] and its
+// node count in tcnt[l]; the leaves end up, left to right, in (loff, ln).  Returns their number.
+__device__ int np_tree_build_warp(WarpCtx &c, int m)
+{
+    const unsigned lt = (1u << c.lane) - 1u;
+    int *off_a = c.loff, *n_a = c.ln, *off_b = c.loff2, *n_b = c.ln2;
+    if (c.lane == 0) { off_a[0] = 0; n_a[0] = m; }
+    __syncwarp();
+    int count = 1, level = 0;
+    for (;; level++) {
+        int carry = 0;
+        for (int i0 = 0; i0 < count; i0 += 32) {
+            const int i = i0 + c.lane;
+            const bool valid = i < count;
+            const int off = valid ? off_a[i] : 0, n = valid ? n_a[i] : 0;
+            const bool split = n > 128 && level < SOLO_LEVELS;
+            const unsigned bits = __ballot_sync(0xffffffffu, split);
+            if (c.lane == 0) c.tflags[level * c.tlw + (i0 >> 5)] = bits;
+            const int pos = i + carry + __popc(bits & lt);
+            if (valid) {
+                if (split) {
+                    const int n2 = (n >> 1) & ~7;
+                    off_b[pos] = off; n_b[pos] = n2;
+                    off_b[pos + 1] = off + n2; n_b[pos + 1] = n - n2;
+                } else {
+                    off_b[pos] = off; n_b[pos] = n;
+                }
+            }
+            carry += __popc(bits);
+        }
+        if (c.lane == 0) c.tcnt[level] = count;
+        __syncwarp();
+        if (carry == 0) break;   // (off_a, n_a) holds the leaves
+        count += carry;
+        int *t = off_a; off_a = off_b; off_b = t;
+        t = n_a; n_a = n_b; n_b = t;
+    }
+    if (off_a != c.loff) {
+        for (int i = c.lane; i < count; i += 32) { c.loff[i] = off_a[i]; c.ln[i] = n_a[i]; }
+    }
+    if (c.lane == 0) c.tcnt[SOLO_LEVELS + 1] = level;   // tcnt[level] == count == number of leaves
+    __syncwarp();
+    return count;
+}
+
+// the leaf sums (c.lsum) combined along that tree, deepest level first: pairwise(left) + pairwise(right)
+__device__ double np_tree_combine_warp(WarpCtx &c)
+{
+    const unsigned lt = (1u << c.lane) - 1u;
+    const int levels = c.tcnt[SOLO_LEVELS + 1];
+    double *va = c.lsum, *vb = c.lsum2;
+    for (int level = levels - 1; level >= 0; level--) {
+        const int count = c.tcnt[level];
+        int carry = 0;
+        for (int i0 = 0; i0 < count; i0 += 32) {
+            const int i = i0 + c.lane;
+            const unsigned bits = c.tflags[level * c.tlw + (i0 >> 5)];
+            const int pos = i + carry + __popc(bits & lt);
+            if (i < count) vb[i] = (bits >> c.lane) & 1u ? __dadd_rn(va[pos], va[pos + 1]) : va[pos];
+            carry += __popc(bits);
+        }
+        __syncwarp();
+        double *t = va; va = vb; vb = t;
+    }
+    return va[0];
+}
+
+__device__ double solo_consume(const KmcArgs &a, WarpCtx &c, int64_t f)
+{
+    SOLO_T(0);   // frame bookkeeping / observables
+    const int p = c.p_next >= 0 ? c.p_next : a.counts[f];
+    c.p_next = f + 1 < a.nframes ? a.counts[f + 1] : -1;   // in flight until the next frame needs it
+    const int64_t base = f * a.stride;
+    const int T = c.nthr, tid = c.tid;
+    c.base = base;
+    c.p = p;
+    const double *val = (a.hyd.on ? a.dist : a.omega) + base;
+    if (f + 1 < a.nframes) {
+        // the next frame's arrays on their way into L2 while this frame is worked on (its pair count
+        // is about this one's; a line too many or too few does not matter)
+        const int *ns = a.start + base + a.stride, *nd = a.dest + base + a.stride;
+        const double *nv = val + a.stride;
+        for (int o = tid * 32; o < p; o += T * 32) {
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(ns + o));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(nd + o));
+        }
+        for (int o = tid * 16; o < p; o += T * 16) asm volatile("prefetch.global.L2 [%0];" :: "l"(nv + o));
+    }
+    // 1. allowed bits in list order, eight independent pairs per thread and trip; rate and pair code
+    //    wait in shared memory (c.cum is idle between moves) for their compacted position
+    for (int k0 = 0; k0 < p; k0 += 8 * T) {
+        int st[8], de[8];
+        double om[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int k = k0 + u * T + tid;
+            st[u] = k < p ? __ldg(a.start + base + k) : 0;
+            de[u] = k < p ? __ldg(a.dest + base + k) : 0;
+            om[u] = k < p ? __ldg(val + k) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int k = k0 + u * T + tid;
+            if (k0 + u * T < p) {   // uniform over the CTA
+                const bool ok = k < p && occupied(c, st[u]) && !occupied(c, de[u]);
+                const unsigned bits = __ballot_sync(0xffffffffu, ok);
+                if (c.lane == 0 && k < p) c.kbits[k >> 5] = bits;
+                if (ok) {
+                    c.cum[k] = a.hyd.on ? hyd_rate(a.hyd, c, st[u], om[u]) : om[u];
+                    c.praw[k] = ((unsigned)st[u] << 16) | (unsigned)de[u];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    SOLO_T(1);   // pass A
+    // 2. compacted position of every allowed transition
+    const int nwords = (p + 31) >> 5;
+    int m = 0;
+    for (int w0 = 0; w0 < nwords; w0 += T) {
+        const int wi = w0 + tid;
+        const int v = wi < nwords ? __popc(c.kbits[wi]) : 0;
+        int tot;
+        const int ex = solo_scan_int(c, v, &tot);
+        if (wi < nwords) c.wpre[wi] = m + ex;
+        m += tot;
+    }
+    c.m = m;
+    __syncthreads();
+    SOLO_T(2);   // scan
+    // 3. the last warp lays out np.sum's tree while the others compact (rate, pair) in list order:
+    //    the arrays jumprate_generator yields (MDMC.py:229-238)
+    if (tid >= T - 32) {
+        if (m >= 8) {
+            const int nl = np_tree_build_warp(c, m);
+            if (c.lane == 0) c.si[1] = nl;
+        }
+    } else {
+        const unsigned lt = (1u << c.lane) - 1u;
+        for (int k = tid; k < p; k += T - 32) {
+            const unsigned bits = c.kbits[k >> 5];
+            if ((bits >> c.lane) & 1u) {
+                const int e = c.wpre[k >> 5] + __popc(bits & lt);
+                c.comp[e] = c.cum[k];
+                c.cpair[e] = c.praw[k];
+            }
+        }
+    }
+    __syncthreads();
+    SOLO_T(3);   // tree + compaction
+    if (m < 8) {  // np.sum of a short array: plain loop
+        double res = 0.;
+        for (int i = 0; i < m; i++) res = __dadd_rn(res, c.comp[i]);
+        return res;
+    }
+    // 4. one 8-lane group per leaf: the 8 accumulators of NumPy's unrolled loop
+    const int nleaf = c.si[1];
+    const int g = tid >> 3, j = tid & 7, ng = T >> 3;
+    const double *x = c.comp;
+    for (int l0 = 0; l0 < nleaf; l0 += ng) {
+        const int l = l0 + g;
+        const bool act = l < nleaf;
+        int off = 0, n = 0;
+        if (act) { off = c.loff[l]; n = c.ln[l]; }
+        double r = 0.0;
+        if (act) {
+            r = x[off + j];
+            for (int i = 8; i < n - (n % 8); i += 8) r = __dadd_rn(r, x[off + i + j]);
+        }
+        r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+        if (act && j == 0) {
+            for (int i = n - (n % 8); i < n; i++) r = __dadd_rn(r, x[off + i]);
+            c.lsum[l] = r;
+        }
+    }
+    __syncthreads();
+    SOLO_T(4);   // leaf sums
+    if (tid < 32) {
+        const double tot = np_tree_combine_warp(c);
+        if (tid == 0) c.sd[0] = tot;
+    }
+    __syncthreads();
+    SOLO_T(5);   // combine
+    return c.sd[0];
+}
+
+// list index k of the e-th allowed transition of the last consumed frame (kbits / wpre)
+__device__ int solo_list_index(const WarpCtx &c, int e)
+{
+    int lo = 0, hi = (c.p + 31) >> 5;   // last word with wpre <= e
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (c.wpre[mid] <= e) lo = mid; else hi = mid;
+    }
+    unsigned bits = c.kbits[lo];
+    for (int q = e - c.wpre[lo]; q > 0; q--) bits &= bits - 1;
+    return lo * 32 + __ffs(bits) - 1;
+}
+
+#define SOLO_PER 8   // compacted transitions per thread held in registers during a move
+
+__device__ bool solo_move(const KmcArgs &a, WarpCtx &c, double u, int64_t slot, int *o_start,
+                          int *o_dest, int *o_proton, int *o_index, unsigned long long *ties)
+{
+    const int m = c.m, T = c.nthr, tid = c.tid;
+    SOLO_T(6);   // scalar state machine up to the move
+    if (tid == 0) { c.si[2] = 0; c.si[3] = -1; c.si[4] = 0; }
+    // 1. filter_allowed_transitions with the current lattice (it differs after a same-frame event):
+    //    thread-contiguous runs of the compacted list, the re-masked rates stay in registers
+    const int per = (m + T - 1) / T;
+    const int lo = min(tid * per, m), hi = min(lo + per, m);
+    const bool in_regs = per <= SOLO_PER;
+    double x[SOLO_PER];
+    double loc = 0.0;
+    if (in_regs) {
+#pragma unroll
+        for (int i = 0; i < SOLO_PER; i++) {
+            const int e = lo + i;
+            x[i] = 0.0;
+            if (e < hi) {
+                const unsigned pr = c.cpair[e];
+                if (occupied(c, pr >> 16) && !occupied(c, pr & 0xffff)) x[i] = c.comp[e];
+            }
+            loc += x[i];
+        }
+    } else {
+        for (int e = lo; e < hi; e++) {
+            const unsigned pr = c.cpair[e];
+            loc += occupied(c, pr >> 16) && !occupied(c, pr & 0xffff) ? c.comp[e] : 0.0;
+        }
+    }
+    SOLO_T(12);  // move: re-mask
+    // 2. parallel prefix
+    double total;
+    const double pre = solo_scan_double(c, loc, &total);
+    SOLO_T(13);  // move: prefix scan
+    const double draw = total * u;
+    const double eps = a.sel_margin * (double)m * total;
+    // 3. searchsorted(side='left'): the first entry whose running sum reaches the draw
+    double run = pre;
+    if (in_regs) {
+#pragma unroll
+        for (int i = 0; i < SOLO_PER; i++) {
+            const double prev = run;
+            run += x[i];
+            if (prev < draw && draw <= run) {
+                atomicAdd(&c.si[2], 1);
+                c.si[3] = lo + i;
+                c.si[4] = (draw - prev > eps && run - draw > eps) ? 1 : 0;
+                if (run - draw < 1e-9 * total || draw - prev < 1e-9 * total) atomicAdd(ties, 1ull);
+            }
+        }
+    } else {
+        for (int e = lo; e < hi; e++) {
+            const double prev = run;
+            const unsigned pr = c.cpair[e];
+            run += occupied(c, pr >> 16) && !occupied(c, pr & 0xffff) ? c.comp[e] : 0.0;
+            if (prev < draw && draw <= run) {
+                atomicAdd(&c.si[2], 1);
+                c.si[3] = e;
+                c.si[4] = (draw - prev > eps && run - draw > eps) ? 1 : 0;
+                if (run - draw < 1e-9 * total || draw - prev < 1e-9 * total) atomicAdd(ties, 1ull);
+            }
+        }
+    }
+    __syncthreads();
+    SOLO_T(7);   // move: re-mask + scan + search
+    int found = c.si[3];
+    if (c.si[2] != 1 || !c.si[4]) {
+        // too close to an interval end for any summation order but the reference's own (or nothing is
+        // allowed, or the total is zero): the leader repeats move_proton literally -- filter, strictly
+        // sequential np.cumsum, draw = uniform(0, S), searchsorted(side='left')
+        __syncthreads();
+        if (tid == 0) {
+            double cum = 0.0;
+            int any = 0;
+            for (int e = 0; e < m; e++) {
+                const unsigned pr = c.cpair[e];
+                if (occupied(c, pr >> 16) && !occupied(c, pr & 0xffff)) { cum = __dadd_rn(cum, c.comp[e]); any = 1; }
+            }
+            int fnd = -1;
+            if (any) {
+                const double d = __dadd_rn(0.0, __dmul_rn(__dadd_rn(cum, -0.0), u));   // uniform(0, S)
+                double run2 = 0.0;
+                for (int e = 0; e < m && fnd < 0; e++) {
+                    const unsigned pr = c.cpair[e];
+                    if (occupied(c, pr >> 16) && !occupied(c, pr & 0xffff)) {
+                        run2 = __dadd_rn(run2, c.comp[e]);
+                        if (run2 >= d) fnd = e;
+                    }
+                }
+                atomicAdd(ties + 1, 1ull);
+            }
+            c.si[3] = fnd;
+        }
+        __syncthreads();
+        found = c.si[3];
+    }
+    if (found < 0) return false;  // nothing allowed: IndexError upstream
+    const unsigned pr = c.cpair[found];
+    const int st = pr >> 16, de = pr & 0xffff;
+    const int proton = c.lat[st];
+    __syncthreads();
+    if (tid == 0) {
+        c.lat[de] = proton;
+        c.lat[st] = 0;
+        c.occ[de >> 5] |= 1u << (de & 31);
+        c.occ[st >> 5] &= ~(1u << (st & 31));
+    }
+    if (tid == 32 && slot >= 0)   // a helper logs the pair's flat index (see kmc_event)
+        ((long long *)a.ev_dist)[slot] = c.base + solo_list_index(c, found);
+    __syncthreads();
+    SOLO_T(8);   // move: tail
+    *o_start = st; *o_dest = de; *o_proton = proton; *o_index = 0;
+    return true;
+}
+
+// first warp: wake the helper warps for one event, then take part in it
+__device__ bool solo_move_request(const KmcArgs &a, WarpCtx &c, double u, int64_t slot, int *o_start,
+                                  int *o_dest, int *o_proton, int *o_index, unsigned long long *ties)
+{
+    if (c.lane == 0) { c.si[8] = 1; c.sd[1] = u; ((long long *)c.sd)[2] = slot; }
+    __syncthreads();
+    return solo_move(a, c, u, slot, o_start, o_dest, o_proton, o_index, ties);
+}
+
+// helper warps: serve the first warp's events until it is done with the frame; true = replica halted
+__device__ bool solo_helpers(const KmcArgs &a, WarpCtx &c)
+{
+    for (;;) {
+        __syncthreads();
+        const int cmd = c.si[8];
+        if (cmd != 1) return cmd == 2;
+        int d0, d1, d2, d3;
+        solo_move(a, c, c.sd[1], ((long long *)c.sd)[2], &d0, &d1, &d2, &d3, a.ties);
+    }
+}
+
 // observables on a consumed frame (MDMC.py:198-208 + output.py); the lattice a frame is seen
 // with is the lattice at consumption == the pre-jump lattice at the flush (Q4)
 __device__ void kmc_observe(const KmcArgs &a, const BoxParams &bx, WarpCtx &c, int r, int64_t f,
@@ -750,28 +1233,110 @@ __device__ void kmc_observe(const KmcArgs &a, const BoxParams &bx, WarpCtx &c, i
     }
 }
 
+// kmc_observe for the solo kernel: the sites are shared by the whole CTA (one warp walking 400 sites
+// through global memory every frame would cost as much as the frame's KMC work).  The per-site
+// arithmetic is kmc_observe's; the MSD sums of a printed row are formed in a different (fixed) order.
+__device__ void solo_observe(const KmcArgs &a, const BoxParams &bx, WarpCtx &c, int r, int64_t f,
+                             KmcState &st)
+{
+    const int64_t gf = a.frames_base + f;
+    const double *pos = a.positions + f * (int64_t)a.n_sites * 3;
+    double *snap = a.snapshot + (int64_t)r * a.n_sites * 3;
+    double *disp = a.disp + (int64_t)r * a.n_sites * 3;
+    int *lat0 = a.lattice0 + (int64_t)r * a.n_sites;
+    if (f + 1 < a.nframes)   // next frame's positions towards L2
+        for (int o = c.tid * 16; o < 3 * a.n_sites; o += c.nthr * 16)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(pos + (int64_t)a.n_sites * 3 + o));
+    if (gf == 0) {  // MDMC.py:193-196: first frame initialises both observables
+        for (int s = c.tid; s < a.n_sites; s += c.nthr) {
+            const int l = c.lat[s];
+            lat0[s] = l;
+            if (l > 0)
+                for (int k = 0; k < 3; k++) { snap[3 * (l - 1) + k] = pos[3 * s + k]; disp[3 * (l - 1) + k] = 0.0; }
+        }
+        return;
+    }
+    const bool reset = a.reset_freq > 0 && (gf % a.reset_freq) == 0;
+    const bool printing = a.print_freq > 0 && (gf % a.print_freq) == 0;
+    double m[3] = {0, 0, 0};
+    int nprot = 0, same = 0;
+    for (int s = c.tid; s < a.n_sites; s += c.nthr) {
+        const int l = c.lat[s];
+        if (reset) lat0[s] = l;
+        if (l > 0) {
+            nprot++;
+            double pa[3], pb[3], d[3];
+            for (int k = 0; k < 3; k++) { pa[k] = snap[3 * (l - 1) + k]; pb[k] = pos[3 * s + k]; }
+            distance_exact(bx, pa, pb, d);  // output.py:41: atombox.distance(snapshot, new)
+            for (int k = 0; k < 3; k++) {
+                const double v = __dadd_rn(reset ? 0.0 : disp[3 * (l - 1) + k], d[k]);
+                disp[3 * (l - 1) + k] = v;
+                snap[3 * (l - 1) + k] = pb[k];
+                m[k] += v * v;
+            }
+            same += (lat0[s] == l);
+        }
+    }
+    if (!printing) return;
+    // block sums: lanes, then the warps in order (two of the scan's slot sets are free here)
+    for (int k = 0; k < 3; k++) m[k] = warp_sum(m[k]);
+    for (int o = 16; o > 0; o >>= 1) {
+        nprot += __shfl_xor_sync(0xffffffffu, nprot, o);
+        same += __shfl_xor_sync(0xffffffffu, same, o);
+    }
+    const int wid = c.tid >> 5, nw = c.nthr >> 5;
+    __syncthreads();
+    if (c.lane == 0) {
+        c.sd[16 + wid] = m[0]; c.sd[32 + wid] = m[1]; c.sd[48 + wid] = m[2];
+        c.si[16 + wid] = nprot; c.si[32 + wid] = same;
+    }
+    __syncthreads();
+    if (c.tid < 32) {
+        double t[3] = {0, 0, 0};
+        int np = 0, sm = 0;
+        for (int w = 0; w < nw; w++) {
+            t[0] += c.sd[16 + w]; t[1] += c.sd[32 + w]; t[2] += c.sd[48 + w];
+            np += c.si[16 + w]; sm += c.si[32 + w];
+        }
+        if (c.leader && st.n_rows < a.row_cap) {
+            double *row = a.rows + ((int64_t)r * a.row_cap + st.n_rows) * 6;
+            row[0] = (double)gf;
+            row[1] = nan("");
+            row[2] = t[0] / np; row[3] = t[1] / np; row[4] = t[2] / np;
+            row[5] = (double)sm;
+        }
+        if (st.n_rows < a.row_cap) st.n_rows++;
+    }
+    __syncthreads();
+}
+
 // event bookkeeping shared by both branches of fastforward_to_next_jump: stamp the cached
 // frames' rows with the event time (Q3), select + move, log.  Returns false if the replica halts.
 __device__ bool kmc_event(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
 {
-    if (c.lane == 0)
+    if (c.leader)
         for (long long q = st.pending_row; q < st.n_rows; q++)
             a.rows[((int64_t)r * a.row_cap + q) * 6 + 1] = st.kmc_time;
     st.pending_row = st.n_rows;
     double u;
     if (a.rng_mode == CMD_RNG_REPLAY) {
         if (st.cursor + 1 >= a.n_u) { st.reason = 1; return false; }
-        u = a.u[(int64_t)r * a.n_u + st.cursor + 1];
+        replay_fetch(a, c, r, st.cursor);
+        u = c.uc1;
     } else {
         u = st.u_sel;   // drawn with the time selector of this event (same Philox counter)
     }
     int es, ed, ep, ek;
-    const bool moved = a.exact ? kmc_move_exact(a, c, u, &es, &ed, &ep, &ek, a.ties)
+    // the jump distance is logged as the flat index of the pair; k_resolve_ev_dist turns it into the
+    // distance after the kernel (a dependent global load here would stall the replica)
+    const int64_t slot = st.log_pos < a.ev_cap ? (int64_t)r * a.ev_cap + st.log_pos : -1;
+    const bool moved = c.solo ? solo_move_request(a, c, u, slot, &es, &ed, &ep, &ek, a.ties)
+                       : a.exact ? kmc_move_exact(a, c, u, &es, &ed, &ep, &ek, a.ties)
                        : a.fast ? kmc_move_fast(a, c, u, r, st.n_events, &es, &ed, &ep, &ek, a.ties)
                                 : kmc_move(a, c, u, &es, &ed, &ep, &ek, a.ties);
     if (!moved) { st.reason = 2; return false; }
-    if (a.hyd.on && c.lane == 0) c.tlast[ep - 1] = st.kmc_time;   // update_time_of_last_jump (MDMC.py:99)
-    if (a.occ_count && c.lane == 0) {
+    if (a.hyd.on && c.leader) c.tlast[ep - 1] = st.kmc_time;   // update_time_of_last_jump (MDMC.py:99)
+    if (a.occ_count && c.leader) {
         // occupancy histogram: the frames consumed so far saw `es` occupied since occ_since[es]; the
         // following ones see `ed` occupied
         const int64_t o = (int64_t)r * a.n_sites;
@@ -779,12 +1344,12 @@ __device__ bool kmc_event(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
         a.occ_since[o + ed] = (int)st.frames_seen;
     }
     __syncwarp();
-    if (c.lane == 0 && st.log_pos < a.ev_cap) {
+    if (c.leader && st.log_pos < a.ev_cap) {
         int64_t q = (int64_t)r * a.ev_cap + st.log_pos;
         a.ev_frame[q] = st.sweep;
         a.ev_time[q] = st.kmc_time;
         a.ev_start[q] = es; a.ev_dest[q] = ed; a.ev_proton[q] = ep;
-        a.ev_dist[q] = __ldg(a.dist + c.base + ek);
+        if (!c.solo) ((long long *)a.ev_dist)[q] = c.base + ek;   // solo: a helper warp wrote it
     }
     st.n_events++;
     if (st.log_pos < a.ev_cap) st.log_pos++;
@@ -800,7 +1365,8 @@ __device__ void kmc_run_until_frame_needed(const KmcArgs &a, WarpCtx &c, int r, 
         if (a.rng_mode == CMD_RNG_REPLAY) {
             if (st.cursor + 1 >= a.n_u) { st.phase = KMC_PHASE_HALT; st.reason = 1; return; }
             // the stream carries -np.log(1 - np.random.random()) as the host evaluated it
-            st.time_selector = a.u[(int64_t)r * a.n_u + st.cursor];   // MDMC.py:148
+            replay_fetch(a, c, r, st.cursor);
+            st.time_selector = c.uc0;                                 // MDMC.py:148
         } else {
             uint32_t ctr[4] = {(uint32_t)st.n_events, (uint32_t)((uint64_t)st.n_events >> 32),
                                (uint32_t)(a.replica_first + r * a.replica_step), 0u};
@@ -810,24 +1376,18 @@ __device__ void kmc_run_until_frame_needed(const KmcArgs &a, WarpCtx &c, int r, 
         }
         double t_trial = st.time_selector / st.current_rate;  // Q1: the rate of frame 0, forever
         double x = st.kmc_time + t_trial;
-        bool same_frame;
-        double rem_t = 0.0;
-        if (a.fast) {   // kmc_time >= 0, dt > 0: exact floor / remainder without fmod
-            double rem_x;
-            same_frame = floor_div_pos(x, a.dt, &rem_x) == floor_div_pos(st.kmc_time, a.dt, &rem_t);
-        } else {
-            if (c.lane == 0) {  // tie audit of the floor-division decision
-                double rm = py_mod(x, a.dt);
-                if (rm < 1e-9 * a.dt || a.dt - rm < 1e-9 * a.dt) atomicAdd(a.ties, 1ull);
-            }
-            same_frame = py_floordiv(x, a.dt) == py_floordiv(st.kmc_time, a.dt);
-        }
+        // kmc_time >= 0, dt > 0: Python's // and % (MDMC.py:152,156) are the exact floor and the exact
+        // remainder; floor_div_pos returns the same values without fmod's division loop
+        double rem_x, rem_t;
+        const bool same_frame = floor_div_pos(x, a.dt, &rem_x) == floor_div_pos(st.kmc_time, a.dt, &rem_t);
+        if (!a.fast && c.leader && (rem_x < 1e-9 * a.dt || a.dt - rem_x < 1e-9 * a.dt))
+            atomicAdd(a.ties, 1ull);   // tie audit of the floor-division decision
         if (same_frame) {
             st.kmc_time = x;
             st.delta_frame = 0;
             if (!kmc_event(a, c, r, st)) { st.phase = KMC_PHASE_HALT; return; }
         } else {
-            st.delta_t = a.dt - (a.fast ? rem_t : py_mod(st.kmc_time, a.dt));
+            st.delta_t = a.dt - rem_t;
             st.delta_frame = 1;
             st.current_probsum = st.current_rate * st.delta_t;
             st.phase = KMC_PHASE_SCAN;
@@ -839,14 +1399,13 @@ __device__ void kmc_run_until_frame_needed(const KmcArgs &a, WarpCtx &c, int r, 
 // the reference's per-frame step once the frame's total allowed rate is known (MDMC.py:146-171)
 __device__ void kmc_after_consume(const KmcArgs &a, WarpCtx &c, int r, KmcState &st, double rate)
 {
-    const int lane = c.lane;
     if (st.phase == KMC_PHASE_START) {  // MDMC.py:146
         st.current_rate = rate;
         kmc_run_until_frame_needed(a, c, r, st);
     } else {  // KMC_PHASE_SCAN, MDMC.py:158-165
         // explicit roundings: no FMA contraction anywhere in the decision arithmetic
         double next_probsum = __dadd_rn(st.current_probsum, __dmul_rn(rate, a.dt));
-        if (lane == 0 && fabs(next_probsum - st.time_selector) < 1e-9 * st.time_selector)
+        if (c.leader && fabs(next_probsum - st.time_selector) < 1e-9 * st.time_selector)
             atomicAdd(a.ties, 1ull);
         if (next_probsum < st.time_selector) {
             st.delta_frame += 1;
@@ -875,6 +1434,9 @@ __global__ void __launch_bounds__(512, 1) k_kmc_advance(const __grid_constant__ 
     const size_t per_warp = base_bytes + (a.hyd.on ? (size_t)a.n_sites * 8 : 0);
     WarpCtx c;
     c.lane = lane;
+    c.solo = false; c.leader = lane == 0; c.tid = lane; c.nthr = 32;
+    c.kbits = nullptr; c.wpre = nullptr; c.si = nullptr; c.sd = nullptr;
+    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.p_next = -1;
     c.lat = (int *)(smem_raw + per_warp * w);
     c.occ = (unsigned *)(c.lat + a.n_sites);
     c.mask0 = c.occ + a.occ_words;
@@ -943,6 +1505,106 @@ __global__ void __launch_bounds__(512, 1) k_kmc_advance(const __grid_constant__ 
 }
 
 
+#define SOLO_THREADS 512
+
+// one CTA per replica, exact arithmetic (see "solo mode" above)
+__global__ void __launch_bounds__(SOLO_THREADS, 1) k_kmc_solo(const __grid_constant__ BoxParams bx,
+                                                              const __grid_constant__ KmcArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int r = blockIdx.x;
+    // lat | occ | mask0 | (tlast) | kbits | wpre | si | sd | exact scratch
+    const size_t base_bytes = ((size_t)a.n_sites * 4 + (size_t)a.occ_words * 4 + (size_t)a.mask_words * 4 + 7) / 8 * 8;
+    const size_t state_bytes = base_bytes + (a.hyd.on ? (size_t)a.n_sites * 8 : 0);
+    WarpCtx c;
+    c.lane = lane;
+    c.solo = true; c.leader = tid == 0; c.tid = tid; c.nthr = blockDim.x;
+    c.lat = (int *)smem_raw;
+    c.occ = (unsigned *)(c.lat + a.n_sites);
+    c.mask0 = c.occ + a.occ_words;
+    c.tlast = (double *)(smem_raw + base_bytes);
+    c.kbits = (unsigned *)(smem_raw + state_bytes);
+    c.wpre = (int *)(c.kbits + a.mask_words);
+    c.si = c.wpre + a.mask_words;   // 2 * mask_words ints behind an 8-byte boundary: still aligned
+    c.sd = (double *)(c.si + 64);
+    c.t_frame = 0.0;
+    c.base = 0; c.p = 0; c.m = 0;
+    c.psum = nullptr; c.ro = nullptr; c.lane_total = 0.0; c.nst = 0;
+    {   // comp | cum (raw rates) | lsum | lsum2 | cpair | praw | loff | ln | loff2 | ln2 | tflags | tcnt
+        unsigned char *x = a.x_smem ? (unsigned char *)(c.sd + 64)
+                                    : (unsigned char *)a.x_comp + (size_t)r * solo_scratch_bytes(a.x_cap, a.x_leaves);
+        c.comp = (double *)x;
+        c.cum = c.comp + a.x_cap;
+        c.lsum = c.cum + a.x_cap;
+        c.lsum2 = c.lsum + a.x_leaves;
+        c.cpair = (unsigned *)(c.lsum2 + a.x_leaves);
+        c.praw = c.cpair + a.x_cap;
+        c.loff = (int *)(c.praw + a.x_cap);
+        c.ln = c.loff + a.x_leaves;
+        c.loff2 = c.ln + a.x_leaves;
+        c.ln2 = c.loff2 + a.x_leaves;
+        c.tlw = (int)((a.x_leaves + 31) / 32);
+        c.tflags = (unsigned *)(c.ln2 + a.x_leaves);
+        c.tcnt = (int *)(c.tflags + (size_t)SOLO_LEVELS * c.tlw);
+        c.cidx = nullptr;
+    }
+    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.p_next = -1;
+#ifdef SOLO_PROFILE
+    for (int i = 0; i < 16; i++) c.prof[i] = 0;
+    c.prof_t = clock64();
+    const long long prof_c0 = c.prof_t;
+    long long prof_n0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_n0));
+#endif
+    KmcState st = a.state[r];
+    for (int s = tid; s < a.n_sites; s += blockDim.x) c.lat[s] = a.lattice[(int64_t)r * a.n_sites + s];
+    if (a.hyd.on)
+        for (int s = tid; s < a.n_sites; s += blockDim.x) c.tlast[s] = a.tlast[(int64_t)r * a.n_sites + s];
+    __syncthreads();
+    for (int q = tid; q < a.occ_words; q += blockDim.x) {
+        unsigned bits = 0;
+        for (int b = 0; b < 32; b++) {
+            const int s = q * 32 + b;
+            if (s < a.n_sites && c.lat[s] > 0) bits |= 1u << b;
+        }
+        c.occ[q] = bits;
+    }
+    __syncthreads();
+    const bool first_warp = tid < 32;
+    bool halt = st.phase == KMC_PHASE_HALT;   // the same for every thread: read from a.state[r]
+    for (int64_t f = 0; f < a.nframes && !halt; f++) {
+        if (a.positions) solo_observe(a, bx, c, r, f, st);
+        c.t_frame = __dmul_rn((double)(a.frames_base + f), a.hyd.frame_dt);   // frame.time
+        const double rate = solo_consume(a, c, f);
+        if (first_warp) {
+            st.site_updates += c.p;
+            st.frames_seen++;
+            kmc_after_consume(a, c, r, st, rate);   // events call the helpers in (solo_move_request)
+            SOLO_T(9);   // scalar state machine after the last move of the frame
+            halt = st.phase == KMC_PHASE_HALT;
+            if (lane == 0) c.si[8] = halt ? 2 : 0;
+            __syncthreads();
+        } else {
+            halt = solo_helpers(a, c);
+        }
+    }
+    __syncthreads();
+    for (int s = tid; s < a.n_sites; s += blockDim.x) a.lattice[(int64_t)r * a.n_sites + s] = c.lat[s];
+    if (a.hyd.on)
+        for (int s = tid; s < a.n_sites; s += blockDim.x) a.tlast[(int64_t)r * a.n_sites + s] = c.tlast[s];
+    if (tid == 0) a.state[r] = st;
+#ifdef SOLO_PROFILE
+    if (tid == 0 && r == 0) {
+        long long prof_n1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_n1));
+        c.prof[10] = clock64() - prof_c0;
+        c.prof[11] = prof_n1 - prof_n0;
+        for (int i = 0; i < 16; i++) atomicAdd(a.ties + 2 + i, (unsigned long long)c.prof[i]);
+    }
+#endif
+}
+
 #define KMC_STAGE 1024   // pairs per ring stage: 8 KB omega + 4 KB start + 4 KB dest
 #define KMC_NSTG 8       // ring depth: a replica busy with events may lag seven stages (~ a frame)
 
@@ -1007,6 +1669,9 @@ __global__ void __launch_bounds__(544, 1) k_kmc_stream(const __grid_constant__ B
                              (size_t)a.occ_words * 4 + 15) / 16 * 16;
     WarpCtx c;
     c.lane = lane;
+    c.solo = false; c.leader = lane == 0; c.tid = lane; c.nthr = 32;
+    c.kbits = nullptr; c.wpre = nullptr; c.si = nullptr; c.sd = nullptr;
+    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.p_next = -1;
     c.psum = (double *)(q + per_warp * w);
     c.mask0 = (unsigned *)(c.psum + (size_t)a.nst_max * 32);
     c.lat = (int *)((unsigned char *)c.mask0 + mask_bytes);
@@ -1103,6 +1768,13 @@ extern "C" int cmd_kmc_create(const cmd_box *box, int n_sites, int n_replicas, c
     k->seed = seed;
     k->replica_first = 0;
     k->replica_step = 1;
+    {   // test / A-B knobs of the solo kernel
+        const char *e = getenv("CMDLMC_B200_KMC_SOLO");
+        k->solo_enabled = !(e && e[0] == '0');
+        e = getenv("CMDLMC_B200_KMC_SELECT_MARGIN");
+        const double scale = e ? atof(e) : 1.0;
+        k->sel_margin = ldexp(1.0, -50) * (scale > 0.0 ? scale : 1.0);
+    }
     cudaStream_t st = cmd_global().stream;
     size_t nl = (size_t)n_replicas * n_sites;
     int rc = CMD_OK;
@@ -1110,7 +1782,7 @@ extern "C" int cmd_kmc_create(const cmd_box *box, int n_sites, int n_replicas, c
         if (cudaMalloc((void **)&k->d_lattice, nl * 4) != cudaSuccess ||
             cudaMalloc((void **)&k->d_lattice0, nl * 4) != cudaSuccess ||
             cudaMalloc((void **)&k->d_state, (size_t)n_replicas * sizeof(KmcState)) != cudaSuccess ||
-            cudaMalloc((void **)&k->d_ties, 8) != cudaSuccess) {
+            cudaMalloc((void **)&k->d_ties, 256) != cudaSuccess) {
             cudaGetLastError();
             rc = cmd_set_error(CMD_ENOMEM, "cudaMalloc failed for the KMC state");
             break;
@@ -1118,7 +1790,7 @@ extern "C" int cmd_kmc_create(const cmd_box *box, int n_sites, int n_replicas, c
         cudaMemcpyAsync(k->d_lattice, lattices, nl * 4, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(k->d_lattice0, lattices, nl * 4, cudaMemcpyHostToDevice, st);
         cudaMemsetAsync(k->d_state, 0, (size_t)n_replicas * sizeof(KmcState), st);
-        cudaMemsetAsync(k->d_ties, 0, 8, st);
+        cudaMemsetAsync(k->d_ties, 0, 256, st);
         if (cudaStreamSynchronize(st) != cudaSuccess) {
             rc = cmd_set_error(CMD_ECUDA, "KMC state upload failed: %s",
                                cudaGetErrorString(cudaGetLastError()));
@@ -1135,8 +1807,34 @@ __global__ void k_kmc_reset_cursor(KmcState *st, int n, int what)
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n) {
         if (what == 0) st[r].cursor = 0;
-        else st[r].log_pos = 0;
+        else { st[r].log_pos = 0; st[r].ev_resolved = 0; }
     }
+}
+
+__global__ void k_max_count(const int *__restrict__ counts, int64_t n, int *__restrict__ out)
+{
+    int m = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, counts[i]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+// jump distances of the events logged since the last call: flat pair index -> distance (kmc_event)
+__global__ void __launch_bounds__(128)
+k_resolve_ev_dist(KmcState *__restrict__ state, double *__restrict__ ev_dist, int64_t ev_cap,
+                  const double *__restrict__ dist)
+{
+    const int r = blockIdx.x;
+    const long long from = state[r].ev_resolved;
+    long long to = state[r].log_pos;
+    if (to > ev_cap) to = ev_cap;
+    for (long long q = from + threadIdx.x; q < to; q += blockDim.x) {
+        const long long idx = ((const long long *)ev_dist)[(int64_t)r * ev_cap + q];
+        ev_dist[(int64_t)r * ev_cap + q] = dist[idx];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && to > from) state[r].ev_resolved = to;
 }
 
 __global__ void k_fill_double(double *p, int64_t n, double v)
@@ -1337,6 +2035,15 @@ extern "C" int cmd_kmc_set_observables(cmd_kmc *k, int reset_frequency, int prin
     return CMD_OK;
 }
 
+static int kmc_resolve_events(cmd_kmc *k, const double *d_dist)
+{
+    if (k->ev_cap > 0) {
+        k_resolve_ev_dist<<<k->n_replicas, 128, 0, cmd_global().stream>>>(k->d_state, k->d_ev_dist, k->ev_cap, d_dist);
+        CMD_LAUNCHED();
+    }
+    return CMD_OK;
+}
+
 extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_positions)
 {
     CMD_REQUIRE_INIT();
@@ -1402,6 +2109,7 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
         a.x_leaves = stride / 64 + 4;
         size_t R = (size_t)k->n_replicas;
         size_t need = R * ((size_t)a.x_cap * 20 + (size_t)a.x_leaves * 16);
+        if (need < R * solo_scratch_bytes(a.x_cap, a.x_leaves)) need = R * solo_scratch_bytes(a.x_cap, a.x_leaves);
         if (need > k->exact_bytes) {
             CMD_CUDA(cudaStreamSynchronize(st));
             cudaFree(k->d_exact);
@@ -1444,7 +2152,7 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
             k_kmc_stream<<<blocks, (rpc + 1) * 32, smem, st>>>(k->bx, a);   // + the producer warp
             CMD_LAUNCHED();
             k->frames_total += nframes;
-            return CMD_OK;
+            return kmc_resolve_events(k, d_dist);
         }
         a.fast = 0;   // state too large for the ring: the plain kernel below
     }
@@ -1455,7 +2163,39 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
         return cmd_set_error(CMD_ECAPACITY, "KMC per-replica state (%zu bytes) exceeds shared memory", per_warp);
     a.replicas_per_cta = rpc;
     size_t smem = per_warp * rpc;
-    if (a.exact && rpc == 1) {   // few replicas (verification runs, `mdmc`): scratch in shared memory
+    if (a.exact && rpc == 1 && k->solo_enabled && k->n_sites < 65536) {
+        // few replicas (`mdmc`, verification runs): one CTA per replica.  Its scratch is sized by the
+        // block's largest pair count, not by the per-frame capacity.
+        int pmax = 0;
+        CMD_CUDA(cudaMemsetAsync(k->d_ties + 31, 0, 8, st));
+        k_max_count<<<64, 256, 0, st>>>(d_counts, nframes, (int *)(k->d_ties + 31));
+        CMD_LAUNCHED();
+        CMD_CUDA(cudaMemcpyAsync(&pmax, k->d_ties + 31, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CMD_CUDA(cudaStreamSynchronize(st));
+        if (pmax < 0 || pmax > stride) pmax = (int)stride;
+        a.x_cap = (pmax + 63) / 64 * 64;
+        a.x_leaves = a.x_cap / 64 + 4;
+        const size_t aux = (size_t)a.mask_words * 8 + 64 * 4 + 64 * 8;
+        const size_t xbytes = solo_scratch_bytes(a.x_cap, a.x_leaves);
+        const size_t xoff = ((per_warp + 7) / 8) * 8 + aux;
+        size_t need = xoff;
+        if (xoff + xbytes <= 226 * 1024) {
+            a.x_smem = 1;
+            need = xoff + xbytes;
+        }
+        if (need <= 226 * 1024) {
+            a.sel_margin = k->sel_margin;
+            CMD_CUDA(cudaFuncSetAttribute(k_kmc_solo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            k_kmc_solo<<<k->n_replicas, SOLO_THREADS, need, st>>>(k->bx, a);
+            CMD_LAUNCHED();
+            k->frames_total += nframes;
+            return kmc_resolve_events(k, d_dist);
+        }
+        a.x_smem = 0;
+        a.x_cap = stride;   // the warp-per-replica kernel below slices the scratch by the capacity
+        a.x_leaves = stride / 64 + 4;
+    }
+    if (a.exact && rpc == 1) {   // scratch in shared memory
         const size_t xbytes = (size_t)a.x_cap * 20 + (size_t)a.x_leaves * 16;
         const size_t xoff = ((per_warp + 15) / 16) * 16;
         if (xoff + xbytes <= 226 * 1024) {
@@ -1468,7 +2208,7 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
     k_kmc_advance<<<blocks, rpc * 32, smem, st>>>(k->bx, a);
     CMD_LAUNCHED();
     k->frames_total += nframes;
-    return CMD_OK;
+    return kmc_resolve_events(k, d_dist);
 }
 
 extern "C" int cmd_kmc_get_state(const cmd_kmc *k, int *lattices, double *time, int64_t *frame,
@@ -1609,6 +2349,27 @@ extern "C" int cmd_kmc_get_observables(const cmd_kmc *k, int replica, int64_t ca
         CMD_CUDA(cudaStreamSynchronize(st));
     }
     return CMD_OK;
+}
+
+extern "C" int64_t cmd_kmc_selection_fallbacks(const cmd_kmc *k)
+{
+    if (!k || !cmd_global().inited) return -1;
+    unsigned long long v = 0;
+    cudaStream_t st = cmd_global().stream;
+    if (cudaMemcpyAsync(&v, k->d_ties + 1, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    cudaStreamSynchronize(st);
+    return (int64_t)v;
+}
+
+// tools only: raw counter i of the tie / fallback / profile block
+extern "C" int64_t cmd_kmc_debug_counter(const cmd_kmc *k, int i)
+{
+    if (!k || !cmd_global().inited || i < 0 || i >= 32) return -1;
+    unsigned long long v = 0;
+    cudaStream_t st = cmd_global().stream;
+    if (cudaMemcpyAsync(&v, k->d_ties + i, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    cudaStreamSynchronize(st);
+    return (int64_t)v;
 }
 
 extern "C" int64_t cmd_kmc_tie_count(const cmd_kmc *k)

@@ -158,6 +158,10 @@ class DeviceKMC:
     def tie_count(self):
         return int(_abi.lib().cmd_kmc_tie_count(self._handle))
 
+    def selection_fallbacks(self):
+        """Events the one-CTA-per-replica kernel re-decided with the sequential np.cumsum."""
+        return int(_abi.lib().cmd_kmc_selection_fallbacks(self._handle))
+
 
 class KMCLattice:
     """Implementation of the time-dependent Kinetic Monte Carlo Scheme (MDMC.py:28-226).

@@ -305,6 +305,12 @@ int cmd_kmc_get_observables(const cmd_kmc *k, int replica, int64_t capacity, int
                             double *h_rows6);
 /* Tie audit: decisions (time stepping / selection) within 1e-9 relative of a boundary. */
 int64_t cmd_kmc_tie_count(const cmd_kmc *k);
+/* Runs with few replicas in exact arithmetic use one CTA per replica and decide move_proton's
+ * searchsorted index (MDMC.py:109-111) on a parallel prefix sum; events whose draw lies within
+ * rounding distance of an interval end are re-decided with the reference's sequential np.cumsum.
+ * Number of such events so far.  (Environment: CMDLMC_B200_KMC_SOLO=0 disables the kernel,
+ * CMDLMC_B200_KMC_SELECT_MARGIN=<x> scales the margin; both are read by cmd_kmc_create.) */
+int64_t cmd_kmc_selection_fallbacks(const cmd_kmc *k);
 
 /* ---------------------------------------------------------------- legacy LMC sweep ------ */
 /* PARITY UNPINNED: the legacy engine (LMCHelper.pyx, LMCRoutine.sweep / sweep_with_jumpmatrix) is

@@ -340,3 +340,62 @@ def test_replay_many_replicas_equals_single_replica_runs():
     same = [r for r in range(R) if r % 35 == 3]
     for r in same[1:]:
         np.testing.assert_array_equal(st["lattices"][r], st["lattices"][same[0]])
+
+
+def _replay_run(w, topo, box, lat0, u, positions=None):
+    from cmdlmc_b200.kmc import DeviceKMC, RNG_REPLAY
+    k = DeviceKMC(box, lat0, w.time_step, RNG_REPLAY)
+    k.set_replay_stream(u)
+    k.set_event_log(20000)
+    if positions is not None:
+        k.set_observables(50, 10)
+    k.advance(topo, positions)
+    st = k.state()
+    out = {"lattices": st["lattices"].copy(), "time": st["time"].copy(), "n_events": st["n_events"].copy(),
+           "events": [k.events(r) for r in range(lat0.shape[0])],
+           "rows": [k.observables(r) for r in range(lat0.shape[0])] if positions is not None else None,
+           "fallbacks": k.selection_fallbacks()}
+    return out
+
+
+@pytest.mark.parametrize("cfg,nfr", [("C1", 400), ("C2", 150)])
+def test_one_cta_per_replica_kernel_equals_warp_kernel(monkeypatch, cfg, nfr):
+    """Few exact replicas run on one CTA each (parallel prefix selection); the result has to be the
+    warp-per-replica kernel's (sequential np.cumsum) bit for bit -- also when every selection is
+    forced through the sequential fallback."""
+    import torch
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.topology import DeviceTopology, MODE_VERLET, build_with_retry
+    w = synth.workload(cfg)
+    frames = synth.trajectory(w, nfr)
+    box = make_box(w.cell)
+    topo = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer,
+                                                       MODE_VERLET, cm.Fermi(*w.rate_params), cap), frames)
+    R = 3
+    lat0 = np.stack([synth.initial_lattice(w.n_oxygen, w.n_protons, 40 + r)[0] for r in range(R)])
+    u = np.stack([np.random.RandomState(70 + r).random_sample(40000) for r in range(R)])
+    pos = torch.from_numpy(frames).cuda()
+    runs = {}
+    for name, env in (("solo", {}), ("warp", {"CMDLMC_B200_KMC_SOLO": "0"}),
+                      ("fallback", {"CMDLMC_B200_KMC_SELECT_MARGIN": "1e40"})):
+        for key in ("CMDLMC_B200_KMC_SOLO", "CMDLMC_B200_KMC_SELECT_MARGIN"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        runs[name] = _replay_run(w, topo, box, lat0, u, pos.data_ptr())
+    ref = runs["warp"]
+    assert (ref["n_events"] > 20).all()
+    assert runs["solo"]["fallbacks"] == 0 and ref["fallbacks"] == 0
+    assert runs["fallback"]["fallbacks"] == int(ref["n_events"].sum())
+    for name in ("solo", "fallback"):
+        got = runs[name]
+        np.testing.assert_array_equal(got["lattices"], ref["lattices"])
+        np.testing.assert_array_equal(got["time"], ref["time"])
+        np.testing.assert_array_equal(got["n_events"], ref["n_events"])
+        for r in range(R):
+            for key in ("frame", "start", "dest", "proton", "time", "dist"):
+                np.testing.assert_array_equal(got["events"][r][key], ref["events"][r][key])
+            # rows: frame, event time stamp and autocorrelation exactly; the MSD sums are formed by
+            # 512 threads instead of 32 lanes, i.e. in another order
+            np.testing.assert_array_equal(got["rows"][r][:, [0, 1, 5]], ref["rows"][r][:, [0, 1, 5]])
+            np.testing.assert_allclose(got["rows"][r][:, 2:5], ref["rows"][r][:, 2:5], rtol=1e-12, atol=0)
