@@ -97,7 +97,7 @@ struct cmd_kmc {
 struct KmcArgs {
     int n_sites, n_replicas, rng_mode, replicas_per_cta, mask_words, occ_words;
     int replica_first, replica_step;
-    double dt;
+    double dt, inv_dt;
     uint64_t seed;
     int64_t stride, nframes, frames_base, n_u, ev_cap, row_cap;
     int reset_freq, print_freq;
@@ -148,12 +148,13 @@ __device__ __forceinline__ double py_mod(double a, double b)
     return mod;
 }
 
-// floor(a / b) and a - floor(a / b) * b for finite a >= 0, b > 0 without fmod's division loop: the
-// quotient estimate is corrected with one exact FMA remainder.  Same values as py_floordiv / py_mod
-// (both are the exact floor of the real quotient and the exact remainder).
-__device__ __forceinline__ double floor_div_pos(double a, double b, double *rem)
+// floor(a / b) and a - floor(a / b) * b for finite a >= 0, b > 0 without fmod's division loop and
+// without a division: the quotient estimate a * (1 / b) is at most one off, and one exact FMA
+// remainder per candidate settles it.  Same values as py_floordiv / py_mod (both are the exact floor
+// of the real quotient and the exact remainder).
+__device__ __forceinline__ double floor_div_pos(double a, double b, double inv_b, double *rem)
 {
-    double q = floor(a / b);
+    double q = floor(a * inv_b);
     double r = fma(-q, b, a);
     if (r < 0.0) { q -= 1.0; r = fma(-q, b, a); }
     else if (r >= b) { q += 1.0; r = fma(-q, b, a); }
@@ -1379,7 +1380,8 @@ __device__ void kmc_run_until_frame_needed(const KmcArgs &a, WarpCtx &c, int r, 
         // kmc_time >= 0, dt > 0: Python's // and % (MDMC.py:152,156) are the exact floor and the exact
         // remainder; floor_div_pos returns the same values without fmod's division loop
         double rem_x, rem_t;
-        const bool same_frame = floor_div_pos(x, a.dt, &rem_x) == floor_div_pos(st.kmc_time, a.dt, &rem_t);
+        const bool same_frame = floor_div_pos(x, a.dt, a.inv_dt, &rem_x) ==
+                                floor_div_pos(st.kmc_time, a.dt, a.inv_dt, &rem_t);
         if (!a.fast && c.leader && (rem_x < 1e-9 * a.dt || a.dt - rem_x < 1e-9 * a.dt))
             atomicAdd(a.ties, 1ull);   // tie audit of the floor-division decision
         if (same_frame) {
@@ -2087,7 +2089,7 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
     memset(&a, 0, sizeof(a));
     a.n_sites = k->n_sites; a.n_replicas = k->n_replicas; a.rng_mode = k->rng_mode;
     a.replica_first = k->replica_first; a.replica_step = k->replica_step;
-    a.dt = k->dt; a.seed = k->seed; a.stride = stride; a.nframes = nframes;
+    a.dt = k->dt; a.inv_dt = 1.0 / k->dt; a.seed = k->seed; a.stride = stride; a.nframes = nframes;
     a.frames_base = k->frames_total; a.n_u = k->n_u; a.ev_cap = k->ev_cap; a.row_cap = k->row_cap;
     a.reset_freq = k->reset_freq; a.print_freq = k->print_freq;
     a.start = d_start; a.dest = d_dest; a.counts = d_counts; a.omega = d_omega; a.dist = d_dist;

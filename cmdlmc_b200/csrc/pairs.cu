@@ -71,6 +71,8 @@ struct cmd_topo {
     int *d_carry_start, *d_carry_dest, *d_carry_count, *d_carry_rowoff;
     int *d_sched;  // [0] n_rebuild, [1] n_refresh, [2] last head (-1 = carry), then ids
     int *d_rebuild_ids, *d_refresh_ids, *d_head, *d_next;
+    double *d_part;      // rate sums of a refresh split over several CTAs per frame
+    size_t part_cap;
     double *d_upload;
     size_t upload_bytes;
     const double *d_frames_last;  // frames of the last block (device)
@@ -337,8 +339,9 @@ k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RatePara
           int *__restrict__ out_dest, double *__restrict__ out_dist,
           double *__restrict__ out_omega, int *__restrict__ out_counts,
           double *__restrict__ out_rate_sum, const int *__restrict__ carry_rowoff,
-          int *__restrict__ out_rowoff)
+          int *__restrict__ out_rowoff, double *__restrict__ part)
 {
+    // gridDim.y CTAs share the pairs of one frame (large systems); their rate sums meet in `part`
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if ((int)blockIdx.x >= *n_ids) return;
     const int64_t f = ids[blockIdx.x];
@@ -353,14 +356,16 @@ k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RatePara
     const int *hs = hd < 0 ? carry_start : out_start + hd * stride;
     const int *hdst = hd < 0 ? carry_dest : out_dest + hd * stride;
     __syncthreads();
-    {   // the list is the head's list: so is its row index
+    if (blockIdx.y == 0) {   // the list is the head's list: so is its row index
         const int *hro = hd < 0 ? carry_rowoff : out_rowoff + hd * (int64_t)cmd_ro_pitch(n);
         int *ro = out_rowoff + f * (int64_t)cmd_ro_pitch(n);
         for (int k = threadIdx.x; k <= n; k += blockDim.x) ro[k] = hro[k];
     }
     const int64_t base = f * stride;
     double rsum = 0.0;
-    for (int k = threadIdx.x; k < p; k += blockDim.x) {
+    const int share = (p + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int k_lo = min((int)blockIdx.y * share, p), k_hi = min(k_lo + share, p);
+    for (int k = k_lo + threadIdx.x; k < k_hi; k += blockDim.x) {
         int a = hs[k], b = hdst[k];
         double pa[3] = {sp[3 * a], sp[3 * a + 1], sp[3 * a + 2]};
         double pb[3] = {sp[3 * b], sp[3 * b + 1], sp[3 * b + 2]};
@@ -383,9 +388,22 @@ k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RatePara
     if (threadIdx.x == 0) {
         double t = 0;
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += wsum[w];
-        out_rate_sum[f] = t;
-        out_counts[f] = p;
+        if (gridDim.y == 1) out_rate_sum[f] = t;
+        else part[(int64_t)blockIdx.x * gridDim.y + blockIdx.y] = t;
+        if (blockIdx.y == 0) out_counts[f] = p;
     }
+}
+
+// per-frame rate sums of a refresh that was split over several CTAs per frame, in CTA order
+__global__ void __launch_bounds__(256)
+k_refresh_sum(const int *__restrict__ ids, const int *__restrict__ n_ids, const double *__restrict__ part,
+              int chunks, double *__restrict__ out_rate_sum)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *n_ids) return;
+    double t = 0.0;
+    for (int y = 0; y < chunks; y++) t += part[(int64_t)i * chunks + y];
+    out_rate_sum[ids[i]] = t;
 }
 
 // keeps the list of the current segment head + the last frame for the next block
@@ -436,6 +454,9 @@ static void topo_free_block(cmd_topo *t)
     t->d_near_dist = nullptr;
     cudaFree(t->d_counts); cudaFree(t->d_rate_sum); cudaFree(t->d_rebuilt); cudaFree(t->d_dr);
     cudaFree(t->d_rebuild_ids); cudaFree(t->d_refresh_ids); cudaFree(t->d_head); cudaFree(t->d_next);
+    cudaFree(t->d_part);
+    t->d_part = nullptr;
+    t->part_cap = 0;
     t->d_start = t->d_dest = t->d_counts = nullptr;
     t->d_dist = t->d_omega = t->d_rate_sum = t->d_dr = nullptr;
     t->d_rebuilt = nullptr;
@@ -970,19 +991,42 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
         rc = launch_pairs(t, d_frames, t->d_rebuild_ids, t->d_sched, nframes, 0, false);
         if (rc) return rc;
         size_t rsmem = (size_t)t->n * 24;
-        if (rsmem > 40 * 1024)
-            k_refresh<false><<<(unsigned)nframes, 256, 0, st>>>(
+        if (rsmem > 40 * 1024) {
+            // frames too large to stage: several CTAs per frame, coordinates through L1 / L2
+            int chunks = (int)((t->stride + 8191) / 8192);
+            if (chunks < 1) chunks = 1;
+            if (chunks > 1024) chunks = 1024;
+            if (chunks > 1 && t->part_cap < (size_t)nframes * chunks) {
+                CMD_CUDA(cudaStreamSynchronize(st));
+                cudaFree(t->d_part);
+                t->d_part = nullptr;
+                t->part_cap = 0;
+                if (cudaMalloc((void **)&t->d_part, (size_t)nframes * chunks * 8) != cudaSuccess) {
+                    cudaGetLastError();
+                    return cmd_set_error(CMD_ENOMEM, "cudaMalloc failed for the refresh partial sums");
+                }
+                t->part_cap = (size_t)nframes * chunks;
+            }
+            k_refresh<false><<<dim3((unsigned)nframes, chunks), 256, 0, st>>>(
                 t->bx_refresh, t->rate, d_frames, t->d_refresh_ids, t->d_sched + 1, t->d_head, t->n, t->stride,
                 t->d_carry_start, t->d_carry_dest, t->d_carry_count, t->d_start, t->d_dest, t->d_dist,
-                t->d_omega, t->d_counts, t->d_rate_sum, t->d_carry_rowoff, t->d_rowoff);
-        else
+                t->d_omega, t->d_counts, t->d_rate_sum, t->d_carry_rowoff, t->d_rowoff, t->d_part);
+            if (chunks > 1) {
+                CMD_LAUNCHED();
+                k_refresh_sum<<<(unsigned)((nframes + 255) / 256), 256, 0, st>>>(
+                    t->d_refresh_ids, t->d_sched + 1, t->d_part, chunks, t->d_rate_sum);
+            }
+        } else
         k_refresh<true><<<(unsigned)nframes, 256, rsmem, st>>>(
             t->bx_refresh, t->rate, d_frames, t->d_refresh_ids, t->d_sched + 1, t->d_head, t->n, t->stride,
             t->d_carry_start, t->d_carry_dest, t->d_carry_count, t->d_start, t->d_dest, t->d_dist,
-            t->d_omega, t->d_counts, t->d_rate_sum, t->d_carry_rowoff, t->d_rowoff);
+            t->d_omega, t->d_counts, t->d_rate_sum, t->d_carry_rowoff, t->d_rowoff, nullptr);
         CMD_LAUNCHED();
         }
-        k_carry<<<8, 256, 0, st>>>(t->d_sched, t->d_start, t->d_dest, t->d_counts, t->stride,
+        int carry_blocks = (int)((t->stride + 2047) / 2048);   // a copy of up to `stride` pairs
+        if (carry_blocks < 8) carry_blocks = 8;
+        if (carry_blocks > 4 * g.sm_count) carry_blocks = 4 * g.sm_count;
+        k_carry<<<carry_blocks, 256, 0, st>>>(t->d_sched, t->d_start, t->d_dest, t->d_counts, t->stride,
                                    t->d_carry_start, t->d_carry_dest, t->d_carry_count,
                                    t->d_rowoff, t->d_carry_rowoff, t->n);
         CMD_LAUNCHED();
