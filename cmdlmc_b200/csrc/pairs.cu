@@ -14,6 +14,7 @@
 // decides a hit on its own.
 #include <math.h>
 #include <stdlib.h>
+#include <cooperative_groups.h>
 
 #include "pairs_cell.cuh"
 
@@ -325,6 +326,117 @@ k_schedule(const double *__restrict__ dr, double *__restrict__ displacement, int
         __syncthreads();
     }
     if (tid == 0) { sched[0] = n_rebuild; sched[1] = n_refresh; sched[2] = cur_head; }
+}
+
+// k_schedule for systems whose displacement vector does not fit one CTA: a CLUSTER of 8 CTAs shares
+// the atoms (displacements in shared memory, the next frame's dr in registers while this frame's
+// two largest displacements are reduced); the CTAs exchange their (max1, max2) through distributed
+// shared memory, one cluster barrier per frame.  Same decisions as k_schedule: the per-atom sums are
+// the same sequential additions and the sum of the two largest values does not depend on the order
+// of the reduction.
+#define SCHED_CLUSTER 8
+#define SCHED_CL_THREADS 1024
+#define SCHED_CL_PER 8    // atoms per thread held in registers for the look-ahead
+
+__device__ __forceinline__ void top2_merge(double &m1, double &m2, double o1, double o2)
+{
+    if (o1 > m1) { m2 = fmax(m1, o2); m1 = o1; } else m2 = fmax(m2, o1);
+}
+
+__global__ void __launch_bounds__(SCHED_CL_THREADS, 1)
+k_schedule_cluster(const double *__restrict__ dr, double *__restrict__ displacement, int n,
+                   int64_t nframes, double buffer, int first_ever, int *__restrict__ sched,
+                   int *__restrict__ rebuild_ids, int *__restrict__ refresh_ids,
+                   int *__restrict__ head, uint8_t *__restrict__ rebuilt, int chunk)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *disp = (double *)smem_raw;                       // [chunk] displacements of this CTA's atoms
+    double2 *slots = (double2 *)(disp + chunk);              // [2][SCHED_CLUSTER] (max1, max2) per CTA
+    double2 *wred = slots + 2 * SCHED_CLUSTER;               // [32] warp results
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int a0 = rank * chunk;
+    const int per = (chunk + SCHED_CL_THREADS - 1) / SCHED_CL_THREADS;   // <= SCHED_CL_PER (host)
+    for (int q = 0; q < per; q++) {
+        const int i = tid + q * SCHED_CL_THREADS;
+        if (i < chunk) disp[i] = a0 + i < n ? displacement[a0 + i] : 0.0;
+    }
+    double nx[SCHED_CL_PER];
+#pragma unroll
+    for (int q = 0; q < SCHED_CL_PER; q++) {
+        const int i = tid + q * SCHED_CL_THREADS;
+        nx[q] = (q < per && i < chunk && a0 + i < n) ? dr[a0 + i] : 0.0;
+    }
+    __syncthreads();
+    cluster.sync();
+    int n_rebuild = 0, n_refresh = 0, cur_head = sched[2];
+    for (int64_t f = 0; f < nframes; f++) {
+        double m1 = -INFINITY, m2 = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < SCHED_CL_PER; q++) {
+            const int i = tid + q * SCHED_CL_THREADS;
+            if (q < per && i < chunk && a0 + i < n) {
+                const double v = __dadd_rn(disp[i], nx[q]);
+                disp[i] = v;
+                if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) m2 = v;
+            }
+        }
+        if (f + 1 < nframes) {   // next frame's dr: in flight during the reduction
+#pragma unroll
+            for (int q = 0; q < SCHED_CL_PER; q++) {
+                const int i = tid + q * SCHED_CL_THREADS;
+                if (q < per && i < chunk && a0 + i < n) nx[q] = dr[(f + 1) * n + a0 + i];
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1)
+            top2_merge(m1, m2, __shfl_down_sync(0xffffffffu, m1, o), __shfl_down_sync(0xffffffffu, m2, o));
+        if (lane == 0) wred[w] = make_double2(m1, m2);
+        __syncthreads();
+        if (w == 0) {
+            const double2 v = wred[lane];
+            m1 = v.x; m2 = v.y;
+            for (int o = 16; o > 0; o >>= 1)
+                top2_merge(m1, m2, __shfl_down_sync(0xffffffffu, m1, o), __shfl_down_sync(0xffffffffu, m2, o));
+            // every CTA of the cluster gets this CTA's pair
+            if (lane < SCHED_CLUSTER) {
+                const double b1 = __shfl_sync(0xffu, m1, 0), b2 = __shfl_sync(0xffu, m2, 0);
+                double2 *remote = cluster.map_shared_rank(slots, lane);
+                remote[(f & 1) * SCHED_CLUSTER + rank] = make_double2(b1, b2);
+            }
+        }
+        cluster.sync();
+        m1 = -INFINITY; m2 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < SCHED_CLUSTER; c++) {
+            const double2 v = slots[(f & 1) * SCHED_CLUSTER + c];
+            top2_merge(m1, m2, v.x, v.y);
+        }
+        // np.sort(displacement)[-2:] -> (m2, m1); displ_max1 + displ_max2 > buffer
+        const bool cross = n >= 2 && __dadd_rn(m2, m1) > buffer;
+        const bool first = first_ever && f == 0;
+        if (cross) {
+            for (int q = 0; q < per; q++) {
+                const int i = tid + q * SCHED_CL_THREADS;
+                if (i < chunk) disp[i] = 0.0;
+            }
+        }
+        if (cross || first) {
+            if (rank == 0 && tid == 0) { rebuild_ids[n_rebuild] = (int)f; head[f] = (int)f; rebuilt[f] = 1; }
+            n_rebuild++;
+            cur_head = (int)f;
+        } else {
+            if (rank == 0 && tid == 0) { refresh_ids[n_refresh] = (int)f; head[f] = cur_head; rebuilt[f] = 0; }
+            n_refresh++;
+        }
+    }
+    for (int q = 0; q < per; q++) {
+        const int i = tid + q * SCHED_CL_THREADS;
+        if (i < chunk && a0 + i < n) displacement[a0 + i] = disp[i];
+    }
+    if (rank == 0 && tid == 0) { sched[0] = n_rebuild; sched[1] = n_refresh; sched[2] = cur_head; }
+    cluster.sync();   // no CTA leaves while its shared memory may still be written
 }
 
 // Refresh of a kept list (topology.py:110): dist = length(frame[row], frame[col]), same pairs.
@@ -970,6 +1082,29 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
             CMD_LAUNCHED();
             k_sched_fill<<<1, 1024, 0, st>>>(t->d_rebuilt, nframes, t->d_sched, t->d_rebuild_ids,
                                              t->d_refresh_ids, t->d_head);
+            CMD_LAUNCHED();
+        } else if (t->n > 4096 && t->n <= SCHED_CLUSTER * SCHED_CL_THREADS * SCHED_CL_PER) {
+            // large systems: one cluster of 8 CTAs walks the frames
+            int chunk = (t->n + SCHED_CLUSTER - 1) / SCHED_CLUSTER;
+            chunk = (chunk + 31) / 32 * 32;
+            const size_t csm = (size_t)chunk * 8 + (2 * SCHED_CLUSTER + 32) * sizeof(double2);
+            CMD_CUDA(cudaFuncSetAttribute(k_schedule_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(SCHED_CLUSTER);
+            cfg.blockDim = dim3(SCHED_CL_THREADS);
+            cfg.dynamicSmemBytes = csm;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = SCHED_CLUSTER;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            CMD_CUDA(cudaLaunchKernelEx(&cfg, k_schedule_cluster, (const double *)t->d_dr, t->d_displacement,
+                                        t->n, (int64_t)nframes, t->buffer, t->total_frames == 0 ? 1 : 0,
+                                        t->d_sched, t->d_rebuild_ids, t->d_refresh_ids, t->d_head,
+                                        t->d_rebuilt, chunk));
             CMD_LAUNCHED();
         } else {
             int sth = (t->n + 31) / 32 * 32;

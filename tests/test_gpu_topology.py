@@ -466,3 +466,49 @@ def test_randomised_sweep_vs_oracle(orc):
         np.testing.assert_array_equal(dist, want[2])
         n_reb += bool(want[3])
     assert 2 < n_reb < nfr
+
+
+def test_large_system_verlet_schedule_and_refresh(orc):
+    """8192 oxygens: the rebuild schedule comes from the cluster kernel (eight CTAs sharing the
+    displacement vector) and the refresh is split over several CTAs per frame.  The rebuild
+    frames have to be the sequential walk's (oracle orc_verlet_step), the lists the brute-force
+    lists of the same frames inside the cutoff."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.topology import DeviceTopology, build_with_retry
+    n, nfr = 8192, 48
+    L = (n / 0.0334) ** (1.0 / 3.0)
+    w = synth.Workload("big", np.array([L, L, L]), n, 0, 1, nfr, 0.5, 3.0, 2.0, "Fermi",
+                       (0.06, 2.3, 0.1), 11, group_size=0)
+    frames = synth.trajectory(w, nfr, amplitude=0.6, noise=0.05)
+    box, obox = make_box(w.cell), orc.OracleBox(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    lib, P = orc.lib(), orc._p
+    disp = np.zeros(n)
+    want_rebuilt = []
+    for f in range(nfr):
+        cur = np.ascontiguousarray(frames[f])
+        reb = lib.orc_verlet_step(obox.handle, P(np.ascontiguousarray(frames[f - 1])) if f else None,
+                                  P(cur), n, float(w.buffer), P(disp))
+        want_rebuilt.append(bool(reb) or f == 0)
+    assert 2 < sum(want_rebuilt) < nfr // 2
+    tv = build_with_retry(lambda cap: DeviceTopology(box, n, w.cutoff, w.buffer, 1, rate, cap), frames)
+    tb = build_with_retry(lambda cap: DeviceTopology(box, n, w.cutoff, w.buffer, 0, rate, cap), frames)
+    cv, rebuilt, rsum_v = tv.frame_info()
+    cb, _, rsum_b = tb.frame_info()
+    np.testing.assert_array_equal(rebuilt.astype(bool), np.array(want_rebuilt))
+    refreshed = [f for f in range(nfr) if not want_rebuilt[f]]
+    for f in (0, refreshed[0], refreshed[-1], int(np.nonzero(want_rebuilt)[0][-1])):
+        sv, dv, xv, ov = tv.get_frame(f, int(cv[f]))
+        sb, db, xb, ob = tb.get_frame(f, int(cb[f]))
+        if want_rebuilt[f]:
+            np.testing.assert_array_equal(sv, sb)
+            np.testing.assert_array_equal(dv, db)
+            np.testing.assert_array_equal(xv, xb)
+            assert rsum_v[f] == pytest.approx(rsum_b[f], rel=1e-12)
+        else:
+            kv, kb = xv <= w.cutoff, xb <= w.cutoff
+            np.testing.assert_array_equal(sv[kv], sb[kb])
+            np.testing.assert_array_equal(dv[kv], db[kb])
+            np.testing.assert_array_equal(xv[kv], xb[kb])
+            np.testing.assert_allclose(ov[kv], ob[kb], rtol=1e-12)
+            assert rsum_v[f] == pytest.approx(ov.sum(), rel=1e-10)
