@@ -385,11 +385,33 @@ def run_b200(args):
     e2e_ms = max(f0.elapsed_time(f1), e2e_wall * 1e3)
     clocks = sampler.stop()
 
+    # the same call on float32 host frames (the reference's HDF5 storage: f32 on disk, up-cast to
+    # f64 before any arithmetic, trajectory_parser.py:324): half the bytes over PCIe.  Reported
+    # beside the headline, which stays on f64 host frames.
+    host32 = torch.empty(host.shape, dtype=torch.float32, pin_memory=True)
+    host32.copy_(host)
+    h32 = host32.data_ptr()
+
+    def step_e2e32():
+        _abi.check(lib.cmd_topo_build(topo.handle, C.c_void_p(h32), 4, B))
+        _abi.check(lib.cmd_topo_frame_info(topo.handle, _abi.ptr(h_counts, C.c_int64),
+                                           _abi.ptr(h_rebuilt, C.c_uint8), _abi.ptr(h_rsum)))
+
+    for _ in range(2):
+        step_e2e32()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_e2e32()
+    barrier()
+    e2e32_ms = (time.perf_counter() - t0) * 1e3
+    del host32
+
     # max over ranks
-    tm = torch.tensor([ms_total, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
+    tm = torch.tensor([ms_total, e2e_ms, kernel_ms, e2e32_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, kernel_ms = [float(x) for x in tm.tolist()]
+    ms_total, e2e_ms, kernel_ms, e2e32_ms = [float(x) for x in tm.tolist()]
 
     value = world * K * B * ppf / (ms_total * 1e-3)
     e2e_value = world * K * B * ppf / (e2e_ms * 1e-3)
@@ -448,7 +470,11 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": B * 13 + 4, "ms_per_step": e2e_ms / K,
                 "api": "cmd_topo_build(host f64 frames) + cmd_topo_frame_info",
-                "numa_node_bound": numa_node},
+                "numa_node_bound": numa_node,
+                "f32_storage": {"value": world * K * B * ppf / (e2e32_ms * 1e-3), "unit": UNIT,
+                                "h2d_bytes_per_step": in_bytes // 2, "ms_per_step": e2e32_ms / K,
+                                "note": "same call on float32 host frames (HDF5 storage layout), "
+                                        "up-cast on the device; not the headline"}},
         "roofline": roofline, "clocks": clocks,
     }
 
@@ -550,6 +576,30 @@ def run_m2(args, w, box, rate, d_frames, world, dev, dist, barrier):
                  "value": float(tot_l[0].item()) / (float(tl.item()) * 1e-3), "unit": "attempts/s",
                  "ms": float(tl.item()), "jumps": float(tot_l[1].item()), "sweeps_per_frame": 1,
                  "rng": "philox4x32-10", "parity": "unpinned upstream (engine not in the reference tree)"}
+    # one replica in exact-replay mode: what a reference `mdmc` run is (k_kmc_solo, one CTA)
+    from cmdlmc_b200.kmc import RNG_REPLAY
+    Fs = min(F, 2048)
+    u = np.random.RandomState(5).random_sample((1, 32 * Fs + 1000))
+    solo_ms = []
+    for it in range(2):
+        one = DeviceKMC(box, lattices[:1], w.time_step, RNG_REPLAY)
+        one.set_replay_stream(u)
+        # a topology view of the first Fs frames is not needed: the kernel walks the block it is given,
+        # so time a block of its own
+        if it == 0:
+            ts = DeviceTopology(box, n, w.cutoff, w.buffer, MODE_VERLET, rate, topo.stride)
+            ts.build_dev(d_frames.data_ptr(), Fs)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        one.advance(ts)
+        b.record()
+        torch.cuda.synchronize()
+        solo_ms.append(a.elapsed_time(b))
+        solo_events = int(one.state()["n_events"].sum())
+    single = {"kernel": "k_kmc_solo", "rng": "replay (reference np.random protocol, bit-exact mode)",
+              "frames": int(Fs), "ms": float(min(solo_ms)), "events": solo_events,
+              "frames_per_s": Fs / (min(solo_ms) * 1e-3),
+              "site_updates_per_s": float(counts[:Fs].sum()) / (min(solo_ms) * 1e-3)}
     tm = torch.tensor([ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(updates), float(events)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -562,7 +612,7 @@ def run_m2(args, w, box, rate, d_frames, world, dev, dist, barrier):
             "replicas_per_gpu": R, "frames": F, "ms": ms, "events": events,
             "rng": "philox4x32-10", "directed_pairs_per_frame_mean": float(counts.mean()),
             "verlet_rebuilds": int(rebuilt.sum()), "verlet_pipeline": verlet, "lmc_sweep": lmc_block,
-            "kernel": "k_kmc_stream",
+            "single_replica_replay": single, "kernel": "k_kmc_stream",
             "roofline": {"bound": "smem", "unit": "GB/s", "achieved": rate_su * 16 / 1e9,
                          "peak": 148 * 128 * 1.965, "frac": rate_su * 16 / 1e9 / (148 * 128 * 1.965),
                          "note": "16 B of (start, dest, omega) read from the shared-memory ring per "
