@@ -109,6 +109,7 @@ SIGNATURES = {
     "cmd_kmc_get_observables": (C.c_int, [vp, C.c_int, C.c_int64, lp, dp]),
     "cmd_kmc_tie_count": (C.c_int64, [vp]),
     "cmd_kmc_selection_fallbacks": (C.c_int64, [vp]),
+    "cmd_kmc_debug_counter": (C.c_int64, [vp, C.c_int]),
     "cmd_lmc_create": (C.c_int, [C.c_int, C.c_int, ip, C.c_int, C.c_uint64, C.POINTER(vp)]),
     "cmd_lmc_destroy": (None, [vp]),
     "cmd_lmc_set_replay_stream": (C.c_int, [vp, ip, dp, C.c_int64]),

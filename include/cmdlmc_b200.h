@@ -311,6 +311,9 @@ int64_t cmd_kmc_tie_count(const cmd_kmc *k);
  * Number of such events so far.  (Environment: CMDLMC_B200_KMC_SOLO=0 disables the kernel,
  * CMDLMC_B200_KMC_SELECT_MARGIN=<x> scales the margin; both are read by cmd_kmc_create.) */
 int64_t cmd_kmc_selection_fallbacks(const cmd_kmc *k);
+/* Tools only: raw 64-bit counter i (0 ties, 1 selection fallbacks, 2.. per-phase cycle counters of
+ * builds with -DSOLO_PROFILE, tools/time_kmc_replay.py); -1 on a bad index. */
+int64_t cmd_kmc_debug_counter(const cmd_kmc *k, int i);
 
 /* ---------------------------------------------------------------- legacy LMC sweep ------ */
 /* PARITY UNPINNED: the legacy engine (LMCHelper.pyx, LMCRoutine.sweep / sweep_with_jumpmatrix) is
