@@ -1138,9 +1138,12 @@ __device__ bool solo_move(const KmcArgs &a, WarpCtx &c, double u, int64_t slot, 
     if (found < 0) return false;  // nothing allowed: IndexError upstream
     const unsigned pr = c.cpair[found];
     const int st = pr >> 16, de = pr & 0xffff;
-    const int proton = c.lat[st];
-    __syncthreads();
+    // Nobody reads the lattice between the barrier above and the next barrier every thread takes
+    // (the first warp's next request / end of frame), so the leader moves the label right away and
+    // no barrier closes the move.  The proton label is the leader's alone.
+    int proton = 0;
     if (tid == 0) {
+        proton = c.lat[st];
         c.lat[de] = proton;
         c.lat[st] = 0;
         c.occ[de >> 5] |= 1u << (de & 31);
@@ -1148,7 +1151,6 @@ __device__ bool solo_move(const KmcArgs &a, WarpCtx &c, double u, int64_t slot, 
     }
     if (tid == 32 && slot >= 0)   // a helper logs the pair's flat index (see kmc_event)
         ((long long *)a.ev_dist)[slot] = c.base + solo_list_index(c, found);
-    __syncthreads();
     SOLO_T(8);   // move: tail
     *o_start = st; *o_dest = de; *o_proton = proton; *o_index = 0;
     return true;
