@@ -2113,7 +2113,11 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
         a.x_leaves = stride / 64 + 4;
         size_t R = (size_t)k->n_replicas;
         size_t need = R * ((size_t)a.x_cap * 20 + (size_t)a.x_leaves * 16);
-        if (need < R * solo_scratch_bytes(a.x_cap, a.x_leaves)) need = R * solo_scratch_bytes(a.x_cap, a.x_leaves);
+        {   // the solo kernel rounds its capacity up to 64 entries
+            const int64_t cap64 = (stride + 63) / 64 * 64;
+            const size_t solo = R * solo_scratch_bytes(cap64, cap64 / 64 + 4);
+            if (need < solo) need = solo;
+        }
         if (need > k->exact_bytes) {
             CMD_CUDA(cudaStreamSynchronize(st));
             cudaFree(k->d_exact);
