@@ -402,3 +402,100 @@ def test_one_cta_per_replica_kernel_equals_warp_kernel(monkeypatch, cfg, nfr):
             # 512 threads instead of 32 lanes, i.e. in another order
             np.testing.assert_array_equal(got["rows"][r][:, [0, 1, 5]], ref["rows"][r][:, [0, 1, 5]])
             np.testing.assert_allclose(got["rows"][r][:, 2:5], ref["rows"][r][:, 2:5], rtol=1e-12, atol=0)
+
+
+def _cluster_topology(frames, rate, cutoff):
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.topology import DeviceTopology, build_with_retry
+    box = cm.AtomBoxCubic(np.array([60.0, 60.0, 60.0]))
+    n = frames.shape[1]
+    topo = build_with_retry(lambda cap: DeviceTopology(box, n, cutoff, 0.0, 0, rate, cap), frames)
+    return box, topo
+
+
+def _grid16(spacing):
+    """16 sites on a 2 x 2 x 4 grid; with spacing 1 every pair is inside a 4 A cutoff."""
+    g = np.stack(np.meshgrid(np.arange(2), np.arange(2), np.arange(4), indexing="ij"), -1).reshape(-1, 3)
+    return 20.0 + spacing * g.astype(float)
+
+
+# The reference tests fastforward_to_next_jump on bare rate generators (tests/LMC/test_MDMC.py:
+# 20-25,59,83).  On the device the rate source is a topology: 16 sites, 8 protons and a distance-
+# independent rate a = omega / 64 (Exponential(a, 0)) give 8 * 8 = 64 allowed transitions in every
+# configuration, i.e. the total rate omega in every frame.  (A one-proton toy lattice would not do:
+# two events inside one frame leave the frame's cached transition list empty and the reference's
+# move_proton raises IndexError there, MDMC.py:110 -- the device halts the replica the same way.)
+LAT16 = np.array([[1, 2, 3, 4, 5, 6, 7, 8] + [0] * 8], dtype=np.int32)
+
+
+def test_reference_fastforward_constant_rates():
+    """tests/LMC/test_MDMC.py:10-51 on the device: with the same rate in every frame the
+    time-dependent KMC reproduces the constant-rate KMC (same uniforms) to 1e-7, and the event's
+    frame counter is int(t // dt)."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.kmc import DeviceKMC, RNG_REPLAY
+    frames = np.tile(_grid16(1.0), (4096, 1, 1))
+    for dt in (0.1, 0.5, 1.3):
+        for omega in (0.03, 0.06, 0.13):
+            box, topo = _cluster_topology(frames, cm.Exponential(omega / 64, 0.0), 4.0)
+            assert (topo.frame_info()[0] == 16 * 15).all()
+            u = np.random.RandomState(7).random_sample((1, 400))
+            u[0, 0:200:2] = np.random.RandomState(0).random_sample(100)
+            kmc = DeviceKMC(box, LAT16, dt, RNG_REPLAY)
+            kmc.set_replay_stream(u)
+            kmc.set_event_log(256)
+            for _ in range(64):
+                kmc.advance(topo)
+                if kmc.state()["n_events"][0] >= 100:
+                    break
+            ev = kmc.events(0)
+            assert len(ev["time"]) >= 100
+            want = np.cumsum(-np.log(1 - np.random.RandomState(0).random_sample(100)) / omega)
+            np.testing.assert_allclose(ev["time"][:100], want, atol=1e-7, rtol=0)
+            np.testing.assert_array_equal((ev["time"][:100] // dt).astype(np.int64), ev["frame"][:100])
+
+
+def test_reference_variable_rates_average():
+    """tests/LMC/test_MDMC.py:54-73: sinusoidal rates, the mean event rate is the mean rate.  Four
+    sites on a regular tetrahedron whose edge changes from frame to frame, two protons: always four
+    allowed transitions of the same rate exp(-edge).  16 Philox replicas x ~2500 events: 0.5 %
+    standard error, asserted within 2 %."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.kmc import DeviceKMC, RNG_PHILOX
+    t = np.linspace(0, 200 * np.pi, 10000)
+    rates = 0.006 + 0.002 * np.sin(t)
+    edge = -np.log(rates / 4)
+    tet = np.array([[1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]], dtype=float) / (2 * np.sqrt(2))
+    frames = 30.0 + edge[:, None, None] * tet[None]
+    box, topo = _cluster_topology(frames, cm.Exponential(1.0, -1.0), 7.5)
+    assert (topo.frame_info()[0] == 12).all()
+    lat0 = np.tile(np.array([[1, 2, 0, 0]], dtype=np.int32), (16, 1))
+    kmc = DeviceKMC(box, lat0, 0.5, RNG_PHILOX, seed=3)
+    for _ in range(84):
+        kmc.advance(topo)
+    st = kmc.state()
+    assert (st["n_events"] > 2000).all()
+    got = st["n_events"].sum() / (84 * 10000 * 0.5 * 16)
+    assert abs(got - rates.mean()) / rates.mean() < 0.02
+
+
+def test_reference_variable_rates_index():
+    """tests/LMC/test_MDMC.py:76-93: the rate is non-zero in one frame of 117 only (the sites are
+    out of range of each other in all the others); every event lands on that frame."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.kmc import DeviceKMC, RNG_REPLAY
+    length, hot, reps = 117, 73, 64
+    one = np.stack([_grid16(1.0) if f == hot else _grid16(9.0) for f in range(length)])
+    box, topo = _cluster_topology(np.tile(one, (reps, 1, 1)), cm.Exponential(0.17 / 64, 0.0), 4.0)
+    counts = topo.frame_info()[0]
+    assert (counts.reshape(reps, length)[:, hot] == 240).all() and counts.sum() == 240 * reps
+    kmc = DeviceKMC(box, LAT16, 0.22, RNG_REPLAY)
+    kmc.set_replay_stream(np.random.RandomState(1).random_sample((1, 400)))
+    kmc.set_event_log(256)
+    for _ in range(200):
+        kmc.advance(topo)
+        if kmc.state()["n_events"][0] >= 101:
+            break
+    ev = kmc.events(0)
+    assert len(ev["frame"]) >= 101
+    assert (ev["frame"][:101] % length == hot).all()
