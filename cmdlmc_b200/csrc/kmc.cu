@@ -208,6 +208,10 @@ struct WarpCtx {
     // replay stream look-ahead: (uc0, uc1) = stream[uc_pos, uc_pos + 1], (un0, un1) the next pair
     double uc0, uc1, un0, un1;
     long long uc_pos;
+    // Philox look-ahead: time selector and selection uniform of event nx_event, computed while the
+    // selection of the previous event waits for its loads (kmc_move_fast)
+    double nx_ts, nx_usel;
+    long long nx_event;
     int scan_par;        // solo scans alternate between two sets of warp-total slots
     int p_next;          // pair count of the next frame, requested a frame ahead (-1: none)
 #ifdef SOLO_PROFILE
@@ -692,8 +696,7 @@ __device__ bool kmc_move_fast(const KmcArgs &a, WarpCtx &c, double u, int r, lon
                               unsigned long long *ties)
 {
     // lane totals -> inclusive scan over lanes; the last value is the total the draw refers to
-    double lt = 0.0;
-    for (int s = 0; s < c.nst; s++) lt += c.psum[s * 32 + c.lane];
+    const double lt = c.lane_total;   // == sum over the frame's stages of psum[s][lane], same order
     double inc = lt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -732,6 +735,17 @@ __device__ bool kmc_move_fast(const KmcArgs &a, WarpCtx &c, double u, int r, lon
         const int k = sfound * 1024 + c.lane * 32 + L;
         const bool ok = k < c.p && ((c.mask0[k >> 5] >> L) & 1u);
         const double om = ok ? __ldg(a.omega + c.base + k) : 0.0;
+        // the pair itself comes along with its rate: one trip to L2 per attempt instead of two
+        const int st_l = ok ? __ldg(a.start + c.base + k) : 0, de_l = ok ? __ldg(a.dest + c.base + k) : 0;
+        if (attempt == 0) {
+            // while the loads are under way: the NEXT event's Philox draw and its logarithm
+            uint32_t ctr[4] = {(uint32_t)(event + 1), (uint32_t)((uint64_t)(event + 1) >> 32),
+                               (uint32_t)(a.replica_first + r * a.replica_step), 0u};
+            philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            c.nx_ts = -log(1 - u53(ctr[0], ctr[1]));
+            c.nx_usel = u53(ctr[2], ctr[3]);
+            c.nx_event = event + 1;
+        }
         double inc2 = om;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -748,7 +762,7 @@ __device__ bool kmc_move_fast(const KmcArgs &a, WarpCtx &c, double u, int r, lon
             if (c.lane == 0) atomicAdd(ties, 1ull);
         }
         const int found = sfound * 1024 + isel * 32 + L;
-        const int st = __ldg(a.start + c.base + found), de = __ldg(a.dest + c.base + found);
+        const int st = __shfl_sync(0xffffffffu, st_l, isel), de = __shfl_sync(0xffffffffu, de_l, isel);
         if (!(occupied(c, st) && !occupied(c, de))) continue;   // left the set since consumption
         const int proton = c.lat[st];
         __syncwarp();
@@ -1371,11 +1385,16 @@ __device__ void kmc_run_until_frame_needed(const KmcArgs &a, WarpCtx &c, int r, 
             replay_fetch(a, c, r, st.cursor);
             st.time_selector = c.uc0;                                 // MDMC.py:148
         } else {
-            uint32_t ctr[4] = {(uint32_t)st.n_events, (uint32_t)((uint64_t)st.n_events >> 32),
-                               (uint32_t)(a.replica_first + r * a.replica_step), 0u};
-            philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-            st.time_selector = -log(1 - u53(ctr[0], ctr[1]));         // MDMC.py:148
-            st.u_sel = u53(ctr[2], ctr[3]);                           // MDMC.py:110, same counter
+            if (c.nx_event == st.n_events) {   // drawn ahead by kmc_move_fast
+                st.time_selector = c.nx_ts;
+                st.u_sel = c.nx_usel;
+            } else {
+                uint32_t ctr[4] = {(uint32_t)st.n_events, (uint32_t)((uint64_t)st.n_events >> 32),
+                                   (uint32_t)(a.replica_first + r * a.replica_step), 0u};
+                philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                st.time_selector = -log(1 - u53(ctr[0], ctr[1]));         // MDMC.py:148
+                st.u_sel = u53(ctr[2], ctr[3]);                           // MDMC.py:110, same counter
+            }
         }
         double t_trial = st.time_selector / st.current_rate;  // Q1: the rate of frame 0, forever
         double x = st.kmc_time + t_trial;
@@ -1440,7 +1459,7 @@ __global__ void __launch_bounds__(512, 1) k_kmc_advance(const __grid_constant__ 
     c.lane = lane;
     c.solo = false; c.leader = lane == 0; c.tid = lane; c.nthr = 32;
     c.kbits = nullptr; c.wpre = nullptr; c.si = nullptr; c.sd = nullptr;
-    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.p_next = -1;
+    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.nx_event = -1; c.nx_ts = c.nx_usel = 0.0; c.p_next = -1;
     c.lat = (int *)(smem_raw + per_warp * w);
     c.occ = (unsigned *)(c.lat + a.n_sites);
     c.mask0 = c.occ + a.occ_words;
@@ -1553,7 +1572,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1) k_kmc_solo(const __grid_const
         c.tcnt = (int *)(c.tflags + (size_t)SOLO_LEVELS * c.tlw);
         c.cidx = nullptr;
     }
-    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.p_next = -1;
+    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.nx_event = -1; c.nx_ts = c.nx_usel = 0.0; c.p_next = -1;
 #ifdef SOLO_PROFILE
     for (int i = 0; i < 16; i++) c.prof[i] = 0;
     c.prof_t = clock64();
@@ -1675,7 +1694,7 @@ __global__ void __launch_bounds__(544, 1) k_kmc_stream(const __grid_constant__ B
     c.lane = lane;
     c.solo = false; c.leader = lane == 0; c.tid = lane; c.nthr = 32;
     c.kbits = nullptr; c.wpre = nullptr; c.si = nullptr; c.sd = nullptr;
-    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.p_next = -1;
+    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.nx_event = -1; c.nx_ts = c.nx_usel = 0.0; c.p_next = -1;
     c.psum = (double *)(q + per_warp * w);
     c.mask0 = (unsigned *)(c.psum + (size_t)a.nst_max * 32);
     c.lat = (int *)((unsigned char *)c.mask0 + mask_bytes);
