@@ -1636,7 +1636,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1) k_kmc_solo(const __grid_const
 // warp is one replica consuming the ring (full / empty mbarriers, no CTA-wide barrier in the
 // loop).  Per replica-frame the work is one branch-free pass over the pairs out of shared memory;
 // events cost a few scans thanks to the per-(stage, lane) partial sums.
-__global__ void __launch_bounds__(544, 1) k_kmc_stream(const __grid_constant__ BoxParams bx,
+__global__ void __maxnreg__(112) k_kmc_stream(const __grid_constant__ BoxParams bx,
                                                        const __grid_constant__ KmcArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
