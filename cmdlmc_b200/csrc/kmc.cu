@@ -210,7 +210,7 @@ struct WarpCtx {
     long long uc_pos;
     // Philox look-ahead: time selector and selection uniform of event nx_event, computed while the
     // selection of the previous event waits for its loads (kmc_move_fast)
-    double nx_ts, nx_usel;
+    double nx_ts, nx_usel, nx_trial, cur_rate;
     long long nx_event;
     int scan_par;        // solo scans alternate between two sets of warp-total slots
     int p_next;          // pair count of the next frame, requested a frame ahead (-1: none)
@@ -744,6 +744,7 @@ __device__ bool kmc_move_fast(const KmcArgs &a, WarpCtx &c, double u, int r, lon
             philox4x32_10(ctr, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
             c.nx_ts = -log(1 - u53(ctr[0], ctr[1]));
             c.nx_usel = u53(ctr[2], ctr[3]);
+            c.nx_trial = c.nx_ts / c.cur_rate;
             c.nx_event = event + 1;
         }
         double inc2 = om;
@@ -1344,6 +1345,7 @@ __device__ bool kmc_event(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
         u = st.u_sel;   // drawn with the time selector of this event (same Philox counter)
     }
     int es, ed, ep, ek;
+    c.cur_rate = st.current_rate;   // for the look-ahead of the next event's trial time
     // the jump distance is logged as the flat index of the pair; k_resolve_ev_dist turns it into the
     // distance after the kernel (a dependent global load here would stall the replica)
     const int64_t slot = st.log_pos < a.ev_cap ? (int64_t)r * a.ev_cap + st.log_pos : -1;
@@ -1379,6 +1381,7 @@ __device__ bool kmc_event(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
 __device__ void kmc_run_until_frame_needed(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
 {
     for (;;) {
+        bool have_trial = false;
         if (a.rng_mode == CMD_RNG_REPLAY) {
             if (st.cursor + 1 >= a.n_u) { st.phase = KMC_PHASE_HALT; st.reason = 1; return; }
             // the stream carries -np.log(1 - np.random.random()) as the host evaluated it
@@ -1388,6 +1391,7 @@ __device__ void kmc_run_until_frame_needed(const KmcArgs &a, WarpCtx &c, int r, 
             if (c.nx_event == st.n_events) {   // drawn ahead by kmc_move_fast
                 st.time_selector = c.nx_ts;
                 st.u_sel = c.nx_usel;
+                have_trial = true;
             } else {
                 uint32_t ctr[4] = {(uint32_t)st.n_events, (uint32_t)((uint64_t)st.n_events >> 32),
                                    (uint32_t)(a.replica_first + r * a.replica_step), 0u};
@@ -1396,7 +1400,8 @@ __device__ void kmc_run_until_frame_needed(const KmcArgs &a, WarpCtx &c, int r, 
                 st.u_sel = u53(ctr[2], ctr[3]);                           // MDMC.py:110, same counter
             }
         }
-        double t_trial = st.time_selector / st.current_rate;  // Q1: the rate of frame 0, forever
+        // Q1: the rate of frame 0, forever (so the quotient can be formed ahead as well)
+        double t_trial = have_trial ? c.nx_trial : st.time_selector / st.current_rate;
         double x = st.kmc_time + t_trial;
         // kmc_time >= 0, dt > 0: Python's // and % (MDMC.py:152,156) are the exact floor and the exact
         // remainder; floor_div_pos returns the same values without fmod's division loop
@@ -1459,7 +1464,7 @@ __global__ void __launch_bounds__(512, 1) k_kmc_advance(const __grid_constant__ 
     c.lane = lane;
     c.solo = false; c.leader = lane == 0; c.tid = lane; c.nthr = 32;
     c.kbits = nullptr; c.wpre = nullptr; c.si = nullptr; c.sd = nullptr;
-    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.nx_event = -1; c.nx_ts = c.nx_usel = 0.0; c.p_next = -1;
+    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.nx_event = -1; c.nx_ts = c.nx_usel = c.nx_trial = 0.0; c.cur_rate = 1.0; c.p_next = -1;
     c.lat = (int *)(smem_raw + per_warp * w);
     c.occ = (unsigned *)(c.lat + a.n_sites);
     c.mask0 = c.occ + a.occ_words;
@@ -1574,7 +1579,7 @@ __global__ void __launch_bounds__(SOLO_THREADS, 1) k_kmc_solo(const __grid_const
         c.tcnt = (int *)(c.tflags + (size_t)SOLO_LEVELS * c.tlw);
         c.cidx = nullptr;
     }
-    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.nx_event = -1; c.nx_ts = c.nx_usel = 0.0; c.p_next = -1;
+    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.nx_event = -1; c.nx_ts = c.nx_usel = c.nx_trial = 0.0; c.cur_rate = 1.0; c.p_next = -1;
 #ifdef SOLO_PROFILE
     for (int i = 0; i < 16; i++) c.prof[i] = 0;
     c.prof_t = clock64();
@@ -1696,7 +1701,7 @@ __global__ void __maxnreg__(112) k_kmc_stream(const __grid_constant__ BoxParams 
     c.lane = lane;
     c.solo = false; c.leader = lane == 0; c.tid = lane; c.nthr = 32;
     c.kbits = nullptr; c.wpre = nullptr; c.si = nullptr; c.sd = nullptr;
-    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.nx_event = -1; c.nx_ts = c.nx_usel = 0.0; c.p_next = -1;
+    c.uc_pos = -8; c.uc0 = c.uc1 = c.un0 = c.un1 = 0.0; c.scan_par = 0; c.nx_event = -1; c.nx_ts = c.nx_usel = c.nx_trial = 0.0; c.cur_rate = 1.0; c.p_next = -1;
     c.psum = (double *)(q + per_warp * w);
     c.mask0 = (unsigned *)(c.psum + (size_t)a.nst_max * 32);
     c.lat = (int *)((unsigned char *)c.mask0 + mask_bytes);
