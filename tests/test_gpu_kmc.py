@@ -499,3 +499,61 @@ def test_reference_variable_rates_index():
     ev = kmc.events(0)
     assert len(ev["frame"]) >= 101
     assert (ev["frame"][:101] % length == hot).all()
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_randomised_small_lattices_replay_vs_oracle(orc, seed):
+    """Random small systems (3-48 sites at about 0.05 per cubic Angstrom, any filling, orthorhombic or triclinic cells, brute-force or
+    Verlet lists, frames with very few or no listed pairs): replay traces against the oracle, bit for
+    bit, including the event at which a run dies of the reference's IndexError (no transition left
+    in the cached frame, MDMC.py:110)."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.kmc import DeviceKMC, RNG_REPLAY
+    from cmdlmc_b200.topology import DeviceTopology, build_with_retry
+    rng = np.random.RandomState(100 + seed)
+    n = int(rng.randint(3, 49))
+    nprot = int(rng.randint(1, n))
+    L = np.maximum(6.5, (n / 0.05) ** (1.0 / 3.0) * rng.uniform(0.85, 1.2, 3))
+    if rng.rand() < 0.5:
+        cell, hm = L.copy(), np.diag(L)
+    else:
+        hm = np.array([[L[0], 0, 0], [rng.uniform(-0.3, 0.3) * L[1], L[1], 0],
+                       [rng.uniform(-0.3, 0.3) * L[2], rng.uniform(-0.3, 0.3) * L[2], L[2]]])
+        cell = hm.reshape(-1).copy()
+    cutoff = float(rng.uniform(2.2, 3.2))
+    buffer = float(rng.choice([0.0, 0.8]))
+    mode = 1 if buffer > 0 else 0
+    nfr = int(rng.randint(40, 160))
+    pos0 = rng.rand(n, 3) @ hm
+    frames = pos0[None] + np.cumsum(rng.normal(0, 0.04, (nfr, n, 3)), axis=0)
+    rate = cm.Fermi(float(rng.uniform(0.05, 0.5)), float(rng.uniform(2.0, 3.2)), float(rng.uniform(0.05, 0.3)))
+    dt = float(rng.uniform(0.2, 2.0))
+    nrep = int(rng.randint(1, 4))
+    box = make_box(cell)
+    topo = build_with_retry(lambda cap: DeviceTopology(box, n, cutoff, buffer, mode, rate, cap), frames)
+    fptr, start, dest, omega = topo_to_host(topo)
+    lattices, streams = [], []
+    nu = 2 * (32 * nfr + 64)
+    for r in range(nrep):
+        lat = np.zeros(n, np.int32)
+        lat[:nprot] = np.arange(1, nprot + 1)
+        rr = np.random.RandomState(5000 + 10 * seed + r)
+        rr.shuffle(lat)
+        lattices.append(lat)
+        streams.append(rr.random_sample(nu))
+    dev = DeviceKMC(box, np.array(lattices), dt, RNG_REPLAY)
+    dev.set_event_log(nu // 2)
+    dev.set_replay_stream(np.array(streams))
+    dev.advance(topo)
+    st = dev.state()
+    for r in range(nrep):
+        lat = lattices[r].copy()
+        want = orc.kmc_replay(fptr, start, dest, omega, lat, dt, streams[r], nu // 2)
+        ev = dev.events(r)
+        assert want["n_events"] == len(ev["time"]) == st["n_events"][r]
+        for key in ("frame", "start", "dest", "proton", "time"):
+            np.testing.assert_array_equal(ev[key], want[key])
+        np.testing.assert_array_equal(st["lattices"][r], lat)
+    print("seed", seed, "sites", n, "protons", nprot, "frames", nfr, "mode", mode, "events", st["n_events"].tolist(),
+          "pairs/frame", float(np.diff(fptr).mean()))
+    assert st["n_events"].sum() > 0
