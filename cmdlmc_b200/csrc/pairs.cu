@@ -47,6 +47,7 @@ struct cmd_topo {
     int4 *d_fxu, *d_sorted;
     int *d_slot, *d_cell_start, *d_rowcount, *d_rowoff_tmp, *d_tmp_j, *d_cap_need;
     double *d_tmp_d;
+    unsigned short *d_tmp_inv;
     // block results
     int64_t cap_frames, nframes;
     int *d_start, *d_dest, *d_counts, *d_err;
@@ -580,6 +581,8 @@ static void cell_free(cmd_topo *t)
 {
     cudaFree(t->d_fxu); cudaFree(t->d_sorted); cudaFree(t->d_slot); cudaFree(t->d_cell_start);
     cudaFree(t->d_rowcount); cudaFree(t->d_rowoff_tmp); cudaFree(t->d_tmp_j); cudaFree(t->d_tmp_d);
+    cudaFree(t->d_tmp_inv);
+    t->d_tmp_inv = nullptr;
     t->d_fxu = t->d_sorted = nullptr;
     t->d_slot = t->d_cell_start = t->d_rowcount = t->d_rowoff_tmp = t->d_tmp_j = nullptr;
     t->d_tmp_d = nullptr;
@@ -819,6 +822,7 @@ static int cell_reserve(cmd_topo *t, int batch)
     CALLOC(t->d_rowoff_tmp, B * (n + 1) * 4);
     CALLOC(t->d_tmp_j, B * n * t->rowcap * 4);
     CALLOC(t->d_tmp_d, B * n * t->rowcap * 8);
+    CALLOC(t->d_tmp_inv, B * n * t->rowcap * 2);
 #undef CALLOC
     t->cell_batch = batch;
     return CMD_OK;
@@ -826,7 +830,7 @@ static int cell_reserve(cmd_topo *t, int batch)
 
 static int cell_batch_size(const cmd_topo *t, int64_t want)
 {
-    const size_t per = (size_t)t->n * (40 + 12 * (size_t)t->rowcap) + (size_t)(t->cg.ncell + 1) * 4 + 8;
+    const size_t per = (size_t)t->n * (40 + 14 * (size_t)t->rowcap) + (size_t)(t->cg.ncell + 1) * 4 + 8;
     int64_t b = (int64_t)((size_t)1 << 30) / (int64_t)per;
     if (b < 1) b = 1;
     if (b > 8192) b = 8192;
@@ -860,8 +864,8 @@ static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, cons
         }
         CMD_LAUNCHED();
         int tpb = 128;
-        while (tpb > 32 && (size_t)t->rowcap * tpb * 12 > 160 * 1024) tpb >>= 1;
-        const size_t psm = (size_t)t->rowcap * tpb * 12;
+        while (tpb > 32 && (size_t)t->rowcap * tpb * 4 > 160 * 1024) tpb >>= 1;
+        const size_t psm = (size_t)t->rowcap * tpb * 4;
         dim3 pgrid((unsigned)((n + tpb - 1) / tpb), (unsigned)batch);
 #define CELL_PAIRS(K, IM)                                                                        \
     do {                                                                                         \
@@ -869,7 +873,8 @@ static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, cons
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));   \
         k_cell_pairs<K, IM><<<pgrid, tpb, psm, st>>>(                                            \
             t->bx, t->fp, t->cg, d_frames, ids, n_ids, (int)first, n, t->rc, t->t2, t->rowcap,   \
-            t->d_sorted, t->d_cell_start, t->d_rowcount, t->d_tmp_j, t->d_tmp_d, t->d_cap_need,  \
+            t->d_sorted, t->d_cell_start, t->d_rowcount, t->d_tmp_j, t->d_tmp_d, t->d_tmp_inv,   \
+            t->d_cap_need,                                                                       \
             t->d_ties);                                                                          \
     } while (0)
         if (ortho) CELL_PAIRS(0, false);
@@ -883,7 +888,7 @@ static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, cons
         CMD_CUDA(cudaStreamSynchronize(st));
         if (need > t->rowcap) {
             CMD_CUDA(cudaMemsetAsync(t->d_cap_need, 0, sizeof(int), st));
-            if ((size_t)(need + 8) * 32 * 12 > 200 * 1024)
+            if ((size_t)(need + 8) * 32 * 4 > 200 * 1024 || need + 8 > 65535)
                 return cmd_set_error(CMD_ECAPACITY, "an atom has %d neighbour candidates: more than "
                                      "the cell-list kernel can hold per row", need);
             t->rowcap = need + 8;
@@ -897,7 +902,7 @@ static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, cons
         if (emit) {
             dim3 egrid((unsigned)((n + 255) / 256), (unsigned)batch);
             k_cell_emit<<<egrid, 256, 0, st>>>(t->rate, ids, n_ids, (int)first, n, stride, t->rowcap,
-                                               t->d_rowoff_tmp, t->d_tmp_j, t->d_tmp_d, start, dest, dist,
+                                               t->d_rowoff_tmp, t->d_tmp_j, t->d_tmp_d, t->d_tmp_inv, start, dest, dist,
                                                omega, rate_sum);
             CMD_LAUNCHED();
         }

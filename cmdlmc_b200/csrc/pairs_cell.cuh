@@ -90,7 +90,10 @@ k_cell_build(const __grid_constant__ BoxParams bx, const __grid_constant__ CellG
 }
 
 // grid = (ceil(n / TPB), frames of the batch), block = TPB (128, 64 or 32: long rows take fewer
-// threads per CTA); dynamic smem = TPB * rowcap * 12 bytes
+// threads per CTA); dynamic smem = TPB * rowcap * 4 bytes (the row's column indices only: the kernel
+// lives on memory latency, so shared memory per thread decides how many warps hide it).  A row is
+// stored in discovery order (tmp_j, tmp_d) together with the order of its columns: tmp_inv[r] = slot
+// of the entry with the r-th smallest column.
 template <int KIND, bool IMAGES>
 __global__ void __launch_bounds__(128)
 k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ FilterParams fp,
@@ -98,15 +101,15 @@ k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ Filte
              const int *__restrict__ ids, const int *__restrict__ n_ids, int first, int n,
              double rc, double t2, int rowcap, const int4 *__restrict__ sorted,
              const int *__restrict__ cell_start, int *__restrict__ rowcount,
-             int *__restrict__ tmp_j, double *__restrict__ tmp_d, int *__restrict__ cap_need,
+             int *__restrict__ tmp_j, double *__restrict__ tmp_d,
+             unsigned short *__restrict__ tmp_inv, int *__restrict__ cap_need,
              unsigned long long *__restrict__ ties)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (n_ids && first + (int)blockIdx.y >= *n_ids) return;
     const int64_t f = ids ? ids[first + blockIdx.y] : first + blockIdx.y;
     const int b = blockIdx.y, tid = threadIdx.x, TPB = blockDim.x;
-    double *sd = (double *)smem_raw;                       // [rowcap][TPB]
-    int *sj = (int *)(sd + (size_t)rowcap * TPB);          // [rowcap][TPB]
+    int *sj = (int *)smem_raw;                             // [rowcap][TPB]
     const int p = blockIdx.x * TPB + tid;
     if (p >= n) return;
     const double *fr = frames + f * (int64_t)n * 3;
@@ -147,6 +150,7 @@ k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ Filte
 
     // ---- exact evaluation of the survivors (reference arithmetic), compaction -----------------
     const double pa[3] = {__ldg(fr + 3 * i), __ldg(fr + 3 * i + 1), __ldg(fr + 3 * i + 2)};
+    const int64_t row = ((int64_t)b * n + i) * rowcap;
     int nh = 0;
     unsigned long long my_ties = 0;
     for (int c = 0; c < ncand; c++) {
@@ -164,30 +168,20 @@ k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ Filte
         const bool hit = (bx.conv == CMD_CONV_NONE ? d2 <= t2 : dist <= rc) && dist != 0.0;
         if (i < j && fabs(dist - rc) <= 1e-11 * rc) my_ties++;   // a pair is seen from both rows
         if (hit) {
-            sj[nh * TPB + tid] = j;
-            sd[nh * TPB + tid] = dist;
+            sj[nh * TPB + tid] = j;      // nh <= c: never ahead of the read position
+            tmp_j[row + nh] = j;
+            tmp_d[row + nh] = dist;
             nh++;
         }
     }
     if (my_ties) atomicAdd(ties, my_ties);
 
-    // ---- row sorted by column (insertion sort; rows are a few dozen entries) ------------------
-    for (int a = 1; a < nh; a++) {
-        const int kj = sj[a * TPB + tid];
-        const double kd = sd[a * TPB + tid];
-        int q = a - 1;
-        while (q >= 0 && sj[q * TPB + tid] > kj) {
-            sj[(q + 1) * TPB + tid] = sj[q * TPB + tid];
-            sd[(q + 1) * TPB + tid] = sd[q * TPB + tid];
-            q--;
-        }
-        sj[(q + 1) * TPB + tid] = kj;
-        sd[(q + 1) * TPB + tid] = kd;
-    }
-    const int64_t row = ((int64_t)b * n + i) * rowcap;
+    // ---- the row's column order by rank counting (columns are distinct) -------------------------
     for (int a = 0; a < nh; a++) {
-        tmp_j[row + a] = sj[a * TPB + tid];
-        tmp_d[row + a] = sd[a * TPB + tid];
+        const int kj = sj[a * TPB + tid];
+        int rank = 0;
+        for (int q = 0; q < nh; q++) rank += sj[q * TPB + tid] < kj;
+        tmp_inv[row + rank] = (unsigned short)a;
     }
     rowcount[(int64_t)b * n + i] = nh;
 }
@@ -235,7 +229,8 @@ __global__ void __launch_bounds__(256)
 k_cell_emit(const __grid_constant__ RateParams rp, const int *__restrict__ ids,
             const int *__restrict__ n_ids, int first, int n, int64_t stride, int rowcap,
             const int *__restrict__ rowoff, const int *__restrict__ tmp_j,
-            const double *__restrict__ tmp_d, int *__restrict__ out_start,
+            const double *__restrict__ tmp_d, const unsigned short *__restrict__ tmp_inv,
+            int *__restrict__ out_start,
             int *__restrict__ out_dest, double *__restrict__ out_dist,
             double *__restrict__ out_omega, double *__restrict__ out_rate_sum)
 {
@@ -264,7 +259,8 @@ k_cell_emit(const __grid_constant__ RateParams rp, const int *__restrict__ ids,
         const int off_lo = __shfl_sync(0xffffffffu, myoff, lo);
         if (g < g1) {
             const int r = r0 + lo;
-            const int64_t src = ((int64_t)b * n + r) * rowcap + (g - off_lo);
+            const int64_t rbase = ((int64_t)b * n + r) * rowcap;
+            const int64_t src = rbase + tmp_inv[rbase + (g - off_lo)];   // columns ascending
             const int j = tmp_j[src];
             const double dist = tmp_d[src];
             const double om = rate_eval(rp, dist, 0.0);
