@@ -127,12 +127,19 @@ k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ Filte
         for (int dy = 0; dy < cg.span[1]; dy++) {
             int cy = cg.span[1] == 1 ? 0 : ic[1] + dy - 1;
             cy += cy < 0 ? cg.nc[1] : 0; cy -= cy >= cg.nc[1] ? cg.nc[1] : 0;
-            for (int dz = 0; dz < cg.span[2]; dz++) {
-                int cz = cg.span[2] == 1 ? 0 : ic[2] + dz - 1;
-                cz += cz < 0 ? cg.nc[2] : 0; cz -= cz >= cg.nc[2] ? cg.nc[2] : 0;
-                const int cell = (cx * cg.nc[1] + cy) * cg.nc[2] + cz;
-                const int k1 = __ldg(cs + cell + 1);
-                for (int k = __ldg(cs + cell); k < k1; k++) {
+            // The cells of one (cx, cy) column are consecutive in the sorted order, so the up to three
+            // z neighbours are ONE index range -- two where the column wraps around.
+            const int col = (cx * cg.nc[1] + cy) * cg.nc[2];
+            int zlo[2], zhi[2], nrange = 1;
+            if (cg.span[2] == 1) { zlo[0] = 0; zhi[0] = cg.nc[2] - 1; }
+            else {
+                zlo[0] = ic[2] - 1; zhi[0] = ic[2] + 1;
+                if (zlo[0] < 0) { zlo[1] = cg.nc[2] - 1; zhi[1] = cg.nc[2] - 1; zlo[0] = 0; nrange = 2; }
+                else if (zhi[0] >= cg.nc[2]) { zlo[1] = 0; zhi[1] = 0; zhi[0] = cg.nc[2] - 1; nrange = 2; }
+            }
+            for (int rg = 0; rg < nrange; rg++) {
+                const int k1 = __ldg(cs + col + zhi[rg] + 1);
+                for (int k = __ldg(cs + col + zlo[rg]); k < k1; k++) {
                     const int4 q = __ldg(srt + k);
                     if (q.w != i && filter_pair<KIND, IMAGES>(fp, me, q)) {
                         if (ncand < rowcap) sj[ncand * TPB + tid] = q.w;
