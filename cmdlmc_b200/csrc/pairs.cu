@@ -163,6 +163,53 @@ k_sched_walk(const double *__restrict__ dr, int n, int64_t nframes, double buffe
     if (threadIdx.x == 0) next[w] = r;
 }
 
+// The same walkers, one WARP each (n <= 32 * PER): the displacements live in registers, the next
+// frame's dr is requested before this frame's two largest values are reduced, no shared memory and
+// no CTA barrier.  Same per-atom additions, and the two largest values do not depend on the order
+// of the reduction: identical next[].
+template <int PER>
+__global__ void __launch_bounds__(128)
+k_sched_walk_warp(const double *__restrict__ dr, int n, int64_t nframes, double buffer,
+                  int *__restrict__ next)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5) + 1;
+    if (w > nframes) return;
+    double disp[PER], nx[PER];
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+        disp[q] = 0.0;
+        const int a = lane + 32 * q;
+        nx[q] = (a < n && w < nframes) ? dr[w * n + a] : 0.0;
+    }
+    int r = (int)nframes;
+    for (int64_t f = w; f < nframes; f++) {
+        if (f - w >= SCHED_CAP) { r = -1; break; }
+        double m1 = -INFINITY, m2 = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            if (lane + 32 * q < n) {
+                const double v = __dadd_rn(disp[q], nx[q]);
+                disp[q] = v;
+                if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) m2 = v;
+            }
+        }
+        if (f + 1 < nframes) {
+#pragma unroll
+            for (int q = 0; q < PER; q++) {
+                const int a = lane + 32 * q;
+                if (a < n) nx[q] = dr[(f + 1) * n + a];
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {   // butterfly: every lane ends with the warp's two largest
+            const double o1 = __shfl_xor_sync(0xffffffffu, m1, o), o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+            if (o1 > m1) { m2 = fmax(m1, o2); m1 = o1; } else m2 = fmax(m2, o1);
+        }
+        if (n >= 2 && __dadd_rn(m2, m1) > buffer) { r = (int)f; break; }
+    }
+    if (lane == 0) next[w] = r;
+}
+
 // follows the chain from the block's start state, marks the rebuild frames, leaves the displacement
 // of the block's end in `displacement`
 __global__ void __launch_bounds__(SCHED_THREADS)
@@ -1074,6 +1121,12 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
         if (ssm <= 48 * 1024 && nframes >= 64) {
             // parallel schedule: next-rebuild function for every start frame, then chain following
             CMD_CUDA(cudaMemsetAsync(t->d_rebuilt, 0, (size_t)nframes, st));
+            const unsigned wblocks = (unsigned)((nframes + 3) / 4);
+            if (t->n <= 128) k_sched_walk_warp<4><<<wblocks, 128, 0, st>>>(t->d_dr, t->n, nframes, t->buffer, t->d_next);
+            else if (t->n <= 256) k_sched_walk_warp<8><<<wblocks, 128, 0, st>>>(t->d_dr, t->n, nframes, t->buffer, t->d_next);
+            else if (t->n <= 384) k_sched_walk_warp<12><<<wblocks, 128, 0, st>>>(t->d_dr, t->n, nframes, t->buffer, t->d_next);
+            else if (t->n <= 512) k_sched_walk_warp<16><<<wblocks, 128, 0, st>>>(t->d_dr, t->n, nframes, t->buffer, t->d_next);
+            else
             k_sched_walk<<<(unsigned)nframes, SCHED_THREADS, ssm, st>>>(t->d_dr, t->n, nframes, t->buffer,
                                                                         t->d_next);
             CMD_LAUNCHED();
