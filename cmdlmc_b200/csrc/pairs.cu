@@ -88,11 +88,10 @@ __global__ void __launch_bounds__(256) k_dr(const __grid_constant__ BoxParams bx
                                             const double *__restrict__ last, int have_last, int n,
                                             int64_t nframes, double *__restrict__ dr)
 {
-    int64_t total = nframes * n;
-    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total;
-         g += (int64_t)gridDim.x * blockDim.x) {
-        int64_t f = g / n;
-        int i = (int)(g - f * n);
+    // grid = (atom blocks, frame lanes): no 64-bit division per element
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int64_t f = blockIdx.y; f < nframes; f += gridDim.y) {
         const double *cur = frames + (f * n + i) * 3;
         const double *prev = f > 0 ? cur - (int64_t)n * 3 : (have_last ? last + (int64_t)i * 3 : nullptr);
         double v = 0.0;  // topology.py:95: first frame -> dr = zeros
@@ -100,7 +99,7 @@ __global__ void __launch_bounds__(256) k_dr(const __grid_constant__ BoxParams bx
             double a[3] = {prev[0], prev[1], prev[2]}, b[3] = {cur[0], cur[1], cur[2]};
             v = length_exact(bx, a, b);
         }
-        dr[g] = v;
+        dr[f * n + i] = v;
     }
 }
 
@@ -1112,10 +1111,15 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
         rc = launch_pairs(t, d_frames, nullptr, nullptr, nframes, 0, true);
         if (rc) return rc;
     } else {
-        int blocks = cmd_div_up(nframes * t->n, 256);
-        if (blocks > g.sm_count * 16) blocks = g.sm_count * 16;
-        k_dr<<<blocks, 256, 0, st>>>(t->bx, d_frames, t->d_last, t->have_last ? 1 : 0, t->n, nframes,
-                                     t->d_dr);
+        {
+            const int ablocks = cmd_div_up(t->n, 256);
+            int64_t flanes = (int64_t)g.sm_count * 16 / ablocks;
+            if (flanes < 1) flanes = 1;
+            if (flanes > nframes) flanes = nframes;
+            if (flanes > 65535) flanes = 65535;
+            k_dr<<<dim3(ablocks, (unsigned)flanes), 256, 0, st>>>(t->bx, d_frames, t->d_last,
+                                                                  t->have_last ? 1 : 0, t->n, nframes, t->d_dr);
+        }
         CMD_LAUNCHED();
         const size_t ssm = ((size_t)t->n + 2 * (SCHED_THREADS / 32)) * 8;
         if (ssm <= 48 * 1024 && nframes >= 64) {
