@@ -33,10 +33,11 @@ struct cmd_topo {
     int n;
     double cutoff, buffer, rc;
     double t2;       // largest d2 with sqrt(d2) <= rc  (exact decision on the squared length)
-    FilterParams fp; // FP32 fixed-point filter of the dense kernel
+    FilterParams fp; // filter constants of the dense kernel (packed-half and FP32 forms)
+    int filt;        // FILT_* variant the dense kernel runs with
     int mode;
     int64_t stride;  // per-frame pair capacity
-    int hit_cap;     // unordered hits per frame that fit the CTA's shared-memory list
+    int hit_cap;     // filter candidates per frame that fit the CTA's shared-memory list
     size_t smem_bytes;
     int threads;
     // cell-list path (boxes the one-CTA-per-frame kernel cannot hold)
@@ -683,12 +684,77 @@ static void topo_filter_params(cmd_topo *t)
         for (int k = 0; k < 3; k++)
             fp.img[m][k] = (float)(q[k][0] * bx.img[m][0] + q[k][1] * bx.img[m][1] +
                                    q[k][2] * bx.img[m][2]);
+
+    // ---- packed-half filter (FILT_H2): 10-bit fractional coordinates, fp16 arithmetic ---------
+    // Error of the computed vector against the true wrapped vector v = R s (s = wrapped fractional
+    // difference), per component r with q_r = sum_c |R_rc| / 1024:
+    //   quantisation   |w_c - 1024 s_c| <= 1 (two roundings of half a unit)          -> q_r
+    //   fp16 matrix    |R16_rc - R_rc/1024| <= 2^-11 |R_rc/1024|, |w_c| <= 512       -> q_r / 4
+    //   fp16 rounding  <= 3 results per component, each <= 2^-11 * 512 q_r (1+2^-11) -> 3 q_r / 4
+    // so |dv| <= 2.1 sqrt(sum q_r^2) =: E, and the squared length carries three more roundings.
+    // A pair within `radius` therefore has a computed d2 <= (radius + E)^2 (1 + 2^-11)^3 + tiny.
+    // The integer wrap may pick the other periodic image when a fractional difference lies within
+    // 2 units of +-1/2; such a pair is farther apart than radius + E as long as every cell height
+    // times (1/2 - 2/1024) exceeds it, which is required below.
+    {
+        const double u10 = 1.0 / 1024.0;
+        double qs = 0, hmin = 1e300;
+        const int rows[3][3] = {{0, 1, 2}, {-1, 3, 4}, {-1, -1, 5}};
+        for (int r = 0; r < 3; r++) {
+            double qr = 0;
+            for (int c = 0; c < 3; c++) if (rows[r][c] >= 0) qr += fabs(rr[rows[r][c]]) * u10;
+            qs += qr * qr;
+        }
+        for (int c = 0; c < 3; c++) {
+            const double height = 1.0 / sqrt(bx.hinv[3 * c] * bx.hinv[3 * c] + bx.hinv[3 * c + 1] * bx.hinv[3 * c + 1] +
+                                             bx.hinv[3 * c + 2] * bx.hinv[3 * c + 2]);
+            if (height < hmin) hmin = height;
+        }
+        const double E = 2.1 * sqrt(qs);
+        const double lim = (radius + E) * (radius + E) * 1.0015 + 1e-6;
+        for (int k = 0; k < 6; k++) {
+            const __half hv = __float2half_rn((float)(rr[k] * u10));
+            const unsigned short bits = *reinterpret_cast<const unsigned short *>(&hv);
+            fp.hR[k] = bits * 0x00010001u;
+        }
+        __half ht = __float2half_ru((float)lim);
+        const unsigned short tb = *reinterpret_cast<const unsigned short *>(&ht);
+        fp.hT2 = tb * 0x00010001u;
+        fp.h2_ok = bx.n_img == 0 && radius > 0 && E <= 0.05 * radius + 0.05 && lim < 60000.0 &&
+                   hmin * (0.5 - 2.0 * u10) > radius + E && getenv("CMDLMC_B200_DENSE_F32") == nullptr;
+        // spatial pruning: atoms binned (256 bins) along the fractional axis with the largest
+        // height; a pair within `radius` differs by <= radius / height in that coordinate, i.e.
+        // by <= radius / height * 1024 + 1 units of the 10-bit coordinates (two roundings) and
+        // by at most ceil(that / 4) + 1 bins.  Forward windows of two rows cannot both hold the
+        // other row while 2 db < 256; it pays while the window is well below half the atoms.
+        int axis = 0;
+        double hbest = 0;
+        for (int c = 0; c < 3; c++) {
+            const double height = 1.0 / sqrt(bx.hinv[3 * c] * bx.hinv[3 * c] + bx.hinv[3 * c + 1] * bx.hinv[3 * c + 1] +
+                                             bx.hinv[3 * c + 2] * bx.hinv[3 * c + 2]);
+            if (height > hbest) { hbest = height; axis = c; }
+        }
+        const int db = (int)ceil((radius / hbest * 1024.0 + 1.0) / 4.0) + 1;
+        fp.sort_axis = -1;
+        fp.sort_db = 0;
+        if (db <= 100 && t->n >= 96 && getenv("CMDLMC_B200_DENSE_NOSORT") == nullptr) {
+            fp.sort_axis = axis;
+            fp.sort_db = db;
+        }
+    }
+    t->filt = fp.h2_ok ? FILT_H2 : bx.n_img == 0 ? FILT_F32 : FILT_F32_IMG;
 }
 
 static int dense_threads(int n)
 {
-    int th = ((n + 1) / 2 + 31) / 32 * 32;   // two rows per thread
+    int th = ((n + 1) / 2 + 31) / 32 * 32;   // FP32 filters: two rows per thread
     return th < 32 ? 32 : th;
+}
+
+static int dense_threads_h2(int n)
+{
+    int th = (n + 31) / 32 * 32;             // packed-half filter: one row per thread
+    return th < 64 ? 64 : th;
 }
 
 // Cells per fractional axis: the cell must be at least one filter radius thick.
@@ -719,18 +785,42 @@ static void topo_cell_grid(cmd_topo *t)
     cg.ncell = cg.nc[0] * cg.nc[1] * cg.nc[2];
 }
 
+// candidate capacity of the dense kernel's shared-memory lists for a per-frame capacity `stride`:
+// stride / 2 unordered hits fit the HBM rows; the filter passes ~1.1x the hits, and the rows are
+// sized 1.5x the first frame, so a list that holds 0.72 * stride / 2 candidates loses nothing in
+// practice -- if two CTAs per SM fit with that, take them (the phases of the two overlap).
+#define DENSE_SMEM_ONE (226 * 1024)
+#define DENSE_SMEM_TWO 115200
+static int dense_candidate_cap(int n, int64_t stride, int filt)
+{
+    int64_t cap = stride / 2;
+    const size_t fixed = dense_smem_fixed(n, filt);
+    if (fixed < DENSE_SMEM_TWO) {
+        int64_t cap2 = (int64_t)((DENSE_SMEM_TWO - fixed) / DENSE_BYTES_PER_CAND) / 4 * 4;
+        if (cap2 >= cap) return (int)(cap > 32764 ? 32764 : cap);
+        if (cap2 * 100 >= cap * 72) return (int)(cap2 > 32764 ? 32764 : cap2);
+    }
+    if (fixed < DENSE_SMEM_ONE) {
+        int64_t cap1 = (int64_t)((DENSE_SMEM_ONE - fixed) / DENSE_BYTES_PER_CAND) / 4 * 4;
+        if (cap1 < cap) cap = cap1;
+    }
+    return (int)(cap > 32764 ? 32764 : cap);   // 15-bit candidate index in the slot map
+}
+
 static int topo_configure(cmd_topo *t, int64_t stride)
 {
-    // per-frame capacity and the matching shared-memory hit list
+    // per-frame capacity and the matching shared-memory candidate list
     stride = (stride + 63) / 64 * 64;
-    int hit_cap = (int)(stride / 2);
-    size_t smem = dense_smem_bytes(t->n, hit_cap);
+    int hit_cap = dense_candidate_cap(t->n, stride, t->filt);
+    size_t smem = dense_smem_bytes(t->n, hit_cap, t->filt);
     t->stride = stride;
     t->threads = dense_threads(t->n);
-    const bool fits = t->n <= 1024 && smem <= 226 * 1024;
+    // the list must hold at least 0.72 * stride / 2 candidates, else the cell list takes over
+    const bool fits = t->n <= 1024 && smem <= DENSE_SMEM_ONE && (int64_t)hit_cap * 100 >= stride / 2 * 72;
     if (!fits && t->force_path == 0)
         return cmd_set_error(CMD_ECAPACITY, "dense pair kernel needs %zu bytes of shared memory for "
-                             "n=%d, capacity %lld (limit 231424)", smem, t->n, (long long)stride);
+                             "n=%d, capacity %lld (limit 231424)",
+                             dense_smem_bytes(t->n, (int)(stride / 2), t->filt), t->n, (long long)stride);
     if (!fits || t->force_path == 1) {   // too large for one CTA per frame: cell list
         t->path = 1;
         t->hit_cap = 0;
@@ -832,12 +922,22 @@ static int launch_dense(cmd_topo *t, const double *d_frames, const int *ids, con
     } while (0)
 #define DENSE_PICK(SP, MT, MB)                                                                   \
     do {                                                                                         \
-        if (ortho) DENSE_LAUNCH(0, false, SP, MT, MB);                                           \
-        else if (t->fp.n_img == 0) DENSE_LAUNCH(1, false, SP, MT, MB);                           \
-        else DENSE_LAUNCH(1, true, SP, MT, MB);                                                  \
+        if (ortho) DENSE_LAUNCH(0, FILT_F32, SP, MT, MB);                                        \
+        else if (t->fp.n_img == 0) DENSE_LAUNCH(1, FILT_F32, SP, MT, MB);                        \
+        else DENSE_LAUNCH(1, FILT_F32_IMG, SP, MT, MB);                                          \
     } while (0)
+    if (t->filt == FILT_H2) {
+        // one row per thread; register budget 64 in every shape
+        const int th = dense_threads_h2(t->n);
+        const int keep = t->threads;
+        t->threads = th;
+        if (th <= 256) { if (ortho) DENSE_LAUNCH(0, FILT_H2, 1, 256, 4); else DENSE_LAUNCH(1, FILT_H2, 1, 256, 4); }
+        else if (th <= 512) { if (ortho) DENSE_LAUNCH(0, FILT_H2, 1, 512, 2); else DENSE_LAUNCH(1, FILT_H2, 1, 512, 2); }
+        else { if (ortho) DENSE_LAUNCH(0, FILT_H2, 1, 1024, 1); else DENSE_LAUNCH(1, FILT_H2, 1, 1024, 1); }
+        t->threads = keep;
+    }
     // t->threads = one thread per two rows; small frames run two copies of the row set
-    if (t->threads <= 128) DENSE_PICK(2, 256, 2);
+    else if (t->threads <= 128) DENSE_PICK(2, 256, 2);
     else if (t->threads <= 256) DENSE_PICK(DENSE_SPLIT_MID, 256 * DENSE_SPLIT_MID, 2);
     else DENSE_PICK(1, 512, 1);
 #undef DENSE_PICK
@@ -966,9 +1066,9 @@ static int topo_autosize(cmd_topo *t, const double *d_frame)
     int rc = cmd_scratch(4, 64, (void **)&d_cnt);
     if (rc) return rc;
     t->threads = dense_threads(t->n);
-    size_t smem = dense_smem_bytes(t->n, 0);
+    size_t smem = dense_smem_bytes(t->n, 0, t->filt);
     CMD_CUDA(cudaMemsetAsync(t->d_err, 0, sizeof(int), st));
-    if (t->n <= 1024 && smem <= 226 * 1024 && t->force_path != 1) {
+    if (t->n <= 1024 && smem <= DENSE_SMEM_ONE && t->force_path != 1) {
         rc = launch_dense(t, d_frame, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, d_cnt,
                           nullptr, nullptr, nullptr, 0, 0, smem);
     } else {
@@ -984,9 +1084,9 @@ static int topo_autosize(cmd_topo *t, const double *d_frame)
     CMD_CUDA(cudaMemsetAsync(t->d_ties, 0, sizeof(unsigned long long), st));
     int64_t p0 = cnt < 0 ? -cnt : cnt;
     int64_t want = p0 + p0 / 2 + 128;
-    // prefer the dense kernel: shrink the head-room to what its shared-memory hit list can hold
+    // prefer the dense kernel: shrink the head-room to what its shared-memory lists can hold
     while (t->n <= 1024 && t->force_path != 1 && want > p0 + p0 / 4 + 64 &&
-           dense_smem_bytes(t->n, (int)((want + 63) / 64 * 64 / 2)) > 226 * 1024)
+           (int64_t)dense_candidate_cap(t->n, (want + 63) / 64 * 64, t->filt) * 100 < (want + 63) / 64 * 64 / 2 * 72)
         want -= 64;
     return topo_configure(t, want);
 }

@@ -1,81 +1,120 @@
 // pairs_dense.cuh -- the all-pairs neighbour-list kernel (row A7 of SURVEY.md section 8):
-// NeighborTopology.get_topology_bruteforce (topology.py:55-72) for one frame per CTA, with the
-// jump rate of every listed pair fused in (jumprate_generators.py:33-34).
+// NeighborTopology.get_topology_bruteforce (topology.py:55-72) for one frame per trip of a
+// persistent CTA, with the jump rate of every listed pair fused in
+// (jumprate_generators.py:33-34).
 //
-// Three phases, all out of shared memory:
-//   1 filter   every unordered pair once.  Coordinates are turned into FRACTIONAL coordinates in
-//              32-bit FIXED POINT (one unit = 2^-32 of a cell vector), so the minimum-image wrap
-//              of a difference is the two's-complement wrap-around of one integer subtraction --
-//              it costs nothing.  The wrapped difference goes through an FP32 upper-triangular
-//              cell matrix (the R of h = QR; lengths do not depend on Q) and is compared with a
-//              conservatively widened radius.  Each thread owns two consecutive rows and walks
-//              the cyclic pairing (i, i+k), k = 1..n/2, so one 16-byte shared-memory load feeds
-//              two pairs; hits are collected in register bit masks and appended to the
-//              candidate list 32 columns at a time.  The filter NEVER decides a hit.
-//   2 exact    the candidates (~4 % of the pairs), densely packed over the CTA, in the reference's
-//              FP64 arithmetic (pbc.cuh *_exact): the `dist <= cutoff + buffer` decision, sqrt,
-//              adjacency bits.
-//   3 emit     row offsets from the adjacency bit matrix (popc + scan) and the ordered write of
-//              (start, dest, dist, omega): both directions, row-major, columns ascending.
+// Everything between the frame's coordinates (24 n bytes in) and its list (24 bytes per directed
+// pair out) happens in shared memory:
+//   1 filter   every unordered pair once, in cheap arithmetic that NEVER decides a hit.
+//              FILT_H2 (default): fractional coordinates in 10-bit fixed point, two columns packed
+//              per 32-bit word.  One integer add per coordinate forms (x_j - x_i + 512) mod 1024
+//              for both columns, one LOP3 turns the two 10-bit fields into the fp16 numbers
+//              1024 + u (exponent trick), and from there the wrapped difference, the
+//              upper-triangular cell matrix (R of h = QR), the squared length and the compare run
+//              as half2 SIMD: ~10 instructions per pair.  The radius is widened by a proven bound
+//              on quantisation + fp16 rounding (topo_filter_params).
+//              FILT_F32 / FILT_F32_IMG: 32-bit fixed point + FP32 (cells so skewed that periodic
+//              images matter, or so large that 10 bits are too coarse).
+//   2 exact    the surviving candidates (~1.1x the hits), densely packed over the CTA, in the
+//              reference's FP64 arithmetic (pbc.cuh *_exact): the `dist <= cutoff + buffer`
+//              decision, sqrt, adjacency bits.
+//   3 emit     row offsets from the adjacency bit matrix (popc + scan); every hit drops its
+//              candidate index into the two output slots it owns (a->b, b->a); then the CTA walks
+//              the output positions IN ORDER, four per thread, and writes (start, dest, dist) and
+//              -- after the rates have replaced the distances in shared memory -- omega with
+//              16-byte stores: full 32-byte sectors only, no partial-sector traffic in HBM.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "pbc.cuh"
 #include "tma.cuh"
 
-// FP32 side of the filter (host-prepared, cmd_topo_create)
+#define FILT_F32 0
+#define FILT_F32_IMG 1
+#define FILT_H2 2
+
+// filter constants (host-prepared, topo_filter_params)
 struct FilterParams {
     float R[6];        // upper-triangular cell matrix * 2^-32: r00 r01 r02 r11 r12 r22
     float t2;          // widened squared radius
     int n_img;         // kept periodic images besides the wrapped vector (0 for every sane cell)
     float img[CMD_MAX_IMAGES][3];  // their shifts in the R frame
+    // packed-half filter
+    unsigned hR[6];    // R / 1024 as half2 (both halves equal)
+    unsigned hT2;      // widened squared radius, half2, rounded up
+    int h2_ok;         // the 10-bit filter is valid and tight enough for this cell / radius
+    int sort_axis;     // fractional axis the atoms are binned along (-1: no spatial pruning)
+    int sort_db;       // window: a pair within the radius is at most this many bins (of 256) apart
 };
 
 struct DenseSmem {
     double *c;              // [n][3] Cartesian coordinates of the frame as they lie in HBM (the
                             // next frame is prefetched into this place by TMA), phases 1-2
-    int4 *fx;               // [2n + 4] fixed-point fractional coordinates, duplicated (cyclic)
-    unsigned short *wpre;   // [n][W] exclusive popc prefix per mask word (aliases fx, phase 3)
-    double *hit_d;          // [hit_cap] distance of a hit, < 0 otherwise
-    unsigned *mask;         // [n][W] adjacency bit matrix
-    unsigned *hit_ij;       // [hit_cap] (a << 16) | b
+    uint4 *col;             // FILT_H2: [2n + 40] overlapping column pairs of the sorted cyclic
+                            // sequence; FILT_F32*: int4 [2n + 4] fixed point
+    unsigned short *wpre;   // [n][W] exclusive popc prefix per mask word (aliases c + col, phase 3)
+    double *hit_d;          // [cap] distance of a hit, < 0 otherwise; omega after the first emit pass
+    double *red;            // [40] block reductions, mbarrier at [36]
+    unsigned *mask;         // [n][W] adjacency bit matrix (FILT_H2: 10-bit coordinates before phase 1)
+    unsigned *hit_ij;       // [cap] (a << 16) | b
+    unsigned short *slot;   // [2 cap] output position -> candidate index | direction << 15
     int *rowoff;            // [n + 1]
     int *misc;              // [0] ncand, [1] total, [2..33] warp sums
-    double *red;            // [34] block reductions
+    int *bins;              // [258] atoms per sort bin -> exclusive prefix (FILT_H2)
+    unsigned short *perm;   // [n] sorted position -> atom (FILT_H2)
+    bool wpre_ok;
 };
 
-__host__ __device__ inline size_t dense_smem_bytes(int n, int hit_cap)
+__host__ __device__ inline size_t dense_al16(size_t b) { return (b + 15) / 16 * 16; }
+
+__host__ __device__ inline size_t dense_col_bytes(int n, int filt)
 {
-    int W = (n + 31) / 32;
-    size_t b = 0;
-    b += (3 * (size_t)n * 8 + 15) / 16 * 16;  // c (padded: fx is read with LDS.128)
-    b += (2 * (size_t)n + 4) * 16;        // fx
-    b += (size_t)hit_cap * 8;             // hit_d
-    b += 40 * 8;                          // red
-    b += (size_t)n * W * 4;               // mask
-    b += (size_t)hit_cap * 4;             // hit_ij
-    b += ((size_t)n + 1) * 4;             // rowoff
-    b += 40 * 4;                          // misc
-    return b + 16;
+    return filt == FILT_H2 ? (2 * (size_t)n + 40) * 16 : (2 * (size_t)n + 4) * 16;
 }
 
-__host__ __device__ inline bool dense_use_wpre(int n)
+__host__ __device__ inline size_t dense_mask_bytes(int n)
 {
-    int W = (n + 31) / 32;
-    return (size_t)n * W * 2 <= (2 * (size_t)n + 4) * 16;
+    const int W = (n + 31) / 32;
+    size_t m = (size_t)n * W * 4;
+    if (m < (size_t)n * 8) m = (size_t)n * 8;   // the 10-bit coordinates are parked here
+    return dense_al16(m);
 }
 
-__device__ __forceinline__ DenseSmem dense_carve(unsigned char *base, int n, int hit_cap)
+// bytes that do not depend on the candidate capacity / bytes per candidate
+__host__ __device__ inline size_t dense_smem_fixed(int n, int filt)
+{
+    return dense_al16(3 * (size_t)n * 8) + dense_col_bytes(n, filt) + 40 * 8 + dense_mask_bytes(n) +
+           dense_al16(((size_t)n + 1) * 4) + 40 * 4 + 264 * 4 + dense_al16((size_t)n * 2) + 16;
+}
+#define DENSE_BYTES_PER_CAND 16   // hit_d 8 + hit_ij 4 + 2 slots of 2
+
+__host__ __device__ inline size_t dense_smem_bytes(int n, int cap, int filt)
+{
+    return dense_smem_fixed(n, filt) + (size_t)cap * DENSE_BYTES_PER_CAND;
+}
+
+__device__ __forceinline__ DenseSmem dense_carve(unsigned char *base, int n, int cap, int filt)
 {
     DenseSmem s;
-    int W = (n + 31) / 32;
+    const int W = (n + 31) / 32;
+    const size_t A = dense_al16(3 * (size_t)n * 8), B = dense_col_bytes(n, filt);
     s.c = (double *)base;
-    s.fx = (int4 *)(base + (3 * (size_t)n * 8 + 15) / 16 * 16);
-    s.wpre = (unsigned short *)s.fx;
-    s.hit_d = (double *)(s.fx + 2 * n + 4);
-    s.red = s.hit_d + hit_cap;
+    s.col = (uint4 *)(base + A);
+    s.wpre = (unsigned short *)base;
+    s.wpre_ok = (size_t)n * W * 2 <= A + B;
+    s.hit_d = (double *)(base + A + B);
+    s.red = s.hit_d + cap;
     s.mask = (unsigned *)(s.red + 40);
-    s.hit_ij = s.mask + (size_t)n * W;
-    s.rowoff = (int *)(s.hit_ij + hit_cap);
-    s.misc = s.rowoff + n + 1;
+    unsigned char *p = (unsigned char *)s.mask + dense_mask_bytes(n);
+    s.hit_ij = (unsigned *)p;
+    p += (size_t)cap * 4;
+    s.slot = (unsigned short *)p;
+    p += (size_t)cap * 4;
+    s.rowoff = (int *)p;
+    p += dense_al16(((size_t)n + 1) * 4);
+    s.misc = (int *)p;
+    s.bins = s.misc + 40;
+    s.perm = (unsigned short *)(s.bins + 264);
     return s;
 }
 
@@ -125,7 +164,7 @@ __device__ __forceinline__ double min_image_norm2_kept(const BoxParams &bx, cons
     return mind;
 }
 
-// the filter's verdict on one pair: wrapped fixed-point difference -> FP32 length^2 <= radius^2
+// the FP32 filter's verdict on one pair: wrapped fixed-point difference -> length^2 <= radius^2
 template <int KIND, bool IMAGES>
 __device__ __forceinline__ bool filter_pair(const FilterParams &fp, const int4 &p, const int4 &q)
 {
@@ -149,10 +188,42 @@ __device__ __forceinline__ bool filter_pair(const FilterParams &fp, const int4 &
     return d2 <= fp.t2;
 }
 
-// One CTA per frame.  grid.x = number of frames to (re)build; frame = ids ? ids[blockIdx.x] :
-// blockIdx.x.  blockDim.x = SPLIT * T2 with T2 >= ceil(n / 2) a multiple of 32: SPLIT copies of
-// the row set share the column blocks of phase 1 (more warps per frame for phases 2-3).
-template <int KIND, bool IMAGES, int SPLIT, int MAXT, int MINB>
+__device__ __forceinline__ __half2 u2h2(unsigned u)
+{
+    __half2 h;
+    *reinterpret_cast<unsigned *>(&h) = u;
+    return h;
+}
+
+// The packed-half filter on one column pair: 0xffff in the half of every column that passes.
+// P = the pair's 10-bit coordinates (low half: even column); C* = (512 - row coordinate) mod 1024
+// in both halves.  Each 16-bit lane of P + C is < 2047, so the packed add never carries across.
+template <int KIND>
+__device__ __forceinline__ unsigned h2_pair_mask(const __half2 (&R)[6], const __half2 T2,
+                                                 const uint4 &P, unsigned CX, unsigned CY, unsigned CZ)
+{
+    // 0x6400 has bit 10 set, so OR-ing it in also reduces the 11-bit lane sum modulo 1024
+    const __half2 bias = u2h2(0x66006600u);   // 1536 = 1024 (exponent trick) + 512 (centring)
+    const __half2 wx = __hsub2(u2h2((P.x + CX) | 0x64006400u), bias);
+    const __half2 wy = __hsub2(u2h2((P.y + CY) | 0x64006400u), bias);
+    const __half2 wz = __hsub2(u2h2((P.z + CZ) | 0x64006400u), bias);
+    __half2 vx, vy, vz;
+    if (KIND == 0) {
+        vx = __hmul2(R[0], wx); vy = __hmul2(R[3], wy); vz = __hmul2(R[5], wz);
+    } else {
+        vx = __hfma2(R[2], wz, __hfma2(R[1], wy, __hmul2(R[0], wx)));
+        vy = __hfma2(R[4], wz, __hmul2(R[3], wy));
+        vz = __hmul2(R[5], wz);
+    }
+    const __half2 d2 = __hfma2(vz, vz, __hfma2(vy, vy, __hmul2(vx, vx)));
+    return __hle2_mask(d2, T2);
+}
+
+// Persistent CTAs: frames item = blockIdx.x, + gridDim.x, ...; frame = ids ? ids[item] : item.
+// FILT_H2: blockDim.x >= n, a multiple of 32 -- one (sorted) row per thread.
+// FILT_F32*: blockDim.x = SPLIT * T2 with T2 >= ceil(n / 2) a multiple of 32: two rows per thread,
+// SPLIT copies of the row set share the column blocks (more warps per frame for phases 2-3).
+template <int KIND, int FILT, int SPLIT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ RateParams rp,
               const __grid_constant__ FilterParams fp, const double *__restrict__ frames,
@@ -166,14 +237,14 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
               unsigned long long *__restrict__ ties)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DenseSmem s = dense_carve(smem_raw, n, hit_cap);
+    DenseSmem s = dense_carve(smem_raw, n, hit_cap, FILT);
     const int W = (n + 31) / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int total_items = n_ids ? *n_ids : n_items;
-    // Persistent CTA: frames item = blockIdx.x, + gridDim.x, ...  The coordinates of a frame are one
-    // contiguous 24n-byte run in HBM; TMA (cp.async.bulk) drops the NEXT frame into s.c while
-    // phase 3 of the current one runs, so a frame never waits for global memory.  (Bulk copies
-    // need 16-byte granules: an odd atom count falls back to plain loads.)
+    // The coordinates of a frame are one contiguous 24n-byte run in HBM; TMA (cp.async.bulk) drops
+    // the NEXT frame into s.c while the emit passes of the current one run, so a frame never waits
+    // for global memory.  (Bulk copies need 16-byte granules: an odd atom count falls back to
+    // plain loads.)
     uint64_t *bar = (uint64_t *)(s.red + 36);
     const bool use_tma = (n & 1) == 0 && (((size_t)frames) & 15) == 0;
     if (tid == 0 && use_tma) {
@@ -188,6 +259,9 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
     };
     if (use_tma && tid == 0 && (int)blockIdx.x < total_items) prefetch(blockIdx.x);
     unsigned tma_phase = 0;
+    const int K = (n - 1) >> 1, half = n >> 1;
+    const bool even = (n & 1) == 0;
+
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
     const int64_t f = ids ? ids[item] : item;
     if (use_tma) {
@@ -197,54 +271,167 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         const double *fr = frames + f * (int64_t)n * 3;
         for (int k = tid; k < 3 * n; k += blockDim.x) s.c[k] = __ldg(fr + k);
     }
-    for (int k = tid; k < n * W; k += blockDim.x) s.mask[k] = 0u;
     if (tid == 0) { s.misc[0] = 0; s.misc[1] = 0; }
-    __syncthreads();
-    // fractional coordinates in 2^-32 fixed point; the low 32 bits of the rounded product ARE the
-    // coordinate modulo one cell vector.  Stored twice so that the cyclic walk needs no modulo.
-    for (int a = tid; a < n; a += blockDim.x) {
-        const double x = s.c[3 * a], y = s.c[3 * a + 1], z = s.c[3 * a + 2];
-        int q[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            double v = KIND == 0 ? (c == 0 ? x : c == 1 ? y : z) * bx.hinv[4 * c]
-                                 : fma(bx.hinv[3 * c + 2], z, fma(bx.hinv[3 * c + 1], y, bx.hinv[3 * c] * x));
-            q[c] = (int)(unsigned)(unsigned long long)__double2ll_rn(v * 4294967296.0);
-        }
-        const int4 p = make_int4(q[0], q[1], q[2], 0);
-        s.fx[a] = p;
-        s.fx[a + n] = p;
-        if (a < 4) s.fx[a + 2 * n] = p;   // n < 4: entries beyond stay unread (see validity below)
-    }
-    __syncthreads();
 
     // ---- phase 1: filter -------------------------------------------------------------------
-    // Control flow is uniform over the CTA (rows beyond n only zero their hit masks), so the
+    // Control flow is uniform over every warp (rows beyond n only zero their hit masks), so the
     // appends can use full-warp shuffles and no loop ever runs with a split warp.
-    {
+    // warp-cooperative append: reserves `cnt` list entries for this lane, -1 if the warp has none
+    auto reserve = [&](int cnt) -> int {
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const int tot = __shfl_sync(0xffffffffu, inc, 31);
+        if (tot == 0) return -1;                    // warp-uniform
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&s.misc[0], tot);
+        return __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+    };
+    if (FILT == FILT_H2) {
+        // (a) 10-bit fractional coordinates, one atom per thread; counting sort of the atoms into
+        // 256 bins along the axis with the largest cell height.  A pair within the radius is at
+        // most sort_db bins apart, so a row only meets the columns that FOLLOW it in the sorted
+        // cyclic order up to that bin distance: each unordered pair once, ~2 rc / height of them.
+        const bool sorted = fp.sort_axis >= 0;
+        ushort4 *q16 = (ushort4 *)s.mask;          // by sorted position; the mask is not needed yet
+        if (sorted) for (int k = tid; k < 258; k += blockDim.x) s.bins[k] = 0;
+        __syncthreads();
+        unsigned q[3] = {0, 0, 0};
+        int key = 0, rnk = 0;
+        if (tid < n) {
+            const double x = s.c[3 * tid], y = s.c[3 * tid + 1], z = s.c[3 * tid + 2];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double v = KIND == 0 ? (c == 0 ? x : c == 1 ? y : z) * bx.hinv[4 * c]
+                                           : fma(bx.hinv[3 * c + 2], z, fma(bx.hinv[3 * c + 1], y, bx.hinv[3 * c] * x));
+                q[c] = (unsigned)(unsigned long long)__double2ll_rn(v * 1024.0) & 1023u;
+            }
+            if (sorted) {
+                key = (int)((fp.sort_axis == 0 ? q[0] : fp.sort_axis == 1 ? q[1] : q[2]) >> 2);
+                rnk = atomicAdd(&s.bins[key], 1);
+            }
+        }
+        __syncthreads();
+        if (sorted && wid == 0) {   // exclusive prefix over the 256 bins, eight per lane
+            int v[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { v[j] = s.bins[8 * lane + j]; sum += v[j]; }
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            int run = inc - sum;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { s.bins[8 * lane + j] = run; run += v[j]; }
+            if (lane == 31) { s.bins[256] = run; s.bins[257] = run; }
+        }
+        if (sorted) __syncthreads();
+        if (tid < n) {
+            const int pos = sorted ? s.bins[key] + rnk : tid;
+            s.perm[pos] = (unsigned short)tid;
+            q16[pos] = make_ushort4((unsigned short)q[0], (unsigned short)q[1], (unsigned short)q[2],
+                                    (unsigned short)key);
+        }
+        __syncthreads();
+        // (b) overlapping column pairs of the cyclic sorted sequence: entry k = positions (k, k+1)
+        const int ncol = 2 * n + 40;
+        for (int k = tid; k < ncol; k += blockDim.x) {
+            const ushort4 lo = q16[k % n], hi = q16[(k + 1) % n];
+            s.col[k] = make_uint4(lo.x | ((unsigned)hi.x << 16), lo.y | ((unsigned)hi.y << 16),
+                                  lo.z | ((unsigned)hi.z << 16), 0u);
+        }
+        // (c) this thread's row: sorted position t, its constants and the length of its window
+        const bool act = tid < n;
+        const int t = act ? tid : 0;
+        unsigned C[3];
+        int len;
+        {
+            const ushort4 me = q16[t];
+            C[0] = ((512u - me.x) & 1023u) * 0x00010001u;
+            C[1] = ((512u - me.y) & 1023u) * 0x00010001u;
+            C[2] = ((512u - me.z) & 1023u) * 0x00010001u;
+            if (sorted) {
+                const int e = (int)me.w + fp.sort_db;   // last bin of the window (inclusive)
+                len = (e < 256 ? s.bins[e + 1] : n + s.bins[e - 255]) - 1 - t;
+            } else {
+                // offsets 1..K are owned by every row, offset n/2 (even n) by the lower half only
+                len = K + ((even && t < half) ? 1 : 0);
+            }
+            if (!act) len = 0;
+        }
+        const unsigned my_tag = (unsigned)s.perm[t] << 16;
+        __syncthreads();
+        for (int k = tid; k < n * W; k += blockDim.x) s.mask[k] = 0u;   // q16 is dead
+        __half2 hR[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) hR[k] = u2h2(fp.hR[k]);
+        const __half2 hT2 = u2h2(fp.hT2);
+        // (d) blocks of 32 offsets: entry pk[2u] holds the columns at offsets 1 + 2u (low half ->
+        // hit bit u) and 2 + 2u (high half -> hit bit 16 + u) from the row
+        const uint4 *pk = s.col + t + 1;
+        const int nblk = __reduce_max_sync(0xffffffffu, (len + 31) >> 5);
+        for (int blk = 0; blk < nblk; blk++) {
+            unsigned ha = 0;
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const uint4 P = pk[32 * blk + 2 * u];
+                ha |= h2_pair_mask<KIND>(hR, hT2, P, C[0], C[1], C[2]) & (0x00010001u << u);
+            }
+            const int rem = len - 32 * blk;                  // offsets 1..rem of this block are owned
+            const int nlo = min(max((rem + 1) >> 1, 0), 16), nhi = min(max(rem >> 1, 0), 16);
+            ha &= ((1u << nlo) - 1u) | (((1u << nhi) - 1u) << 16);
+            int pos = reserve(__popc(ha));
+            if (pos < 0) continue;
+            const int c0 = t + 32 * blk + 1;
+            while (ha) {
+                const int b = __ffs(ha) - 1;
+                ha &= ha - 1;
+                int c = c0 + 2 * (b & 15) + (b >> 4);
+                if (c >= n) c -= n;
+                if (pos < hit_cap) s.hit_ij[pos] = my_tag | (unsigned)s.perm[c];
+                pos++;
+            }
+        }
+    } else {
+        for (int k = tid; k < n * W; k += blockDim.x) s.mask[k] = 0u;
         const int T2 = blockDim.x / SPLIT;          // threads per copy of the row set
         const int part = tid / T2, t = tid - part * T2;
         const int r0 = 2 * t, r1 = r0 + 1;
         const bool act0 = r0 < n, act1 = r1 < n;
-        const int K = (n - 1) >> 1, half = n >> 1;
-        const bool even = (n & 1) == 0;
-        const int4 p0 = s.fx[act0 ? r0 : 0], p1 = s.fx[act1 ? r1 : 0];
-        const int4 *fj = s.fx + (act0 ? r0 : 0) + 1;   // column of step m: atom (r0 + 1 + m) mod n
+        // 32-bit fixed point (unit 2^-32 of a cell vector): the low 32 bits of the rounded product
+        // ARE the coordinate modulo one cell vector, and the minimum-image wrap of a difference is
+        // the two's-complement wrap-around of one integer subtraction.  Stored twice so that the
+        // cyclic walk needs no modulo.
+        int4 *fx = (int4 *)s.col;
+        for (int a = tid; a < n; a += blockDim.x) {
+            const double x = s.c[3 * a], y = s.c[3 * a + 1], z = s.c[3 * a + 2];
+            int q[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                double v = KIND == 0 ? (c == 0 ? x : c == 1 ? y : z) * bx.hinv[4 * c]
+                                     : fma(bx.hinv[3 * c + 2], z, fma(bx.hinv[3 * c + 1], y, bx.hinv[3 * c] * x));
+                q[c] = (int)(unsigned)(unsigned long long)__double2ll_rn(v * 4294967296.0);
+            }
+            const int4 p = make_int4(q[0], q[1], q[2], 0);
+            fx[a] = p;
+            fx[a + n] = p;
+            if (a < 4) fx[a + 2 * n] = p;   // n < 4: entries beyond stay unread (see validity below)
+        }
+        __syncthreads();
+        constexpr bool IMAGES = FILT == FILT_F32_IMG;
+        const int4 p0 = fx[act0 ? r0 : 0], p1 = fx[act1 ? r1 : 0];
+        const int4 *fj = fx + (act0 ? r0 : 0) + 1;   // column of step m: atom (r0 + 1 + m) mod n
         const unsigned tag0 = (unsigned)r0 << 16, tag1 = (unsigned)r1 << 16;
-        // warp-cooperative append of the hits of steps m0 .. m0+31 (bit u of ha / hb = step m0+u)
+        // append of the hits of steps m0 .. m0+31 (bit u of ha / hb = step m0+u)
         auto flush = [&](unsigned ha, unsigned hb, int m0) {
             const int c = __popc(ha) + __popc(hb);
-            int inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            const int tot = __shfl_sync(0xffffffffu, inc, 31);
-            if (tot == 0) return;                    // warp-uniform
-            int base = 0;
-            if (lane == 31) base = atomicAdd(&s.misc[0], tot);
-            int pos = __shfl_sync(0xffffffffu, base, 31) + inc - c;
+            int pos = reserve(c);
+            if (pos < 0) return;
             const int j0 = r0 + 1 + m0;
             while (ha) {
                 int j = j0 + __ffs(ha) - 1;
@@ -322,8 +509,8 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
                 diff_ortho_exact(bx, pa, pb, d);
                 d2[q] = norm2_exact(d);
             } else {
-                diff_general_exact(bx, pa, pb, d);
-                d2[q] = min_image_norm2_kept(bx, d);
+                diff_general_norm_exact(bx, pa, pb, d);
+                d2[q] = FILT == FILT_F32_IMG ? min_image_norm2_kept(bx, d) : fmin(1e6, norm2_exact(d));
             }
         }
 #pragma unroll
@@ -342,88 +529,142 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         }
     }
     if (my_ties) atomicAdd(ties, my_ties);
+    // the coordinates are dead from here on; order the generic-proxy accesses to s.c before the
+    // bulk copy that will overwrite it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    // the coordinates are dead from here on: bring in the next frame of this CTA
-    if (use_tma && tid == 0 && item + (int)gridDim.x < total_items) prefetch(item + gridDim.x);
 
     // ---- phase 3: row counts -> exclusive offsets (LIL->COO order is row-major), write-out ---
+    bool emitted = false;
+    int total = 0;
     if (!overflow) {
-    const bool use_wpre = dense_use_wpre(n);   // the fixed-point coordinates are dead: reuse them
-    int cnt = 0, c0 = 0;
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int i = 2 * tid + q;
-        if (i < n) {
-            int run = 0;
-            for (int w = 0; w < W; w++) {
-                if (use_wpre) s.wpre[i * W + w] = (unsigned short)run;
-                run += __popc(s.mask[i * W + w]);
-            }
-            if (q == 0) c0 = run;
-            cnt += run;
-        }
-    }
-    int off = block_exclusive_scan(cnt, s.misc + 2, &s.misc[1]);
-    if (2 * tid < n) s.rowoff[2 * tid] = off;
-    if (2 * tid + 1 < n) s.rowoff[2 * tid + 1] = off + c0;
-    __syncthreads();
-    const int total = s.misc[1];
-    if (tid == 0) {
-        out_counts[f] = total > stride ? -total : total;
-        if (out_rebuilt) out_rebuilt[f] = 1;
-        if (total > stride) atomicMax(err, total);
-    }
-    if (total <= stride) {
-    if (out_rowoff) {   // row index of the frame's list: row i = [rowoff[i], rowoff[i + 1])
-        int *ro = out_rowoff + f * (int64_t)cmd_ro_pitch(n);
-        for (int k = tid; k < n; k += blockDim.x) ro[k] = s.rowoff[k];
-        if (tid == 0) ro[n] = total;
-    }
-
-    // position of (a -> b) = rowoff[a] + #set bits of row a below column b
-    const int64_t base = f * stride;
-    double rsum = 0.0;
-    for (int h0 = tid; h0 < ncand; h0 += 2 * blockDim.x) {
-        const int h1 = h0 + blockDim.x;
-        const bool two = h1 < ncand;
-        const double dist[2] = {s.hit_d[h0], two ? s.hit_d[h1] : -1.0};
-        const unsigned ij[2] = {s.hit_ij[h0], s.hit_ij[two ? h1 : h0]};
-        double om[2];
-        rate_eval2(rp, fabs(dist[0]), fabs(dist[1]), om);
+        const bool use_wpre = s.wpre_ok;   // coordinates and columns are dead: reuse them
+        const int rpt = (n + (int)blockDim.x - 1) / (int)blockDim.x;   // rows per thread: 1 or 2
+        int cnt = 0, c0 = 0;
 #pragma unroll
         for (int q = 0; q < 2; q++) {
-            if (dist[q] < 0.0) continue;
-            const int a = ij[q] >> 16, b = ij[q] & 0xffff;
-            rsum += om[q];
-            int pa = s.rowoff[a], pb = s.rowoff[b];
-            if (use_wpre) {
-                pa += s.wpre[a * W + (b >> 5)];
-                pb += s.wpre[b * W + (a >> 5)];
-            } else {
-                for (int w = 0; w < (b >> 5); w++) pa += __popc(s.mask[a * W + w]);
-                for (int w = 0; w < (a >> 5); w++) pb += __popc(s.mask[b * W + w]);
+            const int i = rpt * tid + q;
+            if (q < rpt && i < n) {
+                int run = 0;
+                for (int w = 0; w < W; w++) {
+                    if (use_wpre) s.wpre[i * W + w] = (unsigned short)run;
+                    run += __popc(s.mask[i * W + w]);
+                }
+                if (q == 0) c0 = run;
+                cnt += run;
             }
-            pa += __popc(s.mask[a * W + (b >> 5)] & ((1u << (b & 31)) - 1u));
-            pb += __popc(s.mask[b * W + (a >> 5)] & ((1u << (a & 31)) - 1u));
-            out_start[base + pa] = a; out_dest[base + pa] = b;
-            out_dist[base + pa] = dist[q]; out_omega[base + pa] = om[q];
-            out_start[base + pb] = b; out_dest[base + pb] = a;
-            out_dist[base + pb] = dist[q]; out_omega[base + pb] = om[q];
         }
-    }
-    if (out_rate_sum) {
-        // informational per-frame total of all listed rates (both directions)
-        for (int o = 16; o > 0; o >>= 1) rsum += __shfl_down_sync(0xffffffffu, rsum, o);
-        if (lane == 0) s.red[wid] = rsum;
+        int off = block_exclusive_scan(cnt, s.misc + 2, &s.misc[1]);
+        if (rpt * tid < n) s.rowoff[rpt * tid] = off;
+        if (rpt == 2 && 2 * tid + 1 < n) s.rowoff[2 * tid + 1] = off + c0;
         __syncthreads();
+        total = s.misc[1];
         if (tid == 0) {
-            double t = 0;
-            for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) t += s.red[w];
-            out_rate_sum[f] = 2.0 * t;
+            out_counts[f] = total > stride ? -total : total;
+            if (out_rebuilt) out_rebuilt[f] = 1;
+            if (total > stride) atomicMax(err, total);
+        }
+        emitted = total <= stride;
+        if (emitted) {
+            if (out_rowoff) {   // row index of the frame's list: row i = [rowoff[i], rowoff[i + 1])
+                int *ro = out_rowoff + f * (int64_t)cmd_ro_pitch(n);
+                for (int k = tid; k < n; k += blockDim.x) ro[k] = s.rowoff[k];
+                if (tid == 0) ro[n] = total;
+            }
+            // position of (a -> b) = rowoff[a] + #set bits of row a below column b; the hit drops
+            // its candidate index there (bit 15: reversed direction)
+            for (int h = tid; h < ncand; h += blockDim.x) {
+                if (s.hit_d[h] < 0.0) continue;
+                const unsigned ij = s.hit_ij[h];
+                const int a = ij >> 16, b = ij & 0xffff;
+                int pa = s.rowoff[a], pb = s.rowoff[b];
+                if (use_wpre) {
+                    pa += s.wpre[a * W + (b >> 5)];
+                    pb += s.wpre[b * W + (a >> 5)];
+                } else {
+                    for (int w = 0; w < (b >> 5); w++) pa += __popc(s.mask[a * W + w]);
+                    for (int w = 0; w < (a >> 5); w++) pb += __popc(s.mask[b * W + w]);
+                }
+                pa += __popc(s.mask[a * W + (b >> 5)] & ((1u << (b & 31)) - 1u));
+                pb += __popc(s.mask[b * W + (a >> 5)] & ((1u << (a & 31)) - 1u));
+                s.slot[pa] = (unsigned short)h;
+                s.slot[pb] = (unsigned short)(h | 0x8000);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    // wpre (aliasing the coordinate buffer) is dead: bring in the next frame of this CTA
+    if (use_tma && tid == 0 && item + (int)gridDim.x < total_items) prefetch(item + gridDim.x);
+
+    if (emitted) {
+        const int64_t base = f * stride;   // stride is a multiple of 64: 16-byte aligned rows
+        const int total4 = total & ~3;
+        // (start, dest) of the directed pair behind slot entry e
+        auto pair_of = [&](unsigned e, int &st, int &de) -> int {
+            const int h = (int)(e & 0x7fffu);
+            unsigned ij = s.hit_ij[h];
+            if (e & 0x8000u) ij = __funnelshift_l(ij, ij, 16);
+            st = (int)(ij >> 16);
+            de = (int)(ij & 0xffffu);
+            return h;
+        };
+        // pass 1: (start, dest, dist) in output order, four positions per thread
+        for (int p = 4 * tid; p < total4; p += 4 * blockDim.x) {
+            const uint2 e2 = *(const uint2 *)(s.slot + p);
+            int4 st, de;
+            const int h0 = pair_of(e2.x & 0xffffu, st.x, de.x), h1 = pair_of(e2.x >> 16, st.y, de.y);
+            const int h2 = pair_of(e2.y & 0xffffu, st.z, de.z), h3 = pair_of(e2.y >> 16, st.w, de.w);
+            *(int4 *)(out_start + base + p) = st;
+            *(int4 *)(out_dest + base + p) = de;
+            *(double2 *)(out_dist + base + p) = make_double2(s.hit_d[h0], s.hit_d[h1]);
+            *(double2 *)(out_dist + base + p + 2) = make_double2(s.hit_d[h2], s.hit_d[h3]);
+        }
+        if (tid < total - total4) {
+            int st, de;
+            const int h = pair_of(s.slot[total4 + tid], st, de);
+            out_start[base + total4 + tid] = st;
+            out_dest[base + total4 + tid] = de;
+            out_dist[base + total4 + tid] = s.hit_d[h];
+        }
+        __syncthreads();
+        // the rates replace the distances, once per unordered hit
+        for (int h0 = tid; h0 < ncand; h0 += 2 * blockDim.x) {
+            const int h1 = h0 + blockDim.x;
+            const bool two = h1 < ncand;
+            const double dist[2] = {s.hit_d[h0], two ? s.hit_d[h1] : -1.0};
+            double om[2];
+            rate_eval2(rp, fabs(dist[0]), fabs(dist[1]), om);
+            if (dist[0] >= 0.0) s.hit_d[h0] = om[0];
+            if (two && dist[1] >= 0.0) s.hit_d[h1] = om[1];
+        }
+        __syncthreads();
+        // pass 2: omega in output order; the per-frame total of all listed rates in a fixed order
+        double rsum = 0.0;
+        for (int p = 4 * tid; p < total4; p += 4 * blockDim.x) {
+            const uint2 e2 = *(const uint2 *)(s.slot + p);
+            const double o0 = s.hit_d[e2.x & 0x7fffu], o1 = s.hit_d[(e2.x >> 16) & 0x7fffu];
+            const double o2 = s.hit_d[e2.y & 0x7fffu], o3 = s.hit_d[(e2.y >> 16) & 0x7fffu];
+            rsum += (o0 + o1) + (o2 + o3);
+            *(double2 *)(out_omega + base + p) = make_double2(o0, o1);
+            *(double2 *)(out_omega + base + p + 2) = make_double2(o2, o3);
+        }
+        if (tid < total - total4) {
+            const double o = s.hit_d[s.slot[total4 + tid] & 0x7fffu];
+            rsum += o;
+            out_omega[base + total4 + tid] = o;
+        }
+        if (out_rate_sum) {
+            for (int o = 16; o > 0; o >>= 1) rsum += __shfl_down_sync(0xffffffffu, rsum, o);
+            if (lane == 0) s.red[wid] = rsum;
+            __syncthreads();
+            if (tid == 0) {
+                double tsum = 0;
+                for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) tsum += s.red[w];
+                out_rate_sum[f] = tsum;
+            }
         }
     }
-    }   // total <= stride
-    }   // !overflow
-    __syncthreads();   // phase 3 is done with the masks / hit lists before the next frame resets them
+    __syncthreads();   // the emit passes are done with the hit lists before the next frame resets them
     }   // frames of this CTA
 }

@@ -61,6 +61,28 @@ __device__ __forceinline__ double sub_round_exact(double x)
     return w;
 }
 
+// The three components at once: the straight-line path (rint by the magic constant, exact
+// subtraction) plus ONE test on the high words for everything that needs sub_round_exact's care:
+// |x| >= 2^51 / nan / inf, or a tie |x - rint(x)| == 1/2 (|w| <= 1/2 always, so >= suffices).
+__device__ __forceinline__ void sub_round3_exact(double s[3])
+{
+    const double magic = 6755399441055744.0;
+    double w[3];
+    int hs = 0, hw = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        w[i] = __dadd_rn(s[i], -__dadd_rn(__dadd_rn(s[i], magic), -magic));
+        hs = max(hs, __double2hiint(s[i]) & 0x7fffffff);
+        hw = max(hw, __double2hiint(w[i]) & 0x7fffffff);
+    }
+    if (hs >= 0x43200000 || hw >= 0x3fe00000) {   // cold
+#pragma unroll
+        for (int i = 0; i < 3; i++) s[i] = sub_round_exact(s[i]);
+        return;
+    }
+    s[0] = w[0]; s[1] = w[1]; s[2] = w[2];
+}
+
 // ---- A3: numpyatom.pyx:61-74 (diff_ptr_nonortho); round = C99 round, half away from zero ------
 __device__ __forceinline__ void diff_general_exact(const BoxParams &bx, const double a[3],
                                                    const double b[3], double d[3])
@@ -68,9 +90,31 @@ __device__ __forceinline__ void diff_general_exact(const BoxParams &bx, const do
 #pragma unroll
     for (int i = 0; i < 3; i++) d[i] = __dadd_rn(b[i], -a[i]);
     matvec3_exact(bx.hinv, d);
-#pragma unroll
-    for (int i = 0; i < 3; i++) d[i] = sub_round_exact(d[i]);
+    sub_round3_exact(d);
     matvec3_exact(bx.h, d);
+}
+
+// The same vector for callers that only take its NORM: matrix_mult_ptr's leading `0 +` is left
+// out.  0 + x differs from x only for x = -0, and a flipped zero sign can only flip the sign of
+// zero-valued components further down -- the squared length is bit-identical.
+__device__ __forceinline__ void matvec3_norm_exact(const double m[9], double v[3])
+{
+    double r[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        r[i] = __dadd_rn(__dadd_rn(__dmul_rn(m[3 * i], v[0]), __dmul_rn(m[3 * i + 1], v[1])),
+                         __dmul_rn(m[3 * i + 2], v[2]));
+    v[0] = r[0]; v[1] = r[1]; v[2] = r[2];
+}
+
+__device__ __forceinline__ void diff_general_norm_exact(const BoxParams &bx, const double a[3],
+                                                        const double b[3], double d[3])
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++) d[i] = __dadd_rn(b[i], -a[i]);
+    matvec3_norm_exact(bx.hinv, d);
+    sub_round3_exact(d);
+    matvec3_norm_exact(bx.h, d);
 }
 
 // ---- A4: numpyatom.pyx:101-123: min over the 27 images of the wrapped vector, squared ---------
@@ -210,13 +254,68 @@ struct RateParams {
 
 #define CMD_KB_EV 8.617333262e-5
 
+// a / den for den in [1, 1e305): reciprocal seed + two Newton steps + one residual correction
+// (<= 1 ulp; the reference divides in IEEE, the rate gate is 1e-10 relative)
+__device__ __forceinline__ double div_fast(double a, double den)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
+    double e = fma(-den, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-den, y, 1.0);
+    y = fma(y, e, y);
+    const double q = a * y;
+    const double r = fma(-den, q, a);
+    return fma(r, y, q);
+}
+
+// exp(z) for z in [-700, 700]: k = rint(z log2 e), r = z - k ln 2 (two-term Cody-Waite),
+// Taylor polynomial of degree 13 on |r| <= 0.347 (truncation 4e-18), scaled by 2^k through the
+// exponent field.  ~2 ulp; no special cases (the callers clamp).
+__device__ __forceinline__ double exp_core(double z)
+{
+    const double magic = 6755399441055744.0;
+    const double t = fma(z, 1.4426950408889634, magic);
+    const int k = __double2loint(t);
+    const double kf = t - magic;
+    double r = fma(kf, -6.93147180369123816490e-01, z);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return p * __hiloint2double((k + 1023) << 20, 0);
+}
+
+// Fermi rate a / (1 + exp((x - b) / c)) (jumprate_generators.py:33-34): the division by c is a
+// multiplication by the correctly rounded 1/c (loop invariant), exp is exp_core, the outer
+// division div_fast.  One implementation for every kernel, so that lists built by different
+// kernels agree bit for bit; a few ulp from NumPy's value (the gate is 1e-10 relative).
+__device__ __forceinline__ double fermi_eval(const RateParams &r, double x)
+{
+    const double inv_c = __drcp_rn(r.par[2]);
+    const double z = (x - r.par[1]) * inv_c;
+    if (!(z < 700.0)) return r.par[0] / (1.0 + exp((x - r.par[1]) / r.par[2]));   // cold
+    return div_fast(r.par[0], 1.0 + exp_core(fmax(z, -700.0)));
+}
+
 __device__ __forceinline__ double rate_eval(const RateParams &r, double x, double theta)
 {
     switch (r.kind) {
-    case CMD_RATE_FERMI:  // jumprate_generators.py:33-34
-        return r.par[0] / (1.0 + exp((x - r.par[1]) / r.par[2]));
+    case CMD_RATE_FERMI:
+        return fermi_eval(r, x);
     case CMD_RATE_FERMI_ANGLE:  // jumprate_generators.py:42-43
-        return theta < r.par[3] ? 0.0 : r.par[0] / (1.0 + exp((x - r.par[1]) / r.par[2]));
+        return theta < r.par[3] ? 0.0 : fermi_eval(r, x);
     case CMD_RATE_AE: {  // IO/config_parser.py:334-342 (specification text; parity unpinned)
         double u = x - r.par[3];
         if (!(u > 0)) return r.par[0];
@@ -233,9 +332,8 @@ __device__ __forceinline__ double rate_eval(const RateParams &r, double x, doubl
 __device__ __forceinline__ void rate_eval2(const RateParams &r, double x0, double x1, double out[2])
 {
     if (r.kind == CMD_RATE_FERMI) {
-        const double e0 = exp((x0 - r.par[1]) / r.par[2]), e1 = exp((x1 - r.par[1]) / r.par[2]);
-        out[0] = r.par[0] / (1.0 + e0);
-        out[1] = r.par[0] / (1.0 + e1);
+        out[0] = fermi_eval(r, x0);
+        out[1] = fermi_eval(r, x1);
     } else {
         out[0] = rate_eval(r, x0, 0.0);
         out[1] = rate_eval(r, x1, 0.0);
