@@ -743,6 +743,7 @@ static void topo_filter_params(cmd_topo *t)
         }
     }
     t->filt = fp.h2_ok ? FILT_H2 : bx.n_img == 0 ? FILT_F32 : FILT_F32_IMG;
+    fp.wpre_ok = dense_wpre_fits(t->n, t->filt) ? 1 : 0;
 }
 
 static int dense_threads(int n)
@@ -754,7 +755,14 @@ static int dense_threads(int n)
 static int dense_threads_h2(int n)
 {
     int th = (n + 31) / 32 * 32;             // packed-half filter: one row per thread
-    return th < 64 ? 64 : th;
+    if (th < 64) th = 64;
+    // rows leave room below the next launch-bound shape: spend it on warps for the exact / emit
+    // phases (their work is spread over the CTA, not over the rows)
+    static const char *ex = getenv("CMDLMC_B200_DENSE_EXTRA_WARPS");
+    const int extra = ex ? atoi(ex) : 1;
+    const int lim = th <= 256 ? 256 : th <= 512 ? 512 : 1024;
+    th += 32 * extra;
+    return th > lim ? lim : th;
 }
 
 // Cells per fractional axis: the cell must be at least one filter radius thick.

@@ -45,6 +45,7 @@ struct FilterParams {
     int h2_ok;         // the 10-bit filter is valid and tight enough for this cell / radius
     int sort_axis;     // fractional axis the atoms are binned along (-1: no spatial pruning)
     int sort_db;       // window: a pair within the radius is at most this many bins (of 256) apart
+    int wpre_ok;       // the popc prefix table fits the dead coordinate + column buffers
 };
 
 struct DenseSmem {
@@ -62,7 +63,6 @@ struct DenseSmem {
     int *misc;              // [0] ncand, [1] total, [2..33] warp sums
     int *bins;              // [258] atoms per sort bin -> exclusive prefix (FILT_H2)
     unsigned short *perm;   // [n] sorted position -> atom (FILT_H2)
-    bool wpre_ok;
 };
 
 __host__ __device__ inline size_t dense_al16(size_t b) { return (b + 15) / 16 * 16; }
@@ -88,6 +88,12 @@ __host__ __device__ inline size_t dense_smem_fixed(int n, int filt)
 }
 #define DENSE_BYTES_PER_CAND 16   // hit_d 8 + hit_ij 4 + 2 slots of 2
 
+__host__ __device__ inline bool dense_wpre_fits(int n, int filt)
+{
+    const int W = (n + 31) / 32;
+    return (size_t)n * W * 2 <= dense_al16(3 * (size_t)n * 8) + dense_col_bytes(n, filt);
+}
+
 __host__ __device__ inline size_t dense_smem_bytes(int n, int cap, int filt)
 {
     return dense_smem_fixed(n, filt) + (size_t)cap * DENSE_BYTES_PER_CAND;
@@ -96,12 +102,10 @@ __host__ __device__ inline size_t dense_smem_bytes(int n, int cap, int filt)
 __device__ __forceinline__ DenseSmem dense_carve(unsigned char *base, int n, int cap, int filt)
 {
     DenseSmem s;
-    const int W = (n + 31) / 32;
     const size_t A = dense_al16(3 * (size_t)n * 8), B = dense_col_bytes(n, filt);
     s.c = (double *)base;
     s.col = (uint4 *)(base + A);
     s.wpre = (unsigned short *)base;
-    s.wpre_ok = (size_t)n * W * 2 <= A + B;
     s.hit_d = (double *)(base + A + B);
     s.red = s.hit_d + cap;
     s.mask = (unsigned *)(s.red + 40);
@@ -538,7 +542,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
     bool emitted = false;
     int total = 0;
     if (!overflow) {
-        const bool use_wpre = s.wpre_ok;   // coordinates and columns are dead: reuse them
+        const bool use_wpre = fp.wpre_ok != 0;   // coordinates and columns are dead: reuse them
         const int rpt = (n + (int)blockDim.x - 1) / (int)blockDim.x;   // rows per thread: 1 or 2
         int cnt = 0, c0 = 0;
 #pragma unroll
@@ -609,50 +613,86 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
             de = (int)(ij & 0xffffu);
             return h;
         };
-        // pass 1: (start, dest, dist) in output order, four positions per thread
-        for (int p = 4 * tid; p < total4; p += 4 * blockDim.x) {
-            const uint2 e2 = *(const uint2 *)(s.slot + p);
-            int4 st, de;
-            const int h0 = pair_of(e2.x & 0xffffu, st.x, de.x), h1 = pair_of(e2.x >> 16, st.y, de.y);
-            const int h2 = pair_of(e2.y & 0xffffu, st.z, de.z), h3 = pair_of(e2.y >> 16, st.w, de.w);
-            *(int4 *)(out_start + base + p) = st;
-            *(int4 *)(out_dest + base + p) = de;
-            *(double2 *)(out_dist + base + p) = make_double2(s.hit_d[h0], s.hit_d[h1]);
-            *(double2 *)(out_dist + base + p + 2) = make_double2(s.hit_d[h2], s.hit_d[h3]);
+        // The rates of the hits go where the adjacency mask and the column pairs were (both dead),
+        // if they fit: then ONE pass over the output positions writes all four arrays.
+        const int om_split = (int)(dense_mask_bytes(n) / 8);
+        const bool fused = (size_t)hit_cap <= dense_mask_bytes(n) / 8 + dense_col_bytes(n, FILT) / 8;
+        double *om_a = (double *)s.mask, *om_b = (double *)s.col - om_split;
+        auto om_at = [&](int h) -> double * { return (h < om_split ? om_a : om_b) + h; };
+        if (!fused) {
+            // pass 1 of 2: (start, dest, dist) in output order, four positions per thread
+            for (int p = 4 * tid; p < total4; p += 4 * blockDim.x) {
+                const uint2 e2 = *(const uint2 *)(s.slot + p);
+                int4 st, de;
+                const int h0 = pair_of(e2.x & 0xffffu, st.x, de.x), h1 = pair_of(e2.x >> 16, st.y, de.y);
+                const int h2 = pair_of(e2.y & 0xffffu, st.z, de.z), h3 = pair_of(e2.y >> 16, st.w, de.w);
+                *(int4 *)(out_start + base + p) = st;
+                *(int4 *)(out_dest + base + p) = de;
+                *(double2 *)(out_dist + base + p) = make_double2(s.hit_d[h0], s.hit_d[h1]);
+                *(double2 *)(out_dist + base + p + 2) = make_double2(s.hit_d[h2], s.hit_d[h3]);
+            }
+            if (tid < total - total4) {
+                int st, de;
+                const int h = pair_of(s.slot[total4 + tid], st, de);
+                out_start[base + total4 + tid] = st;
+                out_dest[base + total4 + tid] = de;
+                out_dist[base + total4 + tid] = s.hit_d[h];
+            }
+            __syncthreads();
         }
-        if (tid < total - total4) {
-            int st, de;
-            const int h = pair_of(s.slot[total4 + tid], st, de);
-            out_start[base + total4 + tid] = st;
-            out_dest[base + total4 + tid] = de;
-            out_dist[base + total4 + tid] = s.hit_d[h];
-        }
-        __syncthreads();
-        // the rates replace the distances, once per unordered hit
+        // the rates, once per unordered hit (unfused: they replace the distances)
         for (int h0 = tid; h0 < ncand; h0 += 2 * blockDim.x) {
             const int h1 = h0 + blockDim.x;
             const bool two = h1 < ncand;
             const double dist[2] = {s.hit_d[h0], two ? s.hit_d[h1] : -1.0};
             double om[2];
             rate_eval2(rp, fabs(dist[0]), fabs(dist[1]), om);
-            if (dist[0] >= 0.0) s.hit_d[h0] = om[0];
-            if (two && dist[1] >= 0.0) s.hit_d[h1] = om[1];
+            if (dist[0] >= 0.0) *(fused ? om_at(h0) : s.hit_d + h0) = om[0];
+            if (two && dist[1] >= 0.0) *(fused ? om_at(h1) : s.hit_d + h1) = om[1];
         }
         __syncthreads();
-        // pass 2: omega in output order; the per-frame total of all listed rates in a fixed order
+        // output order; the per-frame total of all listed rates is summed in a fixed order
         double rsum = 0.0;
-        for (int p = 4 * tid; p < total4; p += 4 * blockDim.x) {
-            const uint2 e2 = *(const uint2 *)(s.slot + p);
-            const double o0 = s.hit_d[e2.x & 0x7fffu], o1 = s.hit_d[(e2.x >> 16) & 0x7fffu];
-            const double o2 = s.hit_d[e2.y & 0x7fffu], o3 = s.hit_d[(e2.y >> 16) & 0x7fffu];
-            rsum += (o0 + o1) + (o2 + o3);
-            *(double2 *)(out_omega + base + p) = make_double2(o0, o1);
-            *(double2 *)(out_omega + base + p + 2) = make_double2(o2, o3);
-        }
-        if (tid < total - total4) {
-            const double o = s.hit_d[s.slot[total4 + tid] & 0x7fffu];
-            rsum += o;
-            out_omega[base + total4 + tid] = o;
+        if (fused) {
+#pragma unroll 2
+            for (int p = 4 * tid; p < total4; p += 4 * blockDim.x) {
+                const uint2 e2 = *(const uint2 *)(s.slot + p);
+                int4 st, de;
+                const int h0 = pair_of(e2.x & 0xffffu, st.x, de.x), h1 = pair_of(e2.x >> 16, st.y, de.y);
+                const int h2 = pair_of(e2.y & 0xffffu, st.z, de.z), h3 = pair_of(e2.y >> 16, st.w, de.w);
+                const double o0 = *om_at(h0), o1 = *om_at(h1), o2 = *om_at(h2), o3 = *om_at(h3);
+                rsum += (o0 + o1) + (o2 + o3);
+                *(int4 *)(out_start + base + p) = st;
+                *(int4 *)(out_dest + base + p) = de;
+                *(double2 *)(out_dist + base + p) = make_double2(s.hit_d[h0], s.hit_d[h1]);
+                *(double2 *)(out_dist + base + p + 2) = make_double2(s.hit_d[h2], s.hit_d[h3]);
+                *(double2 *)(out_omega + base + p) = make_double2(o0, o1);
+                *(double2 *)(out_omega + base + p + 2) = make_double2(o2, o3);
+            }
+            if (tid < total - total4) {
+                int st, de;
+                const int h = pair_of(s.slot[total4 + tid], st, de);
+                const double o = *om_at(h);
+                rsum += o;
+                out_start[base + total4 + tid] = st;
+                out_dest[base + total4 + tid] = de;
+                out_dist[base + total4 + tid] = s.hit_d[h];
+                out_omega[base + total4 + tid] = o;
+            }
+        } else {
+            for (int p = 4 * tid; p < total4; p += 4 * blockDim.x) {
+                const uint2 e2 = *(const uint2 *)(s.slot + p);
+                const double o0 = s.hit_d[e2.x & 0x7fffu], o1 = s.hit_d[(e2.x >> 16) & 0x7fffu];
+                const double o2 = s.hit_d[e2.y & 0x7fffu], o3 = s.hit_d[(e2.y >> 16) & 0x7fffu];
+                rsum += (o0 + o1) + (o2 + o3);
+                *(double2 *)(out_omega + base + p) = make_double2(o0, o1);
+                *(double2 *)(out_omega + base + p + 2) = make_double2(o2, o3);
+            }
+            if (tid < total - total4) {
+                const double o = s.hit_d[s.slot[total4 + tid] & 0x7fffu];
+                rsum += o;
+                out_omega[base + total4 + tid] = o;
+            }
         }
         if (out_rate_sum) {
             for (int o = 16; o > 0; o >>= 1) rsum += __shfl_down_sync(0xffffffffu, rsum, o);
