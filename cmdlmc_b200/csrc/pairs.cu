@@ -48,7 +48,7 @@ struct cmd_topo {
     int4 *d_fxu, *d_sorted;
     int *d_slot, *d_cell_start, *d_rowcount, *d_rowoff_tmp, *d_tmp_j, *d_cap_need;
     double *d_tmp_d;
-    unsigned short *d_tmp_inv;
+    double *d_cell_part;   // [batch][warps per frame] partial rate sums of k_cell_emit
     // block results
     int64_t cap_frames, nframes;
     int *d_start, *d_dest, *d_counts, *d_err;
@@ -628,8 +628,8 @@ static void cell_free(cmd_topo *t)
 {
     cudaFree(t->d_fxu); cudaFree(t->d_sorted); cudaFree(t->d_slot); cudaFree(t->d_cell_start);
     cudaFree(t->d_rowcount); cudaFree(t->d_rowoff_tmp); cudaFree(t->d_tmp_j); cudaFree(t->d_tmp_d);
-    cudaFree(t->d_tmp_inv);
-    t->d_tmp_inv = nullptr;
+    cudaFree(t->d_cell_part);
+    t->d_cell_part = nullptr;
     t->d_fxu = t->d_sorted = nullptr;
     t->d_slot = t->d_cell_start = t->d_rowcount = t->d_rowoff_tmp = t->d_tmp_j = nullptr;
     t->d_tmp_d = nullptr;
@@ -976,7 +976,7 @@ static int cell_reserve(cmd_topo *t, int batch)
     CALLOC(t->d_rowoff_tmp, B * (n + 1) * 4);
     CALLOC(t->d_tmp_j, B * n * t->rowcap * 4);
     CALLOC(t->d_tmp_d, B * n * t->rowcap * 8);
-    CALLOC(t->d_tmp_inv, B * n * t->rowcap * 2);
+    CALLOC(t->d_cell_part, B * (size_t)cmd_div_up(t->n, 256) * 8 * 8);
 #undef CALLOC
     t->cell_batch = batch;
     return CMD_OK;
@@ -984,7 +984,7 @@ static int cell_reserve(cmd_topo *t, int batch)
 
 static int cell_batch_size(const cmd_topo *t, int64_t want)
 {
-    const size_t per = (size_t)t->n * (40 + 14 * (size_t)t->rowcap) + (size_t)(t->cg.ncell + 1) * 4 + 8;
+    const size_t per = (size_t)t->n * (42 + 12 * (size_t)t->rowcap) + (size_t)(t->cg.ncell + 1) * 4 + 8;
     int64_t b = (int64_t)((size_t)1 << 30) / (int64_t)per;
     if (b < 1) b = 1;
     if (b > 8192) b = 8192;
@@ -1017,20 +1017,24 @@ static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, cons
                                                      t->d_fxu, t->d_slot, t->d_sorted, t->d_cell_start);
         }
         CMD_LAUNCHED();
-        int tpb = 128;
-        while (tpb > 32 && (size_t)t->rowcap * tpb * 4 > 160 * 1024) tpb >>= 1;
-        const size_t psm = (size_t)t->rowcap * tpb * 4;
-        dim3 pgrid((unsigned)((n + tpb - 1) / tpb), (unsigned)batch);
+        CMD_CUDA(cudaMemsetAsync(t->d_rowcount, 0, (size_t)batch * n * 4, st));
+        // whole (x, y) columns per CTA when the batch fills the GPU with them, z segments otherwise
+        const int ncolumn = t->cg.nc[0] * t->cg.nc[1];
+        int zseg = t->cg.nc[2];
+        {
+            const int64_t want = (int64_t)cmd_global().sm_count * 14;
+            if ((int64_t)ncolumn * batch < want) {
+                zseg = (int)(((int64_t)ncolumn * batch * t->cg.nc[2] + want - 1) / want);
+                if (zseg < 1) zseg = 1;
+                if (zseg > t->cg.nc[2]) zseg = t->cg.nc[2];
+            }
+        }
+        dim3 pgrid((unsigned)(ncolumn * cmd_div_up(t->cg.nc[2], zseg)), (unsigned)batch);
 #define CELL_PAIRS(K, IM)                                                                        \
-    do {                                                                                         \
-        CMD_CUDA(cudaFuncSetAttribute(k_cell_pairs<K, IM>,                                       \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));   \
-        k_cell_pairs<K, IM><<<pgrid, tpb, psm, st>>>(                                            \
-            t->bx, t->fp, t->cg, d_frames, ids, n_ids, (int)first, n, t->rc, t->t2, t->rowcap,   \
-            t->d_sorted, t->d_cell_start, t->d_rowcount, t->d_tmp_j, t->d_tmp_d, t->d_tmp_inv,   \
-            t->d_cap_need,                                                                       \
-            t->d_ties);                                                                          \
-    } while (0)
+    k_cell_pairs<K, IM><<<pgrid, CELL_TPB, 0, st>>>(                                             \
+        t->bx, t->fp, t->cg, d_frames, ids, n_ids, (int)first, n, t->rc, t->t2, t->rowcap, zseg, \
+        t->d_sorted, t->d_cell_start, t->d_rowcount, t->d_tmp_j, t->d_tmp_d, t->d_cap_need,      \
+        t->d_ties)
         if (ortho) CELL_PAIRS(0, false);
         else if (t->fp.n_img == 0) CELL_PAIRS(1, false);
         else CELL_PAIRS(1, true);
@@ -1042,9 +1046,9 @@ static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, cons
         CMD_CUDA(cudaStreamSynchronize(st));
         if (need > t->rowcap) {
             CMD_CUDA(cudaMemsetAsync(t->d_cap_need, 0, sizeof(int), st));
-            if ((size_t)(need + 8) * 32 * 4 > 200 * 1024 || need + 8 > 65535)
-                return cmd_set_error(CMD_ECAPACITY, "an atom has %d neighbour candidates: more than "
-                                     "the cell-list kernel can hold per row", need);
+            if ((size_t)(need + 8) * (size_t)n * 12 > ((size_t)1 << 32))
+                return cmd_set_error(CMD_ECAPACITY, "an atom has %d neighbours: more than the "
+                                     "cell-list scratch rows can hold", need);
             t->rowcap = need + 8;
             cell_free(t);
             continue;   // redo this batch with longer rows
@@ -1056,9 +1060,14 @@ static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, cons
         if (emit) {
             dim3 egrid((unsigned)((n + 255) / 256), (unsigned)batch);
             k_cell_emit<<<egrid, 256, 0, st>>>(t->rate, ids, n_ids, (int)first, n, stride, t->rowcap,
-                                               t->d_rowoff_tmp, t->d_tmp_j, t->d_tmp_d, t->d_tmp_inv, start, dest, dist,
-                                               omega, rate_sum);
+                                               t->d_rowoff_tmp, t->d_tmp_j, t->d_tmp_d, start, dest, dist,
+                                               omega, rate_sum ? t->d_cell_part : nullptr);
             CMD_LAUNCHED();
+            if (rate_sum) {
+                k_cell_rsum<<<batch, 256, 0, st>>>(ids, n_ids, (int)first, (int)egrid.x * 8, t->d_cell_part,
+                                                   rate_sum);
+                CMD_LAUNCHED();
+            }
         }
         first += batch;
     }

@@ -11,12 +11,14 @@
 // collapsed to one cell (all its atoms are candidates; the exact stage finds the image).
 //
 //   k_cell_build   one CTA per frame: fixed-point coordinates, counting sort into cells
-//   k_cell_pairs   one thread per row atom (in cell order, so a warp walks the same cells):
-//                  filter (pairs_dense.cuh filter_pair) over the <= 27 adjacent cells, exact
-//                  evaluation of the survivors, per-row sort by column, rows parked in a
+//   k_cell_pairs   one CTA per (x, y) column of cells: the column and its half shell staged in
+//                  shared memory, every unordered pair once; a thread per home atom runs the
+//                  filter (pairs_dense.cuh filter_pair), survivors go to a CTA-wide list that is
+//                  evaluated exactly with every thread busy, hits appended to both rows of a
 //                  fixed-capacity scratch
 //   k_cell_scan    per frame: row counts -> row offsets (the LIL->COO order is row-major)
-//   k_cell_emit    warp per 32 rows: coalesced write of (start, dest, dist, omega)
+//   k_cell_emit    warp per 32 rows: rank of each entry inside its row (columns ascending),
+//                  write of (start, dest, dist, omega); k_cell_rsum: ordered rate sums
 #pragma once
 #include "pairs_dense.cuh"
 
@@ -89,108 +91,195 @@ k_cell_build(const __grid_constant__ BoxParams bx, const __grid_constant__ CellG
     }
 }
 
-// grid = (ceil(n / TPB), frames of the batch), block = TPB (128, 64 or 32: long rows take fewer
-// threads per CTA); dynamic smem = TPB * rowcap * 4 bytes (the row's column indices only: the kernel
-// lives on memory latency, so shared memory per thread decides how many warps hide it).  A row is
-// stored in discovery order (tmp_j, tmp_d) together with the order of its columns: tmp_inv[r] = slot
-// of the entry with the r-th smallest column.
+#define CELL_TPB 128          // threads per CTA: one home atom each
+#define CELL_STAGE_CAP 768    // atoms of the <= 5 staged columns
+#define CELL_PLIST_CAP 512    // filtered pairs per warp and exact round
+
+// exact evaluation of one filtered pair (reference arithmetic); a hit is appended to BOTH rows
+// (one atomicAdd per row on its counter; rows are unordered here, k_cell_emit sorts them)
 template <int KIND, bool IMAGES>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void cell_exact_pair(const BoxParams &bx, const double *__restrict__ fr,
+                                                int i, int j, double rc, double t2, int rowcap,
+                                                int64_t row0, int *__restrict__ rcnt,
+                                                int *__restrict__ tmp_j, double *__restrict__ tmp_d,
+                                                int *__restrict__ cap_need, unsigned long long &my_ties)
+{
+    const double pa[3] = {__ldg(fr + 3 * i), __ldg(fr + 3 * i + 1), __ldg(fr + 3 * i + 2)};
+    const double pb[3] = {__ldg(fr + 3 * j), __ldg(fr + 3 * j + 1), __ldg(fr + 3 * j + 2)};
+    double d[3], d2;
+    if (KIND == 0) {
+        diff_ortho_exact(bx, pa, pb, d);
+        d2 = norm2_exact(d);
+    } else {
+        diff_general_norm_exact(bx, pa, pb, d);
+        d2 = IMAGES ? min_image_norm2_kept(bx, d) : fmin(1e6, norm2_exact(d));
+    }
+    const double dist = convert_distance(bx, sqrt(d2));
+    const bool hit = (bx.conv == CMD_CONV_NONE ? d2 <= t2 : dist <= rc) && dist != 0.0;
+    if (fabs(dist - rc) <= 1e-11 * rc) my_ties++;
+    if (hit) {
+        const int pi = atomicAdd(rcnt + i, 1), pj = atomicAdd(rcnt + j, 1);
+        if (pi < rowcap) {
+            const int64_t at = (row0 + i) * rowcap + pi;
+            tmp_j[at] = j; tmp_d[at] = dist;
+        }
+        if (pj < rowcap) {
+            const int64_t at = (row0 + j) * rowcap + pj;
+            tmp_j[at] = i; tmp_d[at] = dist;
+        }
+        if (pi >= rowcap || pj >= rowcap) atomicMax(cap_need, max(pi, pj) + 1);
+    }
+}
+
+// the pair list is full: evaluate on the spot (cold; kept out of line, it has a dozen call sites)
+template <int KIND, bool IMAGES>
+__device__ __noinline__ void cell_exact_pair_cold(const BoxParams &bx, const double *__restrict__ fr,
+                                                  int i, int j, double rc, double t2, int rowcap,
+                                                  int64_t row0, int *__restrict__ rcnt,
+                                                  int *__restrict__ tmp_j, double *__restrict__ tmp_d,
+                                                  int *__restrict__ cap_need, unsigned long long *ties)
+{
+    unsigned long long my = 0;
+    cell_exact_pair<KIND, IMAGES>(bx, fr, i, j, rc, t2, rowcap, row0, rcnt, tmp_j, tmp_d, cap_need, my);
+    if (my) atomicAdd(ties, my);
+}
+
+// grid = (columns * segments, frames of the batch), block = CELL_TPB.  One CTA per (x, y) column
+// of cells (or per z segment of `zseg` cells of it when the batch is too small to fill the GPU
+// with whole columns).  The sorted order runs z fastest, so a column is ONE contiguous run of the
+// sorted atoms.  The CTA stages its own column and the four columns of the "half shell"
+// ((0,+1), (+1,-1), (+1,0), (+1,+1); offsets (dx, dy, dz) > 0 lexicographically) in shared
+// memory -- every unordered pair of adjacent cells is then looked at exactly once.  One thread
+// per home atom walks the z window of each staged column through the FP32 / fixed-point filter
+// and appends the survivors to a CTA-wide pair list; the list is evaluated in the reference's FP64
+// arithmetic with every thread busy.
+template <int KIND, bool IMAGES>
+__global__ void __launch_bounds__(CELL_TPB)
 k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ FilterParams fp,
              const __grid_constant__ CellGrid cg, const double *__restrict__ frames,
              const int *__restrict__ ids, const int *__restrict__ n_ids, int first, int n,
-             double rc, double t2, int rowcap, const int4 *__restrict__ sorted,
+             double rc, double t2, int rowcap, int zseg, const int4 *__restrict__ sorted,
              const int *__restrict__ cell_start, int *__restrict__ rowcount,
-             int *__restrict__ tmp_j, double *__restrict__ tmp_d,
-             unsigned short *__restrict__ tmp_inv, int *__restrict__ cap_need,
+             int *__restrict__ tmp_j, double *__restrict__ tmp_d, int *__restrict__ cap_need,
              unsigned long long *__restrict__ ties)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int4 stage[CELL_STAGE_CAP];
+    __shared__ int2 plist_all[CELL_TPB / 32][CELL_PLIST_CAP];
+    __shared__ int cs_s[5][68];          // cell starts of the staged columns (nc[2] <= 64)
+    __shared__ int col_of[5], s_off[5], s_np[CELL_TPB / 32], s_next, s_staged;
     if (n_ids && first + (int)blockIdx.y >= *n_ids) return;
     const int64_t f = ids ? ids[first + blockIdx.y] : first + blockIdx.y;
-    const int b = blockIdx.y, tid = threadIdx.x, TPB = blockDim.x;
-    int *sj = (int *)smem_raw;                             // [rowcap][TPB]
-    const int p = blockIdx.x * TPB + tid;
-    if (p >= n) return;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int nz = cg.nc[2];
+    const int nseg = (nz + zseg - 1) / zseg;
+    const int column = blockIdx.x / nseg, seg = blockIdx.x - column * nseg;
+    const int cy = column % cg.nc[1], cx = column / cg.nc[1];
+    const int z0 = seg * zseg, z1 = min(z0 + zseg, nz);
     const double *fr = frames + f * (int64_t)n * 3;
     const int4 *srt = sorted + (int64_t)b * n;
     const int *cs = cell_start + (int64_t)b * (cg.ncell + 1);
-    const int4 me = __ldg(srt + p);
-    const int i = me.w;
-    const int ic[3] = {cell_axis(me.x, cg.nc[0]), cell_axis(me.y, cg.nc[1]), cell_axis(me.z, cg.nc[2])};
+    int *rcnt = rowcount + (int64_t)b * n;
+    const int64_t row0 = (int64_t)b * n;
 
-    // ---- filter over the adjacent cells -------------------------------------------------------
-    int ncand = 0;
-    for (int dx = 0; dx < cg.span[0]; dx++) {
-        int cx = cg.span[0] == 1 ? 0 : ic[0] + dx - 1;
-        cx += cx < 0 ? cg.nc[0] : 0; cx -= cx >= cg.nc[0] ? cg.nc[0] : 0;
-        for (int dy = 0; dy < cg.span[1]; dy++) {
-            int cy = cg.span[1] == 1 ? 0 : ic[1] + dy - 1;
-            cy += cy < 0 ? cg.nc[1] : 0; cy -= cy >= cg.nc[1] ? cg.nc[1] : 0;
-            // The cells of one (cx, cy) column are consecutive in the sorted order, so the up to three
-            // z neighbours are ONE index range -- two where the column wraps around.
-            const int col = (cx * cg.nc[1] + cy) * cg.nc[2];
-            int zlo[2], zhi[2], nrange = 1;
-            if (cg.span[2] == 1) { zlo[0] = 0; zhi[0] = cg.nc[2] - 1; }
-            else {
-                zlo[0] = ic[2] - 1; zhi[0] = ic[2] + 1;
-                if (zlo[0] < 0) { zlo[1] = cg.nc[2] - 1; zhi[1] = cg.nc[2] - 1; zlo[0] = 0; nrange = 2; }
-                else if (zhi[0] >= cg.nc[2]) { zlo[1] = 0; zhi[1] = 0; zhi[0] = cg.nc[2] - 1; nrange = 2; }
-            }
-            for (int rg = 0; rg < nrange; rg++) {
-                const int k1 = __ldg(cs + col + zhi[rg] + 1);
-                for (int k = __ldg(cs + col + zlo[rg]); k < k1; k++) {
-                    const int4 q = __ldg(srt + k);
-                    if (q.w != i && filter_pair<KIND, IMAGES>(fp, me, q)) {
-                        if (ncand < rowcap) sj[ncand * TPB + tid] = q.w;
-                        ncand++;
+    // the staged columns: 0 = own, then the half shell (-1: absent)
+    if (tid == 0) {
+        const int yw = cg.span[1] == 3 ? 1 : 0;
+        const int yp = cy + 1 >= cg.nc[1] ? 0 : cy + 1, ym = cy - 1 < 0 ? cg.nc[1] - 1 : cy - 1;
+        const int xp = cx + 1 >= cg.nc[0] ? 0 : cx + 1;
+        col_of[0] = (cx * cg.nc[1] + cy) * nz;
+        col_of[1] = yw ? (cx * cg.nc[1] + yp) * nz : -1;
+        col_of[2] = cg.span[0] == 3 && yw ? (xp * cg.nc[1] + ym) * nz : -1;
+        col_of[3] = cg.span[0] == 3 ? (xp * cg.nc[1] + cy) * nz : -1;
+        col_of[4] = cg.span[0] == 3 && yw ? (xp * cg.nc[1] + yp) * nz : -1;
+    }
+    if (tid < CELL_TPB / 32) s_np[tid] = 0;
+    __syncthreads();
+    for (int k = tid; k < 5 * (nz + 1); k += CELL_TPB) {
+        const int c = k / (nz + 1), z = k - c * (nz + 1);
+        cs_s[c][z] = col_of[c] >= 0 ? __ldg(cs + col_of[c] + z) : 0;
+    }
+    __syncthreads();
+    if (tid == 0) {   // whole columns are staged; a segment CTA or an overfull one reads global memory
+        int tot = 0;
+        for (int c = 0; c < 5; c++) { s_off[c] = tot; tot += col_of[c] >= 0 ? cs_s[c][nz] - cs_s[c][0] : 0; }
+        s_staged = (nseg == 1 && tot <= CELL_STAGE_CAP) ? 1 : 0;
+        s_next = cs_s[0][z0];
+    }
+    __syncthreads();
+    const bool staged = s_staged != 0;
+    if (staged) {
+        for (int c = 0; c < 5; c++) {
+            if (col_of[c] < 0) continue;
+            const int g0 = cs_s[c][0], cnt = cs_s[c][nz] - g0;
+            for (int q = tid; q < cnt; q += CELL_TPB) stage[s_off[c] + q] = __ldg(srt + g0 + q);
+        }
+    }
+    __syncthreads();   // the last CTA-wide barrier: from here on the warps run on their own
+
+    const int zw = cg.span[2] == 3 ? 1 : 0;
+    const bool zall = 2 * zw + 1 >= nz;           // the z window is the whole column
+    const int home_hi = cs_s[0][z1];
+    int2 *plist = plist_all[wp];
+    int *my_np = &s_np[wp];
+    unsigned long long my_ties = 0;
+    for (;;) {
+        int hb = 0;
+        if (lane == 0) hb = atomicAdd(&s_next, 32);   // the warp's next 32 home atoms
+        hb = __shfl_sync(0xffffffffu, hb, 0);
+        if (hb >= home_hi) break;
+        const int k = hb + lane;
+        if (k < home_hi) {
+            const int4 me = staged ? stage[k - cs_s[0][0]] : __ldg(srt + k);
+            int z = z0;
+            while (cs_s[0][z + 1] <= k) z++;        // the home atom's cell
+            // <= 2 index ranges per column (the z window wraps at the column ends); ONE loop site
+#pragma unroll 1
+            for (int r = 0; r < 10; r++) {
+                const int c = r >> 1;
+                const bool second = r & 1;
+                if (col_of[c] < 0) continue;
+                const int *cc = cs_s[c];
+                int lo = 0, hi = 0;
+                if (c == 0) {
+                    // own column: the rest of the home cell, then cell z + 1 (wrapped)
+                    if (!zw) { if (!second) { lo = k + 1; hi = cc[z + 1]; } }
+                    else if (zall) {   // three cells: z + 1 is distinct, z + 2 = z - 1 is that cell's job
+                        const int zn = z + 1 < nz ? z + 1 : 0;
+                        lo = second ? cc[zn] : k + 1;
+                        hi = second ? cc[zn + 1] : cc[z + 1];
+                    } else if (z + 1 < nz) { if (!second) { lo = k + 1; hi = cc[z + 2]; } }
+                    else { lo = second ? cc[0] : k + 1; hi = second ? cc[1] : cc[nz]; }
+                } else {
+                    // half-shell column: cells z - zw .. z + zw (wrapped)
+                    if (zall) { if (!second) { lo = cc[0]; hi = cc[nz]; } }
+                    else if (z - 1 < 0) { lo = second ? cc[0] : cc[nz - 1]; hi = second ? cc[z + 2] : cc[nz]; }
+                    else if (z + 1 >= nz) { lo = second ? cc[0] : cc[z - 1]; hi = second ? cc[1] : cc[nz]; }
+                    else if (!second) { lo = cc[z - 1]; hi = cc[z + 2]; }
+                }
+                const int4 *bp = staged ? stage + (s_off[c] - cc[0]) : srt;
+                for (int q = lo; q < hi; q++) {
+                    const int4 cand = bp[q];
+                    if (filter_pair<KIND, IMAGES>(fp, me, cand)) {
+                        const int e = atomicAdd(my_np, 1);
+                        if (e < CELL_PLIST_CAP) plist[e] = make_int2(me.w, cand.w);
+                        else cell_exact_pair_cold<KIND, IMAGES>(bx, fr, me.w, cand.w, rc, t2, rowcap, row0,
+                                                               rcnt, tmp_j, tmp_d, cap_need, ties);
                     }
                 }
             }
         }
-    }
-    if (ncand > rowcap) {   // scratch row too small: report the need, the host retries
-        atomicMax(cap_need, ncand);
-        rowcount[(int64_t)b * n + i] = 0;
-        return;
-    }
-
-    // ---- exact evaluation of the survivors (reference arithmetic), compaction -----------------
-    const double pa[3] = {__ldg(fr + 3 * i), __ldg(fr + 3 * i + 1), __ldg(fr + 3 * i + 2)};
-    const int64_t row = ((int64_t)b * n + i) * rowcap;
-    int nh = 0;
-    unsigned long long my_ties = 0;
-    for (int c = 0; c < ncand; c++) {
-        const int j = sj[c * TPB + tid];
-        const double pb[3] = {__ldg(fr + 3 * j), __ldg(fr + 3 * j + 1), __ldg(fr + 3 * j + 2)};
-        double d[3], d2;
-        if (KIND == 0) {
-            diff_ortho_exact(bx, pa, pb, d);
-            d2 = norm2_exact(d);
-        } else {
-            diff_general_exact(bx, pa, pb, d);
-            d2 = min_image_norm2_kept(bx, d);
+        __syncwarp();
+        const int np = min(*my_np, CELL_PLIST_CAP);
+        for (int e = lane; e < np; e += 32) {
+            const int2 pr = plist[e];
+            cell_exact_pair<KIND, IMAGES>(bx, fr, pr.x, pr.y, rc, t2, rowcap, row0, rcnt, tmp_j, tmp_d,
+                                          cap_need, my_ties);
         }
-        const double dist = convert_distance(bx, sqrt(d2));
-        const bool hit = (bx.conv == CMD_CONV_NONE ? d2 <= t2 : dist <= rc) && dist != 0.0;
-        if (i < j && fabs(dist - rc) <= 1e-11 * rc) my_ties++;   // a pair is seen from both rows
-        if (hit) {
-            sj[nh * TPB + tid] = j;      // nh <= c: never ahead of the read position
-            tmp_j[row + nh] = j;
-            tmp_d[row + nh] = dist;
-            nh++;
-        }
+        __syncwarp();
+        if (lane == 0) *my_np = 0;
+        __syncwarp();
     }
     if (my_ties) atomicAdd(ties, my_ties);
-
-    // ---- the row's column order by rank counting (columns are distinct) -------------------------
-    for (int a = 0; a < nh; a++) {
-        const int kj = sj[a * TPB + tid];
-        int rank = 0;
-        for (int q = 0; q < nh; q++) rank += sj[q * TPB + tid] < kj;
-        tmp_inv[row + rank] = (unsigned short)a;
-    }
-    rowcount[(int64_t)b * n + i] = nh;
 }
 
 // per frame: rowcount -> exclusive row offsets (n + 1 entries), frame total -> out_counts
@@ -231,23 +320,29 @@ k_cell_scan(const int *__restrict__ ids, const int *__restrict__ n_ids, int firs
     }
 }
 
-// grid = (ceil(n / 256), frames of the batch), block = 256: a warp writes 32 consecutive rows
+// grid = (ceil(n / 256), frames of the batch), block = 256: a warp writes 32 consecutive rows, one
+// output entry per lane and trip.  The rows arrive unordered; the entry's place inside its row is
+// the number of smaller columns in that row (columns are distinct), counted by the lane itself --
+// the neighbouring lanes read the same few rows, so the loop runs out of L1.  The writes of a warp
+// cover one contiguous range of the four output arrays.
 __global__ void __launch_bounds__(256)
 k_cell_emit(const __grid_constant__ RateParams rp, const int *__restrict__ ids,
             const int *__restrict__ n_ids, int first, int n, int64_t stride, int rowcap,
             const int *__restrict__ rowoff, const int *__restrict__ tmp_j,
-            const double *__restrict__ tmp_d, const unsigned short *__restrict__ tmp_inv,
+            const double *__restrict__ tmp_d,
             int *__restrict__ out_start,
             int *__restrict__ out_dest, double *__restrict__ out_dist,
-            double *__restrict__ out_omega, double *__restrict__ out_rate_sum)
+            double *__restrict__ out_omega, double *__restrict__ part)
 {
     if (n_ids && first + (int)blockIdx.y >= *n_ids) return;
     const int64_t f = ids ? ids[first + blockIdx.y] : first + blockIdx.y;
     const int b = blockIdx.y, lane = threadIdx.x & 31;
-    const int r0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
-    if (r0 >= n) return;
+    const int wglob = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int r0 = wglob * 32;
+    double *my_part = part ? part + (int64_t)b * (gridDim.x * 8) + wglob : nullptr;
+    if (r0 >= n) { if (my_part && lane == 0) *my_part = 0.0; return; }
     const int *ro = rowoff + (int64_t)b * (n + 1);
-    if (ro[n] > stride) return;   // overflow: reported by k_cell_scan
+    if (ro[n] > stride) { if (my_part && lane == 0) *my_part = 0.0; return; }   // overflow: k_cell_scan
     const int myrow = min(r0 + lane, n);
     const int myoff = ro[myrow];                       // offsets of rows r0 .. r0+31 (clamped)
     const int g0 = __shfl_sync(0xffffffffu, myoff, 0);
@@ -264,20 +359,44 @@ k_cell_emit(const __grid_constant__ RateParams rp, const int *__restrict__ ids,
             if (lo + s <= 31 && probe <= g) lo += s;
         }
         const int off_lo = __shfl_sync(0xffffffffu, myoff, lo);
+        const int off_nx = __shfl_sync(0xffffffffu, myoff, min(lo + 1, 31));
         if (g < g1) {
             const int r = r0 + lo;
+            const int cnt = (lo < 31 ? off_nx : g1) - off_lo;
             const int64_t rbase = ((int64_t)b * n + r) * rowcap;
-            const int64_t src = rbase + tmp_inv[rbase + (g - off_lo)];   // columns ascending
-            const int j = tmp_j[src];
-            const double dist = tmp_d[src];
+            const int j = tmp_j[rbase + (g - off_lo)];
+            const double dist = tmp_d[rbase + (g - off_lo)];
+            int rank = 0;
+            for (int q = 0; q < cnt; q++) rank += __ldg(tmp_j + rbase + q) < j;
             const double om = rate_eval(rp, dist, 0.0);
             rsum += om;
-            out_start[base + g] = r; out_dest[base + g] = j;
-            out_dist[base + g] = dist; out_omega[base + g] = om;
+            const int64_t at = base + off_lo + rank;
+            out_start[at] = r; out_dest[at] = j;
+            out_dist[at] = dist; out_omega[at] = om;
         }
     }
-    if (out_rate_sum) {
+    if (my_part) {
         for (int o = 16; o > 0; o >>= 1) rsum += __shfl_down_sync(0xffffffffu, rsum, o);
-        if (lane == 0 && rsum != 0.0) atomicAdd(out_rate_sum + f, rsum);
+        if (lane == 0) *my_part = rsum;
     }
+}
+
+// per frame: the warps' partial rate sums in a fixed order (deterministic, unlike atomics)
+__global__ void __launch_bounds__(256)
+k_cell_rsum(const int *__restrict__ ids, const int *__restrict__ n_ids, int first, int nparts,
+            const double *__restrict__ part, double *__restrict__ out_rate_sum)
+{
+    __shared__ double red[256];
+    if (n_ids && first + (int)blockIdx.x >= *n_ids) return;
+    const int64_t f = ids ? ids[first + blockIdx.x] : first + blockIdx.x;
+    const double *p = part + (int64_t)blockIdx.x * nparts;
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < nparts; k += 256) acc += p[k];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_rate_sum[f] = red[0];
 }
