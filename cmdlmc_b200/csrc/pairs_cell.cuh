@@ -131,6 +131,60 @@ __device__ __forceinline__ void cell_exact_pair(const BoxParams &bx, const doubl
     }
 }
 
+// two filtered pairs at once (the second only if `two`): loads first, then both FP64 chains, then
+// the appends
+template <int KIND, bool IMAGES>
+__device__ __forceinline__ void cell_exact_two(const BoxParams &bx, const double *__restrict__ fr,
+                                               int2 p0, int2 p1, bool two, double rc, double t2,
+                                               int rowcap, int64_t row0, int *__restrict__ rcnt,
+                                               int *__restrict__ tmp_j, double *__restrict__ tmp_d,
+                                               int *__restrict__ cap_need, unsigned long long &my_ties)
+{
+    const int2 pr[2] = {p0, p1};
+    double pa[2][3], pb[2][3], d2[2], dist[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            pa[q][c] = __ldg(fr + 3 * pr[q].x + c);
+            pb[q][c] = __ldg(fr + 3 * pr[q].y + c);
+        }
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        double d[3];
+        if (KIND == 0) {
+            diff_ortho_exact(bx, pa[q], pb[q], d);
+            d2[q] = norm2_exact(d);
+        } else {
+            diff_general_norm_exact(bx, pa[q], pb[q], d);
+            d2[q] = IMAGES ? min_image_norm2_kept(bx, d) : fmin(1e6, norm2_exact(d));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++) dist[q] = convert_distance(bx, sqrt(d2[q]));
+    bool hit[2];
+    int pi[2] = {0, 0}, pj[2] = {0, 0};
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        hit[q] = (q == 0 || two) && (bx.conv == CMD_CONV_NONE ? d2[q] <= t2 : dist[q] <= rc) && dist[q] != 0.0;
+        if ((q == 0 || two) && fabs(dist[q] - rc) <= 1e-11 * rc) my_ties++;
+        if (hit[q]) { pi[q] = atomicAdd(rcnt + pr[q].x, 1); pj[q] = atomicAdd(rcnt + pr[q].y, 1); }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        if (!hit[q]) continue;
+        if (pi[q] < rowcap) {
+            const int64_t at = (row0 + pr[q].x) * rowcap + pi[q];
+            tmp_j[at] = pr[q].y; tmp_d[at] = dist[q];
+        }
+        if (pj[q] < rowcap) {
+            const int64_t at = (row0 + pr[q].y) * rowcap + pj[q];
+            tmp_j[at] = pr[q].x; tmp_d[at] = dist[q];
+        }
+        if (pi[q] >= rowcap || pj[q] >= rowcap) atomicMax(cap_need, max(pi[q], pj[q]) + 1);
+    }
+}
+
 // the pair list is full: evaluate on the spot (cold; kept out of line, it has a dozen call sites)
 template <int KIND, bool IMAGES>
 __device__ __noinline__ void cell_exact_pair_cold(const BoxParams &bx, const double *__restrict__ fr,
@@ -144,7 +198,8 @@ __device__ __noinline__ void cell_exact_pair_cold(const BoxParams &bx, const dou
     if (my) atomicAdd(ties, my);
 }
 
-// grid = (columns * segments, frames of the batch), block = CELL_TPB.  One CTA per (x, y) column
+// grid = (columns * segments, frames of the batch), block = 32 .. CELL_TPB threads (about one per
+// atom of a column).  One CTA per (x, y) column
 // of cells (or per z segment of `zseg` cells of it when the batch is too small to fill the GPU
 // with whole columns).  The sorted order runs z fastest, so a column is ONE contiguous run of the
 // sorted atoms.  The CTA stages its own column and the four columns of the "half shell"
@@ -164,7 +219,7 @@ k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ Filte
              unsigned long long *__restrict__ ties)
 {
     __shared__ int4 stage[CELL_STAGE_CAP];
-    __shared__ int2 plist_all[CELL_TPB / 32][CELL_PLIST_CAP];
+    extern __shared__ int2 plist_dyn[];    // [warps][CELL_PLIST_CAP]
     __shared__ int cs_s[5][68];          // cell starts of the staged columns (nc[2] <= 64)
     __shared__ int col_of[5], s_off[5], s_np[CELL_TPB / 32], s_next, s_staged;
     if (n_ids && first + (int)blockIdx.y >= *n_ids) return;
@@ -194,7 +249,7 @@ k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ Filte
     }
     if (tid < CELL_TPB / 32) s_np[tid] = 0;
     __syncthreads();
-    for (int k = tid; k < 5 * (nz + 1); k += CELL_TPB) {
+    for (int k = tid; k < 5 * (nz + 1); k += blockDim.x) {
         const int c = k / (nz + 1), z = k - c * (nz + 1);
         cs_s[c][z] = col_of[c] >= 0 ? __ldg(cs + col_of[c] + z) : 0;
     }
@@ -211,7 +266,7 @@ k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ Filte
         for (int c = 0; c < 5; c++) {
             if (col_of[c] < 0) continue;
             const int g0 = cs_s[c][0], cnt = cs_s[c][nz] - g0;
-            for (int q = tid; q < cnt; q += CELL_TPB) stage[s_off[c] + q] = __ldg(srt + g0 + q);
+            for (int q = tid; q < cnt; q += blockDim.x) stage[s_off[c] + q] = __ldg(srt + g0 + q);
         }
     }
     __syncthreads();   // the last CTA-wide barrier: from here on the warps run on their own
@@ -219,7 +274,7 @@ k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ Filte
     const int zw = cg.span[2] == 3 ? 1 : 0;
     const bool zall = 2 * zw + 1 >= nz;           // the z window is the whole column
     const int home_hi = cs_s[0][z1];
-    int2 *plist = plist_all[wp];
+    int2 *plist = plist_dyn + wp * CELL_PLIST_CAP;
     int *my_np = &s_np[wp];
     unsigned long long my_ties = 0;
     for (;;) {
@@ -270,10 +325,13 @@ k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ Filte
         }
         __syncwarp();
         const int np = min(*my_np, CELL_PLIST_CAP);
-        for (int e = lane; e < np; e += 32) {
-            const int2 pr = plist[e];
-            cell_exact_pair<KIND, IMAGES>(bx, fr, pr.x, pr.y, rc, t2, rowcap, row0, rcnt, tmp_j, tmp_d,
-                                          cap_need, my_ties);
+        // two pairs per lane and trip: the coordinate loads and the row-counter atomics of one
+        // overlap the arithmetic of the other
+        for (int e = lane; e < np; e += 64) {
+            const bool two = e + 32 < np;
+            const int2 pr0 = plist[e], pr1 = plist[two ? e + 32 : e];
+            cell_exact_two<KIND, IMAGES>(bx, fr, pr0, pr1, two, rc, t2, rowcap, row0, rcnt, tmp_j, tmp_d,
+                                         cap_need, my_ties);
         }
         __syncwarp();
         if (lane == 0) *my_np = 0;
@@ -367,6 +425,7 @@ k_cell_emit(const __grid_constant__ RateParams rp, const int *__restrict__ ids,
             const int j = tmp_j[rbase + (g - off_lo)];
             const double dist = tmp_d[rbase + (g - off_lo)];
             int rank = 0;
+#pragma unroll 4
             for (int q = 0; q < cnt; q++) rank += __ldg(tmp_j + rbase + q) < j;
             const double om = rate_eval(rp, dist, 0.0);
             rsum += om;
