@@ -72,10 +72,19 @@ void cmd_box_prune_images(BoxParams &p, double rc);
                                              "bound (there is no CPU fallback)");           \
     } while (0)
 
+// CMDLMC_B200_SYNC_LAUNCHES=1 (debugging): wait for every kernel, so that a device fault is reported
+// at the launch that caused it
+inline bool cmd_sync_launches()
+{
+    static const bool on = getenv("CMDLMC_B200_SYNC_LAUNCHES") != nullptr;
+    return on;
+}
+
 #define CMD_LAUNCHED()                                                                      \
     do {                                                                                    \
         cmd_global().launches++;                                                            \
         CMD_CUDA(cudaGetLastError());                                                       \
+        if (cmd_sync_launches()) CMD_CUDA(cudaStreamSynchronize(cmd_global().stream));      \
     } while (0)
 
 // row pitch (ints) of the per-frame row index: n + 1 entries padded to 16 bytes (TMA bulk copies)

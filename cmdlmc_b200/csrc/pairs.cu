@@ -1030,12 +1030,8 @@ static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, cons
             }
         }
         dim3 pgrid((unsigned)(ncolumn * cmd_div_up(t->cg.nc[2], zseg)), (unsigned)batch);
-        // about one thread per home atom of a CTA (a warp takes 32 at a time)
-        int ptpb = (int)(((int64_t)n * zseg / ((int64_t)ncolumn * t->cg.nc[2]) + 31) / 32 * 32);
-        if (ptpb < 32) ptpb = 32;
-        if (ptpb > CELL_TPB) ptpb = CELL_TPB;
 #define CELL_PAIRS(K, IM)                                                                        \
-    k_cell_pairs<K, IM><<<pgrid, ptpb, (size_t)(ptpb / 32) * CELL_PLIST_CAP * 8, st>>>(                                                 \
+    k_cell_pairs<K, IM><<<pgrid, CELL_TPB, 0, st>>>(                                             \
         t->bx, t->fp, t->cg, d_frames, ids, n_ids, (int)first, n, t->rc, t->t2, t->rowcap, zseg, \
         t->d_sorted, t->d_cell_start, t->d_rowcount, t->d_tmp_j, t->d_tmp_d, t->d_cap_need,      \
         t->d_ties)
@@ -1053,7 +1049,7 @@ static int launch_cell(cmd_topo *t, const double *d_frames, const int *ids, cons
             if ((size_t)(need + 8) * (size_t)n * 12 > ((size_t)1 << 32))
                 return cmd_set_error(CMD_ECAPACITY, "an atom has %d neighbours: more than the "
                                      "cell-list scratch rows can hold", need);
-            t->rowcap = need + 8;
+            t->rowcap = (need + 8 + 3) / 4 * 4;   // k_cell_emit reads the rows 16 bytes at a time
             cell_free(t);
             continue;   // redo this batch with longer rows
         }

@@ -11,11 +11,13 @@
 // collapsed to one cell (all its atoms are candidates; the exact stage finds the image).
 //
 //   k_cell_build   one CTA per frame: fixed-point coordinates, counting sort into cells
-//   k_cell_pairs   one CTA per (x, y) column of cells: the column and its half shell staged in
-//                  shared memory, every unordered pair once; a thread per home atom runs the
-//                  filter (pairs_dense.cuh filter_pair), survivors go to a CTA-wide list that is
-//                  evaluated exactly with every thread busy, hits appended to both rows of a
-//                  fixed-capacity scratch
+//   k_cell_pairs   one CTA per (x, y) column of cells, a warp per home cell: lanes hold the
+//                  candidates of the half shell (every unordered pair of adjacent cells once),
+//                  the home atoms pass by in a warp-uniform loop through the FP32 / fixed-point
+//                  filter (pairs_dense.cuh filter_pair); survivors are compacted by
+//                  __ballot_sync / __popc into a per-warp list, evaluated 64 at a time in the
+//                  reference's FP64 arithmetic, hits appended to both rows of a fixed-capacity
+//                  scratch
 //   k_cell_scan    per frame: row counts -> row offsets (the LIL->COO order is row-major)
 //   k_cell_emit    warp per 32 rows: rank of each entry inside its row (columns ascending),
 //                  write of (start, dest, dist, omega); k_cell_rsum: ordered rate sums
@@ -91,56 +93,42 @@ k_cell_build(const __grid_constant__ BoxParams bx, const __grid_constant__ CellG
     }
 }
 
-#define CELL_TPB 128          // threads per CTA: one home atom each
-#define CELL_STAGE_CAP 768    // atoms of the <= 5 staged columns
-#define CELL_PLIST_CAP 512    // filtered pairs per warp and exact round
+#define CELL_WARPS 4          // warps per CTA: each walks home cells of the CTA's column on its own
+#define CELL_TPB (32 * CELL_WARPS)
+#ifndef CELL_UNROLL
+#define CELL_UNROLL 1
+#endif
+#ifndef CELL_MINB
+#define CELL_MINB 8            // resident CTAs per SM the register budget is cut for
+#endif
+#define CELL_PLIST 96         // filtered pairs a warp holds: drained 64 at a time, < 32 appended per step
 
-// exact evaluation of one filtered pair (reference arithmetic); a hit is appended to BOTH rows
-// (one atomicAdd per row on its counter; rows are unordered here, k_cell_emit sorts them)
-template <int KIND, bool IMAGES>
-__device__ __forceinline__ void cell_exact_pair(const BoxParams &bx, const double *__restrict__ fr,
-                                                int i, int j, double rc, double t2, int rowcap,
-                                                int64_t row0, int *__restrict__ rcnt,
-                                                int *__restrict__ tmp_j, double *__restrict__ tmp_d,
-                                                int *__restrict__ cap_need, unsigned long long &my_ties)
+// numpyatom.pyx:33-42 for a difference that is at most 1.5 box lengths long (everything the
+// filter lets through): the reference's loops run at most once, in one direction.  `cold` is
+// raised for anything else (the caller then takes wrap_ortho_exact).
+__device__ __forceinline__ double wrap_ortho_once(double d, double L, double hL, bool &cold)
 {
-    const double pa[3] = {__ldg(fr + 3 * i), __ldg(fr + 3 * i + 1), __ldg(fr + 3 * i + 2)};
-    const double pb[3] = {__ldg(fr + 3 * j), __ldg(fr + 3 * j + 1), __ldg(fr + 3 * j + 2)};
-    double d[3], d2;
-    if (KIND == 0) {
-        diff_ortho_exact(bx, pa, pb, d);
-        d2 = norm2_exact(d);
-    } else {
-        diff_general_norm_exact(bx, pa, pb, d);
-        d2 = IMAGES ? min_image_norm2_kept(bx, d) : fmin(1e6, norm2_exact(d));
-    }
-    const double dist = convert_distance(bx, sqrt(d2));
-    const bool hit = (bx.conv == CMD_CONV_NONE ? d2 <= t2 : dist <= rc) && dist != 0.0;
-    if (fabs(dist - rc) <= 1e-11 * rc) my_ties++;
-    if (hit) {
-        const int pi = atomicAdd(rcnt + i, 1), pj = atomicAdd(rcnt + j, 1);
-        if (pi < rowcap) {
-            const int64_t at = (row0 + i) * rowcap + pi;
-            tmp_j[at] = j; tmp_d[at] = dist;
-        }
-        if (pj < rowcap) {
-            const int64_t at = (row0 + j) * rowcap + pj;
-            tmp_j[at] = i; tmp_d[at] = dist;
-        }
-        if (pi >= rowcap || pj >= rowcap) atomicMax(cap_need, max(pi, pj) + 1);
-    }
+    cold |= !(fabs(d) <= 1.5 * L);
+    if (d < -hL) d = __dadd_rn(d, L);
+    else if (d > hL) d = __dadd_rn(d, -L);
+    return d;
 }
 
-// two filtered pairs at once (the second only if `two`): loads first, then both FP64 chains, then
-// the appends
+// Exact evaluation (reference arithmetic) of the first `cnt` (<= 64) pairs of a warp's list, two per
+// lane: loads first, then both FP64 chains, then the appends.  A hit is appended to BOTH rows
+// (one atomicAdd per row on its counter; rows are unordered here, k_cell_emit sorts them).
 template <int KIND, bool IMAGES>
-__device__ __forceinline__ void cell_exact_two(const BoxParams &bx, const double *__restrict__ fr,
-                                               int2 p0, int2 p1, bool two, double rc, double t2,
-                                               int rowcap, int64_t row0, int *__restrict__ rcnt,
-                                               int *__restrict__ tmp_j, double *__restrict__ tmp_d,
-                                               int *__restrict__ cap_need, unsigned long long &my_ties)
+__device__ __forceinline__ void cell_exact_drain(const BoxParams &bx, const double *__restrict__ fr,
+                                                 const int2 *plist, int cnt, double rc, double t2,
+                                                 int rowcap, unsigned row0, int *__restrict__ rcnt,
+                                                 int *__restrict__ tmp_j, double *__restrict__ tmp_d,
+                                                 int *__restrict__ cap_need,
+                                                 unsigned long long *__restrict__ ties)
 {
-    const int2 pr[2] = {p0, p1};
+    const int lane = threadIdx.x & 31;
+    if (lane >= cnt) return;
+    const bool two = lane + 32 < cnt;
+    const int2 pr[2] = {plist[lane], plist[two ? lane + 32 : lane]};
     double pa[2][3], pb[2][3], d2[2], dist[2];
 #pragma unroll
     for (int q = 0; q < 2; q++)
@@ -153,7 +141,11 @@ __device__ __forceinline__ void cell_exact_two(const BoxParams &bx, const double
     for (int q = 0; q < 2; q++) {
         double d[3];
         if (KIND == 0) {
-            diff_ortho_exact(bx, pa[q], pb[q], d);
+            bool cold = false;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                d[c] = wrap_ortho_once(__dadd_rn(pb[q][c], -pa[q][c]), bx.L[c], bx.hL[c], cold);
+            if (cold) diff_ortho_exact(bx, pa[q], pb[q], d);
             d2[q] = norm2_exact(d);
         } else {
             diff_general_norm_exact(bx, pa[q], pb[q], d);
@@ -164,52 +156,51 @@ __device__ __forceinline__ void cell_exact_two(const BoxParams &bx, const double
     for (int q = 0; q < 2; q++) dist[q] = convert_distance(bx, sqrt(d2[q]));
     bool hit[2];
     int pi[2] = {0, 0}, pj[2] = {0, 0};
+    unsigned nt = 0;
 #pragma unroll
     for (int q = 0; q < 2; q++) {
-        hit[q] = (q == 0 || two) && (bx.conv == CMD_CONV_NONE ? d2[q] <= t2 : dist[q] <= rc) && dist[q] != 0.0;
-        if ((q == 0 || two) && fabs(dist[q] - rc) <= 1e-11 * rc) my_ties++;
+        const bool live = q == 0 || two;
+        hit[q] = live && (bx.conv == CMD_CONV_NONE ? d2[q] <= t2 : dist[q] <= rc) && dist[q] != 0.0;
+        nt += live && fabs(dist[q] - rc) <= 1e-11 * rc;
         if (hit[q]) { pi[q] = atomicAdd(rcnt + pr[q].x, 1); pj[q] = atomicAdd(rcnt + pr[q].y, 1); }
     }
+    if (nt) atomicAdd(ties, (unsigned long long)nt);
 #pragma unroll
     for (int q = 0; q < 2; q++) {
         if (!hit[q]) continue;
+        // scratch indices fit 32 bits: a batch is sized to at most 2^30 bytes of 12-byte entries
         if (pi[q] < rowcap) {
-            const int64_t at = (row0 + pr[q].x) * rowcap + pi[q];
+            const unsigned at = (row0 + (unsigned)pr[q].x) * (unsigned)rowcap + (unsigned)pi[q];
             tmp_j[at] = pr[q].y; tmp_d[at] = dist[q];
         }
         if (pj[q] < rowcap) {
-            const int64_t at = (row0 + pr[q].y) * rowcap + pj[q];
+            const unsigned at = (row0 + (unsigned)pr[q].y) * (unsigned)rowcap + (unsigned)pj[q];
             tmp_j[at] = pr[q].x; tmp_d[at] = dist[q];
         }
         if (pi[q] >= rowcap || pj[q] >= rowcap) atomicMax(cap_need, max(pi[q], pj[q]) + 1);
     }
 }
 
-// the pair list is full: evaluate on the spot (cold; kept out of line, it has a dozen call sites)
+// grid = (columns * segments, frames of the batch), block = CELL_TPB.  One CTA per (x, y) column of
+// cells (or per z segment of `zseg` cells of it when the batch is too small to fill the GPU with
+// whole columns); its warps take the column's home cells in turn and never meet at a barrier
+// after the prologue.
+//
+// The sorted order runs z fastest, so a column is ONE contiguous run of the sorted atoms and the
+// cells z-1 .. z+1 of a column are one run of it (cyclic at the column ends).  The candidates of a
+// home cell are the rest of the "half shell": its own column from the home cell on (cells z, z+1;
+// inside the home cell only the atoms BEHIND the home atom), and cells z-1 .. z+1 of the columns
+// (0,+1), (+1,-1), (+1,0), (+1,+1) -- every unordered pair of adjacent cells exactly once.
+//
+// Lanes hold CANDIDATES (one per lane and round, in registers); the home atoms of the cell are
+// walked in a warp-uniform loop, their coordinates broadcast from shared memory.  Each step runs the
+// FP32 / fixed-point filter (pairs_dense.cuh filter_pair) on 32 pairs with no divergence; the
+// survivors are compacted with __ballot_sync / __popc into the warp's pair list, and whenever 64
+// are waiting they are evaluated in the reference's FP64 arithmetic, two per lane (the memory
+// latency of that stage -- coordinate loads, row-counter atomics -- hides under the filter work
+// of the SM's other warps; a separate exact kernel was 1.4x slower, profiles/README.md).
 template <int KIND, bool IMAGES>
-__device__ __noinline__ void cell_exact_pair_cold(const BoxParams &bx, const double *__restrict__ fr,
-                                                  int i, int j, double rc, double t2, int rowcap,
-                                                  int64_t row0, int *__restrict__ rcnt,
-                                                  int *__restrict__ tmp_j, double *__restrict__ tmp_d,
-                                                  int *__restrict__ cap_need, unsigned long long *ties)
-{
-    unsigned long long my = 0;
-    cell_exact_pair<KIND, IMAGES>(bx, fr, i, j, rc, t2, rowcap, row0, rcnt, tmp_j, tmp_d, cap_need, my);
-    if (my) atomicAdd(ties, my);
-}
-
-// grid = (columns * segments, frames of the batch), block = 32 .. CELL_TPB threads (about one per
-// atom of a column).  One CTA per (x, y) column
-// of cells (or per z segment of `zseg` cells of it when the batch is too small to fill the GPU
-// with whole columns).  The sorted order runs z fastest, so a column is ONE contiguous run of the
-// sorted atoms.  The CTA stages its own column and the four columns of the "half shell"
-// ((0,+1), (+1,-1), (+1,0), (+1,+1); offsets (dx, dy, dz) > 0 lexicographically) in shared
-// memory -- every unordered pair of adjacent cells is then looked at exactly once.  One thread
-// per home atom walks the z window of each staged column through the FP32 / fixed-point filter
-// and appends the survivors to a CTA-wide pair list; the list is evaluated in the reference's FP64
-// arithmetic with every thread busy.
-template <int KIND, bool IMAGES>
-__global__ void __launch_bounds__(CELL_TPB)
+__global__ void __launch_bounds__(CELL_TPB, CELL_MINB)
 k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ FilterParams fp,
              const __grid_constant__ CellGrid cg, const double *__restrict__ frames,
              const int *__restrict__ ids, const int *__restrict__ n_ids, int first, int n,
@@ -218,126 +209,132 @@ k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ Filte
              int *__restrict__ tmp_j, double *__restrict__ tmp_d, int *__restrict__ cap_need,
              unsigned long long *__restrict__ ties)
 {
-    __shared__ int4 stage[CELL_STAGE_CAP];
-    extern __shared__ int2 plist_dyn[];    // [warps][CELL_PLIST_CAP]
-    __shared__ int cs_s[5][68];          // cell starts of the staged columns (nc[2] <= 64)
-    __shared__ int col_of[5], s_off[5], s_np[CELL_TPB / 32], s_next, s_staged;
+    __shared__ int4 wbuf_s[CELL_WARPS][32];          // the home atoms in flight
+    __shared__ int2 plist_s[CELL_WARPS][CELL_PLIST];
+    __shared__ int4 desc_s[CELL_WARPS][6];   // [c] = (ring start, first slot, column begin, column end); [5] = first slots of columns 1..4
+    __shared__ int cs_s[5][68];              // cell starts of the five columns (nc[2] <= 64)
+    __shared__ int colbase_s[5];
     if (n_ids && first + (int)blockIdx.y >= *n_ids) return;
-    const int64_t f = ids ? ids[first + blockIdx.y] : first + blockIdx.y;
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
     const int nz = cg.nc[2];
     const int nseg = (nz + zseg - 1) / zseg;
     const int column = blockIdx.x / nseg, seg = blockIdx.x - column * nseg;
     const int cy = column % cg.nc[1], cx = column / cg.nc[1];
     const int z0 = seg * zseg, z1 = min(z0 + zseg, nz);
-    const double *fr = frames + f * (int64_t)n * 3;
     const int4 *srt = sorted + (int64_t)b * n;
     const int *cs = cell_start + (int64_t)b * (cg.ncell + 1);
+    const int64_t f = ids ? ids[first + blockIdx.y] : first + blockIdx.y;
+    const double *fr = frames + f * (int64_t)n * 3;
     int *rcnt = rowcount + (int64_t)b * n;
-    const int64_t row0 = (int64_t)b * n;
+    const unsigned row0 = (unsigned)b * (unsigned)n;
 
-    // the staged columns: 0 = own, then the half shell (-1: absent)
-    if (tid == 0) {
-        const int yw = cg.span[1] == 3 ? 1 : 0;
+    // the five columns: 0 = own, then the half shell (-1: absent)
+    if (tid < 5) {
+        const int yw = cg.span[1] == 3 ? 1 : 0, xw = cg.span[0] == 3 ? 1 : 0;
         const int yp = cy + 1 >= cg.nc[1] ? 0 : cy + 1, ym = cy - 1 < 0 ? cg.nc[1] - 1 : cy - 1;
         const int xp = cx + 1 >= cg.nc[0] ? 0 : cx + 1;
-        col_of[0] = (cx * cg.nc[1] + cy) * nz;
-        col_of[1] = yw ? (cx * cg.nc[1] + yp) * nz : -1;
-        col_of[2] = cg.span[0] == 3 && yw ? (xp * cg.nc[1] + ym) * nz : -1;
-        col_of[3] = cg.span[0] == 3 ? (xp * cg.nc[1] + cy) * nz : -1;
-        col_of[4] = cg.span[0] == 3 && yw ? (xp * cg.nc[1] + yp) * nz : -1;
+        int cb = -1;
+        if (tid == 0) cb = (cx * cg.nc[1] + cy) * nz;
+        if (tid == 1 && yw) cb = (cx * cg.nc[1] + yp) * nz;
+        if (tid == 2 && xw && yw) cb = (xp * cg.nc[1] + ym) * nz;
+        if (tid == 3 && xw) cb = (xp * cg.nc[1] + cy) * nz;
+        if (tid == 4 && xw && yw) cb = (xp * cg.nc[1] + yp) * nz;
+        colbase_s[tid] = cb;
     }
-    if (tid < CELL_TPB / 32) s_np[tid] = 0;
     __syncthreads();
-    for (int k = tid; k < 5 * (nz + 1); k += blockDim.x) {
+    for (int k = tid; k < 5 * (nz + 1); k += CELL_TPB) {
         const int c = k / (nz + 1), z = k - c * (nz + 1);
-        cs_s[c][z] = col_of[c] >= 0 ? __ldg(cs + col_of[c] + z) : 0;
+        cs_s[c][z] = colbase_s[c] >= 0 ? __ldg(cs + colbase_s[c] + z) : 0;
     }
     __syncthreads();
-    if (tid == 0) {   // whole columns are staged; a segment CTA or an overfull one reads global memory
-        int tot = 0;
-        for (int c = 0; c < 5; c++) { s_off[c] = tot; tot += col_of[c] >= 0 ? cs_s[c][nz] - cs_s[c][0] : 0; }
-        s_staged = (nseg == 1 && tot <= CELL_STAGE_CAP) ? 1 : 0;
-        s_next = cs_s[0][z0];
-    }
-    __syncthreads();
-    const bool staged = s_staged != 0;
-    if (staged) {
-        for (int c = 0; c < 5; c++) {
-            if (col_of[c] < 0) continue;
-            const int g0 = cs_s[c][0], cnt = cs_s[c][nz] - g0;
-            for (int q = tid; q < cnt; q += blockDim.x) stage[s_off[c] + q] = __ldg(srt + g0 + q);
-        }
-    }
-    __syncthreads();   // the last CTA-wide barrier: from here on the warps run on their own
 
-    const int zw = cg.span[2] == 3 ? 1 : 0;
-    const bool zall = 2 * zw + 1 >= nz;           // the z window is the whole column
-    const int home_hi = cs_s[0][z1];
-    int2 *plist = plist_dyn + wp * CELL_PLIST_CAP;
-    int *my_np = &s_np[wp];
-    unsigned long long my_ties = 0;
-    for (;;) {
-        int hb = 0;
-        if (lane == 0) hb = atomicAdd(&s_next, 32);   // the warp's next 32 home atoms
-        hb = __shfl_sync(0xffffffffu, hb, 0);
-        if (hb >= home_hi) break;
-        const int k = hb + lane;
-        if (k < home_hi) {
-            const int4 me = staged ? stage[k - cs_s[0][0]] : __ldg(srt + k);
-            int z = z0;
-            while (cs_s[0][z + 1] <= k) z++;        // the home atom's cell
-            // <= 2 index ranges per column (the z window wraps at the column ends); ONE loop site
-#pragma unroll 1
-            for (int r = 0; r < 10; r++) {
-                const int c = r >> 1;
-                const bool second = r & 1;
-                if (col_of[c] < 0) continue;
-                const int *cc = cs_s[c];
-                int lo = 0, hi = 0;
-                if (c == 0) {
-                    // own column: the rest of the home cell, then cell z + 1 (wrapped)
-                    if (!zw) { if (!second) { lo = k + 1; hi = cc[z + 1]; } }
-                    else if (zall) {   // three cells: z + 1 is distinct, z + 2 = z - 1 is that cell's job
-                        const int zn = z + 1 < nz ? z + 1 : 0;
-                        lo = second ? cc[zn] : k + 1;
-                        hi = second ? cc[zn + 1] : cc[z + 1];
-                    } else if (z + 1 < nz) { if (!second) { lo = k + 1; hi = cc[z + 2]; } }
-                    else { lo = second ? cc[0] : k + 1; hi = second ? cc[1] : cc[nz]; }
-                } else {
-                    // half-shell column: cells z - zw .. z + zw (wrapped)
-                    if (zall) { if (!second) { lo = cc[0]; hi = cc[nz]; } }
-                    else if (z - 1 < 0) { lo = second ? cc[0] : cc[nz - 1]; hi = second ? cc[z + 2] : cc[nz]; }
-                    else if (z + 1 >= nz) { lo = second ? cc[0] : cc[z - 1]; hi = second ? cc[1] : cc[nz]; }
-                    else if (!second) { lo = cc[z - 1]; hi = cc[z + 2]; }
+    int4 *wbuf = wbuf_s[wp];
+    int2 *plist = plist_s[wp];
+    int4 *desc = desc_s[wp];
+    int np = 0;                      // filtered pairs waiting in the list (warp-uniform)
+    const int *ccs = cs_s[lane < 5 ? lane : 0];
+    const bool have = lane < 5 && colbase_s[lane < 5 ? lane : 0] >= 0;
+    const int cbeg = ccs[0], cend = ccs[nz];
+
+    for (int z = z0 + wp; z < z1; z += CELL_WARPS) {
+        // run of column `lane` for home cell z: a ring segment [start, start + len) of [cbeg, cend)
+        int start = 0, len = 0;
+        if (have) {
+            if (nz < 3) { start = cbeg; len = cend - cbeg; }
+            else if (lane == 0) {
+                const int zn = z + 1 < nz ? z + 1 : 0;
+                start = ccs[z];
+                len = (ccs[z + 1] - start) + (ccs[zn + 1] - ccs[zn]);
+            } else {
+                const int zm = z - 1 < 0 ? nz - 1 : z - 1, zp = z + 1 < nz ? z + 1 : 0;
+                start = ccs[zm];
+                len = (ccs[zm + 1] - start) + (ccs[z + 1] - ccs[z]) + (ccs[zp + 1] - ccs[zp]);
+            }
+        }
+        const int h0 = cs_s[0][z], nA = cs_s[0][z + 1] - h0;
+        if (nA == 0) continue;       // warp-uniform
+        int inc = len;               // lanes >= 5 hold 0
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const int v = __shfl_up_sync(full, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const int C = __shfl_sync(full, inc, 4);
+        __syncwarp();
+        if (lane < 5) desc[lane] = make_int4(start, inc - len, cbeg, cend);
+        if (lane < 4) ((int *)&desc[5])[lane] = inc;
+        __syncwarp();
+        const int4 bounds = desc[5];
+        // the home atoms go to shared memory (one broadcast load per step), 32 at a time
+        for (int a0 = 0; a0 < nA; a0 += 32) {
+            const int na = min(nA - a0, 32);
+            __syncwarp();
+            if (lane < na) wbuf[lane] = __ldg(srt + h0 + a0 + lane);
+            __syncwarp();
+            // one candidate per lane and round, held in registers while the home atoms pass by
+            for (int s = lane; s - lane < C; s += 32) {
+                int4 cand = make_int4(0, 0, 0, -1);
+                int alim = 0;            // home atoms (by position in the cell) the candidate pairs with: those before alim
+                if (s < C) {
+                    const int c = (s >= bounds.x) + (s >= bounds.y) + (s >= bounds.z) + (s >= bounds.w);
+                    const int4 d = desc[c];
+                    int p = d.x + (s - d.y);
+                    if (p >= d.w) p -= d.w - d.z;
+                    cand = __ldg(srt + p);
+                    // slot s < nA is home atom s itself: it pairs with the home atoms before it
+                    alim = (s < nA ? s : nA) - a0;
                 }
-                const int4 *bp = staged ? stage + (s_off[c] - cc[0]) : srt;
-                for (int q = lo; q < hi; q++) {
-                    const int4 cand = bp[q];
-                    if (filter_pair<KIND, IMAGES>(fp, me, cand)) {
-                        const int e = atomicAdd(my_np, 1);
-                        if (e < CELL_PLIST_CAP) plist[e] = make_int2(me.w, cand.w);
-                        else cell_exact_pair_cold<KIND, IMAGES>(bx, fr, me.w, cand.w, rc, t2, rowcap, row0,
-                                                               rcnt, tmp_j, tmp_d, cap_need, ties);
+                const int amax = __reduce_max_sync(full, alim);   // steps anybody needs (<= na)
+#if CELL_UNROLL == 2
+#pragma unroll 2
+#else
+#pragma unroll 1
+#endif
+                for (int a = 0; a < min(amax, na); a++) {
+                    const int4 me = wbuf[a];
+                    const bool ok = filter_pair<KIND, IMAGES>(fp, me, cand) & (a < alim);
+                    const unsigned hb = __ballot_sync(full, ok);
+                    if (ok) plist[np + __popc(hb & lt)] = make_int2(me.w, cand.w);
+                    np += __popc(hb);
+                    if (np >= 64) {
+                        __syncwarp();
+                        cell_exact_drain<KIND, IMAGES>(bx, fr, plist, 64, rc, t2, rowcap, row0, rcnt, tmp_j,
+                                                       tmp_d, cap_need, ties);
+                        __syncwarp();
+                        np -= 64;
+                        if (lane < np) { const int2 e = plist[64 + lane]; plist[lane] = e; }
+                        __syncwarp();
                     }
                 }
             }
         }
-        __syncwarp();
-        const int np = min(*my_np, CELL_PLIST_CAP);
-        // two pairs per lane and trip: the coordinate loads and the row-counter atomics of one
-        // overlap the arithmetic of the other
-        for (int e = lane; e < np; e += 64) {
-            const bool two = e + 32 < np;
-            const int2 pr0 = plist[e], pr1 = plist[two ? e + 32 : e];
-            cell_exact_two<KIND, IMAGES>(bx, fr, pr0, pr1, two, rc, t2, rowcap, row0, rcnt, tmp_j, tmp_d,
-                                         cap_need, my_ties);
-        }
-        __syncwarp();
-        if (lane == 0) *my_np = 0;
-        __syncwarp();
     }
-    if (my_ties) atomicAdd(ties, my_ties);
+    if (np > 0) {
+        __syncwarp();
+        cell_exact_drain<KIND, IMAGES>(bx, fr, plist, np, rc, t2, rowcap, row0, rcnt, tmp_j, tmp_d,
+                                       cap_need, ties);
+    }
 }
 
 // per frame: rowcount -> exclusive row offsets (n + 1 entries), frame total -> out_counts
@@ -407,14 +404,28 @@ k_cell_emit(const __grid_constant__ RateParams rp, const int *__restrict__ ids,
     const int g1 = ro[min(r0 + 32, n)];
     const int64_t base = f * stride;
     double rsum = 0.0;
+    // No empty row among the 32 (the rule): the row of entry g follows from ONE warp reduction per
+    // trip -- every row lane drops a bit at the entry its row starts with, entry g belongs to the
+    // row `rows starting at or before gb` + `bits in (gb, g]`.  An empty row shares its start with
+    // the next one (the bits would merge): then a binary search over the offsets.
+    const int nxoff = __shfl_down_sync(0xffffffffu, myoff, 1);
+    const bool dense_rows = __ballot_sync(0xffffffffu, lane < 31 && r0 + lane < n && nxoff == myoff) == 0u;
+    const unsigned le_mask = lane == 31 ? 0xfffffffeu : (((2u << lane) - 1u) & ~1u);
     for (int gb = g0; gb < g1; gb += 32) {   // warp-uniform trip count: the shuffles need all lanes
         const int g = gb + lane;
-        // the row holding entry g: last row of the 32 with offset <= g
-        int lo = 0;
+        int lo;
+        if (dense_rows) {
+            const int rel = myoff - gb;
+            const unsigned starts = __reduce_or_sync(0xffffffffu, rel > 0 && rel < 32 ? 1u << rel : 0u);
+            const int cur = __popc(__ballot_sync(0xffffffffu, rel <= 0)) - 1;
+            lo = cur + __popc(starts & le_mask);
+        } else {
+            lo = 0;   // last row of the 32 with offset <= g
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            const int probe = __shfl_sync(0xffffffffu, myoff, min(lo + s, 31));
-            if (lo + s <= 31 && probe <= g) lo += s;
+            for (int s = 16; s > 0; s >>= 1) {
+                const int probe = __shfl_sync(0xffffffffu, myoff, min(lo + s, 31));
+                if (lo + s <= 31 && probe <= g) lo += s;
+            }
         }
         const int off_lo = __shfl_sync(0xffffffffu, myoff, lo);
         const int off_nx = __shfl_sync(0xffffffffu, myoff, min(lo + 1, 31));
@@ -424,9 +435,19 @@ k_cell_emit(const __grid_constant__ RateParams rp, const int *__restrict__ ids,
             const int64_t rbase = ((int64_t)b * n + r) * rowcap;
             const int j = tmp_j[rbase + (g - off_lo)];
             const double dist = tmp_d[rbase + (g - off_lo)];
+            // rank = smaller columns in the row; the row is 16-byte aligned (rowcap % 4 == 0)
+            const int4 *rj = (const int4 *)(tmp_j + rbase);
             int rank = 0;
-#pragma unroll 4
-            for (int q = 0; q < cnt; q++) rank += __ldg(tmp_j + rbase + q) < j;
+            const int c4 = cnt >> 2;
+            for (int q = 0; q < c4; q++) {
+                const int4 v = __ldg(rj + q);
+                rank += (v.x < j) + (v.y < j) + (v.z < j) + (v.w < j);
+            }
+            if (cnt & 3) {
+                const int4 v = __ldg(rj + c4);
+                const int rem = cnt & 3;
+                rank += (v.x < j) + (rem > 1 && v.y < j) + (rem > 2 && v.z < j);
+            }
             const double om = rate_eval(rp, dist, 0.0);
             rsum += om;
             const int64_t at = base + off_lo + rank;
