@@ -117,6 +117,19 @@ SIGNATURES = {
     "cmd_lmc_advance": (C.c_int, [vp, vp, C.c_double, C.c_int]),
     "cmd_lmc_get_state": (C.c_int, [vp, ip, lp, lp, lp, ip]),
     "cmd_lmc_get_jump_matrix": (C.c_int, [vp, lp]),
+    "cmd_comm_unique_id": (C.c_int, [u8p]),
+    "cmd_comm_init": (C.c_int, [C.c_int, C.c_int, u8p]),
+    "cmd_comm_destroy": (C.c_int, []),
+    "cmd_comm_rank": (C.c_int, []),
+    "cmd_comm_world": (C.c_int, []),
+    "cmd_comm_nccl_version": (C.c_int, []),
+    "cmd_stats_allreduce": (C.c_int, [dp, C.c_int64, lp, C.c_int64]),
+    "cmd_stats_allreduce_dev": (C.c_int, [vp, C.c_int64, vp, C.c_int64]),
+    "cmd_allgather_dev": (C.c_int, [vp, vp, C.c_int64]),
+    "cmd_topo_block_stats_dev": (C.c_int, [vp, vp]),
+    "cmd_topo_dr_dev": (C.c_int, [vp, vp, C.c_int64, vp, vp]),
+    "cmd_topo_skip_dr_dev": (C.c_int, [vp, vp, C.c_int64, lp]),
+    "cmd_topo_seed_dev": (C.c_int, [vp, vp, vp]),
 }
 
 

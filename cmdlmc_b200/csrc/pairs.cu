@@ -1204,6 +1204,72 @@ extern "C" int cmd_topo_skip_dev(cmd_topo *t, const double *d_frames, int64_t nf
     return topo_build_impl(t, d_frames, nframes, true);
 }
 
+// Rebuild schedule of `nframes` frames from their step lengths dr[nframes][n] (topology.py:96-107),
+// continuing from the carried displacement: fills d_rebuilt / d_rebuild_ids / d_refresh_ids / d_head
+// / d_sched and leaves the displacement after the last frame in d_displacement.
+static int topo_schedule(cmd_topo *t, const double *dr, int64_t nframes)
+{
+    CmdGlobal &g = cmd_global();
+    cudaStream_t st = g.stream;
+    (void)g;
+    const size_t ssm = ((size_t)t->n + 2 * (SCHED_THREADS / 32)) * 8;
+    if (ssm <= 48 * 1024 && nframes >= 64) {
+        // parallel schedule: next-rebuild function for every start frame, then chain following
+        CMD_CUDA(cudaMemsetAsync(t->d_rebuilt, 0, (size_t)nframes, st));
+        const unsigned wblocks = (unsigned)((nframes + 3) / 4);
+        if (t->n <= 128) k_sched_walk_warp<4><<<wblocks, 128, 0, st>>>(dr, t->n, nframes, t->buffer, t->d_next);
+        else if (t->n <= 256) k_sched_walk_warp<8><<<wblocks, 128, 0, st>>>(dr, t->n, nframes, t->buffer, t->d_next);
+        else if (t->n <= 384) k_sched_walk_warp<12><<<wblocks, 128, 0, st>>>(dr, t->n, nframes, t->buffer, t->d_next);
+        else if (t->n <= 512) k_sched_walk_warp<16><<<wblocks, 128, 0, st>>>(dr, t->n, nframes, t->buffer, t->d_next);
+        else
+        k_sched_walk<<<(unsigned)nframes, SCHED_THREADS, ssm, st>>>(dr, t->n, nframes, t->buffer,
+                                                                    t->d_next);
+        CMD_LAUNCHED();
+        const size_t nsm = ((size_t)nframes + 2) * 4;
+        const int next_smem = ssm + nsm <= 200 * 1024 ? 1 : 0;
+        const size_t csm = ssm + (next_smem ? nsm : 0);
+        CMD_CUDA(cudaFuncSetAttribute(k_sched_chase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+        k_sched_chase<<<1, SCHED_THREADS, csm, st>>>(dr, t->d_displacement, t->n, nframes,
+                                                    t->buffer, t->total_frames == 0 ? 1 : 0,
+                                                    t->d_next, t->d_rebuilt, next_smem);
+        CMD_LAUNCHED();
+        k_sched_fill<<<1, 1024, 0, st>>>(t->d_rebuilt, nframes, t->d_sched, t->d_rebuild_ids,
+                                         t->d_refresh_ids, t->d_head);
+        CMD_LAUNCHED();
+    } else if (t->n > 4096 && t->n <= SCHED_CLUSTER * SCHED_CL_THREADS * SCHED_CL_PER) {
+        // large systems: one cluster of 8 CTAs walks the frames
+        int chunk = (t->n + SCHED_CLUSTER - 1) / SCHED_CLUSTER;
+        chunk = (chunk + 31) / 32 * 32;
+        const size_t csm = (size_t)chunk * 8 + (2 * SCHED_CLUSTER + 32) * sizeof(double2);
+        CMD_CUDA(cudaFuncSetAttribute(k_schedule_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(SCHED_CLUSTER);
+        cfg.blockDim = dim3(SCHED_CL_THREADS);
+        cfg.dynamicSmemBytes = csm;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = SCHED_CLUSTER;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CMD_CUDA(cudaLaunchKernelEx(&cfg, k_schedule_cluster, (const double *)dr, t->d_displacement,
+                                    t->n, (int64_t)nframes, t->buffer, t->total_frames == 0 ? 1 : 0,
+                                    t->d_sched, t->d_rebuild_ids, t->d_refresh_ids, t->d_head,
+                                    t->d_rebuilt, chunk));
+        CMD_LAUNCHED();
+    } else {
+        int sth = (t->n + 31) / 32 * 32;
+        if (sth > 1024) sth = 1024;
+        k_schedule<<<1, sth, 0, st>>>(dr, t->d_displacement, t->n, nframes, t->buffer,
+                                      t->total_frames == 0 ? 1 : 0, t->d_sched, t->d_rebuild_ids,
+                                      t->d_refresh_ids, t->d_head, t->d_rebuilt);
+        CMD_LAUNCHED();
+    }
+    return CMD_OK;
+}
+
 static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes, bool skip)
 {
     CMD_REQUIRE_INIT();
@@ -1238,61 +1304,7 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
                                                                   t->have_last ? 1 : 0, t->n, nframes, t->d_dr);
         }
         CMD_LAUNCHED();
-        const size_t ssm = ((size_t)t->n + 2 * (SCHED_THREADS / 32)) * 8;
-        if (ssm <= 48 * 1024 && nframes >= 64) {
-            // parallel schedule: next-rebuild function for every start frame, then chain following
-            CMD_CUDA(cudaMemsetAsync(t->d_rebuilt, 0, (size_t)nframes, st));
-            const unsigned wblocks = (unsigned)((nframes + 3) / 4);
-            if (t->n <= 128) k_sched_walk_warp<4><<<wblocks, 128, 0, st>>>(t->d_dr, t->n, nframes, t->buffer, t->d_next);
-            else if (t->n <= 256) k_sched_walk_warp<8><<<wblocks, 128, 0, st>>>(t->d_dr, t->n, nframes, t->buffer, t->d_next);
-            else if (t->n <= 384) k_sched_walk_warp<12><<<wblocks, 128, 0, st>>>(t->d_dr, t->n, nframes, t->buffer, t->d_next);
-            else if (t->n <= 512) k_sched_walk_warp<16><<<wblocks, 128, 0, st>>>(t->d_dr, t->n, nframes, t->buffer, t->d_next);
-            else
-            k_sched_walk<<<(unsigned)nframes, SCHED_THREADS, ssm, st>>>(t->d_dr, t->n, nframes, t->buffer,
-                                                                        t->d_next);
-            CMD_LAUNCHED();
-            const size_t nsm = ((size_t)nframes + 2) * 4;
-            const int next_smem = ssm + nsm <= 200 * 1024 ? 1 : 0;
-            const size_t csm = ssm + (next_smem ? nsm : 0);
-            CMD_CUDA(cudaFuncSetAttribute(k_sched_chase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-            k_sched_chase<<<1, SCHED_THREADS, csm, st>>>(t->d_dr, t->d_displacement, t->n, nframes,
-                                                        t->buffer, t->total_frames == 0 ? 1 : 0,
-                                                        t->d_next, t->d_rebuilt, next_smem);
-            CMD_LAUNCHED();
-            k_sched_fill<<<1, 1024, 0, st>>>(t->d_rebuilt, nframes, t->d_sched, t->d_rebuild_ids,
-                                             t->d_refresh_ids, t->d_head);
-            CMD_LAUNCHED();
-        } else if (t->n > 4096 && t->n <= SCHED_CLUSTER * SCHED_CL_THREADS * SCHED_CL_PER) {
-            // large systems: one cluster of 8 CTAs walks the frames
-            int chunk = (t->n + SCHED_CLUSTER - 1) / SCHED_CLUSTER;
-            chunk = (chunk + 31) / 32 * 32;
-            const size_t csm = (size_t)chunk * 8 + (2 * SCHED_CLUSTER + 32) * sizeof(double2);
-            CMD_CUDA(cudaFuncSetAttribute(k_schedule_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(SCHED_CLUSTER);
-            cfg.blockDim = dim3(SCHED_CL_THREADS);
-            cfg.dynamicSmemBytes = csm;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = SCHED_CLUSTER;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            CMD_CUDA(cudaLaunchKernelEx(&cfg, k_schedule_cluster, (const double *)t->d_dr, t->d_displacement,
-                                        t->n, (int64_t)nframes, t->buffer, t->total_frames == 0 ? 1 : 0,
-                                        t->d_sched, t->d_rebuild_ids, t->d_refresh_ids, t->d_head,
-                                        t->d_rebuilt, chunk));
-            CMD_LAUNCHED();
-        } else {
-            int sth = (t->n + 31) / 32 * 32;
-            if (sth > 1024) sth = 1024;
-            k_schedule<<<1, sth, 0, st>>>(t->d_dr, t->d_displacement, t->n, nframes, t->buffer,
-                                          t->total_frames == 0 ? 1 : 0, t->d_sched, t->d_rebuild_ids,
-                                          t->d_refresh_ids, t->d_head, t->d_rebuilt);
-            CMD_LAUNCHED();
-        }
+        if ((rc = topo_schedule(t, t->d_dr, nframes))) return rc;
         if (skip) {
             int sched[3] = {0, 0, -1};
             CMD_CUDA(cudaMemcpyAsync(sched, t->d_sched, sizeof(sched), cudaMemcpyDeviceToHost, st));
@@ -1351,6 +1363,102 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
         t->have_last = true;
     }
     t->total_frames += nframes;
+    return topo_check_capacity(t);
+}
+
+// ---- frame-block sharding from all-gathered step lengths --------------------------------------
+// dr[f][i] = length(frame[f-1][i], frame[f][i]) of a block on the device (topology.py:98);
+// frame 0 of the block is measured against d_prev (the frame before the block; NULL: zeros, the
+// very first frame of a trajectory, topology.py:95).  Touches no state of the topology.
+extern "C" int cmd_topo_dr_dev(const cmd_topo *t, const double *d_frames, int64_t nframes,
+                               const double *d_prev, double *d_dr)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || !d_frames || !d_dr || nframes < 1) return cmd_set_error(CMD_EINVAL, "bad argument");
+    CmdGlobal &g = cmd_global();
+    const int ablocks = cmd_div_up(t->n, 256);
+    int64_t flanes = (int64_t)g.sm_count * 16 / ablocks;
+    if (flanes < 1) flanes = 1;
+    if (flanes > nframes) flanes = nframes;
+    if (flanes > 65535) flanes = 65535;
+    k_dr<<<dim3(ablocks, (unsigned)flanes), 256, 0, g.stream>>>(t->bx, d_frames, d_prev, d_prev ? 1 : 0,
+                                                              t->n, nframes, d_dr);
+    CMD_LAUNCHED();
+    return CMD_OK;
+}
+
+// A Verlet topology that has built no list yet walks the rebuild schedule of frames that PRECEDE
+// this rank's block from their step lengths alone (every rank's dr, all-gathered: N x 8 bytes per
+// frame instead of the coordinates).  May be called chunk after chunk (the displacement carries
+// over).  *h_last_rebuild = index, relative to this chunk, of its last rebuild frame (the list in
+// force afterwards was built there), -1 if the chunk holds none.  Follow with cmd_topo_seed_dev.
+extern "C" int cmd_topo_skip_dr_dev(cmd_topo *t, const double *d_dr, int64_t nframes,
+                                    int64_t *h_last_rebuild)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || !h_last_rebuild || nframes < 0 || (nframes && !d_dr))
+        return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (t->mode != CMD_TOPO_VERLET) return cmd_set_error(CMD_ESTATE, "not a Verlet-mode topology");
+    if (t->have_last) return cmd_set_error(CMD_ESTATE, "the topology has built lists already");
+    if (t->stride == 0) return cmd_set_error(CMD_ESTATE, "create the topology with a capacity first");
+    *h_last_rebuild = -1;
+    if (nframes == 0) return CMD_OK;
+    if (nframes > 0x7fffffff / 2) return cmd_set_error(CMD_EINVAL, "block too large");
+    cudaStream_t st = cmd_global().stream;
+    int rc;
+    if ((rc = topo_reserve(t, nframes))) return rc;
+    if ((rc = topo_schedule(t, d_dr, nframes))) return rc;
+    int sched[3] = {0, 0, -1};
+    CMD_CUDA(cudaMemcpyAsync(sched, t->d_sched, sizeof(sched), cudaMemcpyDeviceToHost, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
+    if (sched[0] > 0) {
+        int last = -1;
+        CMD_CUDA(cudaMemcpyAsync(&last, t->d_rebuild_ids + sched[0] - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CMD_CUDA(cudaStreamSynchronize(st));
+        *h_last_rebuild = last;
+    }
+    // the chunk's heads are never materialised: the list in force is seeded by cmd_topo_seed_dev
+    CMD_CUDA(cudaMemsetAsync(t->d_sched + 2, 0xff, sizeof(int), st));
+    t->total_frames += nframes;
+    t->nframes = 0;
+    return CMD_OK;
+}
+
+// Completes cmd_topo_skip_dr_dev: builds the list of the last rebuild frame from its coordinates
+// (d_frame_rebuild, one frame) and carries it, and remembers d_frame_prev (the frame right before
+// the block) for the first step length of the block.  After this the topology is in exactly the
+// state a sequential run has at the block start.
+extern "C" int cmd_topo_seed_dev(cmd_topo *t, const double *d_frame_rebuild, const double *d_frame_prev)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || !d_frame_rebuild || !d_frame_prev) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (t->mode != CMD_TOPO_VERLET || t->total_frames == 0 || t->stride == 0)
+        return cmd_set_error(CMD_ESTATE, "call cmd_topo_skip_dr_dev first");
+    CmdGlobal &g = cmd_global();
+    cudaStream_t st = g.stream;
+    int rc;
+    if ((rc = topo_reserve(t, 1))) return rc;
+    if (!t->d_carry_start) {
+        if (cudaMalloc((void **)&t->d_carry_start, t->stride * 4) != cudaSuccess ||
+            cudaMalloc((void **)&t->d_carry_dest, t->stride * 4) != cudaSuccess ||
+            cudaMalloc((void **)&t->d_carry_rowoff, (size_t)(t->n + 1) * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return cmd_set_error(CMD_ENOMEM, "cudaMalloc failed for the carried pair list");
+        }
+    }
+    if ((rc = launch_pairs(t, d_frame_rebuild, nullptr, nullptr, 1, 0, false))) return rc;
+    CMD_CUDA(cudaMemsetAsync(t->d_sched + 2, 0, sizeof(int), st));      // head = slot 0
+    int carry_blocks = (int)((t->stride + 2047) / 2048);
+    if (carry_blocks < 8) carry_blocks = 8;
+    if (carry_blocks > 4 * g.sm_count) carry_blocks = 4 * g.sm_count;
+    k_carry<<<carry_blocks, 256, 0, st>>>(t->d_sched, t->d_start, t->d_dest, t->d_counts, t->stride,
+                                          t->d_carry_start, t->d_carry_dest, t->d_carry_count,
+                                          t->d_rowoff, t->d_carry_rowoff, t->n);
+    CMD_LAUNCHED();
+    CMD_CUDA(cudaMemsetAsync(t->d_sched + 2, 0xff, sizeof(int), st));   // the head lives in the carry
+    CMD_CUDA(cudaMemcpyAsync(t->d_last, d_frame_prev, (size_t)t->n * 24, cudaMemcpyDeviceToDevice, st));
+    t->have_last = true;
+    t->nframes = 0;
     return topo_check_capacity(t);
 }
 
@@ -1490,6 +1598,16 @@ extern "C" int cmd_topo_frame_info(const cmd_topo *t, int64_t *counts, uint8_t *
         CMD_CUDA(cudaMemcpyAsync(rate_sum, t->d_rate_sum, t->nframes * 8, cudaMemcpyDeviceToHost, st));
     CMD_CUDA(cudaStreamSynchronize(st));
     return CMD_OK;
+}
+
+int cmd_block_stats_launch(const int *d_counts, const double *d_rate_sum, int64_t nframes, double *d_out);
+
+extern "C" int cmd_topo_block_stats_dev(const cmd_topo *t, double *d_out)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || !d_out) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (t->nframes < 1) return cmd_set_error(CMD_ESTATE, "no block has been built");
+    return cmd_block_stats_launch(t->d_counts, t->d_rate_sum, t->nframes, d_out);
 }
 
 extern "C" int cmd_topo_set_path(cmd_topo *t, int path)

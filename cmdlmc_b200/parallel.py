@@ -44,11 +44,74 @@ def replica_ids(n_replicas, rank, world):
     return np.arange(rank, int(n_replicas), world, dtype=np.int64)
 
 
+_comm = {"up": False, "rank": 0, "world": 1}
+
+
+def comm_init(rank=None, world=None, unique_id=None):
+    """Builds the LIBRARY's communicator (cmd_comm_init: NCCL bound inside libcmdlmc_b200, over
+    NVLink / NVSwitch) for this process's GPU.  Rank 0 creates the 128-byte unique id; it travels
+    to the other ranks over torch.distributed when a process group exists (any backend), or is
+    passed in by a host that has its own transport.  Returns a small dict for logging."""
+    import ctypes as C
+    from . import _abi, runtime
+    if _comm["up"]:
+        return dict(_comm)
+    r0, w0 = rank_world()
+    rank = r0 if rank is None else int(rank)
+    world = w0 if world is None else int(world)
+    runtime.ensure_init()
+    lib = _abi.lib()
+    ident = np.zeros(128, np.uint8)
+    if world > 1:
+        if unique_id is not None:
+            ident[:] = np.frombuffer(bytes(unique_id), np.uint8)[:128]
+        else:
+            import torch
+            import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("comm_init needs a unique_id or an initialised torch.distributed group")
+            if rank == 0:
+                _abi.check(lib.cmd_comm_unique_id(ident.ctypes.data_as(_abi.u8p)))
+            t = torch.from_numpy(ident)
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            dist.broadcast(t, 0)
+            ident[:] = t.cpu().numpy()
+    _abi.check(lib.cmd_comm_init(rank, world, ident.ctypes.data_as(_abi.u8p)))
+    _comm.update(up=True, rank=rank, world=world,
+                 nccl_version=int(lib.cmd_comm_nccl_version()) if world > 1 else None)
+    return dict(_comm)
+
+
+def comm_destroy():
+    from . import _abi
+    if _comm["up"]:
+        _abi.lib().cmd_comm_destroy()
+    _comm.update(up=False, rank=0, world=1)
+
+
 def allreduce_sum(stats, device=None):
     """Sums a dict of NumPy arrays (float64 or integer) over all ranks with ONE all-reduce per
-    dtype class; returns new arrays of the same shapes.  Without an initialised process group
-    (single process) the input is returned as copies."""
+    dtype class; returns new arrays of the same shapes.  With the library communicator up
+    (comm_init) the reduction is cmd_stats_allreduce -- NCCL inside the C ABI, no torch involved;
+    otherwise torch.distributed (gloo in the CPU tests).  Single process: copies of the input."""
     out = {k: np.array(v, copy=True) for k, v in stats.items()}
+    if _comm["up"] and _comm["world"] > 1:
+        import ctypes as C
+        from . import _abi
+        fk = [k for k in sorted(out) if np.issubdtype(out[k].dtype, np.floating)]
+        ik = [k for k in sorted(out) if not np.issubdtype(out[k].dtype, np.floating)]
+        f = np.concatenate([out[k].astype(np.float64).ravel() for k in fk]) if fk else np.zeros(0)
+        i = np.concatenate([out[k].astype(np.int64).ravel() for k in ik]) if ik else np.zeros(0, np.int64)
+        _abi.check(_abi.lib().cmd_stats_allreduce(_abi.ptr(f) if f.size else None, f.size,
+                                                  _abi.ptr(i, C.c_int64) if i.size else None, i.size))
+        for keys, flat in ((fk, f), (ik, i)):
+            pos = 0
+            for k in keys:
+                m = out[k].size
+                out[k] = flat[pos:pos + m].reshape(out[k].shape).astype(out[k].dtype)
+                pos += m
+        return out
     try:
         import torch
         import torch.distributed as dist
@@ -117,6 +180,8 @@ class ShardedTopology:
         self.rank = r if rank is None else rank
         self.world = w if world is None else world
         self.start, self.stop = frame_block(n_frames, self.rank, self.world)
+        self.n_frames = int(n_frames)
+        self.topo_n_atoms = int(n_atoms)
         self.chunk = int(chunk)
         self.mode = mode
         self.frames_source = frames_source
@@ -126,8 +191,19 @@ class ShardedTopology:
 
     def blocks(self):
         """Yields (first_frame, DeviceTopology) for every chunk of this rank's block; the lists of
-        the chunk stay in HBM until the next chunk is built."""
+        the chunk stay in HBM until the next chunk is built.
+
+        Verlet mode over several ranks: with the library communicator up (comm_init) every rank
+        uploads ONLY its own block, the ranks all-gather the per-frame step lengths
+        (N x 8 bytes per frame over NVLink) and each replays the rebuild schedule of the frames
+        before its block from those (`_blocks_gathered`).  Without a communicator (a single
+        process playing one rank of several) the frames before the block are walked through the
+        displacement pass from their coordinates (cmd_topo_skip)."""
         from .topology import MODE_VERLET, build_with_retry
+        if (self.mode == MODE_VERLET and self.world > 1 and _comm["up"]
+                and _comm["world"] == self.world and _comm["rank"] == self.rank):
+            yield from self._blocks_gathered()
+            return
         pos = 0
         if self.mode == MODE_VERLET and self.start > 0:
             # the very first frames size the capacity and create the object
@@ -147,6 +223,55 @@ class ShardedTopology:
             self.topo.build(fr)
             yield pos, self.topo
             pos = hi
+
+    def _blocks_gathered(self):
+        import ctypes as C
+        import torch
+        from . import _abi, runtime
+        dev = torch.device("cuda", runtime.ensure_init())
+        n = self.topo_n_atoms
+        own = self.stop - self.start
+        halo = 1 if self.start > 0 else 0
+        base, extra = divmod(int(self.n_frames), self.world)
+        maxlen = base + (1 if extra else 0)
+        # this rank's frames (+ the frame before them), resident in HBM for the whole pass
+        lo = self.start - halo
+        fr = np.ascontiguousarray(self.frames_source(lo, max(self.stop, lo + 1)), dtype=np.float64)
+        if self.topo is None:
+            self.topo = self._sized(fr[halo:halo + 1] if own else fr[:1])
+        d_all = torch.from_numpy(fr).to(dev)
+        d_own = d_all[halo:]
+        send = torch.zeros((max(maxlen, 1), n), dtype=torch.float64, device=dev)
+        recv = torch.empty((self.world, max(maxlen, 1), n), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        if own:
+            self.topo.dr_dev(d_own.data_ptr(), own, d_all.data_ptr() if halo else None, send.data_ptr())
+        _abi.check(_abi.lib().cmd_allgather_dev(C.c_void_p(send.data_ptr()), C.c_void_p(recv.data_ptr()),
+                                                send.numel() * 8))
+        runtime.sync()
+        if self.start > 0 and own:
+            lens = [frame_block(self.n_frames, r, self.world) for r in range(self.rank)]
+            before = torch.cat([recv[r, :b - a] for r, (a, b) in enumerate(lens)]).contiguous()
+            torch.cuda.synchronize()
+            last, pos = -1, 0
+            while pos < self.start:
+                hi = min(self.start, pos + self.chunk)
+                k = self.topo.skip_dr_dev(before[pos:].data_ptr(), hi - pos)
+                if k >= 0:
+                    last = pos + k
+                pos = hi
+            reb = torch.from_numpy(np.ascontiguousarray(self.frames_source(last, last + 1)[0],
+                                                        dtype=np.float64)).to(dev)
+            torch.cuda.synchronize()
+            self.topo.seed_dev(reb.data_ptr(), d_all.data_ptr())
+            self.last_rebuild_before_block = last
+        pos = 0
+        while pos < own:
+            cn = min(self.chunk, own - pos)
+            self.topo.build_dev(d_own[pos:].data_ptr(), cn)
+            yield self.start + pos, self.topo
+            pos += cn
+        runtime.sync()   # d_all must outlive the kernels that read it
 
     def _sized(self, first_frame):
         """Creates the topology with a capacity probed on one frame WITHOUT consuming it."""

@@ -58,6 +58,28 @@ def fp64_peak_tflops(iters=20000):
     return v.value
 
 
+def numa_topology(device=None):
+    """What the host says about NUMA placement of this GPU: node count of the machine, the node of
+    the GPU's PCIe function (-1: the platform reports none, as on single-node or virtualised
+    hosts) and the CPUs this process may run on.  Facts for the bench line, nothing is changed."""
+    info = {"nodes": None, "gpu_node": None, "cpus_allowed": None}
+    try:
+        info["cpus_allowed"] = len(os.sched_getaffinity(0))
+        info["nodes"] = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+    except OSError:
+        pass
+    try:
+        import torch
+        dev = _state["device"] if device is None else device
+        p = torch.cuda.get_device_properties(0 if dev is None else dev)
+        bus = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            info["gpu_node"] = int(f.read().strip())
+    except Exception:
+        pass
+    return info
+
+
 def bind_to_gpu_numa_node(device=None):
     """Pins this process (one process per GPU) to the CPUs of the NUMA node its GPU hangs off, so
     that pinned staging buffers allocated afterwards are local to the GPU's PCIe root: with eight

@@ -147,6 +147,27 @@ class DeviceTopology:
         """Frames already in HBM: raw device pointer to float64 [F, n, 3]."""
         check(_abi.lib().cmd_topo_build_dev(self._handle, C.c_void_p(int(data_ptr)), int(nframes)))
 
+    def dr_dev(self, frames_ptr, nframes, prev_ptr, out_ptr):
+        """Step lengths dr[F, n] of a device block (topology.py:98); prev_ptr: the frame before the
+        block, or None for the first frame of a trajectory (zeros)."""
+        check(_abi.lib().cmd_topo_dr_dev(self._handle, C.c_void_p(int(frames_ptr)), int(nframes),
+                                         C.c_void_p(int(prev_ptr)) if prev_ptr else None,
+                                         C.c_void_p(int(out_ptr))))
+
+    def skip_dr_dev(self, dr_ptr, nframes):
+        """Walks `nframes` frames of the rebuild schedule from their step lengths (device [F, n]);
+        returns the chunk-relative index of the last rebuild frame, -1 if there is none."""
+        last = C.c_int64(-1)
+        check(_abi.lib().cmd_topo_skip_dr_dev(self._handle, C.c_void_p(int(dr_ptr)), int(nframes),
+                                              C.byref(last)))
+        return int(last.value)
+
+    def seed_dev(self, rebuild_frame_ptr, prev_frame_ptr):
+        """After skip_dr_dev: the list of the last rebuild frame from its coordinates, and the
+        frame right before the block (both device [n, 3])."""
+        check(_abi.lib().cmd_topo_seed_dev(self._handle, C.c_void_p(int(rebuild_frame_ptr)),
+                                           C.c_void_p(int(prev_frame_ptr))))
+
     def frame_info(self):
         n = self.nframes
         counts = np.zeros(n, np.int64)

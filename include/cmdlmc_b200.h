@@ -336,6 +336,42 @@ int cmd_lmc_get_state(const cmd_lmc *k, int *h_lattices, int64_t *h_jumps, int64
                       int64_t *h_sweeps, int *h_halted);
 int cmd_lmc_get_jump_matrix(const cmd_lmc *k, int64_t *h_matrix);
 
+/* ---------------------------------------------------------------- multi-GPU ------------- */
+/* One process per GPU.  The hot path shards by trajectory-frame block and by independent replica
+ * with NO data-path collective; what crosses GPUs is (a) the SUM of the statistics the reference
+ * accumulates per run -- MSD sums and autocorrelation of mdlmc/LMC/output.py:17-49, jump counts,
+ * the jumpstat histograms -- and (b) the per-frame step lengths dr[N] of
+ * mdlmc/topo/topology.py:98 so that every rank can walk the rebuild schedule of the WHOLE
+ * trajectory while holding only its own block.  NCCL (NVLink / NVSwitch) is bound with dlopen at
+ * the first call; world == 1 turns every collective into an identity. */
+/* rank 0: a fresh NCCL unique id (128 bytes) for the host to hand to the other ranks */
+int cmd_comm_unique_id(unsigned char h_id[128]);
+/* every rank, after cmd_init: builds the communicator on this process's device */
+int cmd_comm_init(int rank, int world, const unsigned char h_id[128]);
+int cmd_comm_destroy(void);
+int cmd_comm_rank(void);
+int cmd_comm_world(void);
+int cmd_comm_nccl_version(void);
+/* in-place sums over all ranks of n_f64 doubles and n_i64 64-bit integers (host buffers) */
+int cmd_stats_allreduce(double *h_f64, int64_t n_f64, int64_t *h_i64, int64_t n_i64);
+/* the same on device buffers, enqueued on the library stream (no host synchronisation) */
+int cmd_stats_allreduce_dev(double *d_f64, int64_t n_f64, int64_t *d_i64, int64_t n_i64);
+/* d_recv[r * bytes_per_rank ...] = rank r's d_send, on the library stream */
+int cmd_allgather_dev(const void *d_send, void *d_recv, int64_t bytes_per_rank);
+/* Frame-block sharding of a Verlet run (topology.py:80-114) WITHOUT walking the coordinates of the
+ * frames before the block: every rank computes the step lengths of its own block
+ * (cmd_topo_dr_dev), the ranks all-gather them (cmd_allgather_dev), and a fresh topology replays
+ * the rebuild schedule of the preceding frames from those numbers alone (cmd_topo_skip_dr_dev),
+ * then takes the coordinates of just two frames -- the last rebuild frame and the frame before
+ * the block (cmd_topo_seed_dev).  The state equals that of a sequential run at the block start. */
+int cmd_topo_dr_dev(const cmd_topo *t, const double *d_frames, int64_t nframes,
+                    const double *d_prev, double *d_dr);
+int cmd_topo_skip_dr_dev(cmd_topo *t, const double *d_dr, int64_t nframes, int64_t *h_last_rebuild);
+int cmd_topo_seed_dev(cmd_topo *t, const double *d_frame_rebuild, const double *d_frame_prev);
+/* ADDS (number of listed directed pairs, sum of the listed rates) of the current block to
+ * d_out[0..1] on the device: the block statistics a frame-block shard contributes per step */
+int cmd_topo_block_stats_dev(const cmd_topo *t, double *d_out);
+
 #ifdef __cplusplus
 }
 #endif
