@@ -102,12 +102,15 @@ SIGNATURES = {
     "cmd_kmc_set_replay_stream": (C.c_int, [vp, dp, C.c_int64]),
     "cmd_kmc_set_event_log": (C.c_int, [vp, C.c_int64]),
     "cmd_kmc_set_observables": (C.c_int, [vp, C.c_int, C.c_int]),
+    "cmd_kmc_seed_observables": (C.c_int, [vp, dp]),
     "cmd_kmc_advance": (C.c_int, [vp, vp, vp]),
     "cmd_kmc_get_state": (C.c_int, [vp, ip, dp, lp, lp, lp]),
     "cmd_kmc_get_status": (C.c_int, [vp, ip, ip, lp]),
     "cmd_kmc_get_events": (C.c_int, [vp, C.c_int, C.c_int64, lp, lp, dp, ip, ip, ip]),
     "cmd_kmc_get_observables": (C.c_int, [vp, C.c_int, C.c_int64, lp, dp]),
+    "cmd_kmc_get_observable_rows": (C.c_int, [vp, C.c_int, C.c_int64, C.c_int64, dp]),
     "cmd_kmc_tie_count": (C.c_int64, [vp]),
+    "cmd_kmc_events_dropped": (C.c_int64, [vp]),
     "cmd_kmc_selection_fallbacks": (C.c_int64, [vp]),
     "cmd_kmc_debug_counter": (C.c_int64, [vp, C.c_int]),
     "cmd_lmc_create": (C.c_int, [C.c_int, C.c_int, ip, C.c_int, C.c_uint64, C.POINTER(vp)]),

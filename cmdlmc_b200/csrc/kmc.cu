@@ -81,6 +81,7 @@ struct cmd_kmc {
     double *d_disp;      // [R][n_sites][3]
     unsigned long long *d_ties;
     int64_t frames_total;
+    int64_t obs_offset;  // observable frame numbers run ahead of the walked frames by this much
     HydParams hyd;
     double *d_tlast;     // [R][n_sites] time of the last jump per proton label - 1 (-1: never)
     // occupancy histogram: frames a site was seen occupied, kept as (closed intervals, open since)
@@ -99,7 +100,7 @@ struct KmcArgs {
     int replica_first, replica_step;
     double dt, inv_dt;
     uint64_t seed;
-    int64_t stride, nframes, frames_base, n_u, ev_cap, row_cap;
+    int64_t stride, nframes, frames_base, obs_base, n_u, ev_cap, row_cap;
     int reset_freq, print_freq;
     const int *start, *dest, *counts;
     const double *omega, *positions, *u, *dist;
@@ -1197,7 +1198,7 @@ __device__ bool solo_helpers(const KmcArgs &a, WarpCtx &c)
 __device__ void kmc_observe(const KmcArgs &a, const BoxParams &bx, WarpCtx &c, int r, int64_t f,
                             KmcState &st)
 {
-    const int64_t gf = a.frames_base + f;
+    const int64_t gf = a.obs_base + f;
     const double *pos = a.positions + f * (int64_t)a.n_sites * 3;
     double *snap = a.snapshot + (int64_t)r * a.n_sites * 3;
     double *disp = a.disp + (int64_t)r * a.n_sites * 3;
@@ -1257,7 +1258,7 @@ __device__ void kmc_observe(const KmcArgs &a, const BoxParams &bx, WarpCtx &c, i
 __device__ void solo_observe(const KmcArgs &a, const BoxParams &bx, WarpCtx &c, int r, int64_t f,
                              KmcState &st)
 {
-    const int64_t gf = a.frames_base + f;
+    const int64_t gf = a.obs_base + f;
     const double *pos = a.positions + f * (int64_t)a.n_sites * 3;
     double *snap = a.snapshot + (int64_t)r * a.n_sites * 3;
     double *disp = a.disp + (int64_t)r * a.n_sites * 3;
@@ -1371,7 +1372,7 @@ __device__ bool kmc_event(const KmcArgs &a, WarpCtx &c, int r, KmcState &st)
         if (!c.solo) ((long long *)a.ev_dist)[q] = c.base + ek;   // solo: a helper warp wrote it
     }
     st.n_events++;
-    if (st.log_pos < a.ev_cap) st.log_pos++;
+    if (a.ev_cap > 0) st.log_pos++;   // counts on past the capacity: cmd_kmc_events_dropped reports the excess
     st.draws += 2;
     st.cursor += 2;
     return true;
@@ -2065,6 +2066,43 @@ extern "C" int cmd_kmc_set_observables(cmd_kmc *k, int reset_frequency, int prin
     return CMD_OK;
 }
 
+// frame number 0 of the observables from positions handed in by the host (see the header)
+__global__ void k_obs_seed(const int *__restrict__ lattice, const double *__restrict__ pos, int n_sites,
+                           int *__restrict__ lattice0, double *__restrict__ snapshot,
+                           double *__restrict__ disp)
+{
+    const int r = blockIdx.x;
+    for (int s = threadIdx.x; s < n_sites; s += blockDim.x) {
+        const int l = lattice[(int64_t)r * n_sites + s];
+        lattice0[(int64_t)r * n_sites + s] = l;
+        if (l > 0)
+            for (int k = 0; k < 3; k++) {
+                snapshot[((int64_t)r * n_sites + (l - 1)) * 3 + k] = pos[3 * s + k];
+                disp[((int64_t)r * n_sites + (l - 1)) * 3 + k] = 0.0;
+            }
+    }
+}
+
+extern "C" int cmd_kmc_seed_observables(cmd_kmc *k, const double *h_positions)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || !h_positions) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (k->print_freq <= 0 || !k->d_snapshot)
+        return cmd_set_error(CMD_ESTATE, "call cmd_kmc_set_observables first");
+    if (k->frames_total != 0) return cmd_set_error(CMD_ESTATE, "frames have been walked already");
+    cudaStream_t st = cmd_global().stream;
+    void *buf;
+    int rc = cmd_scratch(4, (size_t)k->n_sites * 24, &buf);
+    if (rc) return rc;
+    CMD_CUDA(cudaMemcpyAsync(buf, h_positions, (size_t)k->n_sites * 24, cudaMemcpyHostToDevice, st));
+    k_obs_seed<<<k->n_replicas, 256, 0, st>>>(k->d_lattice, (const double *)buf, k->n_sites, k->d_lattice0,
+                                              k->d_snapshot, k->d_disp);
+    CMD_LAUNCHED();
+    CMD_CUDA(cudaStreamSynchronize(st));   // h_positions is borrowed for the call only
+    k->obs_offset = 1;
+    return CMD_OK;
+}
+
 static int kmc_resolve_events(cmd_kmc *k, const double *d_dist)
 {
     if (k->ev_cap > 0) {
@@ -2098,7 +2136,7 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
     }
     // observable rows: grow to hold this block's prints
     if (obs) {
-        int64_t need = (k->frames_total + nframes) / k->print_freq + 2;
+        int64_t need = (k->frames_total + k->obs_offset + nframes) / k->print_freq + 2;
         if (need > k->row_cap) {
             int64_t cap = need + need / 2 + 16;
             double *nr = nullptr;
@@ -2118,7 +2156,7 @@ extern "C" int cmd_kmc_advance(cmd_kmc *k, const cmd_topo *t, const double *d_po
     a.n_sites = k->n_sites; a.n_replicas = k->n_replicas; a.rng_mode = k->rng_mode;
     a.replica_first = k->replica_first; a.replica_step = k->replica_step;
     a.dt = k->dt; a.inv_dt = 1.0 / k->dt; a.seed = k->seed; a.stride = stride; a.nframes = nframes;
-    a.frames_base = k->frames_total; a.n_u = k->n_u; a.ev_cap = k->ev_cap; a.row_cap = k->row_cap;
+    a.frames_base = k->frames_total; a.obs_base = k->frames_total + k->obs_offset; a.n_u = k->n_u; a.ev_cap = k->ev_cap; a.row_cap = k->row_cap;
     a.reset_freq = k->reset_freq; a.print_freq = k->print_freq;
     a.start = d_start; a.dest = d_dest; a.counts = d_counts; a.omega = d_omega; a.dist = d_dist;
     a.positions = obs ? d_positions : nullptr;
@@ -2376,10 +2414,32 @@ extern "C" int cmd_kmc_get_observables(const cmd_kmc *k, int replica, int64_t ca
     CMD_CUDA(cudaStreamSynchronize(st));
     // only rows whose frames were flushed by an event carry a time stamp (MDMC.py:94-96)
     int64_t have = hs.pending_row;
+    if (!rows) { *n = have; return CMD_OK; }   // query: how many rows there are
     if (have > capacity) have = capacity;
     *n = have;
     if (have > 0 && rows) {
         CMD_CUDA(cudaMemcpyAsync(rows, k->d_rows + (int64_t)replica * k->row_cap * 6, have * 48,
+                                 cudaMemcpyDeviceToHost, st));
+        CMD_CUDA(cudaStreamSynchronize(st));
+    }
+    return CMD_OK;
+}
+
+extern "C" int cmd_kmc_get_observable_rows(const cmd_kmc *k, int replica, int64_t first, int64_t count,
+                                           double *rows)
+{
+    CMD_REQUIRE_INIT();
+    if (!k || replica < 0 || replica >= k->n_replicas || first < 0 || count < 0 || (count && !rows))
+        return cmd_set_error(CMD_EINVAL, "bad argument");
+    cudaStream_t st = cmd_global().stream;
+    KmcState hs;
+    CMD_CUDA(cudaMemcpyAsync(&hs, k->d_state + replica, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
+    if (first + count > hs.pending_row)
+        return cmd_set_error(CMD_EINVAL, "rows [%lld, %lld) asked for, %lld time-stamped rows exist",
+                             (long long)first, (long long)(first + count), (long long)hs.pending_row);
+    if (count) {
+        CMD_CUDA(cudaMemcpyAsync(rows, k->d_rows + ((int64_t)replica * k->row_cap + first) * 6, count * 48,
                                  cudaMemcpyDeviceToHost, st));
         CMD_CUDA(cudaStreamSynchronize(st));
     }
@@ -2403,6 +2463,31 @@ extern "C" int64_t cmd_kmc_debug_counter(const cmd_kmc *k, int i)
     unsigned long long v = 0;
     cudaStream_t st = cmd_global().stream;
     if (cudaMemcpyAsync(&v, k->d_ties + i, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    cudaStreamSynchronize(st);
+    return (int64_t)v;
+}
+
+// events that did not fit the log since the last cmd_kmc_set_event_log, summed over the replicas
+__global__ void k_events_dropped(const KmcState *__restrict__ state, int n_replicas, int64_t ev_cap,
+                                 unsigned long long *__restrict__ out)
+{
+    unsigned long long v = 0;
+    for (int r = threadIdx.x; r < n_replicas; r += blockDim.x)
+        if (state[r].log_pos > ev_cap) v += (unsigned long long)(state[r].log_pos - ev_cap);
+    if (v) atomicAdd(out, v);
+}
+
+extern "C" int64_t cmd_kmc_events_dropped(const cmd_kmc *k)
+{
+    if (!k || !cmd_global().inited) return -1;
+    if (k->ev_cap <= 0) return 0;
+    cudaStream_t st = cmd_global().stream;
+    void *buf;
+    if (cmd_scratch(4, 8, &buf)) return -1;
+    if (cudaMemsetAsync(buf, 0, 8, st) != cudaSuccess) return -1;
+    k_events_dropped<<<1, 256, 0, st>>>(k->d_state, k->n_replicas, k->ev_cap, (unsigned long long *)buf);
+    unsigned long long v = 0;
+    if (cudaMemcpyAsync(&v, buf, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
     cudaStreamSynchronize(st);
     return (int64_t)v;
 }

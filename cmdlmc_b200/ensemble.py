@@ -81,6 +81,10 @@ def run_kmc_ensemble(atom_box, frames_source, n_frames, *, n_sites, n_protons, c
     if histogram:
         jh = np.zeros(histogram[2], np.int64)
         if kmc is not None:
+            dropped = kmc.events_dropped()
+            if dropped:
+                raise RuntimeError("%d jumps did not fit the event log (64 per frame and replica): the "
+                                   "jump-distance histogram would be incomplete" % dropped)
             kmc.jump_histogram(histogram[0], histogram[1], histogram[2], out=jh)
         stats["jump_hist"] = jh
         stats["pair_hist"] = pair_hist if rank == 0 else np.zeros_like(pair_hist)

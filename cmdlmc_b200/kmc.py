@@ -146,17 +146,32 @@ class DeviceKMC:
                                                 ptr(out, C.c_int64)))
         return out
 
-    def observables(self, replica=0, capacity=1 << 20):
+    def seed_observables(self, positions):
+        """Donor positions [n_sites, 3] of a frame that becomes frame number 0 of the observables
+        without being walked by the KMC (cmd_kmc_seed_observables)."""
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        if pos.shape != (self.n_sites, 3):
+            raise ValueError("positions must have shape [%d, 3]" % self.n_sites)
+        check(_abi.lib().cmd_kmc_seed_observables(self._handle, ptr(pos)))
+
+    def observables(self, replica=0, first=0):
+        """Time-stamped observable rows [first:] of a replica: (frame, time, msd_x, msd_y, msd_z,
+        autocorrelation) each."""
         n = C.c_int64(0)
         check(_abi.lib().cmd_kmc_get_observables(self._handle, int(replica), 0, C.byref(n), None))
-        # first call with capacity 0 only clamps; ask again with the real size
-        rows = np.zeros((capacity, 6))
-        check(_abi.lib().cmd_kmc_get_observables(self._handle, int(replica), capacity,
-                                                 C.byref(n), ptr(rows)))
-        return rows[:n.value].copy()
+        count = max(int(n.value) - int(first), 0)
+        rows = np.zeros((count, 6))
+        if count:
+            check(_abi.lib().cmd_kmc_get_observable_rows(self._handle, int(replica), int(first), count,
+                                                         ptr(rows)))
+        return rows
 
     def tie_count(self):
         return int(_abi.lib().cmd_kmc_tie_count(self._handle))
+
+    def events_dropped(self):
+        """Events that did not fit the event log since set_event_log (all replicas)."""
+        return int(_abi.lib().cmd_kmc_events_dropped(self._handle))
 
     def selection_fallbacks(self):
         """Events the one-CTA-per-replica kernel re-decided with the sequential np.cumsum."""
@@ -221,8 +236,21 @@ class KMCLattice:
         mode = RNG_REPLAY if self._rng == "replay" else RNG_PHILOX
         dev = DeviceKMC(self._atom_box, self._lattice, self._time_step, mode, self._seed)
         self._device = dev
+        # Frames the topology consumed before the iteration starts (AngleTopology._determine_groups
+        # pulls the first trajectory frame, topology.py:145) sit in the reference's frame cache and
+        # come out first at the first event (MDMC.py:92-94): they take the frame numbers 0.., the
+        # frames the KMC walks follow.
+        cache = getattr(self.topology, "_cache", None)
+        self._pre_frames = list(cache) if cache else []
+        if cache:
+            cache.clear()
         if observables:
             dev.set_observables(*observables)
+            if len(self._pre_frames) > 1:
+                raise NotImplementedError("more than one frame consumed before the KMC iteration")
+            if self._pre_frames:
+                f0 = self._pre_frames[0]
+                dev.seed_observables(np.asarray(f0[self.donor_atoms].atom_positions, dtype=float))
         if hasattr(self.topology, "hydronium_parameters"):
             dev.set_hydronium(self._jumprate_function, **self.topology.hydronium_parameters())
         first = 0
@@ -240,6 +268,11 @@ class KMCLattice:
             if reason[0] == 1:
                 raise RuntimeError("replay stream exhausted inside a block: raise "
                                    "KMCLattice.events_per_frame_bound")
+            dropped = dev.events_dropped()
+            if dropped:   # the lattices / flush times of the outputs are rebuilt from this log
+                raise RuntimeError("%d events did not fit the event log of a block of %d frames: raise "
+                                   "KMCLattice.events_per_frame_bound (now %d)"
+                                   % (dropped, nfr, self.events_per_frame_bound))
             if mode == RNG_REPLAY:
                 self._pending_u = self._pending_u[int(cursor[0]):]
             self._lattice[:] = dev.state()["lattices"][0]
@@ -261,23 +294,27 @@ class KMCLattice:
             yield item[0], item[1], item[2]
 
     def _frames_with_lattice(self):
-        carry = []      # frames consumed but not yet flushed by an event (kept across blocks)
+        carry = None    # frames consumed but not yet flushed by an event (kept across blocks)
         lattice = self._lattice.copy()
         for first, full_frames, ev in self._blocks():
-            frames = carry + [(first + k, f) for k, f in enumerate(full_frames)]
+            if carry is None:   # (frame number, sweep it was consumed in, frame); see _blocks
+                carry = [(k, -1, f) for k, f in enumerate(self._pre_frames)]
+            m = len(self._pre_frames)
+            frames = carry + [(first + m + k, first + k, f) for k, f in enumerate(full_frames)]
             e = 0
             out_upto = 0
             n_ev = len(ev["frame"])
-            for idx, (fn, frame) in enumerate(frames):
-                # frame fn is flushed by the first event whose sweep >= fn; events before it
-                # have already moved their protons (pre-jump lattice of the flushing event)
-                while e < n_ev and ev["frame"][e] < fn:
+            for idx, (number, sweep, frame) in enumerate(frames):
+                # a frame is flushed by the first event whose sweep >= the sweep that consumed it;
+                # events before it have already moved their protons (pre-jump lattice of the
+                # flushing event)
+                while e < n_ev and ev["frame"][e] < sweep:
                     lattice[ev["dest"][e]] = lattice[ev["start"][e]]
                     lattice[ev["start"][e]] = 0
                     e += 1
                 if e >= n_ev:
                     break
-                yield fn, ev["time"][e], frame, lattice.copy()
+                yield number, ev["time"][e], frame, lattice.copy()
                 out_upto = idx + 1
             carry = frames[out_upto:]
             while e < n_ev:
@@ -296,10 +333,10 @@ class KMCLattice:
         """(frame_number, kmc_time, msd[3], autocorrelation) rows computed on the device."""
         done = 0
         for _ in self._blocks(observables=(reset_frequency, print_frequency)):
-            rows = self._device.observables(0)
-            for row in rows[done:]:
+            rows = self._device.observables(0, first=done)
+            for row in rows:
                 yield int(row[0]), row[1], row[2:5].copy(), int(row[5])
-            done = len(rows)
+            done += len(rows)
 
     @property
     def event_log(self):

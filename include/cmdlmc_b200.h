@@ -272,10 +272,22 @@ int cmd_kmc_set_replay_stream(cmd_kmc *k, const double *h_u, int64_t n_per_repli
 /* Event log capacity per replica (0 disables logging); (re)starts the log: events are logged
  * from slot 0 again, so a caller drains the log after every cmd_kmc_advance. */
 int cmd_kmc_set_event_log(cmd_kmc *k, int64_t max_events_per_replica);
+/* Events that did NOT fit the log since the last cmd_kmc_set_event_log, summed over the replicas
+ * (the run itself is unaffected; outputs rebuilt from the log would be wrong): 0 is the rule, a
+ * caller that reconstructs lattices from the log must check it after every cmd_kmc_advance. */
+int64_t cmd_kmc_events_dropped(const cmd_kmc *k);
 /* Observables (MDMC.py:179-208, output.py): MSD per axis and covalent autocorrelation every
  * print_frequency frames, reset every reset_frequency frames. d_positions are the donor
  * positions of the frames handed to cmd_kmc_advance. 0/0 disables. */
 int cmd_kmc_set_observables(cmd_kmc *k, int reset_frequency, int print_frequency);
+/* Frame number 0 of the observables from positions that never pass through the topology: with
+ * AngleTopology the reference's _determine_groups (mdlmc/topo/topology.py:142-146) pulls the
+ * first trajectory frame through the cached one-shot iterator, so continuous_output
+ * (MDMC.py:92-94) yields it as frame 0 at the first event -- the MSD / autocorrelation start
+ * there (MDMC.py:193-196) -- while the KMC walks the trajectory from its SECOND frame, which is
+ * frame number 1.  h_positions: donor positions [n_sites][3] of that frame.  After
+ * cmd_kmc_set_observables, before the first cmd_kmc_advance. */
+int cmd_kmc_seed_observables(cmd_kmc *k, const double *h_positions);
 /* Consumes the frames of the topology's current block (KMCLattice.continuous_output,
  * MDMC.py:77-99, fastforward_to_next_jump :121-171, move_proton :101-119).  d_positions:
  * f64 [nframes][n_sites][3] of the same block (needed only when observables are enabled). */
@@ -303,6 +315,10 @@ int cmd_kmc_jump_histogram_dev(const cmd_kmc *k, double lo, double hi, int nbins
 /* Observable rows of one replica: (frame, time, msd_x, msd_y, msd_z, autocorr) per row. */
 int cmd_kmc_get_observables(const cmd_kmc *k, int replica, int64_t capacity, int64_t *n,
                             double *h_rows6);
+/* rows [first, first + count) of the same table (a caller that drains block by block copies only
+ * what is new); cmd_kmc_get_observables with h_rows == NULL returns the number of rows in *n */
+int cmd_kmc_get_observable_rows(const cmd_kmc *k, int replica, int64_t first, int64_t count,
+                                double *h_rows);
 /* Tie audit: decisions (time stepping / selection) within 1e-9 relative of a boundary. */
 int64_t cmd_kmc_tie_count(const cmd_kmc *k);
 /* Runs with few replicas in exact arithmetic use one CTA per replica and decide move_proton's

@@ -172,20 +172,22 @@ def gen_angle():
 
 
 def run_reference_kmc(w, frames, seed, n_events, reset_frequency=None, print_frequency=None,
-                      make_topology=None):
+                      make_topology=None, names=None, jumprate=None):
     """Drives the reference KMCLattice; records events, lattices and (optionally) observables."""
     from mdlmc.topo.topology import NeighborTopology
     from mdlmc.LMC.MDMC import KMCLattice
     from mdlmc.LMC.jumprate_generators import Fermi
     box = make_box(w.cell)
-    names = np.array(["O"] * w.n_oxygen)
+    if names is None:
+        names = np.array(["O"] * w.n_oxygen)
     if make_topology is not None:
         topo = make_topology(MockTrajectory(frames, w.time_step, names), box)
     else:
         topo = NeighborTopology(MockTrajectory(frames, w.time_step, names), box, donor_atoms="O",
                                 cutoff=w.cutoff, buffer=w.buffer)
     np.random.seed(seed)
-    kmc = KMCLattice(topo, atom_box=box, jumprate_function=Fermi(*w.rate_params),
+    kmc = KMCLattice(topo, atom_box=box,
+                     jumprate_function=jumprate if jumprate is not None else Fermi(*w.rate_params),
                      lattice_size=w.n_oxygen, proton_number=w.n_protons, donor_atoms="O",
                      time_step=w.time_step)
     lattice0 = kmc.lattice.copy()
@@ -211,10 +213,14 @@ def run_reference_kmc(w, frames, seed, n_events, reset_frequency=None, print_fre
     kmc.fastforward_to_next_jump = fastforward
     obs = []
     frame_times = []
+    lattice_marks = []
     try:
         if reset_frequency is None:
             for n, t, frame in kmc:
                 frame_times.append((n, t))
+                # what xyz_output (MDMC.py:173-177) would append to this frame: the occupied sites
+                lattice_marks.append((float(np.dot(kmc.lattice, np.arange(1, len(kmc.lattice) + 1))),
+                                      float(frame["O"].atom_positions[kmc.occupied_sites].sum())))
                 if len(events) >= n_events:
                     break
         else:
@@ -237,7 +243,38 @@ def run_reference_kmc(w, frames, seed, n_events, reset_frequency=None, print_fre
                 ev_frame=ffa[:, 0].astype(np.int64), ev_dframe=ffa[:, 1].astype(np.int64),
                 ev_time=ffa[:, 2], u=u, obs=np.array(obs, dtype=float).reshape(-1, 6),
                 frame_times=np.array(frame_times, dtype=float).reshape(-1, 2),
+                lattice_marks=np.array(lattice_marks, dtype=float).reshape(-1, 2),
                 lattice_final=kmc.lattice.copy())
+
+
+def gen_angle_kmc():
+    """The reference KMCLattice on AngleTopology + FermiAngle (the integration config,
+    tests/integration/mdlmc_run.py:37-70): _determine_groups leaves trajectory frame 0 in the frame
+    cache, so continuous_output numbers it 0 and the KMC walks the trajectory from frame 1
+    (topology.py:142-146, MDMC.py:92-94).  Event trace, (frame number, time) of every yielded frame
+    with a mark of the lattice xyz_output would see, and observables_output rows."""
+    from mdlmc.topo.topology import AngleTopology
+    from mdlmc.LMC.jumprate_generators import FermiAngle
+    w = synth.workload("C1")
+    nfr = 260
+    frames = synth.trajectory(w, nfr + 1, with_extra=True)
+    names = np.array(["O"] * w.n_oxygen + ["P"] * w.n_extra)
+
+    def mk(traj, box):
+        return AngleTopology(traj, box, donor_atoms="O", extra_atoms="P", group_size=w.group_size,
+                             cutoff=w.cutoff, buffer=w.buffer)
+    rate = FermiAngle(*w.rate_params, np.pi / 2)
+    out = {"nframes": nfr + 1, "seed": 17}
+    res = run_reference_kmc(w, frames, 17, 10 ** 9, make_topology=mk, names=names, jumprate=rate)
+    for k, v in res.items():
+        out["cont_" + k] = v
+    res = run_reference_kmc(w, frames, 17, 10 ** 9, reset_frequency=100, print_frequency=10,
+                            make_topology=mk, names=names, jumprate=rate)
+    for k in ("obs", "ev_frame", "ev_start", "ev_dest", "lattice_final", "u", "lattice0"):
+        out["obs_" + k] = res[k]
+    np.savez_compressed(os.path.join(GOLD, "angle_kmc.npz"), **out)
+    print("angle_kmc.npz: events", len(out["cont_ev_start"]), "frames yielded", len(out["cont_frame_times"]),
+          "first frame numbers", out["cont_frame_times"][:3, 0], "observable rows", len(out["obs_obs"]))
 
 
 HYD_RELU = dict(a=0.9, b=2.35, d0=2.5, left_bound=2.2, right_bound=3.2)
@@ -343,7 +380,7 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     only = sys.argv[1:]
     for name, fn in (("geometry", gen_geometry), ("topology", gen_topology),
-                     ("fastforward", gen_fastforward), ("kmc", gen_kmc), ("angle", gen_angle),
+                     ("fastforward", gen_fastforward), ("kmc", gen_kmc), ("angle", gen_angle), ("angle_kmc", gen_angle_kmc),
                      ("hydronium", gen_hydronium)):
         if not only or name in only:
             fn()

@@ -137,7 +137,7 @@ def test_multi_replica_replay_vs_oracle(orc, cfg, nfr, nrep):
 
 def test_philox_statistics_vs_oracle(orc):
     """Philox mode: mean event count and mean squared hop count over 128 GPU replicas agree with
-    128 CPU-oracle replicas within 4 combined standard errors; runs are reproducible in the
+    128 CPU-oracle replicas within 3 combined standard errors; runs are reproducible in the
     seed and differ between seeds."""
     from cmdlmc_b200.kmc import DeviceKMC, RNG_PHILOX
     w = synth.workload("C1")
@@ -177,7 +177,7 @@ def test_philox_statistics_vs_oracle(orc):
         gpu_back.append(np.mean(ev["start"][1:] == ev["dest"][:-1]))
     for a, b in ((gpu_counts, np.array(ref_counts, float)), (np.array(gpu_back), np.array(ref_back))):
         se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
-        assert abs(a.mean() - b.mean()) < 4 * se + 1e-12, (a.mean(), b.mean(), se)
+        assert abs(a.mean() - b.mean()) < 3 * se + 1e-12, (a.mean(), b.mean(), se)
 
 
 def test_xyz_output_and_errors():
@@ -557,3 +557,198 @@ def test_randomised_small_lattices_replay_vs_oracle(orc, seed):
     print("seed", seed, "sites", n, "protons", nprot, "frames", nfr, "mode", mode, "events", st["n_events"].tolist(),
           "pairs/frame", float(np.diff(fptr).mean()))
     assert st["n_events"].sum() > 0
+
+
+@pytest.mark.parametrize("cfg,nfr", [("C1", 800), ("C4", 400)])
+def test_philox_msd_and_jump_counts_vs_oracle_replicas(orc, cfg, nfr):
+    """north_star correctness, part 4: in Philox mode the MSD PER AXIS (output.py:35-49) at every
+    printed row and the jump counts of 128 GPU replicas (k_kmc_stream, observables on the device)
+    agree with 128 CPU replicas of the oracle (exact-replay arithmetic on legacy RandomState
+    streams) within 3 * sqrt(se_gpu^2 + se_cpu^2).  Seeds are fixed: the outcome is deterministic."""
+    from cmdlmc_b200.kmc import DeviceKMC, RNG_PHILOX
+    w = synth.workload(cfg)
+    nrep, pf = 128, nfr // 4
+    frames = synth.trajectory(w, nfr)
+    box, topo = device_topology(w, frames)
+    fptr, start, dest, omega = topo_to_host(topo)
+    obox = orc.OracleBox(w.cell)
+    lattices = np.array([synth.initial_lattice(w.n_oxygen, w.n_protons, 300 + r)[0] for r in range(nrep)])
+    dev = DeviceKMC(box, lattices, w.time_step, RNG_PHILOX, seed=2024)
+    dev.set_observables(nfr + 1, pf)          # no reset inside the run
+    dev.advance(topo, topo.positions_ptr())
+    st = dev.state()
+    gpu_rows = [dev.observables(r) for r in range(nrep)]
+    cpu_rows, cpu_counts = [], []
+    for r in range(nrep):
+        lat = lattices[r].copy()
+        u = np.random.RandomState(77000 + r).random_sample(2 * (24 * nfr + 64))
+        res = orc.kmc_replay(fptr, start, dest, omega, lat, w.time_step, u, 24 * nfr + 64)
+        cpu_counts.append(res["n_events"])
+        obs = orc.observables(obox, frames, lattices[r], res, nfr + 1, pf)
+        cpu_rows.append(np.array([[f, t, m[0], m[1], m[2], a] for f, t, m, a in obs]))
+    n_rows = min(min(len(x) for x in gpu_rows), min(len(x) for x in cpu_rows))
+    assert n_rows >= 2          # the last printed frame may not have been flushed by an event
+    checked = 0
+    for k in range(n_rows):
+        g = np.array([x[k] for x in gpu_rows])
+        c = np.array([x[k] for x in cpu_rows])
+        assert (g[:, 0] == c[:, 0]).all() and g[0, 0] == (k + 1) * pf
+        for axis in (2, 3, 4):
+            a, b = g[:, axis], c[:, axis]
+            se = np.sqrt(a.var(ddof=1) / nrep + b.var(ddof=1) / nrep)
+            assert a.mean() > 0 and abs(a.mean() - b.mean()) < 3 * se, (cfg, k, axis, a.mean(), b.mean(), se)
+            checked += 1
+        a, b = g[:, 5], c[:, 5]             # covalent autocorrelation
+        se = np.sqrt(a.var(ddof=1) / nrep + b.var(ddof=1) / nrep)
+        assert abs(a.mean() - b.mean()) < 3 * se + 1e-12, (cfg, k, "autocorr", a.mean(), b.mean(), se)
+    a, b = st["n_events"].astype(float), np.array(cpu_counts, float)
+    se = np.sqrt(a.var(ddof=1) / nrep + b.var(ddof=1) / nrep)
+    assert abs(a.mean() - b.mean()) < 3 * se, (cfg, "jump counts", a.mean(), b.mean(), se)
+    assert checked >= 6
+
+
+@pytest.mark.parametrize("engine", ["kmc", "lmc"])
+def test_c4_verified_replay_subset_64_replicas(orc, engine):
+    """BASELINE config 4's verification leg at its stated size: 64 replicas on the 384-O lattice
+    over 1000 frames in exact-replay mode, every replica bit-identical with the CPU oracle
+    (KMC: the reference's RandomState protocol; legacy LMC sweep: GSL MT19937 streams)."""
+    w = synth.workload("C4")
+    nfr, nrep = 1000, 64
+    frames = synth.trajectory(w, nfr)
+    box, topo = device_topology(w, frames)
+    fptr, start, dest, omega = topo_to_host(topo)
+    if engine == "kmc":
+        from cmdlmc_b200.kmc import DeviceKMC, RNG_REPLAY
+        nu = 2 * (24 * nfr + 64)
+        lattices, streams = [], []
+        for r in range(nrep):
+            lat, rng = synth.initial_lattice(w.n_oxygen, w.n_protons, 1000 + r)
+            lattices.append(lat)
+            streams.append(rng.random_sample(nu))
+        dev = DeviceKMC(box, np.array(lattices), w.time_step, RNG_REPLAY)
+        dev.set_event_log(nu // 2)
+        dev.set_replay_stream(np.array(streams))
+        dev.advance(topo)
+        assert dev.events_dropped() == 0
+        st = dev.state()
+        total = 0
+        for r in range(nrep):
+            lat = lattices[r].copy()
+            want = orc.kmc_replay(fptr, start, dest, omega, lat, w.time_step, streams[r], nu // 2)
+            ev = dev.events(r)
+            assert want["n_events"] == len(ev["time"]) == st["n_events"][r] and want["n_events"] > 1000
+            for key in ("frame", "start", "dest", "proton", "time"):
+                np.testing.assert_array_equal(ev[key], want[key], err_msg="replica %d %s" % (r, key))
+            np.testing.assert_array_equal(st["lattices"][r], lat)
+            total += want["n_events"]
+        assert total > 64 * 1000
+    else:
+        # four blocks of 250 frames (the pregenerated streams of 64 replicas x 1000 frames would
+        # take 5 GB of host memory at once); lattices carry over, every block gets fresh streams
+        from cmdlmc_b200.lmc import DeviceLMC, RNG_REPLAY, gsl_streams
+        lattices = np.array([synth.initial_lattice(w.n_oxygen, w.n_protons, 1000 + r)[0] for r in range(nrep)])
+        want = lattices.copy()
+        dev = DeviceLMC(lattices, RNG_REPLAY)
+        jumps_want = np.zeros(nrep, np.int64)
+        for blk in range(4):
+            if blk:
+                box, topo = device_topology(w, synth.trajectory(w, 250, start=250 * blk))
+                fptr, start, dest, omega = topo_to_host(topo)
+            else:
+                fptr, start, dest, omega = fptr[:251], start[:fptr[250]], dest[:fptr[250]], omega[:fptr[250]]
+                box, topo = device_topology(w, frames[:250])
+            counts = np.diff(fptr)
+            streams = [gsl_streams(500 + r + 1000 * blk, counts) for r in range(nrep)]
+            pick, acc = np.stack([x[0] for x in streams]), np.stack([x[1] for x in streams])
+            del streams
+            dev.set_replay_stream(pick, acc)
+            dev.advance(topo, w.time_step, 1)
+            prob = omega * w.time_step
+            for r in range(nrep):
+                pos = 0
+                for f in range(250):
+                    a, b = fptr[f], fptr[f + 1]
+                    jumps_want[r] += orc.lmc_sweep(start[a:b], dest[a:b], prob[a:b], want[r],
+                                                   pick[r, pos:pos + b - a], acc[r, pos:pos + b - a])
+                    pos += b - a
+            st = dev.state()
+            np.testing.assert_array_equal(st["lattices"], want, err_msg="block %d" % blk)
+            del pick, acc
+        np.testing.assert_array_equal(st["jumps"], jumps_want)
+        assert (jumps_want > 100).all()
+
+
+def test_angle_topology_kmc_outputs_vs_reference(golden):
+    """The flagship config of the reference (tests/integration/mdlmc_run.py:37-70): KMCLattice on
+    AngleTopology + FermiAngle.  _determine_groups leaves trajectory frame 0 in the frame cache
+    (topology.py:142-146), so continuous_output numbers it 0 and flushes it with the first event,
+    xyz_output starts with it, the MSD / autocorrelation start there, and the reset / print
+    phases count from it.  Event trace, frame numbers, flush times, the lattice every yielded
+    frame is seen with, and the observable rows against the reference's own seeded run
+    (tests/golden/angle_kmc.npz, oracle/make_golden.py gen_angle_kmc)."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.kmc import KMCLattice
+    from cmdlmc_b200.topology import AngleTopology
+    from cmdlmc_b200.trajectory import ArrayTrajectory
+    g = golden("angle_kmc")
+    w = synth.workload("C1")
+    nfr = int(g["nframes"])
+    frames = synth.trajectory(w, nfr, with_extra=True)
+    names = np.array(["O"] * w.n_oxygen + ["P"] * w.n_extra)
+    box = make_box(w.cell)
+
+    def make(chunk):
+        np.random.seed(int(g["seed"]))
+        top = AngleTopology(ArrayTrajectory(frames, names, time_step=w.time_step), box, donor_atoms="O",
+                            extra_atoms="P", group_size=w.group_size, cutoff=w.cutoff, buffer=w.buffer)
+        return KMCLattice(top, atom_box=box, jumprate_function=cm.FermiAngle(*w.rate_params, np.pi / 2),
+                          lattice_size=w.n_oxygen, proton_number=w.n_protons, donor_atoms="O",
+                          time_step=w.time_step, rng="replay", chunk_size=chunk)
+
+    for chunk in (1024, 41):
+        # continuous output + the lattice xyz_output appends
+        kmc = make(chunk)
+        np.testing.assert_array_equal(kmc.lattice, g["cont_lattice0"])
+        got = list(kmc._frames_with_lattice())
+        ev = kmc.event_log
+        ne = len(g["cont_ev_start"])
+        n = min(ne, len(ev["start"]))
+        assert n >= ne - 1 and n > 5
+        np.testing.assert_array_equal(ev["frame"][:n], g["cont_ev_frame"][:n])
+        np.testing.assert_array_equal(ev["start"][:n], g["cont_ev_start"][:n])
+        np.testing.assert_array_equal(ev["dest"][:n], g["cont_ev_dest"][:n])
+        np.testing.assert_allclose(ev["time"][:n], g["cont_ev_time"][:n], rtol=1e-12)
+        ft, marks = g["cont_frame_times"], g["cont_lattice_marks"]
+        m = min(len(ft), len(got))
+        assert m >= len(ft) - 1 and m > 100
+        assert got[0][0] == 0 and got[1][0] == 1
+        np.testing.assert_array_equal([x[0] for x in got[:m]], ft[:m, 0].astype(int))
+        np.testing.assert_allclose([x[1] for x in got[:m]], ft[:m, 1], rtol=1e-12)
+        # frame number 0 is trajectory frame 0, which the topology never walked
+        np.testing.assert_array_equal(got[0][2]["O"].atom_positions, frames[0, :w.n_oxygen])
+        idx = np.arange(1, w.n_oxygen + 1)
+        for (num, t, frame, lat), (mark_lat, mark_pos) in zip(got[:m], marks[:m]):
+            assert float(np.dot(lat, idx)) == mark_lat, num
+            assert frame["O"].atom_positions[np.where(lat > 0)[0]].sum() == pytest.approx(mark_pos, rel=1e-12)
+        # observables
+        rows = list(make(chunk).observables_output(100, 10))
+        want = g["obs_obs"]
+        assert len(want) > 10 and len(rows) >= len(want) - 1
+        for (f, t, msd, auto), wr in zip(rows, want):
+            assert f == int(wr[0])
+            assert t == pytest.approx(wr[1], rel=1e-12)
+            np.testing.assert_allclose(msd, wr[2:5], rtol=1e-9, atol=1e-12)
+            assert auto == int(wr[5])
+
+
+def test_event_log_overflow_is_an_error():
+    """Philox mode has no stream to run out of: a block with more events than the log holds must
+    not hand back outputs rebuilt from a truncated log."""
+    w = synth.workload("C2")
+    frames = synth.trajectory(w, 64)
+    kmc = make_kmc(w, frames, rng="philox", seed=3)
+    kmc.events_per_frame_bound = 1          # C2 makes ~3.4 events per frame
+    with pytest.raises(RuntimeError, match="event log"):
+        list(kmc)
+    kmc = make_kmc(w, frames, rng="philox", seed=3)
+    assert len(list(kmc)) > 40
