@@ -14,6 +14,7 @@
 struct BoxParams {
     int kind;        // 0 orthorhombic (AtomBoxCubic), 1 general cell (AtomBoxMonoclinic)
     int conv;        // CMD_CONV_*
+    int sparse;      // structural zeros of h and hinv (pbc.cuh cmd_box_sparsity); set per topology
     double L[3];     // periodic_boundaries_extended (ortho)
     double hL[3];    // L/2
     double h[9];     // row-major, columns = cell vectors (extended)
@@ -53,6 +54,10 @@ struct CmdGlobal {
 CmdGlobal &cmd_global();
 int cmd_set_error(int code, const char *fmt, ...);
 int cmd_scratch(int slot, size_t bytes, void **out);  // grows slot to >= bytes
+// staging.cu: dst (device) <- src (any host pointer), ordered on `stream`; pageable sources pass
+// through the page-locked ring
+int cmd_h2d_staged(void *dst, const void *src, size_t bytes, cudaStream_t stream);
+void cmd_staging_shutdown();
 // Rebuilds p.img / p.img_ijk: the periodic images a pair filter with radius `rc` has to look at
 // besides the fractionally wrapped vector (rc < 0: no radius, every image that can beat it).
 void cmd_box_prune_images(BoxParams &p, double rc);

@@ -89,6 +89,7 @@ extern "C" int cmd_shutdown(void)
     CmdGlobal &g = cmd_global();
     if (!g.inited) return CMD_OK;
     cudaStreamSynchronize(g.stream);
+    cmd_staging_shutdown();
     for (int i = 0; i < 6; i++) {
         if (g.scratch[i]) cudaFree(g.scratch[i]);
         g.scratch[i] = nullptr;

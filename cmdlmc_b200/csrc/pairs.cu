@@ -533,7 +533,9 @@ k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RatePara
         if (bx.kind == 0) dist = length_exact(bx, pa, pb);
         else {   // zero image + the images kept for the refresh radius == the 27-image minimum here
             double d[3];
-            diff_general_exact(bx, pa, pb, d);
+            if (bx.sparse == 2) diff_general_norm_sp<2>(bx, pa, pb, d);
+            else if (bx.sparse == 1) diff_general_norm_sp<1>(bx, pa, pb, d);
+            else diff_general_norm_exact(bx, pa, pb, d);
             dist = sqrt(min_image_norm2_kept(bx, d));
         }
         double om = rate_eval(rp, dist, 0.0);
@@ -856,6 +858,9 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
     cmd_topo *t = (cmd_topo *)calloc(1, sizeof(cmd_topo));
     if (!t) return cmd_set_error(CMD_ENOMEM, "out of host memory");
     t->bx = box->p;
+    // structural zeros of the cell matrix shorten the exact stage (CMDLMC_B200_NO_SPARSE=1: the
+    // full products, for A/B tests of the bit-identity)
+    t->bx.sparse = getenv("CMDLMC_B200_NO_SPARSE") ? 0 : cmd_box_sparsity(t->bx);
     // FermiAngle = Fermi masked by the angle colvar: the list kernels evaluate the Fermi part, the
     // mask is applied by cmd_topo_apply_angles once the angles of the block are known
     t->rate_is_fermi_angle = rate_kind == CMD_RATE_FERMI_ANGLE;
@@ -872,6 +877,7 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
     // its rebuild) is never farther apart than rc + buffer when it is refreshed: the images that
     // cannot come within that radius cannot hold the reference's 27-image minimum either.
     t->bx_refresh = box->p;
+    t->bx_refresh.sparse = t->bx.sparse;
     cmd_box_prune_images(t->bx_refresh, (t->rc + buffer) * (1.0 + 1e-9) + 1e-9);
     topo_filter_params(t);
     topo_cell_grid(t);
@@ -1479,11 +1485,12 @@ static int topo_stage(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_
         }
         t->upload_bytes = need;
     }
+    int rc;
     if (dtype_bytes == 8) {
-        CMD_CUDA(cudaMemcpyAsync(t->d_upload, h_frames, elems * 8, cudaMemcpyHostToDevice, st));
+        if ((rc = cmd_h2d_staged(t->d_upload, h_frames, elems * 8, st))) return rc;
     } else {
         float *d32 = (float *)(t->d_upload + elems);
-        CMD_CUDA(cudaMemcpyAsync(d32, h_frames, elems * 4, cudaMemcpyHostToDevice, st));
+        if ((rc = cmd_h2d_staged(d32, h_frames, elems * 4, st))) return rc;
         int blocks = cmd_div_up(elems, 256);
         if (blocks > cmd_global().sm_count * 16) blocks = cmd_global().sm_count * 16;
         k_upcast_f32<<<blocks, 256, 0, st>>>(d32, t->d_upload, (int64_t)elems);
@@ -1530,11 +1537,10 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
         const int64_t cn = nframes - c0 < chunk ? nframes - c0 : chunk;
         const size_t off = (size_t)c0 * per_frame, ce = (size_t)cn * per_frame;
         if (dtype_bytes == 8)
-            CMD_CUDA(cudaMemcpyAsync(t->d_upload + off, (const double *)h_frames + off, ce * 8,
-                                     cudaMemcpyHostToDevice, g.copy_stream));
+            rc = cmd_h2d_staged(t->d_upload + off, (const double *)h_frames + off, ce * 8, g.copy_stream);
         else
-            CMD_CUDA(cudaMemcpyAsync(d32 + off, (const float *)h_frames + off, ce * 4,
-                                     cudaMemcpyHostToDevice, g.copy_stream));
+            rc = cmd_h2d_staged(d32 + off, (const float *)h_frames + off, ce * 4, g.copy_stream);
+        if (rc) return rc;
         CMD_CUDA(cudaEventRecord(g.copy_event[1], g.copy_stream));
         CMD_CUDA(cudaStreamWaitEvent(st, g.copy_event[1], 0));
         if (dtype_bytes == 4) {
@@ -1773,10 +1779,12 @@ extern "C" int cmd_topo_apply_angles(cmd_topo *t, const void *h_extra_frames, in
         t->extra_upload_bytes = need;
     }
     if (dtype_bytes == 8) {
-        CMD_CUDA(cudaMemcpyAsync(t->d_extra_upload, h_extra_frames, elems * 8, cudaMemcpyHostToDevice, st));
+        int rc = cmd_h2d_staged(t->d_extra_upload, h_extra_frames, elems * 8, st);
+        if (rc) return rc;
     } else {
         float *d32 = (float *)(t->d_extra_upload + elems);
-        CMD_CUDA(cudaMemcpyAsync(d32, h_extra_frames, elems * 4, cudaMemcpyHostToDevice, st));
+        int rc = cmd_h2d_staged(d32, h_extra_frames, elems * 4, st);
+        if (rc) return rc;
         int blocks = cmd_div_up(elems, 256);
         if (blocks > cmd_global().sm_count * 16) blocks = cmd_global().sm_count * 16;
         k_upcast_f32<<<blocks, 256, 0, st>>>(d32, t->d_extra_upload, (int64_t)elems);

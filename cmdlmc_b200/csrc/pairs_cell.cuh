@@ -148,7 +148,9 @@ __device__ __forceinline__ void cell_exact_drain(const BoxParams &bx, const doub
             if (cold) diff_ortho_exact(bx, pa[q], pb[q], d);
             d2[q] = norm2_exact(d);
         } else {
-            diff_general_norm_exact(bx, pa[q], pb[q], d);
+            if (bx.sparse == 2) diff_general_norm_sp<2>(bx, pa[q], pb[q], d);
+            else if (bx.sparse == 1) diff_general_norm_sp<1>(bx, pa[q], pb[q], d);
+            else diff_general_norm_exact(bx, pa[q], pb[q], d);
             d2[q] = IMAGES ? min_image_norm2_kept(bx, d) : fmin(1e6, norm2_exact(d));
         }
     }

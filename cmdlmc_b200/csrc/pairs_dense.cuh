@@ -26,6 +26,8 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "pbc.cuh"
 #include "tma.cuh"
 
@@ -345,7 +347,10 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         // (b) overlapping column pairs of the cyclic sorted sequence: entry k = positions (k, k+1)
         const int ncol = 2 * n + 40;
         for (int k = tid; k < ncol; k += blockDim.x) {
-            const ushort4 lo = q16[k % n], hi = q16[(k + 1) % n];
+            int k0 = k, k1 = k + 1;            // mod n without the integer division
+            while (k0 >= n) k0 -= n;
+            while (k1 >= n) k1 -= n;
+            const ushort4 lo = q16[k0], hi = q16[k1];
             s.col[k] = make_uint4(lo.x | ((unsigned)hi.x << 16), lo.y | ((unsigned)hi.y << 16),
                                   lo.z | ((unsigned)hi.z << 16), 0u);
         }
@@ -501,22 +506,29 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         const bool two = c1 < ncand;
         const unsigned ij[2] = {s.hit_ij[c0], s.hit_ij[two ? c1 : c0]};
         double d2[2], dist[2];
+        // SP: structural zeros of the cell matrix (pbc.cuh matvec3_norm_sp), warp-uniform
+        auto length2_pair = [&](auto spc) {
+            constexpr int SP = decltype(spc)::value;
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
-            const int a = ij[q] >> 16, b = ij[q] & 0xffff;
-            const double pa[3] = {s.c[3 * a], s.c[3 * a + 1], s.c[3 * a + 2]};
-            const double pb[3] = {s.c[3 * b], s.c[3 * b + 1], s.c[3 * b + 2]};
-            double d[3];
-            if (KIND == 0) {
-                // reference: length(frame[hi], frame[lo]) (topology.py:62-66); the arithmetic is
-                // sign-symmetric, so the direction does not change a bit
-                diff_ortho_exact(bx, pa, pb, d);
-                d2[q] = norm2_exact(d);
-            } else {
-                diff_general_norm_exact(bx, pa, pb, d);
-                d2[q] = FILT == FILT_F32_IMG ? min_image_norm2_kept(bx, d) : fmin(1e6, norm2_exact(d));
+            for (int q = 0; q < 2; q++) {
+                const int a = ij[q] >> 16, b = ij[q] & 0xffff;
+                const double pa[3] = {s.c[3 * a], s.c[3 * a + 1], s.c[3 * a + 2]};
+                const double pb[3] = {s.c[3 * b], s.c[3 * b + 1], s.c[3 * b + 2]};
+                double d[3];
+                if (KIND == 0) {
+                    // reference: length(frame[hi], frame[lo]) (topology.py:62-66); the arithmetic
+                    // is sign-symmetric, so the direction does not change a bit
+                    diff_ortho_exact(bx, pa, pb, d);
+                    d2[q] = norm2_exact(d);
+                } else {
+                    diff_general_norm_sp<SP>(bx, pa, pb, d);
+                    d2[q] = FILT == FILT_F32_IMG ? min_image_norm2_kept(bx, d) : fmin(1e6, norm2_exact(d));
+                }
             }
-        }
+        };
+        if (KIND != 0 && bx.sparse == 2) length2_pair(std::integral_constant<int, 2>{});
+        else if (KIND != 0 && bx.sparse == 1) length2_pair(std::integral_constant<int, 1>{});
+        else length2_pair(std::integral_constant<int, 0>{});
 #pragma unroll
         for (int q = 0; q < 2; q++) dist[q] = convert_distance(bx, sqrt(d2[q]));
 #pragma unroll

@@ -117,6 +117,46 @@ __device__ __forceinline__ void diff_general_norm_exact(const BoxParams &bx, con
     matvec3_norm_exact(bx.h, d);
 }
 
+// The same again for cell matrices with structural zeros (BoxParams::sparse, set by
+// cmd_box_sparsity): a cell given in the usual convention -- a along x, b in the xy plane -- has an
+// upper-triangular h (columns = cell vectors) and so has its inverse; a monoclinic cell with unique
+// axis b keeps four entries.  A product with an exact zero is +-0 and x + (+-0) == x up to the
+// sign of a zero result, which the squared length cannot see (same argument as above), so leaving
+// those terms out is bit-identical for finite coordinates.
+//   SP 1: m[3] = m[6] = m[7] = 0          SP 2: additionally m[1] = m[5] = 0
+template <int SP>
+__device__ __forceinline__ void matvec3_norm_sp(const double m[9], double v[3])
+{
+    if (SP == 0) { matvec3_norm_exact(m, v); return; }
+    double r0;
+    if (SP == 1) r0 = __dadd_rn(__dadd_rn(__dmul_rn(m[0], v[0]), __dmul_rn(m[1], v[1])), __dmul_rn(m[2], v[2]));
+    else r0 = __dadd_rn(__dmul_rn(m[0], v[0]), __dmul_rn(m[2], v[2]));
+    const double r1 = SP == 1 ? __dadd_rn(__dmul_rn(m[4], v[1]), __dmul_rn(m[5], v[2])) : __dmul_rn(m[4], v[1]);
+    const double r2 = __dmul_rn(m[8], v[2]);
+    v[0] = r0; v[1] = r1; v[2] = r2;
+}
+
+template <int SP>
+__device__ __forceinline__ void diff_general_norm_sp(const BoxParams &bx, const double a[3],
+                                                     const double b[3], double d[3])
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++) d[i] = __dadd_rn(b[i], -a[i]);
+    matvec3_norm_sp<SP>(bx.hinv, d);
+    sub_round3_exact(d);
+    matvec3_norm_sp<SP>(bx.h, d);
+}
+
+// host: structural zeros of BOTH h and hinv (0, 1 or 2 as above; 0 for orthorhombic boxes, which
+// never take this path)
+static inline int cmd_box_sparsity(const BoxParams &p)
+{
+    if (p.kind == 0) return 0;
+    auto z = [&](int k) { return p.h[k] == 0.0 && p.hinv[k] == 0.0; };
+    if (!(z(3) && z(6) && z(7))) return 0;
+    return z(1) && z(5) ? 2 : 1;
+}
+
 // ---- A4: numpyatom.pyx:101-123: min over the 27 images of the wrapped vector, squared ---------
 __device__ __forceinline__ double min_image_norm2_exact(const BoxParams &bx, const double d[3])
 {

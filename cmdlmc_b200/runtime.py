@@ -50,6 +50,48 @@ def launch_count():
     return int(_abi.lib().cmd_launch_count())
 
 
+class _PinnedBlock:
+    """Owner of one cmd_host_alloc buffer; exposes the buffer protocol through ctypes."""
+
+    def __init__(self, nbytes):
+        import ctypes as C
+        self._ptr = C.c_void_p()
+        _abi.check(_abi.lib().cmd_host_alloc(int(nbytes), C.byref(self._ptr)))
+        self.nbytes = int(nbytes)
+        self.buf = (C.c_ubyte * self.nbytes).from_address(self._ptr.value)
+
+    def __del__(self):
+        p = getattr(self, "_ptr", None)
+        if p is not None and p.value:
+            try:
+                _abi.lib().cmd_host_free(p)
+            except Exception:
+                pass
+            self._ptr = None
+
+
+def pinned_empty(shape, dtype):
+    """NumPy array in page-locked host memory (cmd_host_alloc): what a trajectory reader should fill
+    so that cmd_topo_build copies from it directly and the copy overlaps the kernels
+    (trajectory_parser.py:296,322 reads its 1000-frame chunks into plain arrays).  The memory is
+    freed when the last array referring to it goes away."""
+    import numpy as np
+    ensure_init()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    block = _PinnedBlock(max(n, 1))
+    return np.frombuffer(block.buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def staging_stats():
+    """(bytes uploaded through the library's staging ring, bytes copied straight from page-locked
+    memory, host copy threads of the ring)."""
+    import ctypes as C
+    a, b, t = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+    _abi.check(_abi.lib().cmd_staging_stats(C.byref(a), C.byref(b), C.byref(t)))
+    return a.value, b.value, t.value
+
+
 def fp64_peak_tflops(iters=20000):
     import ctypes as C
     ensure_init()

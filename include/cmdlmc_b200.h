@@ -133,6 +133,18 @@ int cmd_rates(int kind, const double h_par[CMD_RATE_NPAR], const double *h_x,
 int cmd_rates_dev(int kind, const double h_par[CMD_RATE_NPAR], const double *d_x,
                   const double *d_theta, int64_t n, double *d_out);
 
+/* ---------------------------------------------------------------- trajectory staging ---- */
+/* Page-locked host buffers for trajectory chunks -- what the reference's chunked readers
+ * (mdlmc/IO/trajectory_parser.py:296,322: 1000-frame chunks out of HDF5) should fill so that the
+ * upload of chunk i+1 overlaps the kernels of chunk i.  Any other host pointer is accepted
+ * everywhere too and goes through the library's own staging ring (3 x 8 MiB, page-locked,
+ * CMDLMC_B200_STAGE_THREADS host threads, default 4). */
+int cmd_host_alloc(size_t bytes, void **out);
+int cmd_host_free(void *p);
+/* bytes uploaded through the ring / straight from page-locked memory since the library was
+ * loaded, and the number of host copy threads (0 before the ring's first use) */
+int cmd_staging_stats(uint64_t *staged_bytes, uint64_t *direct_bytes, int *threads);
+
 /* ---------------------------------------------------------------- neighbour topology ---- */
 /* A cmd_topo owns, in HBM, the neighbour lists and jump rates of a block of frames:
  *   frame f -> P_f directed pairs stored at [f * stride, f * stride + P_f) of
@@ -164,7 +176,10 @@ int cmd_topo_path(const cmd_topo *t);
  * previous block are overwritten. */
 int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t nframes);
 /* Same with host frames: uploads, then builds.  dtype_bytes is 8 (float64) or 4 (float32, as
- * stored by HDF5Trajectory, IO/trajectory_parser.py:324, up-cast on the device). */
+ * stored by HDF5Trajectory, IO/trajectory_parser.py:324, up-cast on the device).  Page-locked
+ * blocks (cmd_host_alloc) are copied from directly and the call returns while the DMA runs;
+ * pageable blocks pass through the library's page-locked staging ring (the host copy of one piece
+ * overlaps the DMA of the previous one and the kernels of the chunk before). */
 int cmd_topo_build(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes);
 /* Frame-block sharding across GPUs: walks a block of frames that precedes this rank's own block
  * through the Verlet displacement / rebuild-decision pass only (topology.py:96-107) and builds

@@ -201,6 +201,33 @@ def test_cell_list_path_equals_dense(orc, cfg, nfr):
             np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize("cfg,path,mode", [("C2", 0, 0), ("C2", 0, 1), ("C3", 1, 0), ("C4", 1, 0)])
+def test_structural_zeros_of_the_cell_matrix_change_no_bit(monkeypatch, cfg, path, mode):
+    """C2/C4 (monoclinic, four non-zero entries) and C3 (upper-triangular h) take the shortened
+    matrix products of pbc.cuh matvec3_norm_sp; CMDLMC_B200_NO_SPARSE=1 forces the full products of
+    math_helper.pyx:50-60.  Lists, distances and rates have to agree bit for bit."""
+    from cmdlmc_b200.topology import DeviceTopology, build_with_retry
+    import cmdlmc_b200 as cm
+    w = synth.workload(cfg)
+    nfr = 12
+    frames = synth.trajectory(w, nfr)
+    box = make_box(w.cell)
+    rate = cm.Fermi(*w.rate_params) if w.rate_kind == "Fermi" else cm.ActivationEnergy(*w.rate_params)
+    res = []
+    for full in (False, True):
+        if full:
+            monkeypatch.setenv("CMDLMC_B200_NO_SPARSE", "1")
+        else:
+            monkeypatch.delenv("CMDLMC_B200_NO_SPARSE", raising=False)
+        t = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, mode, rate,
+                                                        cap, path=path), frames)
+        counts = t.frame_info()[0]
+        res.append([t.get_frame(f, int(counts[f])) for f in range(nfr)])
+    for fa, fb in zip(*res):
+        for a, b in zip(fa, fb):
+            np.testing.assert_array_equal(a, b)
+
+
 @pytest.mark.parametrize("cfg,nfr", [("C3", 3)])
 def test_large_box_vs_oracle(orc, cfg, nfr):
     """C3: 2048 O in a triclinic cell, activation-energy rate -- cell-list path vs the oracle's
