@@ -464,6 +464,12 @@ def run_b200(args):
 
     e2e32_ms = e2e_leg(host32.data_ptr(), 4)
     e2e64_ms = e2e_leg(host.data_ptr(), 8)
+    # a caller that hands over plain (pageable) NumPy memory: the library's page-locked staging ring
+    pageable32 = host32.numpy().copy()
+    st0 = runtime.staging_stats()
+    e2e_page_ms = e2e_leg(pageable32.ctypes.data, 4)
+    st1 = runtime.staging_stats()
+    del pageable32
 
     # the hardware ceiling of that step: the bare pinned host -> device copies, all ranks at once
     def h2d_ceiling(src):
@@ -485,8 +491,8 @@ def run_b200(args):
     del host32
 
     # max over ranks
-    ms_total, e2e32_ms, e2e64_ms, kernel_ms, copy32_ms, copy64_ms = R.max(
-        [ms_total, e2e32_ms, e2e64_ms, kernel_ms, copy32_ms, copy64_ms])
+    ms_total, e2e32_ms, e2e64_ms, kernel_ms, copy32_ms, copy64_ms, e2e_page_ms = R.max(
+        [ms_total, e2e32_ms, e2e64_ms, kernel_ms, copy32_ms, copy64_ms, e2e_page_ms])
     value = world * K * B * ppf / (ms_total * 1e-3)
 
     # ---- roofline of the dominant kernel (k_pairs_dense) --------------------------------------
@@ -534,6 +540,13 @@ def run_b200(args):
                     "trajectory_parser.py:324) + cmd_topo_frame_info")
     e2e["f64_frames"] = e2e_block(e2e64_ms, in_bytes, copy64_ms,
                                   "the same calls on float64 host frames")
+    e2e["pageable_f32_frames"] = {
+        "value": world * K * B * ppf / (e2e_page_ms * 1e-3), "unit": UNIT,
+        "ms_per_step": e2e_page_ms / K, "h2d_bytes_per_step": in_bytes // 2,
+        "host_gbs_per_rank": in_bytes / 2 / (e2e_page_ms / K * 1e-3) / 1e9,
+        "ring_bytes_staged": int(st1[0] - st0[0]), "ring_host_threads": int(st1[2]),
+        "api": "the same calls on a plain NumPy array: cmd_topo_build stages it through the library's "
+               "page-locked ring (csrc/staging.cu)"}
     e2e["numa"] = dict(numa, bound_node=numa_node)
     e2e["note"] = ("h2d_only_ms_per_step = the bare pinned host->device copies of the same bytes on all "
                    "ranks at once: the hardware ceiling of the step on this host")

@@ -72,6 +72,7 @@ SIGNATURES = {
     "cmd_topo_skip": (C.c_int, [vp, vp, C.c_int, C.c_int64]),
     "cmd_topo_frame_info": (C.c_int, [vp, lp, u8p, dp]),
     "cmd_topo_stride": (C.c_int64, [vp]),
+    "cmd_topo_capacity_needed": (C.c_int64, [vp]),
     "cmd_topo_n_images": (C.c_int, [vp]),
     "cmd_topo_nframes": (C.c_int64, [vp]),
     "cmd_topo_get_frame": (C.c_int, [vp, C.c_int64, ip, ip, dp, dp]),

@@ -116,32 +116,28 @@ class AtomBox:
                                                         C.byref(idx), C.byref(dist)))
         return idx.value, dist.value
 
-    # -- PBCHelper.pyx:187-196
     def determine_phosphorus_oxygen_pairs(self, oxygen_atoms, phosphorus_atoms):
-        oxygen_atoms = as_f64(oxygen_atoms)
-        n_ext = oxygen_atoms.shape[0] * int(np.prod(self.box_multiplier))
-        neighbors = np.zeros(n_ext, np.int32)
-        for oxygen_index in range(n_ext):
-            neighbors[oxygen_index], _ = self.next_neighbor_extended_box(
-                oxygen_index, oxygen_atoms, phosphorus_atoms)
-        return neighbors
+        """int32 [oxygens of the extended box]: the phosphorus of the extended box each of them is
+        closest to (same result as PBCHelper.pyx:187-196)."""
+        oxygens = as_f64(oxygen_atoms)
+        count = oxygens.shape[0] * int(np.prod(self.box_multiplier))
+        nearest = (self.next_neighbor_extended_box(k, oxygens, phosphorus_atoms)[0] for k in range(count))
+        return np.fromiter(nearest, dtype=np.int32, count=count)
 
-    # -- PBCHelper.pyx:198-211
     def get_acidic_proton_indices(self, atoms, verbose=False):
-        """Expects numpy array 'atoms' of dtype 'xyz_dtype'"""
-        acidic_indices = []
-        protons = atoms[atoms["name"] == "H"]
-        proton_indices, = np.where(atoms["name"] == "H")
-        all_other_atoms = atoms[atoms["name"] != "H"]
-        other_pos = as_f64(all_other_atoms["pos"])
-        for i, single_proton in enumerate(protons):
-            nn_index, _ = self.next_neighbor(single_proton["pos"], other_pos)
-            if all_other_atoms["name"][nn_index] == "O":
-                acidic_indices.append(proton_indices[i])
+        """Indices (into `atoms`, a record array with 'name' and 'pos') of the hydrogens whose
+        nearest heavy atom is an oxygen (same result as PBCHelper.pyx:198-211), from one
+        all-to-all distance matrix on the device."""
+        is_h = atoms["name"] == "H"
+        heavy = atoms[~is_h]
+        if not is_h.any() or heavy.size == 0:
+            return []
+        dist = self.length_all_to_all(as_f64(atoms["pos"][is_h]), as_f64(heavy["pos"]))
+        bonded_to_oxygen = heavy["name"][np.argmin(dist, axis=1)] == "O"
+        acidic = [int(i) for i in np.flatnonzero(is_h)[bonded_to_oxygen]]
         if verbose:
-            print("# Acidic indices: ", acidic_indices)
-            print("# Number of acidic protons: ", len(acidic_indices))
-        return acidic_indices
+            print("# %d acidic protons: %s" % (len(acidic), acidic))
+        return acidic
 
 
 class AtomBoxCubic(AtomBox):

@@ -37,6 +37,7 @@ struct cmd_topo {
     int filt;        // FILT_* variant the dense kernel runs with
     int mode;
     int64_t stride;  // per-frame pair capacity
+    int64_t capacity_needed;   // directed pairs of the frame that overflowed (last CMD_ECAPACITY)
     int hit_cap;     // filter candidates per frame that fit the CTA's shared-memory list
     size_t smem_bytes;
     int threads;
@@ -1186,6 +1187,7 @@ static int topo_check_capacity(cmd_topo *t)
     CMD_CUDA(cudaStreamSynchronize(st));
     if (err > 0) {
         CMD_CUDA(cudaMemsetAsync(t->d_err, 0, sizeof(int), st));
+        t->capacity_needed = err;
         return cmd_set_error(CMD_ECAPACITY, "a frame has %d directed pairs but the per-frame "
                              "capacity is %lld: re-create the topology with a larger "
                              "capacity_per_frame", err, (long long)t->stride);
@@ -1629,6 +1631,7 @@ extern "C" int cmd_topo_set_path(cmd_topo *t, int path)
 extern "C" int cmd_topo_path(const cmd_topo *t) { return t ? t->path : -1; }
 
 extern "C" int64_t cmd_topo_stride(const cmd_topo *t) { return t ? t->stride : -1; }
+extern "C" int64_t cmd_topo_capacity_needed(const cmd_topo *t) { return t ? t->capacity_needed : -1; }
 extern "C" int cmd_topo_n_images(const cmd_topo *t) { return t ? t->bx.n_img : -1; }
 extern "C" int64_t cmd_topo_nframes(const cmd_topo *t) { return t ? t->nframes : -1; }
 

@@ -50,37 +50,32 @@ def launch_count():
     return int(_abi.lib().cmd_launch_count())
 
 
-class _PinnedBlock:
-    """Owner of one cmd_host_alloc buffer; exposes the buffer protocol through ctypes."""
-
-    def __init__(self, nbytes):
-        import ctypes as C
-        self._ptr = C.c_void_p()
-        _abi.check(_abi.lib().cmd_host_alloc(int(nbytes), C.byref(self._ptr)))
-        self.nbytes = int(nbytes)
-        self.buf = (C.c_ubyte * self.nbytes).from_address(self._ptr.value)
-
-    def __del__(self):
-        p = getattr(self, "_ptr", None)
-        if p is not None and p.value:
-            try:
-                _abi.lib().cmd_host_free(p)
-            except Exception:
-                pass
-            self._ptr = None
+def _host_free(address):
+    import ctypes as C
+    try:
+        _abi.lib().cmd_host_free(C.c_void_p(address))
+    except Exception:
+        pass
 
 
 def pinned_empty(shape, dtype):
     """NumPy array in page-locked host memory (cmd_host_alloc): what a trajectory reader should fill
     so that cmd_topo_build copies from it directly and the copy overlaps the kernels
     (trajectory_parser.py:296,322 reads its 1000-frame chunks into plain arrays).  The memory is
-    freed when the last array referring to it goes away."""
+    freed when the last array (or view) referring to it goes away."""
+    import ctypes as C
+    import weakref
     import numpy as np
     ensure_init()
     dtype = np.dtype(dtype)
-    n = int(np.prod(shape)) * dtype.itemsize
-    block = _PinnedBlock(max(n, 1))
-    return np.frombuffer(block.buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    count = int(np.prod(shape))
+    nbytes = max(count * dtype.itemsize, 1)
+    p = C.c_void_p()
+    _abi.check(_abi.lib().cmd_host_alloc(nbytes, C.byref(p)))
+    buf = (C.c_ubyte * nbytes).from_address(p.value)
+    # the arrays keep `buf` alive through the buffer protocol; the allocation follows its lifetime
+    weakref.finalize(buf, _host_free, p.value)
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
 
 def staging_stats():

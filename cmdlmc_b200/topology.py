@@ -107,6 +107,12 @@ class DeviceTopology:
         return int(_abi.lib().cmd_topo_stride(self._handle))
 
     @property
+    def capacity_needed(self):
+        """Directed pairs of the largest frame of a block that overflowed the per-frame capacity
+        (0 when no build has returned CMD_ECAPACITY)."""
+        return int(_abi.lib().cmd_topo_capacity_needed(self._handle))
+
+    @property
     def n_images(self):
         """Periodic images the pair filter evaluates besides the wrapped vector."""
         return int(_abi.lib().cmd_topo_n_images(self._handle))
@@ -231,9 +237,7 @@ def build_with_retry(make, frames):
         except _abi.CmdError as e:
             if e.code != -5:
                 raise
-            import re
-            m = re.search(r"has (\d+) directed pairs", str(e))
-            need = int(m.group(1)) if m else max(64, topo.stride * 2)
+            need = topo.capacity_needed or max(64, topo.stride * 2)
             capacity = need + need // 4 + 64
     raise RuntimeError("could not size the per-frame pair capacity")
 

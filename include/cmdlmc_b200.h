@@ -192,6 +192,9 @@ int cmd_topo_skip(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nf
 int cmd_topo_frame_info(const cmd_topo *t, int64_t *h_counts, uint8_t *h_rebuilt,
                         double *h_rate_sum);
 int64_t cmd_topo_stride(const cmd_topo *t);
+/* After a build returned CMD_ECAPACITY: the number of directed pairs of the largest frame seen,
+ * i.e. the per-frame capacity a re-created topology needs at least (0: no overflow so far). */
+int64_t cmd_topo_capacity_needed(const cmd_topo *t);
 /* Number of periodic images, besides the fractionally wrapped vector, that the pair filter of
  * this topology evaluates (general cells; depends on cutoff + buffer against the cell heights). */
 int cmd_topo_n_images(const cmd_topo *t);

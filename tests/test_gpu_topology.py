@@ -180,6 +180,39 @@ def test_float32_frames_and_full_size_properties():
         assert (omega > 0).all() and (omega <= w.rate_params[0]).all()
 
 
+@pytest.mark.parametrize("mode,dtype", [(0, np.float64), (0, np.float32), (1, np.float32)])
+def test_pageable_blocks_go_through_the_staging_ring(mode, dtype):
+    """A plain NumPy block (pageable) is staged through the library's page-locked ring, a block in
+    runtime.pinned_empty memory is copied from directly; both give the same lists.  The block is
+    larger than the ring (3 x 8 MiB), so slots are recycled while their DMA is in flight."""
+    from cmdlmc_b200 import runtime
+    from cmdlmc_b200.topology import DeviceTopology, build_with_retry
+    import cmdlmc_b200 as cm
+    w = synth.workload("C2")
+    nfr = 6144 if dtype == np.float32 else 3072            # 29.5 MB either way
+    frames = np.ascontiguousarray(synth.trajectory(w, nfr).astype(dtype))
+    box = make_box(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    make = lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, mode, rate, cap)
+    s0 = runtime.staging_stats()
+    tp = build_with_retry(make, frames)
+    s1 = runtime.staging_stats()
+    assert s1[0] - s0[0] >= frames.nbytes and s1[2] >= 1      # went through the ring
+    pinned = runtime.pinned_empty(frames.shape, dtype)
+    pinned[...] = frames
+    tq = build_with_retry(make, pinned)
+    s2 = runtime.staging_stats()
+    assert s2[0] == s1[0] and s2[1] - s1[1] >= frames.nbytes  # copied from directly
+    cp, rp_, sp = tp.frame_info()
+    cq, rq, sq = tq.frame_info()
+    np.testing.assert_array_equal(cp, cq)
+    np.testing.assert_array_equal(rp_, rq)
+    np.testing.assert_array_equal(sp, sq)
+    for f in (0, nfr // 2, nfr - 1):
+        for a, b in zip(tp.get_frame(f, int(cp[f])), tq.get_frame(f, int(cq[f]))):
+            np.testing.assert_array_equal(a, b)
+
+
 @pytest.mark.parametrize("cfg,nfr", [("C1", 6), ("C2", 6), ("C4", 3)])
 def test_cell_list_path_equals_dense(orc, cfg, nfr):
     """The cell-list search (large boxes) and the dense search give the same arrays, bit for bit."""
