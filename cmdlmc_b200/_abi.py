@@ -73,6 +73,7 @@ SIGNATURES = {
     "cmd_topo_frame_info": (C.c_int, [vp, lp, u8p, dp]),
     "cmd_topo_stride": (C.c_int64, [vp]),
     "cmd_topo_capacity_needed": (C.c_int64, [vp]),
+    "cmd_topo_skin_stats": (C.c_int, [vp, lp, lp, lp]),
     "cmd_topo_n_images": (C.c_int, [vp]),
     "cmd_topo_nframes": (C.c_int64, [vp]),
     "cmd_topo_get_frame": (C.c_int, [vp, C.c_int64, ip, ip, dp, dp]),
@@ -149,6 +150,8 @@ def lib():
                 "cmdlmc_b200 has no CPU fallback." % LIB_PATH)
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if "CMDLMC_B200_LIB" in os.environ and not hasattr(L, name):
+                continue   # A/B test against an older build: newer entry points are simply absent
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

@@ -69,6 +69,9 @@ struct cmd_topo {
     double *d_dist, *d_omega, *d_rate_sum;
     uint8_t *d_rebuilt;
     unsigned long long *d_ties;
+    unsigned *d_lists;     // skin lists of the dense kernel's persistent CTAs (pairs_dense.cuh)
+    size_t lists_words;
+    int cap_l;             // entries per CTA
     // Verlet state carried across blocks
     bool have_last;
     double *d_last, *d_displacement, *d_dr;
@@ -647,7 +650,7 @@ extern "C" void cmd_topo_destroy(cmd_topo *t)
     cudaFree(t->d_err); cudaFree(t->d_ties); cudaFree(t->d_last); cudaFree(t->d_displacement);
     cudaFree(t->d_carry_start); cudaFree(t->d_carry_dest); cudaFree(t->d_carry_count);
     cudaFree(t->d_carry_rowoff);
-    cudaFree(t->d_sched); cudaFree(t->d_upload); cudaFree(t->d_cap_need);
+    cudaFree(t->d_sched); cudaFree(t->d_upload); cudaFree(t->d_cap_need); cudaFree(t->d_lists);
     cudaFree(t->d_group); cudaFree(t->d_extra_upload);
     cell_free(t);
     free(t);
@@ -730,6 +733,31 @@ static void topo_filter_params(cmd_topo *t)
         // by <= radius / height * 1024 + 1 units of the 10-bit coordinates (two roundings) and
         // by at most ceil(that / 4) + 1 bins.  Forward windows of two rows cannot both hold the
         // other row while 2 db < 256; it pays while the window is well below half the atoms.
+        // skin list (pairs_dense.cuh): the same filter at radius + skin, valid under the same
+        // conditions -- including that no periodic image besides the wrapped vector matters out
+        // to that radius -- plus the FP32 displacement test on 16-bit fractional coordinates
+        // (error per displacement <= 2 units of every coordinate: two roundings of half a unit,
+        // FP32 noise far below).
+        {
+            static const char *sk = getenv("CMDLMC_B200_DENSE_SKIN");
+            const double skin = sk ? atof(sk) : 0.6;
+            const double rm = radius + skin;
+            const double lim_m = (rm + E) * (rm + E) * 1.0015 + 1e-6;
+            __half htm = __float2half_ru((float)lim_m);
+            fp.hT2m = *reinterpret_cast<const unsigned short *>(&htm) * 0x00010001u;
+            BoxParams wide = bx;
+            cmd_box_prune_images(wide, rm * (1.0 + 1e-9) + 1e-9);
+            double e16 = 0;
+            for (int r = 0; r < 3; r++) {
+                double qr = 0;
+                for (int c = 0; c < 3; c++) if (rows[r][c] >= 0) qr += fabs(rr[rows[r][c]]) / 65536.0;
+                e16 += qr * qr;
+            }
+            for (int k = 0; k < 6; k++) fp.R16[k] = (float)(rr[k] / 65536.0);
+            fp.skin_eff = (float)(skin - 2.0 * (2.0 * sqrt(e16)) * 1.001 - 1e-4 * (1.0 + rsum * 1e-2));
+            fp.coh_ok = fp.h2_ok && skin > 0 && wide.n_img == 0 && lim_m < 60000.0 && fp.skin_eff > 0 &&
+                        hmin * (0.5 - 2.0 * u10) > rm + E;
+        }
         int axis = 0;
         double hbest = 0;
         for (int c = 0; c < 3; c++) {
@@ -740,9 +768,14 @@ static void topo_filter_params(cmd_topo *t)
         const int db = (int)ceil((radius / hbest * 1024.0 + 1.0) / 4.0) + 1;
         fp.sort_axis = -1;
         fp.sort_db = 0;
+        fp.sort_db_m = 0;
         if (db <= 100 && t->n >= 96 && getenv("CMDLMC_B200_DENSE_NOSORT") == nullptr) {
             fp.sort_axis = axis;
             fp.sort_db = db;
+            static const char *sk = getenv("CMDLMC_B200_DENSE_SKIN");
+            const double rm = radius + (sk ? atof(sk) : 0.6);
+            fp.sort_db_m = (int)ceil((rm / hbest * 1024.0 + 1.0) / 4.0) + 1;
+            if (fp.sort_db_m > 100) fp.coh_ok = 0;
         }
     }
     t->filt = fp.h2_ok ? FILT_H2 : bx.n_img == 0 ? FILT_F32 : FILT_F32_IMG;
@@ -894,7 +927,7 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
         return cmd_set_error(CMD_ENOMEM, "cudaMalloc failed for %s", #ptr);      \
     }
     TALLOC(t->d_err, sizeof(int));
-    TALLOC(t->d_ties, sizeof(unsigned long long));
+    TALLOC(t->d_ties, 4 * sizeof(unsigned long long));   // [0] ties, [1..3] skin-list statistics
     TALLOC(t->d_last, (size_t)n * 24);
     TALLOC(t->d_displacement, (size_t)n * 8);
     TALLOC(t->d_carry_count, sizeof(int));
@@ -902,7 +935,7 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
     TALLOC(t->d_cap_need, sizeof(int));
     cudaStream_t st = cmd_global().stream;
     CMD_CUDA(cudaMemsetAsync(t->d_err, 0, sizeof(int), st));
-    CMD_CUDA(cudaMemsetAsync(t->d_ties, 0, sizeof(unsigned long long), st));
+    CMD_CUDA(cudaMemsetAsync(t->d_ties, 0, 4 * sizeof(unsigned long long), st));
     CMD_CUDA(cudaMemsetAsync(t->d_displacement, 0, (size_t)n * 8, st));
     CMD_CUDA(cudaMemsetAsync(t->d_carry_count, 0, sizeof(int), st));
     CMD_CUDA(cudaMemsetAsync(t->d_cap_need, 0, sizeof(int), st));
@@ -913,6 +946,27 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
     return CMD_OK;
 }
 
+// Skin lists: one per persistent CTA, 3x the exact stage's candidate capacity (the list is taken at
+// radius + skin: (1 + skin / radius)^3 times the candidates; a list that does not fit only costs the
+// frame the direct path).
+static int dense_lists_reserve(cmd_topo *t, int64_t ctas, int hit_cap)
+{
+    const int cap_l = 3 * hit_cap;
+    const size_t words = (size_t)ctas * cap_l;
+    if (t->d_lists && t->lists_words >= words && t->cap_l == cap_l) return CMD_OK;
+    CMD_CUDA(cudaStreamSynchronize(cmd_global().stream));
+    cudaFree(t->d_lists);
+    t->d_lists = nullptr;
+    t->lists_words = 0;
+    if (cudaMalloc((void **)&t->d_lists, words * 4) != cudaSuccess) {
+        cudaGetLastError();
+        return cmd_set_error(CMD_ENOMEM, "cudaMalloc of %zu skin-list bytes failed", words * 4);
+    }
+    t->lists_words = words;
+    t->cap_l = cap_l;
+    return CMD_OK;
+}
+
 static int launch_dense(cmd_topo *t, const double *d_frames, const int *ids, const int *n_ids,
                         int64_t grid, int *start, int *dest, double *dist, double *omega,
                         int *counts, double *rate_sum, uint8_t *rebuilt, int *rowoff,
@@ -920,6 +974,9 @@ static int launch_dense(cmd_topo *t, const double *d_frames, const int *ids, con
 {
     cudaStream_t st = cmd_global().stream;
     const bool ortho = t->bx.kind == 0;
+    // the skin list needs consecutive frames of one trajectory: contiguous items, at least a few
+    // frames per CTA (CMDLMC_B200_DENSE_SKIN=0 switches it off)
+    const bool use_skin = t->fp.coh_ok && ids == nullptr && grid >= 4 * (int64_t)cmd_global().sm_count;
     // persistent CTAs: as many as are resident at once, each walking its share of the frames
 #define DENSE_LAUNCH(K, IM, SP, MT, MB)                                                          \
     do {                                                                                         \
@@ -930,10 +987,17 @@ static int launch_dense(cmd_topo *t, const double *d_frames, const int *ids, con
             &nb_, k_pairs_dense<K, IM, SP, MT, MB>, t->threads * SP, smem));                     \
         int64_t pgrid = (int64_t)cmd_global().sm_count * (nb_ > 0 ? nb_ : 1);                    \
         if (pgrid > grid) pgrid = grid;                                                          \
+        unsigned *lists_ = nullptr;                                                              \
+        if (IM == FILT_H2 && use_skin) {                                                         \
+            int rc_ = dense_lists_reserve(t, pgrid, hit_cap);                                    \
+            if (rc_) return rc_;                                                                 \
+            lists_ = t->d_lists;                                                                 \
+        }                                                                                        \
         k_pairs_dense<K, IM, SP, MT, MB><<<(unsigned)pgrid, t->threads * SP, smem, st>>>(        \
             t->bx, t->rate, t->fp, d_frames, ids, n_ids, (int)grid, t->n, t->rc, t->t2, stride,  \
             hit_cap,                                                                             \
-            start, dest, dist, omega, counts, rate_sum, rebuilt, rowoff, t->d_err, t->d_ties);   \
+            start, dest, dist, omega, counts, rate_sum, rebuilt, rowoff, t->d_err, t->d_ties,    \
+            lists_, t->cap_l, dense_layout(t->n, hit_cap, IM));                                  \
     } while (0)
 #define DENSE_PICK(SP, MT, MB)                                                                   \
     do {                                                                                         \
@@ -1105,7 +1169,7 @@ static int topo_autosize(cmd_topo *t, const double *d_frame)
     CMD_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
     CMD_CUDA(cudaStreamSynchronize(st));
     CMD_CUDA(cudaMemsetAsync(t->d_err, 0, sizeof(int), st));
-    CMD_CUDA(cudaMemsetAsync(t->d_ties, 0, sizeof(unsigned long long), st));
+    CMD_CUDA(cudaMemsetAsync(t->d_ties, 0, 4 * sizeof(unsigned long long), st));
     int64_t p0 = cnt < 0 ? -cnt : cnt;
     int64_t want = p0 + p0 / 2 + 128;
     // prefer the dense kernel: shrink the head-room to what its shared-memory lists can hold
@@ -1979,6 +2043,20 @@ extern "C" int cmd_topo_distance_histogram(const cmd_topo *t, double lo, double 
     if (e == cudaSuccess) for (int b = 0; b < nbins; b++) h_hist[b] += tmp[b];
     free(tmp);
     CMD_CUDA(e);
+    return CMD_OK;
+}
+
+extern "C" int cmd_topo_skin_stats(const cmd_topo *t, int64_t *frames, int64_t *rebuilds, int64_t *list_entries)
+{
+    CMD_REQUIRE_INIT();
+    if (!t) return cmd_set_error(CMD_EINVAL, "bad argument");
+    unsigned long long v[4] = {0, 0, 0, 0};
+    cudaStream_t st = cmd_global().stream;
+    CMD_CUDA(cudaMemcpyAsync(v, t->d_ties, sizeof(v), cudaMemcpyDeviceToHost, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
+    if (frames) *frames = (int64_t)v[2];
+    if (rebuilds) *rebuilds = (int64_t)v[1];
+    if (list_entries) *list_entries = (int64_t)v[3];
     return CMD_OK;
 }
 

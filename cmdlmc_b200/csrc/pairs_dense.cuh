@@ -48,6 +48,12 @@ struct FilterParams {
     int sort_axis;     // fractional axis the atoms are binned along (-1: no spatial pruning)
     int sort_db;       // window: a pair within the radius is at most this many bins (of 256) apart
     int wpre_ok;       // the popc prefix table fits the dead coordinate + column buffers
+    // skin list (frame-to-frame coherence of the candidate set, FILT_H2 only)
+    int coh_ok;        // the 10-bit filter is valid at radius + skin as well
+    unsigned hT2m;     // widened (radius + skin)^2, half2, rounded up
+    int sort_db_m;     // bin window for radius + skin
+    float R16[6];      // R * 2^-16: displacement of an atom from 16-bit fractional coordinates
+    float skin_eff;    // skin minus the error bound of two such displacements
 };
 
 struct DenseSmem {
@@ -65,6 +71,7 @@ struct DenseSmem {
     int *misc;              // [0] ncand, [1] total, [2..33] warp sums
     int *bins;              // [258] atoms per sort bin -> exclusive prefix (FILT_H2)
     unsigned short *perm;   // [n] sorted position -> atom (FILT_H2)
+    ushort4 *ref16;         // [n] 16-bit fractional coordinates of the frame the skin list was built on
 };
 
 __host__ __device__ inline size_t dense_al16(size_t b) { return (b + 15) / 16 * 16; }
@@ -78,7 +85,8 @@ __host__ __device__ inline size_t dense_mask_bytes(int n)
 {
     const int W = (n + 31) / 32;
     size_t m = (size_t)n * W * 4;
-    if (m < (size_t)n * 8) m = (size_t)n * 8;   // the 10-bit coordinates are parked here
+    if (m < (size_t)n * 24) m = (size_t)n * 24;   // the 10-bit coordinates are parked here: by sorted
+                                                  // position, by atom, and the row constants by atom
     return dense_al16(m);
 }
 
@@ -86,7 +94,8 @@ __host__ __device__ inline size_t dense_mask_bytes(int n)
 __host__ __device__ inline size_t dense_smem_fixed(int n, int filt)
 {
     return dense_al16(3 * (size_t)n * 8) + dense_col_bytes(n, filt) + 40 * 8 + dense_mask_bytes(n) +
-           dense_al16(((size_t)n + 1) * 4) + 40 * 4 + 264 * 4 + dense_al16((size_t)n * 2) + 16;
+           dense_al16(((size_t)n + 1) * 4) + 40 * 4 + 264 * 4 + dense_al16((size_t)n * 2) + 16 +
+           (filt == FILT_H2 ? (size_t)n * 8 : 0);
 }
 #define DENSE_BYTES_PER_CAND 16   // hit_d 8 + hit_ij 4 + 2 slots of 2
 
@@ -101,7 +110,7 @@ __host__ __device__ inline size_t dense_smem_bytes(int n, int cap, int filt)
     return dense_smem_fixed(n, filt) + (size_t)cap * DENSE_BYTES_PER_CAND;
 }
 
-__device__ __forceinline__ DenseSmem dense_carve(unsigned char *base, int n, int cap, int filt)
+__host__ __device__ __forceinline__ DenseSmem dense_carve(unsigned char *base, int n, int cap, int filt)
 {
     DenseSmem s;
     const size_t A = dense_al16(3 * (size_t)n * 8), B = dense_col_bytes(n, filt);
@@ -121,7 +130,35 @@ __device__ __forceinline__ DenseSmem dense_carve(unsigned char *base, int n, int
     s.misc = (int *)p;
     s.bins = s.misc + 40;
     s.perm = (unsigned short *)(s.bins + 264);
+    s.ref16 = (ushort4 *)((unsigned char *)s.perm + dense_al16((size_t)n * 2) + 16);
     return s;
+}
+
+// The same carve as byte offsets, prepared on the host and handed to the kernel as a
+// __grid_constant__ parameter: a shared-memory address is then one constant-bank operand instead of
+// a chain of integer instructions on n and the capacity at every use.
+struct DenseLayout {
+    unsigned c, col, hit_d, red, mask, hit_ij, slot, rowoff, misc, bins, perm, ref16;
+    int W;          // mask words per row
+    int om_split;   // doubles that fit the mask's place (the rates of the fused emit pass)
+    int fused;      // the rates of all candidates fit the dead mask + column buffers
+    int park_hd;    // the quantised coordinates fit the (then dead) distance buffer
+};
+
+static inline DenseLayout dense_layout(int n, int cap, int filt)
+{
+    unsigned char *base = nullptr;
+    const DenseSmem s = dense_carve(base, n, cap, filt);
+    auto off = [&](const void *p) { return (unsigned)((const unsigned char *)p - base); };
+    DenseLayout l;
+    l.c = off(s.c); l.col = off(s.col); l.hit_d = off(s.hit_d); l.red = off(s.red);
+    l.mask = off(s.mask); l.hit_ij = off(s.hit_ij); l.slot = off(s.slot); l.rowoff = off(s.rowoff);
+    l.misc = off(s.misc); l.bins = off(s.bins); l.perm = off(s.perm); l.ref16 = off(s.ref16);
+    l.W = (n + 31) / 32;
+    l.om_split = (int)(dense_mask_bytes(n) / 8);
+    l.fused = (size_t)cap <= dense_mask_bytes(n) / 8 + dense_col_bytes(n, filt) / 8;
+    l.park_hd = (size_t)cap * 8 >= (size_t)n * 24;
+    return l;
 }
 
 // exclusive scan of one int per thread over the CTA; returns the exclusive prefix, total in *tot
@@ -240,11 +277,25 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
               double *__restrict__ out_omega, int *__restrict__ out_counts,
               double *__restrict__ out_rate_sum, uint8_t *__restrict__ out_rebuilt,
               int *__restrict__ out_rowoff, int *__restrict__ err,
-              unsigned long long *__restrict__ ties)
+              unsigned long long *__restrict__ ties, unsigned *__restrict__ lists, int cap_l,
+              const __grid_constant__ DenseLayout lay)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DenseSmem s = dense_carve(smem_raw, n, hit_cap, FILT);
-    const int W = (n + 31) / 32;
+    DenseSmem s;
+    s.c = (double *)(smem_raw + lay.c);
+    s.col = (uint4 *)(smem_raw + lay.col);
+    s.wpre = (unsigned short *)(smem_raw + lay.c);
+    s.hit_d = (double *)(smem_raw + lay.hit_d);
+    s.red = (double *)(smem_raw + lay.red);
+    s.mask = (unsigned *)(smem_raw + lay.mask);
+    s.hit_ij = (unsigned *)(smem_raw + lay.hit_ij);
+    s.slot = (unsigned short *)(smem_raw + lay.slot);
+    s.rowoff = (int *)(smem_raw + lay.rowoff);
+    s.misc = (int *)(smem_raw + lay.misc);
+    s.bins = (int *)(smem_raw + lay.bins);
+    s.perm = (unsigned short *)(smem_raw + lay.perm);
+    s.ref16 = (ushort4 *)(smem_raw + lay.ref16);
+    const int W = lay.W;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int total_items = n_ids ? *n_ids : n_items;
     // The coordinates of a frame are one contiguous 24n-byte run in HBM; TMA (cp.async.bulk) drops
@@ -263,12 +314,23 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         mbar_expect_tx(bar, (uint32_t)n * 24u);
         tma_load_1d(s.c, frames + fn * (int64_t)n * 3, (uint32_t)n * 24u, bar);
     };
-    if (use_tma && tid == 0 && (int)blockIdx.x < total_items) prefetch(blockIdx.x);
+    // every CTA takes ONE contiguous run of the items: consecutive frames of a trajectory, so that
+    // the skin list of the packed-half filter carries over from frame to frame
+    // (without a list the CTAs interleave: the frames in flight are neighbours in HBM)
+    const int per_cta = total_items / (int)gridDim.x, extra_items = total_items % (int)gridDim.x;
+    const int item_step = lists ? 1 : (int)gridDim.x;
+    const int item_lo = lists ? (int)blockIdx.x * per_cta + min((int)blockIdx.x, extra_items) : (int)blockIdx.x;
+    const int item_hi = lists ? item_lo + per_cta + ((int)blockIdx.x < extra_items ? 1 : 0) : total_items;
+    if (use_tma && tid == 0 && item_lo < item_hi) prefetch(item_lo);
     unsigned tma_phase = 0;
     const int K = (n - 1) >> 1, half = n >> 1;
     const bool even = (n & 1) == 0;
+    // skin list state (CTA-uniform): the list in `my_list` was built on the frame in s.ref16
+    unsigned *my_list = lists ? lists + (size_t)blockIdx.x * cap_l : nullptr;
+    bool list_valid = false;
+    int n_list = 0;
 
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    for (int item = item_lo; item < item_hi; item += item_step) {
     const int64_t f = ids ? ids[item] : item;
     if (use_tma) {
         mbar_wait(bar, tma_phase & 1u);
@@ -297,16 +359,20 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         return __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
     };
     if (FILT == FILT_H2) {
-        // (a) 10-bit fractional coordinates, one atom per thread; counting sort of the atoms into
-        // 256 bins along the axis with the largest cell height.  A pair within the radius is at
-        // most sort_db bins apart, so a row only meets the columns that FOLLOW it in the sorted
-        // cyclic order up to that bin distance: each unordered pair once, ~2 rc / height of them.
+        if (!use_tma) __syncthreads();   // the plain loads of s.c
+        // (a) fractional coordinates in 10-bit fixed point (the filter) and in 16-bit fixed point
+        // (the displacement test of the skin list), one atom per thread
         const bool sorted = fp.sort_axis >= 0;
-        ushort4 *q16 = (ushort4 *)s.mask;          // by sorted position; the mask is not needed yet
-        if (sorted) for (int k = tid; k < 258; k += blockDim.x) s.bins[k] = 0;
-        __syncthreads();
-        unsigned q[3] = {0, 0, 0};
-        int key = 0, rnk = 0;
+        // the quantised coordinates are parked in the distance buffer of the exact stage (dead
+        // until then) -- then the adjacency mask can be cleared right away; a candidate list too
+        // short for that lends the mask's own space and is cleared after the filter
+        const bool park_hd = lay.park_hd != 0;
+        ushort4 *q16 = park_hd ? (ushort4 *)s.hit_d : (ushort4 *)s.mask;   // by sorted position
+        if (park_hd)
+            for (int k = tid; k < n * W; k += blockDim.x) s.mask[k] = 0u;
+        ushort4 *qa = q16 + n;                     // by atom: the coordinates
+        ushort4 *qc = qa + n;                      // by atom: (512 - coordinate) mod 1024
+        unsigned q[3] = {0, 0, 0}, r16[3] = {0, 0, 0};
         if (tid < n) {
             const double x = s.c[3 * tid], y = s.c[3 * tid + 1], z = s.c[3 * tid + 2];
 #pragma unroll
@@ -314,11 +380,62 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
                 const double v = KIND == 0 ? (c == 0 ? x : c == 1 ? y : z) * bx.hinv[4 * c]
                                            : fma(bx.hinv[3 * c + 2], z, fma(bx.hinv[3 * c + 1], y, bx.hinv[3 * c] * x));
                 q[c] = (unsigned)(unsigned long long)__double2ll_rn(v * 1024.0) & 1023u;
+                if (my_list) r16[c] = (unsigned)(unsigned long long)__double2ll_rn(v * 65536.0) & 65535u;
             }
-            if (sorted) {
-                key = (int)((fp.sort_axis == 0 ? q[0] : fp.sort_axis == 1 ? q[1] : q[2]) >> 2);
-                rnk = atomicAdd(&s.bins[key], 1);
+            if (my_list) {
+                qa[tid] = make_ushort4((unsigned short)q[0], (unsigned short)q[1], (unsigned short)q[2], 0);
+                qc[tid] = make_ushort4((unsigned short)((512u - q[0]) & 1023u), (unsigned short)((512u - q[1]) & 1023u),
+                                       (unsigned short)((512u - q[2]) & 1023u), 0);
             }
+        }
+        // (a') Skin list: the candidates of the frame the list was built on, taken with the radius
+        // widened by the skin, hold every pair of THIS frame that is within the radius as long as
+        // the two largest displacements since then sum to less than the skin (triangle inequality
+        // of the periodic metric; fp.skin_eff carries the error bound of the 16-bit coordinates).
+        bool rebuild = true;
+        if (my_list && list_valid) {
+            unsigned d2b = 0;
+            if (tid < n) {
+                const ushort4 rf = s.ref16[tid];
+                const float wx = (float)(short)(unsigned short)(r16[0] - rf.x);
+                const float wy = (float)(short)(unsigned short)(r16[1] - rf.y);
+                const float wz = (float)(short)(unsigned short)(r16[2] - rf.z);
+                const float vx = fmaf(fp.R16[2], wz, fmaf(fp.R16[1], wy, fp.R16[0] * wx));
+                const float vy = fmaf(fp.R16[4], wz, fp.R16[3] * wy);
+                const float vz = fp.R16[5] * wz;
+                d2b = __float_as_uint(fmaf(vz, vz, fmaf(vy, vy, vx * vx)));   // >= 0: ordered as integers
+            }
+            // the two largest of the CTA: per warp, then over the warps (every warp redundantly)
+            unsigned m1 = __reduce_max_sync(0xffffffffu, d2b);
+            const unsigned holder = __ballot_sync(0xffffffffu, d2b == m1);
+            unsigned m2 = __reduce_max_sync(0xffffffffu, lane == __ffs(holder) - 1 ? 0u : d2b);
+            unsigned *top = (unsigned *)s.red;
+            if (lane == 0) { top[2 * wid] = m1; top[2 * wid + 1] = m2; }
+            __syncthreads();
+            const int nw2 = 2 * (int)(blockDim.x >> 5);
+            unsigned v0 = lane < nw2 ? top[lane] : 0u, v1 = lane + 32 < nw2 ? top[lane + 32] : 0u;
+            // two values per lane -> top two over 64
+            unsigned hi = max(v0, v1), lo = min(v0, v1);
+            m1 = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned holder2 = __ballot_sync(0xffffffffu, hi == m1);
+            m2 = __reduce_max_sync(0xffffffffu, lane == __ffs(holder2) - 1 ? lo : hi);
+            rebuild = !(sqrtf(__uint_as_float(m1)) + sqrtf(__uint_as_float(m2)) <= fp.skin_eff);
+        }
+        // window filter of the sorted rows -> candidate pairs (atom indices) in dst[0 .. cap)
+        bool direct = my_list == nullptr;      // no skin list: the window filter feeds the exact stage
+        while (rebuild) {
+        const int db = direct ? fp.sort_db : fp.sort_db_m;
+        const __half2 hT2w = u2h2(direct ? fp.hT2 : fp.hT2m);
+        // counting sort of the atoms into 256 bins along the axis with the largest cell height.
+        // A pair within the radius is at most db bins apart, so a row only meets the columns that
+        // FOLLOW it in the sorted cyclic order up to that bin distance: each unordered pair once,
+        // ~2 rc / height of them.
+        if (sorted) for (int k = tid; k < 258; k += blockDim.x) s.bins[k] = 0;
+        __syncthreads();
+        int key = 0, rnk = 0;
+        if (tid < n && sorted) {
+            key = (int)((fp.sort_axis == 0 ? q[0] : fp.sort_axis == 1 ? q[1] : q[2]) >> 2);
+            rnk = atomicAdd(&s.bins[key], 1);
         }
         __syncthreads();
         if (sorted && wid == 0) {   // exclusive prefix over the 256 bins, eight per lane
@@ -365,7 +482,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
             C[1] = ((512u - me.y) & 1023u) * 0x00010001u;
             C[2] = ((512u - me.z) & 1023u) * 0x00010001u;
             if (sorted) {
-                const int e = (int)me.w + fp.sort_db;   // last bin of the window (inclusive)
+                const int e = (int)me.w + db;   // last bin of the window (inclusive)
                 len = (e < 256 ? s.bins[e + 1] : n + s.bins[e - 255]) - 1 - t;
             } else {
                 // offsets 1..K are owned by every row, offset n/2 (even n) by the lower half only
@@ -375,11 +492,9 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         }
         const unsigned my_tag = (unsigned)s.perm[t] << 16;
         __syncthreads();
-        for (int k = tid; k < n * W; k += blockDim.x) s.mask[k] = 0u;   // q16 is dead
         __half2 hR[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) hR[k] = u2h2(fp.hR[k]);
-        const __half2 hT2 = u2h2(fp.hT2);
         // (d) blocks of 32 offsets: entry pk[2u] holds the columns at offsets 1 + 2u (low half ->
         // hit bit u) and 2 + 2u (high half -> hit bit 16 + u) from the row
         const uint4 *pk = s.col + t + 1;
@@ -389,7 +504,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
 #pragma unroll
             for (int u = 0; u < 16; u++) {
                 const uint4 P = pk[32 * blk + 2 * u];
-                ha |= h2_pair_mask<KIND>(hR, hT2, P, C[0], C[1], C[2]) & (0x00010001u << u);
+                ha |= h2_pair_mask<KIND>(hR, hT2w, P, C[0], C[1], C[2]) & (0x00010001u << u);
             }
             const int rem = len - 32 * blk;                  // offsets 1..rem of this block are owned
             const int nlo = min(max((rem + 1) >> 1, 0), 16), nhi = min(max(rem >> 1, 0), 16);
@@ -402,9 +517,80 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
                 ha &= ha - 1;
                 int c = c0 + 2 * (b & 15) + (b >> 4);
                 if (c >= n) c -= n;
-                if (pos < hit_cap) s.hit_ij[pos] = my_tag | (unsigned)s.perm[c];
+                const unsigned e = my_tag | (unsigned)s.perm[c];
+                if (direct) { if (pos < hit_cap) s.hit_ij[pos] = e; }
+                else if (pos < cap_l) my_list[pos] = e;
                 pos++;
             }
+        }
+        if (direct) break;
+        // the skin list of this frame is complete: it becomes the reference -- unless it does not
+        // fit, then this frame goes the direct way and the next one tries again
+        __syncthreads();
+        n_list = s.misc[0];
+        __syncthreads();
+        if (tid == 0) s.misc[0] = 0;
+        list_valid = n_list <= cap_l;
+        if (!list_valid) { direct = true; continue; }
+        if (tid < n) s.ref16[tid] = make_ushort4((unsigned short)r16[0], (unsigned short)r16[1],
+                                                 (unsigned short)r16[2], 0);
+        __threadfence_block();
+        break;
+        }   // window filter
+        if (my_list && tid == 0) {   // statistics: frames, rebuilds, list entries filtered
+            atomicAdd(ties + 2, 1ull);
+            if (rebuild) atomicAdd(ties + 1, 1ull);
+            if (!direct) atomicAdd(ties + 3, (unsigned long long)n_list);
+        }
+        if (!direct) {
+            // (e) the skin list through the same packed-half filter at the radius itself, two
+            // candidates per thread (low / high halves); survivors -> the exact stage's list
+            __syncthreads();   // s.misc[0] == 0, my_list visible to the CTA
+            __half2 hR[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) hR[k] = u2h2(fp.hR[k]);
+            const __half2 hT2 = u2h2(fp.hT2);
+            const uint2 *qa2 = (const uint2 *)qa, *qc2 = (const uint2 *)qc;
+            const unsigned ltm = (1u << lane) - 1u;
+            // LIST_U double trips per round: their list loads (L2) are all in flight before the
+            // first one is used
+            constexpr int LIST_U = 4;
+            const int T = (int)blockDim.x;
+            for (int k0 = 0; k0 < n_list; k0 += 2 * LIST_U * T) {
+                unsigned ija[LIST_U], ijb[LIST_U];
+#pragma unroll
+                for (int u = 0; u < LIST_U; u++) {
+                    const int ka = k0 + 2 * u * T + tid, kb = ka + T;
+                    ija[u] = ka < n_list ? my_list[ka] : 0u;
+                    ijb[u] = kb < n_list ? my_list[kb] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < LIST_U; u++) {
+                    if (k0 + 2 * u * T >= n_list) break;         // CTA-uniform
+                    const int ka = k0 + 2 * u * T + tid, kb = ka + T;
+                    const bool va = ka < n_list, vb = kb < n_list;
+                    const uint2 Ca = qc2[ija[u] >> 16], Pa = qa2[ija[u] & 0xffffu];
+                    const uint2 Cb = qc2[ijb[u] >> 16], Pb = qa2[ijb[u] & 0xffffu];
+                    const uint4 P = make_uint4(__byte_perm(Pa.x, Pb.x, 0x5410), __byte_perm(Pa.x, Pb.x, 0x7632),
+                                               __byte_perm(Pa.y, Pb.y, 0x5410), 0u);
+                    const unsigned m = h2_pair_mask<KIND>(hR, hT2, P, __byte_perm(Ca.x, Cb.x, 0x5410),
+                                                          __byte_perm(Ca.x, Cb.x, 0x7632),
+                                                          __byte_perm(Ca.y, Cb.y, 0x5410));
+                    const bool pa = va && (m & 0xffffu), pb = vb && (m >> 16);
+                    const unsigned ba = __ballot_sync(0xffffffffu, pa), bb = __ballot_sync(0xffffffffu, pb);
+                    const int na = __popc(ba), tot = na + __popc(bb);
+                    if (tot == 0) continue;                     // warp-uniform
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s.misc[0], tot);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (pa) { const int pos = base + __popc(ba & ltm); if (pos < hit_cap) s.hit_ij[pos] = ija[u]; }
+                    if (pb) { const int pos = base + na + __popc(bb & ltm); if (pos < hit_cap) s.hit_ij[pos] = ijb[u]; }
+                }
+            }
+        }
+        if (!park_hd) {
+            __syncthreads();
+            for (int k = tid; k < n * W; k += blockDim.x) s.mask[k] = 0u;   // the parked coordinates are dead
         }
     } else {
         for (int k = tid; k < n * W; k += blockDim.x) s.mask[k] = 0u;
@@ -611,7 +797,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
     }
     __syncthreads();
     // wpre (aliasing the coordinate buffer) is dead: bring in the next frame of this CTA
-    if (use_tma && tid == 0 && item + (int)gridDim.x < total_items) prefetch(item + gridDim.x);
+    if (use_tma && tid == 0 && item + item_step < item_hi) prefetch(item + item_step);
 
     if (emitted) {
         const int64_t base = f * stride;   // stride is a multiple of 64: 16-byte aligned rows
@@ -627,8 +813,8 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         };
         // The rates of the hits go where the adjacency mask and the column pairs were (both dead),
         // if they fit: then ONE pass over the output positions writes all four arrays.
-        const int om_split = (int)(dense_mask_bytes(n) / 8);
-        const bool fused = (size_t)hit_cap <= dense_mask_bytes(n) / 8 + dense_col_bytes(n, FILT) / 8;
+        const int om_split = lay.om_split;
+        const bool fused = lay.fused != 0;
         double *om_a = (double *)s.mask, *om_b = (double *)s.col - om_split;
         auto om_at = [&](int h) -> double * { return (h < om_split ? om_a : om_b) + h; };
         if (!fused) {

@@ -112,6 +112,12 @@ class DeviceTopology:
         (0 when no build has returned CMD_ECAPACITY)."""
         return int(_abi.lib().cmd_topo_capacity_needed(self._handle))
 
+    def skin_stats(self):
+        """(frames, rebuilds, list entries filtered) of the dense kernel's skin list so far."""
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(_abi.lib().cmd_topo_skin_stats(self._handle, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     @property
     def n_images(self):
         """Periodic images the pair filter evaluates besides the wrapped vector."""

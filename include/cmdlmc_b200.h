@@ -195,6 +195,10 @@ int64_t cmd_topo_stride(const cmd_topo *t);
 /* After a build returned CMD_ECAPACITY: the number of directed pairs of the largest frame seen,
  * i.e. the per-frame capacity a re-created topology needs at least (0: no overflow so far). */
 int64_t cmd_topo_capacity_needed(const cmd_topo *t);
+/* Diagnostics of the dense pair kernel's skin list (frame-to-frame reuse of the filter's
+ * candidate set, csrc/pairs_dense.cuh): frames that went through it, how many of them rebuilt the
+ * list, and the list entries filtered in total.  All zero when the list is not in use. */
+int cmd_topo_skin_stats(const cmd_topo *t, int64_t *frames, int64_t *rebuilds, int64_t *list_entries);
 /* Number of periodic images, besides the fractionally wrapped vector, that the pair filter of
  * this topology evaluates (general cells; depends on cutoff + buffer against the cell heights). */
 int cmd_topo_n_images(const cmd_topo *t);

@@ -13,7 +13,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import cmdlmc_b200 as cm  # noqa: E402
-from cmdlmc_b200 import runtime, synth  # noqa: E402
+from cmdlmc_b200 import _abi, runtime, synth  # noqa: E402
 from cmdlmc_b200.topology import DeviceTopology, MODE_BRUTEFORCE  # noqa: E402
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
@@ -46,4 +46,4 @@ alg = 24.0 * n * B + 24.0 * float(counts.sum())
 print(json.dumps({"cfg": cfg, "frames": B, "n": n, "path": topo.path, "ms": ms, "best_ms": best,
                   "pairs_per_s": B * n * (n - 1) / 2 / (best * 1e-3),
                   "directed_pairs_per_frame": float(counts.mean()), "stride": topo.stride,
-                  "algorithmic_gb_s": alg / (best * 1e-3) / 1e9}))
+                  "algorithmic_gb_s": alg / (best * 1e-3) / 1e9, "skin_stats": topo.skin_stats() if hasattr(_abi.lib(), "cmd_topo_skin_stats") else None}))
