@@ -308,6 +308,9 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // skin list state (CTA-uniform, kept in shared memory to spare the registers of the phases):
+    // s.misc[34] = entries of the list, s.misc[35] = the list is valid for the frame in s.ref16
+    if (tid == 0) { s.misc[34] = 0; s.misc[35] = 0; }
     __syncthreads();
     auto prefetch = [&](int item) {
         const int64_t fn = ids ? ids[item] : item;
@@ -325,10 +328,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
     unsigned tma_phase = 0;
     const int K = (n - 1) >> 1, half = n >> 1;
     const bool even = (n & 1) == 0;
-    // skin list state (CTA-uniform): the list in `my_list` was built on the frame in s.ref16
-    unsigned *my_list = lists ? lists + (size_t)blockIdx.x * cap_l : nullptr;
-    bool list_valid = false;
-    int n_list = 0;
+    const bool have_list = lists != nullptr;
 
     for (int item = item_lo; item < item_hi; item += item_step) {
     const int64_t f = ids ? ids[item] : item;
@@ -380,9 +380,9 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
                 const double v = KIND == 0 ? (c == 0 ? x : c == 1 ? y : z) * bx.hinv[4 * c]
                                            : fma(bx.hinv[3 * c + 2], z, fma(bx.hinv[3 * c + 1], y, bx.hinv[3 * c] * x));
                 q[c] = (unsigned)(unsigned long long)__double2ll_rn(v * 1024.0) & 1023u;
-                if (my_list) r16[c] = (unsigned)(unsigned long long)__double2ll_rn(v * 65536.0) & 65535u;
+                if (have_list) r16[c] = (unsigned)(unsigned long long)__double2ll_rn(v * 65536.0) & 65535u;
             }
-            if (my_list) {
+            if (have_list) {
                 qa[tid] = make_ushort4((unsigned short)q[0], (unsigned short)q[1], (unsigned short)q[2], 0);
                 qc[tid] = make_ushort4((unsigned short)((512u - q[0]) & 1023u), (unsigned short)((512u - q[1]) & 1023u),
                                        (unsigned short)((512u - q[2]) & 1023u), 0);
@@ -393,7 +393,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         // the two largest displacements since then sum to less than the skin (triangle inequality
         // of the periodic metric; fp.skin_eff carries the error bound of the 16-bit coordinates).
         bool rebuild = true;
-        if (my_list && list_valid) {
+        if (have_list && s.misc[35]) {
             unsigned d2b = 0;
             if (tid < n) {
                 const ushort4 rf = s.ref16[tid];
@@ -422,7 +422,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
             rebuild = !(sqrtf(__uint_as_float(m1)) + sqrtf(__uint_as_float(m2)) <= fp.skin_eff);
         }
         // window filter of the sorted rows -> candidate pairs (atom indices) in dst[0 .. cap)
-        bool direct = my_list == nullptr;      // no skin list: the window filter feeds the exact stage
+        bool direct = !have_list;              // no skin list: the window filter feeds the exact stage
         while (rebuild) {
         const int db = direct ? fp.sort_db : fp.sort_db_m;
         const __half2 hT2w = u2h2(direct ? fp.hT2 : fp.hT2m);
@@ -519,7 +519,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
                 if (c >= n) c -= n;
                 const unsigned e = my_tag | (unsigned)s.perm[c];
                 if (direct) { if (pos < hit_cap) s.hit_ij[pos] = e; }
-                else if (pos < cap_l) my_list[pos] = e;
+                else if (pos < cap_l) lists[(size_t)blockIdx.x * cap_l + pos] = e;
                 pos++;
             }
         }
@@ -527,66 +527,77 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         // the skin list of this frame is complete: it becomes the reference -- unless it does not
         // fit, then this frame goes the direct way and the next one tries again
         __syncthreads();
-        n_list = s.misc[0];
+        const int n_new = s.misc[0];
         __syncthreads();
-        if (tid == 0) s.misc[0] = 0;
-        list_valid = n_list <= cap_l;
-        if (!list_valid) { direct = true; continue; }
+        if (tid == 0) { s.misc[0] = 0; s.misc[34] = n_new; s.misc[35] = n_new <= cap_l; }
+        if (n_new > cap_l) { direct = true; continue; }
         if (tid < n) s.ref16[tid] = make_ushort4((unsigned short)r16[0], (unsigned short)r16[1],
                                                  (unsigned short)r16[2], 0);
         __threadfence_block();
         break;
         }   // window filter
-        if (my_list && tid == 0) {   // statistics: frames, rebuilds, list entries filtered
-            atomicAdd(ties + 2, 1ull);
-            if (rebuild) atomicAdd(ties + 1, 1ull);
-            if (!direct) atomicAdd(ties + 3, (unsigned long long)n_list);
-        }
         if (!direct) {
             // (e) the skin list through the same packed-half filter at the radius itself, two
             // candidates per thread (low / high halves); survivors -> the exact stage's list
-            __syncthreads();   // s.misc[0] == 0, my_list visible to the CTA
+            __syncthreads();   // s.misc[0] == 0, the list and its length visible to the CTA
+            const int n_list = s.misc[34];
+            const unsigned *my_list = lists + (size_t)blockIdx.x * cap_l;
+            if (tid == 0) {   // statistics: frames, rebuilds, list entries filtered
+                atomicAdd(ties + 2, 1ull);
+                if (rebuild) atomicAdd(ties + 1, 1ull);
+                atomicAdd(ties + 3, (unsigned long long)n_list);
+            }
             __half2 hR[6];
 #pragma unroll
             for (int k = 0; k < 6; k++) hR[k] = u2h2(fp.hR[k]);
             const __half2 hT2 = u2h2(fp.hT2);
             const uint2 *qa2 = (const uint2 *)qa, *qc2 = (const uint2 *)qc;
-            const unsigned ltm = (1u << lane) - 1u;
             // LIST_U double trips per round: their list loads (L2) are all in flight before the
             // first one is used
-            constexpr int LIST_U = 4;
             const int T = (int)blockDim.x;
-            for (int k0 = 0; k0 < n_list; k0 += 2 * LIST_U * T) {
-                unsigned ija[LIST_U], ijb[LIST_U];
+            // the double trips are spread evenly over rounds of at most four (5 = 3 + 2, not 4 + 1);
+            // the round body is compiled for each size, so that its loads are all in flight before
+            // the first one is used and no slot of a round is idle
+            const int n_dt = (n_list + 2 * T - 1) / (2 * T), n_rounds = (n_dt + 3) / 4;
+            const int per_round = n_rounds ? (n_dt + n_rounds - 1) / n_rounds : 1;
+            auto rounds = [&](auto uc) {
+                constexpr int LIST_U = decltype(uc)::value;
+                for (int k0 = 0; k0 < n_list; k0 += 2 * LIST_U * T) {
+                    unsigned ija[LIST_U], ijb[LIST_U];
 #pragma unroll
-                for (int u = 0; u < LIST_U; u++) {
-                    const int ka = k0 + 2 * u * T + tid, kb = ka + T;
-                    ija[u] = ka < n_list ? my_list[ka] : 0u;
-                    ijb[u] = kb < n_list ? my_list[kb] : 0u;
-                }
+                    for (int u = 0; u < LIST_U; u++) {
+                        const int ka = k0 + 2 * u * T + tid, kb = ka + T;
+                        ija[u] = ka < n_list ? my_list[ka] : 0u;
+                        ijb[u] = kb < n_list ? my_list[kb] : 0u;
+                    }
+                    unsigned pass = 0;   // bit 2u: entry a of trip u, bit 2u + 1: entry b
 #pragma unroll
-                for (int u = 0; u < LIST_U; u++) {
-                    if (k0 + 2 * u * T >= n_list) break;         // CTA-uniform
-                    const int ka = k0 + 2 * u * T + tid, kb = ka + T;
-                    const bool va = ka < n_list, vb = kb < n_list;
-                    const uint2 Ca = qc2[ija[u] >> 16], Pa = qa2[ija[u] & 0xffffu];
-                    const uint2 Cb = qc2[ijb[u] >> 16], Pb = qa2[ijb[u] & 0xffffu];
-                    const uint4 P = make_uint4(__byte_perm(Pa.x, Pb.x, 0x5410), __byte_perm(Pa.x, Pb.x, 0x7632),
-                                               __byte_perm(Pa.y, Pb.y, 0x5410), 0u);
-                    const unsigned m = h2_pair_mask<KIND>(hR, hT2, P, __byte_perm(Ca.x, Cb.x, 0x5410),
-                                                          __byte_perm(Ca.x, Cb.x, 0x7632),
-                                                          __byte_perm(Ca.y, Cb.y, 0x5410));
-                    const bool pa = va && (m & 0xffffu), pb = vb && (m >> 16);
-                    const unsigned ba = __ballot_sync(0xffffffffu, pa), bb = __ballot_sync(0xffffffffu, pb);
-                    const int na = __popc(ba), tot = na + __popc(bb);
-                    if (tot == 0) continue;                     // warp-uniform
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s.misc[0], tot);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (pa) { const int pos = base + __popc(ba & ltm); if (pos < hit_cap) s.hit_ij[pos] = ija[u]; }
-                    if (pb) { const int pos = base + na + __popc(bb & ltm); if (pos < hit_cap) s.hit_ij[pos] = ijb[u]; }
+                    for (int u = 0; u < LIST_U; u++) {
+                        const int ka = k0 + 2 * u * T + tid, kb = ka + T;
+                        const uint2 Ca = qc2[ija[u] >> 16], Pa = qa2[ija[u] & 0xffffu];
+                        const uint2 Cb = qc2[ijb[u] >> 16], Pb = qa2[ijb[u] & 0xffffu];
+                        const uint4 P = make_uint4(__byte_perm(Pa.x, Pb.x, 0x5410), __byte_perm(Pa.x, Pb.x, 0x7632),
+                                                   __byte_perm(Pa.y, Pb.y, 0x5410), 0u);
+                        const unsigned m = h2_pair_mask<KIND>(hR, hT2, P, __byte_perm(Ca.x, Cb.x, 0x5410),
+                                                              __byte_perm(Ca.x, Cb.x, 0x7632),
+                                                              __byte_perm(Ca.y, Cb.y, 0x5410));
+                        if (ka < n_list && (m & 0xffffu)) pass |= 1u << (2 * u);
+                        if (kb < n_list && (m >> 16)) pass |= 2u << (2 * u);
+                    }
+                    // one reservation per warp and round
+                    int pos = reserve(__popc(pass));
+                    if (pos < 0) continue;                          // warp-uniform
+#pragma unroll
+                    for (int u = 0; u < LIST_U; u++) {
+                        if (pass & (1u << (2 * u))) { if (pos < hit_cap) s.hit_ij[pos] = ija[u]; pos++; }
+                        if (pass & (2u << (2 * u))) { if (pos < hit_cap) s.hit_ij[pos] = ijb[u]; pos++; }
+                    }
                 }
-            }
+            };
+            if (per_round == 3) rounds(std::integral_constant<int, 3>{});
+            else if (per_round == 4) rounds(std::integral_constant<int, 4>{});
+            else if (per_round == 2) rounds(std::integral_constant<int, 2>{});
+            else rounds(std::integral_constant<int, 1>{});
         }
         if (!park_hd) {
             __syncthreads();
