@@ -81,8 +81,16 @@ class ArrayTrajectory(Trajectory):
     trajectory_parser.py:324, or float64) + atom names [atoms].  The GPU pipeline uploads whole
     frame blocks of `positions` instead of iterating Frame objects."""
 
+    #: page-locked chunk buffers block() cycles through (a buffer is reused three blocks later)
+    _ring_slots = 3
+
     def __init__(self, positions, atom_names, *, time_step: float, repeat: bool = False):
-        self.positions = np.asarray(positions)
+        # anything that slices like an array is taken as it is (an open HDF5 dataset stays on disk
+        # and is read chunk by chunk, trajectory_parser.py:296,322)
+        lazy = all(hasattr(positions, a) for a in ("shape", "ndim", "dtype", "__getitem__"))
+        self.positions = positions if lazy else np.asarray(positions)
+        self._ring = []
+        self._ring_next = 0
         if self.positions.ndim != 3 or self.positions.shape[2] != 3:
             raise ValueError("positions must have shape [frames, atoms, 3]")
         self.atom_names = np.asarray(atom_names)
@@ -113,13 +121,43 @@ class ArrayTrajectory(Trajectory):
         """Indices of the atoms called `name`."""
         return np.where(self.atom_names == name)[0]
 
+    def _chunk_buffer(self, shape, dtype):
+        """The next buffer of the page-locked ring (runtime.pinned_empty: the library copies from it
+        directly, the copy overlaps the kernels); plain memory when no CUDA device is bound."""
+        need = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if len(self._ring) < self._ring_slots:
+            self._ring.append(None)
+        k = self._ring_next % len(self._ring)
+        self._ring_next += 1
+        buf = self._ring[k]
+        if buf is None or buf.nbytes < need:
+            try:
+                from . import runtime
+                buf = runtime.pinned_empty((max(need, 1),), np.uint8)
+            except Exception:          # no device / no library: host-side tools only
+                buf = np.empty(max(need, 1), np.uint8)
+            self._ring[k] = buf
+        else:
+            try:                       # its last upload may still be in flight
+                from . import runtime
+                runtime.sync()
+            except Exception:
+                pass
+        return buf[:need].view(dtype).reshape(shape)
+
     def block(self, name, start, stop):
-        """float64 [stop-start, n_selected, 3] donor positions of a frame block."""
+        """[stop-start, n_selected, 3] positions of the atoms called `name` in a frame block, in the
+        stored precision (float32 blocks are up-cast on the device, exactly) and in page-locked
+        memory.  The array is valid until block() has been called `_ring_slots` more times."""
         sel = self.selection(name)
-        blk = self.positions[start:stop]
-        if sel.size != blk.shape[1]:
-            blk = blk[:, sel]
-        return np.ascontiguousarray(blk, dtype=np.float64)
+        blk = self.positions[start:stop]          # an HDF5 dataset reads the chunk here
+        dtype = np.float32 if blk.dtype == np.float32 else np.float64
+        out = self._chunk_buffer((blk.shape[0], sel.size, 3), dtype)
+        if sel.size == blk.shape[1]:
+            out[...] = blk
+        else:
+            np.take(blk, sel, axis=1, out=out) if blk.dtype == dtype else out.__setitem__(Ellipsis, blk[:, sel])
+        return out
 
 
 class XYZTrajectory(ArrayTrajectory):
@@ -188,9 +226,25 @@ class HDF5Trajectory(ArrayTrajectory):
             import h5py
         except ImportError as e:   # pragma: no cover - h5py is absent from the build image
             raise ImportError("HDF5Trajectory needs h5py; use NpzTrajectory / XYZTrajectory") from e
-        with h5py.File(filename, "r") as f:
-            names = f["atom_names"][:].astype("<U2")
-            positions = f["trajectory"][:]
+        self._file = h5py.File(filename, "r")
+        names = np.asarray(self._file["atom_names"][:]).astype("<U2")
+        positions = self._file["trajectory"]      # stays on disk: block() reads chunk by chunk
+        if selection is not None and selection != "None":   # trajectory_parser.py:298-300 ignores it too
+            import warnings
+            warnings.warn("Selection is not implemented yet!")
+        self.selection_spec = selection
         super().__init__(positions, names, time_step=time_step, repeat=repeat)
         self.filename = filename
         self._chunk_size = chunk_size
+
+    def __iter__(self):
+        step = 0
+        while True:
+            for c0 in range(0, len(self), self._chunk_size):     # trajectory_parser.py:313-337
+                chunk = np.asarray(self.positions[c0:c0 + self._chunk_size], dtype=float)
+                for pos in chunk:
+                    self._current_frame_number = step
+                    yield Frame(self.atom_names, pos, time=step * self.time_step)
+                    step += 1
+            if not self.repeat:
+                break
