@@ -522,8 +522,8 @@ def run_b200(args):
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else
                        "fallback of B200_PROFILING.md",
         "kernel_ms_per_launch": kernel_ms,
-        "note": "the kernel is bound by instruction issue (ncu: issue slots 58 %, FP64 pipe 18 %, "
-                "DRAM 17 % of peak; profiles/r2a_ncu_dense_summary.txt), not by HBM",
+        "note": "the kernel is bound by instruction issue (ncu: issue slots 56 %, FP64 pipe 16 %, "
+                "DRAM 21 % of peak; profiles/r2p_ncu_dense_summary.txt), not by HBM",
         "fp64_peak_tflops_measured": peak_tf,
         "reference_equivalent_tflops": B * ppf * (FLOP_ORTHO if kind == 0 else
                                                   FLOP_GENERAL_REFERENCE) / (kernel_ms * 1e-3) / 1e12,

@@ -1592,8 +1592,16 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
         CMD_CUDA(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) CMD_CUDA(cudaEventCreateWithFlags(&g.copy_event[i], cudaEventDisableTiming));
     }
+    // Chunk schedule in 32nds of the block: a small first chunk (its copy is the only one no kernel
+    // hides when the kernel is the slower side), large middle chunks (few launches, long runs of
+    // consecutive frames per CTA for the skin list), small last chunks (the last chunk's kernel is
+    // what stays exposed when the copies are the slower side).  CMDLMC_B200_UPLOAD_EQUAL=1: the
+    // equal chunks of round 1.
+    static const int sched32[TOPO_UPLOAD_CHUNKS] = {1, 7, 8, 8, 4, 2, 1, 1};
+    static const bool equal_chunks = getenv("CMDLMC_B200_UPLOAD_EQUAL") != nullptr;
     int64_t chunk = (nframes + TOPO_UPLOAD_CHUNKS - 1) / TOPO_UPLOAD_CHUNKS;
     if (chunk < 256) chunk = 256;
+    const int64_t unit = (nframes + 31) / 32;
     // the staging buffer may still be read by kernels of the previous block
     CMD_CUDA(cudaEventRecord(g.copy_event[0], st));
     CMD_CUDA(cudaStreamWaitEvent(g.copy_stream, g.copy_event[0], 0));
@@ -1602,8 +1610,10 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
     bool sized = t->stride != 0;
     t->nframes = nframes;
     t->d_frames_last = t->d_upload;
-    for (int64_t c0 = 0; c0 < nframes; c0 += chunk) {
-        const int64_t cn = nframes - c0 < chunk ? nframes - c0 : chunk;
+    int ci = 0;
+    for (int64_t c0 = 0; c0 < nframes; ci++) {
+        int64_t want = equal_chunks || unit < 64 || ci >= TOPO_UPLOAD_CHUNKS ? chunk : unit * sched32[ci];
+        const int64_t cn = nframes - c0 < want ? nframes - c0 : want;
         const size_t off = (size_t)c0 * per_frame, ce = (size_t)cn * per_frame;
         if (dtype_bytes == 8)
             rc = cmd_h2d_staged(t->d_upload + off, (const double *)h_frames + off, ce * 8, g.copy_stream);
@@ -1624,6 +1634,7 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
         }
         if (c0 == 0 && (rc = topo_reserve(t, nframes))) return rc;
         if ((rc = launch_pairs(t, t->d_upload + off, nullptr, nullptr, cn, c0, true))) return rc;
+        c0 += cn;
     }
     t->total_frames += nframes;
     return topo_check_capacity(t);
