@@ -1392,6 +1392,9 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
         rc = launch_pairs(t, d_frames, t->d_rebuild_ids, t->d_sched, nframes, 0, false);
         if (rc) return rc;
         size_t rsmem = (size_t)t->n * 24;
+        // up to 100 KB (4266 atoms) the frame is staged in shared memory: two or more CTAs per SM
+        // (staging frames of up to 100 KB through opt-in shared memory was measured on C3, 2048
+        // atoms: 0.70 ms per 512 frames against 0.64 ms for the split path -- not taken)
         if (rsmem > 40 * 1024) {
             // frames too large to stage: several CTAs per frame, coordinates through L1 / L2
             int chunks = (int)((t->stride + 8191) / 8192);
@@ -1592,16 +1595,13 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
         CMD_CUDA(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) CMD_CUDA(cudaEventCreateWithFlags(&g.copy_event[i], cudaEventDisableTiming));
     }
-    // Chunk schedule in 32nds of the block: a small first chunk (its copy is the only one no kernel
-    // hides when the kernel is the slower side), large middle chunks (few launches, long runs of
-    // consecutive frames per CTA for the skin list), small last chunks (the last chunk's kernel is
-    // what stays exposed when the copies are the slower side).  CMDLMC_B200_UPLOAD_EQUAL=1: the
-    // equal chunks of round 1.
-    static const int sched32[TOPO_UPLOAD_CHUNKS] = {1, 7, 8, 8, 4, 2, 1, 1};
-    static const bool equal_chunks = getenv("CMDLMC_B200_UPLOAD_EQUAL") != nullptr;
+    // Equal chunks.  (Measured and dropped in round 2: a small first chunk followed by large ones --
+    // the kernel and the copy of a chunk take about the same time, so the second chunk's copy is
+    // not done when the first chunk's kernel ends and the SMs idle: float32 2.04 -> 2.2-2.6 ms per
+    // 16 384 C2 frames; tapered last chunks for float64 blocks gain 3 %, within the noise of the
+    // host.)
     int64_t chunk = (nframes + TOPO_UPLOAD_CHUNKS - 1) / TOPO_UPLOAD_CHUNKS;
     if (chunk < 256) chunk = 256;
-    const int64_t unit = (nframes + 31) / 32;
     // the staging buffer may still be read by kernels of the previous block
     CMD_CUDA(cudaEventRecord(g.copy_event[0], st));
     CMD_CUDA(cudaStreamWaitEvent(g.copy_stream, g.copy_event[0], 0));
@@ -1610,10 +1610,8 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
     bool sized = t->stride != 0;
     t->nframes = nframes;
     t->d_frames_last = t->d_upload;
-    int ci = 0;
-    for (int64_t c0 = 0; c0 < nframes; ci++) {
-        int64_t want = equal_chunks || unit < 64 || ci >= TOPO_UPLOAD_CHUNKS ? chunk : unit * sched32[ci];
-        const int64_t cn = nframes - c0 < want ? nframes - c0 : want;
+    for (int64_t c0 = 0; c0 < nframes;) {
+        const int64_t cn = nframes - c0 < chunk ? nframes - c0 : chunk;
         const size_t off = (size_t)c0 * per_frame, ce = (size_t)cn * per_frame;
         if (dtype_bytes == 8)
             rc = cmd_h2d_staged(t->d_upload + off, (const double *)h_frames + off, ce * 8, g.copy_stream);
