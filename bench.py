@@ -739,8 +739,26 @@ def m2_e2e(args, w, box, rate, pairs_per_frame_mean, R):
         best = R.max([best])[0]
         res[mode] = {"seconds": best, "frames_per_s": R.world * nfr / best, "rows": rows_n, "events": ev_n,
                      "site_updates_per_s": R.world * nfr * pairs_per_frame_mean / best}
+    # the reference's own generator protocol (topology.py:80-114): one (start, destination, distance,
+    # frame) tuple of HOST arrays per frame -- every list leaves the GPU again, the slowest way to
+    # use the library and the one an unmodified reference driver takes
+    gen_frames = min(nfr, 2048)
+    R.barrier()
+    t0 = time.perf_counter()
+    top = NeighborTopology(ArrayTrajectory(frames[:gen_frames], names, time_step=w.time_step), box,
+                           donor_atoms="O", cutoff=w.cutoff, buffer=w.buffer)
+    listed = 0
+    for start, dest, dist, frame in top.topology_verlet_list_generator():
+        listed += len(start)
+    gen_s = R.max([time.perf_counter() - t0])[0]
+    del top
+    gc.collect()
+    res["generator"] = {"frames": gen_frames, "seconds": gen_s, "frames_per_s": R.world * gen_frames / gen_s,
+                        "listed_pair_frames_per_s": R.world * listed / gen_s,
+                        "d2h_bytes": int(listed) * 16,
+                        "api": "NeighborTopology.topology_verlet_list_generator(): host arrays per frame"}
     return {"value": res["philox"]["site_updates_per_s"], "unit": "site-updates/s",
-            "frames": nfr, "replicas_per_gpu": 1,
+            "frames": nfr, "replicas_per_gpu": 1, "reference_protocol_generator": res["generator"],
             "h2d_bytes_per_run": int(frames.nbytes), "d2h": "observable rows + event log",
             "api": "ArrayTrajectory -> NeighborTopology -> KMCLattice -> ObservablesOutput "
                    "(float32 host frames, wall clock incl. the Python layer, best of 2)",

@@ -1711,6 +1711,29 @@ extern "C" int64_t cmd_topo_capacity_needed(const cmd_topo *t) { return t ? t->c
 extern "C" int cmd_topo_n_images(const cmd_topo *t) { return t ? t->bx.n_img : -1; }
 extern "C" int64_t cmd_topo_nframes(const cmd_topo *t) { return t ? t->nframes : -1; }
 
+// The lists of frames [f0, f0 + nf) of the last block in ONE strided copy per array: host rows of
+// `width` entries (>= the largest count among them; the counts come from cmd_topo_frame_info).
+extern "C" int cmd_topo_get_block(const cmd_topo *t, int64_t f0, int64_t nf, int64_t width, int *start,
+                                  int *dest, double *dist, double *omega)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || f0 < 0 || nf < 1 || f0 + nf > t->nframes || width < 1 || width > t->stride)
+        return cmd_set_error(CMD_EINVAL, "bad frame range or row width");
+    cudaStream_t st = cmd_global().stream;
+    const int64_t base = f0 * t->stride;
+    const size_t sp = (size_t)t->stride;
+#define GET2D(h, d, T)                                                                            \
+    if (h) CMD_CUDA(cudaMemcpy2DAsync(h, (size_t)width * sizeof(T), (d) + base, sp * sizeof(T),   \
+                                      (size_t)width * sizeof(T), (size_t)nf, cudaMemcpyDeviceToHost, st))
+    GET2D(start, t->d_start, int);
+    GET2D(dest, t->d_dest, int);
+    GET2D(dist, t->d_dist, double);
+    GET2D(omega, t->d_omega, double);
+#undef GET2D
+    CMD_CUDA(cudaStreamSynchronize(st));
+    return CMD_OK;
+}
+
 extern "C" int cmd_topo_get_frame(const cmd_topo *t, int64_t f, int *start, int *dest, double *dist,
                                   double *omega)
 {

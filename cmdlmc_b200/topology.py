@@ -198,6 +198,17 @@ class DeviceTopology:
                                             ptr(dest, C.c_int), ptr(dist), ptr(omega)))
         return start, dest, dist, omega
 
+    def get_block(self, f0, nf, counts, omega=False):
+        """(start, dest, dist[, omega]) of frames [f0, f0+nf) as host arrays [nf, width], width = the
+        largest count among them: one strided copy per array instead of one round trip per frame."""
+        width = max(int(np.max(counts[f0:f0 + nf])), 1)
+        start, dest = np.empty((nf, width), np.int32), np.empty((nf, width), np.int32)
+        dist = np.empty((nf, width))
+        om = np.empty((nf, width)) if omega else None
+        check(_abi.lib().cmd_topo_get_block(self._handle, int(f0), int(nf), width, ptr(start, C.c_int),
+                                            ptr(dest, C.c_int), ptr(dist), ptr(om) if omega else None))
+        return (start, dest, dist, om) if omega else (start, dest, dist)
+
     def tie_count(self):
         return int(_abi.lib().cmd_topo_tie_count(self._handle))
 
@@ -353,10 +364,15 @@ class NeighborTopology:
     def _generate(self, mode):
         for topo, full_frames, _ in self.device_blocks(mode):
             counts, _, _ = topo.frame_info()
+            if (counts < 0).any():
+                raise _abi.CmdError(-5, "a frame overflowed its pair capacity")
+            # the block's lists leave the GPU in three strided copies; the per-frame arrays the
+            # protocol yields are fresh copies of their rows
+            start, dest, dist = topo.get_block(0, len(counts), counts)
             for k, full_frame in enumerate(full_frames):
-                start, dest, dist, _ = topo.get_frame(k, int(counts[k]))
+                c = int(counts[k])
                 self._cache.append(full_frame)
-                yield start, dest, dist, full_frame
+                yield start[k, :c].copy(), dest[k, :c].copy(), dist[k, :c].copy(), full_frame
 
     # -- topology.py:74-78
     def topology_bruteforce_generator(self):

@@ -203,6 +203,12 @@ int cmd_topo_skin_stats(const cmd_topo *t, int64_t *frames, int64_t *rebuilds, i
  * this topology evaluates (general cells; depends on cutoff + buffer against the cell heights). */
 int cmd_topo_n_images(const cmd_topo *t);
 int64_t cmd_topo_nframes(const cmd_topo *t);
+/* The lists of frames [f0, f0 + nf) of the last block in one strided copy per array: host rows of
+ * `width` entries each, width >= the largest P_f among them (cmd_topo_frame_info) -- what the
+ * reference's per-frame generator protocol (topology.py:80-114) is served from without one
+ * round trip per frame.  Pointers may be NULL. */
+int cmd_topo_get_block(const cmd_topo *t, int64_t f0, int64_t nf, int64_t width, int *h_start,
+                       int *h_dest, double *h_dist, double *h_omega);
 /* Copies frame f of the last block to host arrays of at least P_f elements (any may be NULL):
  * the (row, col, data) triple get_topology_bruteforce returns, plus the rates. */
 int cmd_topo_get_frame(const cmd_topo *t, int64_t f, int *h_start, int *h_dest, double *h_dist,
