@@ -739,7 +739,7 @@ static void topo_filter_params(cmd_topo *t)
         // (error per displacement <= 2 units of every coordinate: two roundings of half a unit,
         // FP32 noise far below).
         {
-            static const char *sk = getenv("CMDLMC_B200_DENSE_SKIN");
+            const char *sk = getenv("CMDLMC_B200_DENSE_SKIN");
             const double skin = sk ? atof(sk) : 0.6;
             const double rm = radius + skin;
             const double lim_m = (rm + E) * (rm + E) * 1.0015 + 1e-6;
@@ -772,7 +772,7 @@ static void topo_filter_params(cmd_topo *t)
         if (db <= 100 && t->n >= 96 && getenv("CMDLMC_B200_DENSE_NOSORT") == nullptr) {
             fp.sort_axis = axis;
             fp.sort_db = db;
-            static const char *sk = getenv("CMDLMC_B200_DENSE_SKIN");
+            const char *sk = getenv("CMDLMC_B200_DENSE_SKIN");
             const double rm = radius + (sk ? atof(sk) : 0.6);
             fp.sort_db_m = (int)ceil((rm / hbest * 1024.0 + 1.0) / 4.0) + 1;
             if (fp.sort_db_m > 100) fp.coh_ok = 0;
@@ -954,7 +954,9 @@ extern "C" int cmd_topo_create(const cmd_box *box, int n, double cutoff, double 
 // frame the direct path).
 static int dense_lists_reserve(cmd_topo *t, int64_t ctas, int hit_cap)
 {
-    const int cap_l = 3 * hit_cap;
+    // (CMDLMC_B200_DENSE_LIST_CAP: entries per list, for tests of the overflow path)
+    const char *lc = getenv("CMDLMC_B200_DENSE_LIST_CAP");
+    const int cap_l = lc ? (atoi(lc) > 64 ? atoi(lc) : 64) : 3 * hit_cap;
     const size_t words = (size_t)ctas * cap_l;
     if (t->d_lists && t->lists_words >= words && t->cap_l == cap_l) return CMD_OK;
     CMD_CUDA(cudaStreamSynchronize(cmd_global().stream));
@@ -1601,7 +1603,7 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
     // 16 384 C2 frames; tapered last chunks for float64 blocks gain 3 %, within the noise of the
     // host.)
     int64_t chunk = (nframes + TOPO_UPLOAD_CHUNKS - 1) / TOPO_UPLOAD_CHUNKS;
-    if (chunk < 256) chunk = 256;
+    if (chunk < 1024) chunk = 1024;   // several consecutive frames per persistent CTA (skin list)
     // the staging buffer may still be read by kernels of the previous block
     CMD_CUDA(cudaEventRecord(g.copy_event[0], st));
     CMD_CUDA(cudaStreamWaitEvent(g.copy_stream, g.copy_event[0], 0));

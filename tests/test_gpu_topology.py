@@ -213,6 +213,72 @@ def test_pageable_blocks_go_through_the_staging_ring(mode, dtype):
             np.testing.assert_array_equal(a, b)
 
 
+def _lists(box, w, frames, rate):
+    """One launch over the whole resident block (host blocks are cut into upload chunks, and a
+    chunk of a few hundred frames leaves a persistent CTA too few frames for a list)."""
+    import torch
+    from cmdlmc_b200.topology import DeviceTopology
+    d = torch.from_numpy(frames).cuda()
+    t = DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, 0, rate, 0, path=0)
+    t.build_dev(d.data_ptr(), frames.shape[0])
+    counts, _, rsum = t.frame_info()
+    assert (counts > 0).all()
+    start, dest, dist, om = t.get_block(0, len(counts), counts, omega=True)
+    pad = np.arange(start.shape[1])[None, :] >= counts[:, None]     # beyond a frame's count: not written
+    for a in (start, dest, dist, om):
+        a[pad] = 0
+    return t, counts, rsum, start, dest, dist, om
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2"])
+def test_skin_list_of_the_dense_kernel_changes_no_bit(orc, monkeypatch, cfg):
+    """The dense kernel keeps the filter's candidate set (radius + skin) across consecutive frames
+    and re-filters it while the two largest displacements stay below the skin
+    (pairs_dense.cuh).  Whatever the skin -- none, the default, a huge one, a list too short to
+    hold the candidates -- the lists, distances and rates are the same bits, and they are the
+    oracle's.  The trajectory holds what the displacement test has to survive: atoms re-imaged by
+    whole cell vectors between frames, one atom jumping 3 A in a single step, a frame repeated."""
+    import cmdlmc_b200 as cm
+    w = synth.workload(cfg)
+    nfr = 4096                                   # several frames for every resident CTA
+    frames = synth.trajectory(w, nfr)
+    rng = np.random.RandomState(11)
+    cellm = w.cell_matrix
+    for f in range(40, nfr, 97):                 # re-imaging: whole cell vectors, from here on
+        a = rng.randint(w.n_oxygen)
+        frames[f:, a] += rng.randint(-1, 2, size=3) @ cellm
+    frames[700:, 5] += np.array([1.9, -1.7, 1.6])          # a 3 A jump inside one time step
+    frames[901] = frames[900]                               # no displacement at all
+    box, obox = make_box(w.cell), orc.OracleBox(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    runs = {}
+    for name, env in (("direct", {"CMDLMC_B200_DENSE_SKIN": "0"}), ("default", {}),
+                      ("wide", {"CMDLMC_B200_DENSE_SKIN": "1.5"}),
+                      ("short list", {"CMDLMC_B200_DENSE_LIST_CAP": "3000"})):
+        for k in ("CMDLMC_B200_DENSE_SKIN", "CMDLMC_B200_DENSE_LIST_CAP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        runs[name] = _lists(box, w, frames, rate)
+    fr_d, reb_d, _ = runs["direct"][0].skin_stats()
+    fr_s, reb_s, _ = runs["default"][0].skin_stats()
+    assert fr_d == 0 and fr_s >= nfr - 16 and 0 < reb_s < fr_s // 2      # the list really is reused
+    fr_l, reb_l, _ = runs["short list"][0].skin_stats()
+    if cfg == "C2":
+        assert fr_l < fr_s                        # frames whose list did not fit went the direct way
+    ref = runs["direct"]
+    for name, got in runs.items():
+        for a, b in zip(ref[1:], got[1:]):
+            np.testing.assert_array_equal(a, b, err_msg=name)
+    _, counts, _, start, dest, dist, _ = ref
+    for f in (0, 39, 40, 41, 699, 700, 701, 900, 901, 2500, nfr - 1):
+        orow, ocol, odist = orc.topology_bruteforce(obox, frames[f], w.cutoff, w.buffer)
+        c = int(counts[f])
+        np.testing.assert_array_equal(start[f, :c], orow)
+        np.testing.assert_array_equal(dest[f, :c], ocol)
+        np.testing.assert_array_equal(dist[f, :c], odist)
+
+
 @pytest.mark.parametrize("cfg,nfr", [("C1", 6), ("C2", 6), ("C4", 3)])
 def test_cell_list_path_equals_dense(orc, cfg, nfr):
     """The cell-list search (large boxes) and the dense search give the same arrays, bit for bit."""
