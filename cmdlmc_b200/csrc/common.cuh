@@ -45,6 +45,10 @@ struct CmdGlobal {
     // second stream for host->device copies that overlap kernels (cmd_topo_build)
     cudaStream_t copy_stream = 0;
     cudaEvent_t copy_event[2] = {0, 0};
+    // every other chunk of a host block runs on this stream: the CTAs of chunk i+1 move onto the SMs
+    // as those of chunk i drain (cmd_topo_build)
+    cudaStream_t aux_stream = 0;
+    cudaEvent_t aux_event[2] = {0, 0};
     int64_t launches = 0;
     // stream-ordered scratch for the host-pointer entry points
     void *scratch[6] = {0, 0, 0, 0, 0, 0};

@@ -69,9 +69,11 @@ struct cmd_topo {
     double *d_dist, *d_omega, *d_rate_sum;
     uint8_t *d_rebuilt;
     unsigned long long *d_ties;
-    unsigned *d_lists;     // skin lists of the dense kernel's persistent CTAs (pairs_dense.cuh)
-    size_t lists_words;
+    unsigned *d_lists;     // skin lists of the dense kernel's persistent CTAs (pairs_dense.cuh): two
+                           // sets, so that two launches on different streams never share one
+    size_t lists_words;    // words per set
     int cap_l;             // entries per CTA
+    int list_set;          // the set the next launch takes
     // Verlet state carried across blocks
     bool have_last;
     double *d_last, *d_displacement, *d_dr;
@@ -963,7 +965,7 @@ static int dense_lists_reserve(cmd_topo *t, int64_t ctas, int hit_cap)
     cudaFree(t->d_lists);
     t->d_lists = nullptr;
     t->lists_words = 0;
-    if (cudaMalloc((void **)&t->d_lists, words * 4) != cudaSuccess) {
+    if (cudaMalloc((void **)&t->d_lists, 2 * words * 4) != cudaSuccess) {
         cudaGetLastError();
         return cmd_set_error(CMD_ENOMEM, "cudaMalloc of %zu skin-list bytes failed", words * 4);
     }
@@ -996,7 +998,7 @@ static int launch_dense(cmd_topo *t, const double *d_frames, const int *ids, con
         if (IM == FILT_H2 && use_skin) {                                                         \
             int rc_ = dense_lists_reserve(t, pgrid, hit_cap);                                    \
             if (rc_) return rc_;                                                                 \
-            lists_ = t->d_lists;                                                                 \
+            lists_ = t->d_lists + (size_t)(t->list_set & 1) * t->lists_words;                    \
         }                                                                                        \
         k_pairs_dense<K, IM, SP, MT, MB><<<(unsigned)pgrid, t->threads * SP, smem, st>>>(        \
             t->bx, t->rate, t->fp, d_frames, ids, n_ids, (int)grid, t->n, t->rc, t->t2, stride,  \
@@ -1597,6 +1599,11 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
         CMD_CUDA(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) CMD_CUDA(cudaEventCreateWithFlags(&g.copy_event[i], cudaEventDisableTiming));
     }
+    if (!g.aux_stream) {
+        CMD_CUDA(cudaStreamCreateWithFlags(&g.aux_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) CMD_CUDA(cudaEventCreateWithFlags(&g.aux_event[i], cudaEventDisableTiming));
+    }
+    static const bool one_stream = getenv("CMDLMC_B200_UPLOAD_ONE_STREAM") != nullptr;
     // Equal chunks.  (Measured and dropped in round 2: a small first chunk followed by large ones --
     // the kernel and the copy of a chunk take about the same time, so the second chunk's copy is
     // not done when the first chunk's kernel ends and the SMs idle: float32 2.04 -> 2.2-2.6 ms per
@@ -1612,20 +1619,35 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
     bool sized = t->stride != 0;
     t->nframes = nframes;
     t->d_frames_last = t->d_upload;
-    for (int64_t c0 = 0; c0 < nframes;) {
+    // Chunks alternate between the library's stream and a second one: a kernel on one stream does
+    // not wait for the last CTAs of the chunk before it, whose SMs it fills as they drain (each
+    // launch has its own set of skin lists).  The second stream starts behind whatever is queued
+    // on the first and is joined into it at the end.
+    CMD_CUDA(cudaEventRecord(g.aux_event[0], st));
+    CMD_CUDA(cudaStreamWaitEvent(g.aux_stream, g.aux_event[0], 0));
+    int ci = 0;
+    struct StreamGuard {   // launch_pairs and the macros launch on cmd_global().stream
+        CmdGlobal &g; cudaStream_t keep;
+        ~StreamGuard() { g.stream = keep; }
+    } guard{g, st};
+    for (int64_t c0 = 0; c0 < nframes; ci++) {
         const int64_t cn = nframes - c0 < chunk ? nframes - c0 : chunk;
         const size_t off = (size_t)c0 * per_frame, ce = (size_t)cn * per_frame;
+        const bool on_aux = !one_stream && (ci & 1) && sized;
+        g.stream = st;
         if (dtype_bytes == 8)
             rc = cmd_h2d_staged(t->d_upload + off, (const double *)h_frames + off, ce * 8, g.copy_stream);
         else
             rc = cmd_h2d_staged(d32 + off, (const float *)h_frames + off, ce * 4, g.copy_stream);
         if (rc) return rc;
         CMD_CUDA(cudaEventRecord(g.copy_event[1], g.copy_stream));
-        CMD_CUDA(cudaStreamWaitEvent(st, g.copy_event[1], 0));
+        cudaStream_t cs = on_aux ? g.aux_stream : st;
+        CMD_CUDA(cudaStreamWaitEvent(cs, g.copy_event[1], 0));
+        g.stream = cs;
         if (dtype_bytes == 4) {
             int blocks = cmd_div_up(ce, 256);
             if (blocks > g.sm_count * 16) blocks = g.sm_count * 16;
-            k_upcast_f32<<<blocks, 256, 0, st>>>(d32 + off, t->d_upload + off, (int64_t)ce);
+            k_upcast_f32<<<blocks, 256, 0, cs>>>(d32 + off, t->d_upload + off, (int64_t)ce);
             CMD_LAUNCHED();
         }
         if (!sized) {   // first block ever: probe the capacity on the first frame, then allocate
@@ -1633,9 +1655,14 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
             sized = true;
         }
         if (c0 == 0 && (rc = topo_reserve(t, nframes))) return rc;
+        t->list_set = on_aux ? 1 : 0;
         if ((rc = launch_pairs(t, t->d_upload + off, nullptr, nullptr, cn, c0, true))) return rc;
         c0 += cn;
     }
+    g.stream = st;
+    t->list_set = 0;
+    CMD_CUDA(cudaEventRecord(g.aux_event[1], g.aux_stream));
+    CMD_CUDA(cudaStreamWaitEvent(st, g.aux_event[1], 0));
     t->total_frames += nframes;
     return topo_check_capacity(t);
 }
