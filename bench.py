@@ -937,7 +937,7 @@ def run_config_legs(args, R, rank, world):
     # ---- C5: 32768-O water-like box, cell list + pair-distance histogram, frames sharded -------
     w = synth.workload("C5")
     box, rate = _workload_objects(w)
-    n, F5 = w.n_oxygen, 16
+    n, F5 = w.n_oxygen, 32    # BASELINE C5: 200 frames over the GPUs of a box (25 each at N = 8)
     d = frames_dev(w, F5, rank * F5)
     t = DeviceTopology(box, n, w.cutoff, w.buffer, MODE_BRUTEFORCE, rate, 0)
     t.build_dev(d.data_ptr(), F5)

@@ -1609,7 +1609,9 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
     // not done when the first chunk's kernel ends and the SMs idle: float32 2.04 -> 2.2-2.6 ms per
     // 16 384 C2 frames; tapered last chunks for float64 blocks gain 3 %, within the noise of the
     // host.)
-    int64_t chunk = (nframes + TOPO_UPLOAD_CHUNKS - 1) / TOPO_UPLOAD_CHUNKS;
+    static const char *nch_env = getenv("CMDLMC_B200_UPLOAD_CHUNKS");
+    const int nch = nch_env && atoi(nch_env) > 0 ? atoi(nch_env) : TOPO_UPLOAD_CHUNKS;
+    int64_t chunk = (nframes + nch - 1) / nch;
     if (chunk < 1024) chunk = 1024;   // several consecutive frames per persistent CTA (skin list)
     // the staging buffer may still be read by kernels of the previous block
     CMD_CUDA(cudaEventRecord(g.copy_event[0], st));
