@@ -181,9 +181,15 @@ class DeviceKMC:
 class KMCLattice:
     """Implementation of the time-dependent Kinetic Monte Carlo Scheme (MDMC.py:28-226).
 
-    rng="replay" (default) consumes the global legacy np.random state exactly like the reference
-    (one shuffle at construction, then random() / uniform(0, S) alternating per event), so a run
-    after np.random.seed(s) reproduces the reference's proton trajectory bit for bit.
+    rng="replay" (default) follows the reference's use of the global legacy np.random state (one
+    shuffle at construction, then random() / uniform(0, S) alternating per event): after
+    np.random.seed(s) the event trace (frame, start, destination, proton) is the one the oracle's
+    restatement of MDMC.py produces from the same stream, bit for bit, and the reference's own
+    seeded runs are reproduced by the golden tests (decisions closer than 1e-9 to a boundary are
+    counted in `tie_count`: the rates come from CUDA's exp, a few ulp from NumPy's).  The uniforms
+    are drawn from np.random one frame block AHEAD of their use (2 * (events_per_frame_bound *
+    frames + 64) per block), so the global generator state differs from upstream during and after
+    the run: other np.random consumers interleaved with the iteration see different numbers.
     rng="philox" uses the counter-based device generator (key = seed, counter = replica, event).
     """
 

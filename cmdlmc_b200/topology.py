@@ -70,6 +70,12 @@ class DeviceTopology:
 
     def __init__(self, atom_box, n_atoms, cutoff, buffer, mode, jumprate=None, capacity=0,
                  path=-1):
+        if jumprate is not None and (getattr(jumprate, "kind", None) is None or not hasattr(jumprate, "_par")):
+            # the reference accepts any callable JumpRate(*colvars); the rate is evaluated inside
+            # the list kernels here, so it has to be one the device knows
+            raise TypeError("jump rate %r cannot be evaluated on the device: use Fermi, FermiAngle, "
+                            "ActivationEnergy or Exponential from cmdlmc_b200.jumprate (a JumpRate "
+                            "subclass needs `kind` and `params`)" % (jumprate,))
         runtime.ensure_init()
         self.atom_box = atom_box          # keeps the box handle alive
         self.n_atoms = int(n_atoms)

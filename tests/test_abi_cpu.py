@@ -169,3 +169,11 @@ def test_diffusion_coefficient_from_rows():
     r = diffusion_coefficient(rows, reset_frequency=1000)
     assert r["intervals"] == 4 or r["intervals"] == 3
     assert abs(r["slope"] - 0.6) < 5e-3 and abs(r["diffusion_coefficient"] - 0.1) < 1e-3
+
+
+def test_unknown_jump_rate_is_rejected_with_a_clear_error():
+    """The reference takes any callable as JumpRate; the device evaluates the rate inside the list
+    kernels, so anything it does not know is refused before a handle is created."""
+    from cmdlmc_b200.topology import DeviceTopology
+    with pytest.raises(TypeError, match="cannot be evaluated on the device"):
+        DeviceTopology(None, 4, 3.0, 2.0, 0, jumprate=lambda d: d)
