@@ -230,7 +230,7 @@ def _lists(box, w, frames, rate):
     return t, counts, rsum, start, dest, dist, om
 
 
-@pytest.mark.parametrize("cfg", ["C1", "C2"])
+@pytest.mark.parametrize("cfg", ["C1", "C2", "T333"])
 def test_skin_list_of_the_dense_kernel_changes_no_bit(orc, monkeypatch, cfg):
     """The dense kernel keeps the filter's candidate set (radius + skin) across consecutive frames
     and re-filters it while the two largest displacements stay below the skin
@@ -239,7 +239,11 @@ def test_skin_list_of_the_dense_kernel_changes_no_bit(orc, monkeypatch, cfg):
     oracle's.  The trajectory holds what the displacement test has to survive: atoms re-imaged by
     whole cell vectors between frames, one atom jumping 3 A in a single step, a frame repeated."""
     import cmdlmc_b200 as cm
-    w = synth.workload(cfg)
+    if cfg == "T333":   # a full triclinic cell and an odd atom count (no TMA: plain frame loads)
+        w = synth.Workload("T333", synth._triclinic_cell(24.0, 23.0, 25.0, 0.15, -0.2, 0.1), 333, 0, 100,
+                           4096, 0.5, 3.0, 2.0, "Fermi", (0.06, 2.3, 0.1), 21, group_size=0)
+    else:
+        w = synth.workload(cfg)
     nfr = 4096                                   # several frames for every resident CTA
     frames = synth.trajectory(w, nfr)
     rng = np.random.RandomState(11)
@@ -264,7 +268,7 @@ def test_skin_list_of_the_dense_kernel_changes_no_bit(orc, monkeypatch, cfg):
     fr_s, reb_s, _ = runs["default"][0].skin_stats()
     assert fr_d == 0 and fr_s >= nfr - 16 and 0 < reb_s < fr_s // 2      # the list really is reused
     fr_l, reb_l, _ = runs["short list"][0].skin_stats()
-    if cfg == "C2":
+    if cfg != "C1":
         assert fr_l < fr_s                        # frames whose list did not fit went the direct way
     ref = runs["direct"]
     for name, got in runs.items():
