@@ -77,6 +77,7 @@ SIGNATURES = {
     "cmd_topo_n_images": (C.c_int, [vp]),
     "cmd_topo_nframes": (C.c_int64, [vp]),
     "cmd_topo_get_frame": (C.c_int, [vp, C.c_int64, ip, ip, dp, dp]),
+    "cmd_topo_set_selection": (C.c_int, [vp, C.c_int, ip]),
     "cmd_topo_get_block": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int64, ip, ip, dp, dp]),
     "cmd_topo_device_arrays": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                          C.POINTER(vp), C.POINTER(vp)]),

@@ -84,6 +84,10 @@ struct cmd_topo {
     size_t part_cap;
     double *d_upload;
     size_t upload_bytes;
+    // donor selection on the device (cmd_topo_set_selection): host blocks hold n_total atoms per
+    // frame, the donors are rows d_sel[0 .. n) of each
+    int *d_sel;
+    int n_total;
     const double *d_frames_last;  // frames of the last block (device)
     int64_t total_frames;
 };
@@ -601,6 +605,42 @@ __global__ void k_upcast_f32(const float *__restrict__ in, double *__restrict__ 
         out[i] = (double)in[i];
 }
 
+// donor rows of whole frames, up-cast on the way: out[f][i][:] = in[f][sel[i]][:]
+template <typename T>
+__global__ void k_gather_cast(const T *__restrict__ in, const int *__restrict__ sel, int n_total, int n,
+                              int64_t nframes, double *__restrict__ out)
+{
+    const int64_t per = (int64_t)n * 3, total = nframes * per;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = i / per;
+        const int r = (int)(i - f * per), a = r / 3, c = r - 3 * a;
+        out[i] = (double)in[(f * n_total + sel[a]) * 3 + c];
+    }
+}
+
+// the conversion behind a host copy: raw (float32 / float64, all atoms or the donors only) ->
+// float64 donor frames
+static int topo_convert(cmd_topo *t, const void *d_raw, int dtype_bytes, int64_t nframes, double *d_out,
+                        cudaStream_t st)
+{
+    const int64_t elems = nframes * (int64_t)t->n * 3;
+    int blocks = cmd_div_up(elems, 256);
+    if (blocks > cmd_global().sm_count * 16) blocks = cmd_global().sm_count * 16;
+    if (t->d_sel) {
+        if (dtype_bytes == 4)
+            k_gather_cast<float><<<blocks, 256, 0, st>>>((const float *)d_raw, t->d_sel, t->n_total, t->n, nframes, d_out);
+        else
+            k_gather_cast<double><<<blocks, 256, 0, st>>>((const double *)d_raw, t->d_sel, t->n_total, t->n, nframes, d_out);
+    } else if (dtype_bytes == 4) {
+        k_upcast_f32<<<blocks, 256, 0, st>>>((const float *)d_raw, d_out, elems);
+    } else {
+        return CMD_OK;   // float64 donors: copied in place
+    }
+    CMD_LAUNCHED();
+    return CMD_OK;
+}
+
 // ------------------------------------------------------------------ host side ------------------
 static double exact_sq_threshold(double rc)
 {
@@ -653,6 +693,7 @@ extern "C" void cmd_topo_destroy(cmd_topo *t)
     cudaFree(t->d_carry_start); cudaFree(t->d_carry_dest); cudaFree(t->d_carry_count);
     cudaFree(t->d_carry_rowoff);
     cudaFree(t->d_sched); cudaFree(t->d_upload); cudaFree(t->d_cap_need); cudaFree(t->d_lists);
+    cudaFree(t->d_sel);
     cudaFree(t->d_group); cudaFree(t->d_extra_upload);
     cell_free(t);
     free(t);
@@ -1548,8 +1589,10 @@ extern "C" int cmd_topo_seed_dev(cmd_topo *t, const double *d_frame_rebuild, con
 static int topo_stage(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes)
 {
     cudaStream_t st = cmd_global().stream;
-    size_t elems = (size_t)nframes * t->n * 3;
-    size_t need = elems * 8 + (dtype_bytes == 4 ? elems * 4 : 0);
+    const size_t elems = (size_t)nframes * t->n * 3;
+    const bool raw = t->d_sel != nullptr || dtype_bytes == 4;   // the copy lands behind the frames
+    const size_t raw_bytes = (size_t)nframes * (t->d_sel ? t->n_total : t->n) * 3 * dtype_bytes;
+    const size_t need = elems * 8 + (raw ? raw_bytes : 0);
     if (t->upload_bytes < need) {
         CMD_CUDA(cudaStreamSynchronize(st));
         cudaFree(t->d_upload);
@@ -1561,18 +1604,10 @@ static int topo_stage(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_
         }
         t->upload_bytes = need;
     }
+    void *dst = raw ? (void *)(t->d_upload + elems) : (void *)t->d_upload;
     int rc;
-    if (dtype_bytes == 8) {
-        if ((rc = cmd_h2d_staged(t->d_upload, h_frames, elems * 8, st))) return rc;
-    } else {
-        float *d32 = (float *)(t->d_upload + elems);
-        if ((rc = cmd_h2d_staged(d32, h_frames, elems * 4, st))) return rc;
-        int blocks = cmd_div_up(elems, 256);
-        if (blocks > cmd_global().sm_count * 16) blocks = cmd_global().sm_count * 16;
-        k_upcast_f32<<<blocks, 256, 0, st>>>(d32, t->d_upload, (int64_t)elems);
-        CMD_LAUNCHED();
-    }
-    return CMD_OK;
+    if ((rc = cmd_h2d_staged(dst, h_frames, raw ? raw_bytes : elems * 8, st))) return rc;
+    return topo_convert(t, dst, dtype_bytes, nframes, t->d_upload, st);
 }
 
 // Brute-force blocks from host memory: frames are independent, so the block is cut into chunks and
@@ -1583,7 +1618,9 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
     cudaStream_t st = g.stream;
     const size_t per_frame = (size_t)t->n * 3;
     const size_t elems = (size_t)nframes * per_frame;
-    const size_t need = elems * 8 + (dtype_bytes == 4 ? elems * 4 : 0);
+    const bool raw = t->d_sel != nullptr || dtype_bytes == 4;
+    const size_t raw_per_frame = (size_t)(t->d_sel ? t->n_total : t->n) * 3 * dtype_bytes;   // bytes
+    const size_t need = elems * 8 + (raw ? (size_t)nframes * raw_per_frame : 0);
     if (t->upload_bytes < need) {
         CMD_CUDA(cudaStreamSynchronize(st));
         cudaFree(t->d_upload);
@@ -1616,7 +1653,7 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
     // the staging buffer may still be read by kernels of the previous block
     CMD_CUDA(cudaEventRecord(g.copy_event[0], st));
     CMD_CUDA(cudaStreamWaitEvent(g.copy_stream, g.copy_event[0], 0));
-    float *d32 = (float *)(t->d_upload + elems);
+    unsigned char *d_raw = (unsigned char *)(t->d_upload + elems);
     int rc;
     bool sized = t->stride != 0;
     t->nframes = nframes;
@@ -1637,21 +1674,19 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
         const size_t off = (size_t)c0 * per_frame, ce = (size_t)cn * per_frame;
         const bool on_aux = !one_stream && (ci & 1) && sized;
         g.stream = st;
-        if (dtype_bytes == 8)
+        if (!raw)
             rc = cmd_h2d_staged(t->d_upload + off, (const double *)h_frames + off, ce * 8, g.copy_stream);
         else
-            rc = cmd_h2d_staged(d32 + off, (const float *)h_frames + off, ce * 4, g.copy_stream);
+            rc = cmd_h2d_staged(d_raw + (size_t)c0 * raw_per_frame,
+                                (const unsigned char *)h_frames + (size_t)c0 * raw_per_frame,
+                                (size_t)cn * raw_per_frame, g.copy_stream);
         if (rc) return rc;
         CMD_CUDA(cudaEventRecord(g.copy_event[1], g.copy_stream));
         cudaStream_t cs = on_aux ? g.aux_stream : st;
         CMD_CUDA(cudaStreamWaitEvent(cs, g.copy_event[1], 0));
         g.stream = cs;
-        if (dtype_bytes == 4) {
-            int blocks = cmd_div_up(ce, 256);
-            if (blocks > g.sm_count * 16) blocks = g.sm_count * 16;
-            k_upcast_f32<<<blocks, 256, 0, cs>>>(d32 + off, t->d_upload + off, (int64_t)ce);
-            CMD_LAUNCHED();
-        }
+        if (raw && (rc = topo_convert(t, d_raw + (size_t)c0 * raw_per_frame, dtype_bytes, cn, t->d_upload + off, cs)))
+            return rc;
         if (!sized) {   // first block ever: probe the capacity on the first frame, then allocate
             if ((rc = topo_autosize(t, t->d_upload))) return rc;
             sized = true;
@@ -1667,6 +1702,30 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
     CMD_CUDA(cudaStreamWaitEvent(st, g.aux_event[1], 0));
     t->total_frames += nframes;
     return topo_check_capacity(t);
+}
+
+extern "C" int cmd_topo_set_selection(cmd_topo *t, int n_total, const int *h_index)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || n_total < 0 || (n_total > 0 && (!h_index || n_total < t->n)))
+        return cmd_set_error(CMD_EINVAL, "bad argument");
+    cudaStream_t st = cmd_global().stream;
+    CMD_CUDA(cudaStreamSynchronize(st));
+    cudaFree(t->d_sel);
+    t->d_sel = nullptr;
+    t->n_total = 0;
+    if (n_total == 0) return CMD_OK;
+    for (int i = 0; i < t->n; i++)
+        if (h_index[i] < 0 || h_index[i] >= n_total)
+            return cmd_set_error(CMD_EINVAL, "selection index %d out of range (%d atoms)", h_index[i], n_total);
+    if (cudaMalloc((void **)&t->d_sel, (size_t)t->n * 4) != cudaSuccess) {
+        cudaGetLastError();
+        return cmd_set_error(CMD_ENOMEM, "cudaMalloc failed for the selection");
+    }
+    CMD_CUDA(cudaMemcpyAsync(t->d_sel, h_index, (size_t)t->n * 4, cudaMemcpyHostToDevice, st));
+    CMD_CUDA(cudaStreamSynchronize(st));
+    t->n_total = n_total;
+    return CMD_OK;
 }
 
 extern "C" int cmd_topo_build(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes)

@@ -133,13 +133,24 @@ class DeviceTopology:
     def nframes(self):
         return int(_abi.lib().cmd_topo_nframes(self._handle))
 
+    def set_selection(self, n_total, index):
+        """Donor selection on the device: from now on build() / skip() take whole frames
+        [F, n_total, 3] and the donors are rows `index` of each (n_total = 0: off again)."""
+        index = np.ascontiguousarray(index, dtype=np.int32) if n_total else None
+        if n_total and index.shape != (self.n_atoms,):
+            raise ValueError("one selection index per donor atom expected")
+        check(_abi.lib().cmd_topo_set_selection(self._handle, int(n_total),
+                                                ptr(index, C.c_int) if n_total else None))
+        self._n_rows = int(n_total) if n_total else self.n_atoms
+
     def build(self, frames):
-        """frames: host ndarray [F, n, 3] float64 or float32."""
+        """frames: host ndarray [F, n, 3] float64 or float32 ([F, n_total, 3] after set_selection)."""
         frames = np.ascontiguousarray(frames)
         if frames.dtype not in (np.float32, np.float64):
             frames = frames.astype(np.float64)
-        if frames.ndim != 3 or frames.shape[1:] != (self.n_atoms, 3):
-            raise ValueError("frames must have shape [F, %d, 3]" % self.n_atoms)
+        rows = getattr(self, "_n_rows", self.n_atoms)
+        if frames.ndim != 3 or frames.shape[1:] != (rows, 3):
+            raise ValueError("frames must have shape [F, %d, 3]" % rows)
         check(_abi.lib().cmd_topo_build(self._handle, frames.ctypes.data_as(C.c_void_p),
                                         frames.dtype.itemsize, frames.shape[0]))
 
@@ -149,6 +160,9 @@ class DeviceTopology:
         frames = np.ascontiguousarray(frames)
         if frames.dtype not in (np.float32, np.float64):
             frames = frames.astype(np.float64)
+        rows = getattr(self, "_n_rows", self.n_atoms)
+        if frames.ndim != 3 or frames.shape[1:] != (rows, 3):
+            raise ValueError("frames must have shape [F, %d, 3]" % rows)
         check(_abi.lib().cmd_topo_skip(self._handle, frames.ctypes.data_as(C.c_void_p),
                                        frames.dtype.itemsize, frames.shape[0]))
 
@@ -349,20 +363,40 @@ class NeighborTopology:
                 return
 
     def device_blocks(self, mode=MODE_VERLET, chunk_size=None):
-        """Yields (DeviceTopology, full_frames, donor_positions) per block of frames: the block's
-        neighbour lists and rates stay in HBM for the KMC kernel (no per-frame host traffic)."""
+        """Yields (DeviceTopology, full_frames, host block) per block of frames: the block's neighbour
+        lists and rates stay in HBM for the KMC kernel (no per-frame host traffic).  The host block is
+        what was uploaded: the donor positions, or whole frames when the selection ran on the device."""
         if chunk_size is not None:
             self.chunk_size = int(chunk_size)
         topo = None
+        select = None     # (n_total, donor rows): the selection runs on the device
         for full_frames in self._chunks():
             if isinstance(full_frames, _LazyFrames):   # array trajectory: one slice, no Frame objects
-                pos = self.trajectory.block(self.donor_atoms, full_frames.k0, full_frames.k1)
+                traj = self.trajectory
+                rows = traj.selection(self.donor_atoms)
+                n_total = traj.positions.shape[1]
+                if rows.size < n_total and 2 * rows.size >= n_total:
+                    # most atoms are donors: the chunk goes up as it lies in memory (no pass over it
+                    # on the host, the library stages pageable memory itself) and a gather kernel
+                    # picks the donor rows; with few donors the host gather moves fewer bytes
+                    select = (n_total, rows)
+                    pos = traj.positions[full_frames.k0:full_frames.k1]
+                    if not isinstance(pos, np.ndarray) or pos.dtype not in (np.float32, np.float64):
+                        pos = np.asarray(pos, dtype=np.float32 if pos.dtype == np.float32 else np.float64)
+                else:
+                    pos = traj.block(self.donor_atoms, full_frames.k0, full_frames.k1)
             else:
                 pos = np.stack([self._donor_positions(f) for f in full_frames])
             if topo is None:
-                topo = build_with_retry(
-                    lambda cap: DeviceTopology(self.atombox, pos.shape[1], self.cutoff,
-                                               self.buffer, mode, self._jumprate, cap), pos)
+                n_donors = select[1].size if select else pos.shape[1]
+
+                def make(cap):
+                    t = DeviceTopology(self.atombox, n_donors, self.cutoff, self.buffer, mode,
+                                       self._jumprate, cap)
+                    if select:
+                        t.set_selection(*select)
+                    return t
+                topo = build_with_retry(make, pos)
             else:
                 topo.build(pos)   # a capacity overflow mid-trajectory raises CmdError(-5)
             yield topo, full_frames, pos

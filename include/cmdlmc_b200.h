@@ -181,6 +181,12 @@ int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t nframes);
  * pageable blocks pass through the library's page-locked staging ring (the host copy of one piece
  * overlaps the DMA of the previous one and the kernels of the chunk before). */
 int cmd_topo_build(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes);
+/* Donor selection on the device: after this call the host blocks handed to cmd_topo_build /
+ * cmd_topo_skip hold ALL n_total atoms of every frame ([nframes][n_total][3], as a trajectory file
+ * stores them) and the topology's n_atoms donors are rows h_index[0 .. n_atoms) of each frame --
+ * the selection by atom name of trajectory_parser.py:69-71, done by a gather kernel behind the
+ * copy instead of a pass over the chunk on the host.  n_total = 0 switches it off again. */
+int cmd_topo_set_selection(cmd_topo *t, int n_total, const int *h_index);
 /* Frame-block sharding across GPUs: walks a block of frames that precedes this rank's own block
  * through the Verlet displacement / rebuild-decision pass only (topology.py:96-107) and builds
  * just the list of its last rebuild frame -- the state a sequential run has at the block end.

@@ -283,6 +283,44 @@ def test_skin_list_of_the_dense_kernel_changes_no_bit(orc, monkeypatch, cfg):
         np.testing.assert_array_equal(dist[f, :c], odist)
 
 
+@pytest.mark.parametrize("mode,dtype,nfr", [(0, np.float32, 2304), (1, np.float32, 300), (1, np.float64, 300)])
+def test_donor_selection_on_the_device_equals_the_host_gather(mode, dtype, nfr):
+    """Whole frames (oxygens and the heavy atoms they are bonded to, in shuffled order) go up as they
+    lie in memory and a gather kernel behind the copy picks the donor rows
+    (cmd_topo_set_selection); the lists are those of a block gathered on the host first -- through
+    the chunked brute-force upload and through the one-piece Verlet upload."""
+    from cmdlmc_b200.topology import DeviceTopology, build_with_retry
+    import cmdlmc_b200 as cm
+    w = synth.workload("C2")
+    allpos = synth.trajectory(w, nfr, with_extra=True)                 # [F, 400 O + 100 P, 3]
+    order = np.random.RandomState(2).permutation(allpos.shape[1])
+    allpos = np.ascontiguousarray(allpos[:, order].astype(dtype))
+    rows = np.flatnonzero(order < w.n_oxygen).astype(np.int32)         # where the oxygens ended up
+    rows = rows[np.argsort(order[rows])]                               # donor i = oxygen i
+    box = make_box(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+
+    def on_device(cap):
+        t = DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, mode, rate, cap)
+        t.set_selection(allpos.shape[1], rows)
+        return t
+    td = build_with_retry(on_device, allpos)
+    th = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, mode, rate, cap),
+                          np.ascontiguousarray(allpos[:, rows]))
+    cd, rd, sd = td.frame_info()
+    ch, rh, sh = th.frame_info()
+    np.testing.assert_array_equal(cd, ch)
+    np.testing.assert_array_equal(rd, rh)
+    np.testing.assert_array_equal(sd, sh)
+    for a, b in zip(td.get_block(0, nfr, cd, omega=True), th.get_block(0, nfr, ch, omega=True)):
+        pad = np.arange(a.shape[1])[None, :] >= cd[:, None]
+        a[pad] = 0
+        b[pad] = 0
+        np.testing.assert_array_equal(a, b)
+    with pytest.raises(ValueError):
+        td.build(allpos[:, rows])          # donor-only block while the selection is on
+
+
 @pytest.mark.parametrize("cfg,nfr", [("C1", 6), ("C2", 6), ("C4", 3)])
 def test_cell_list_path_equals_dense(orc, cfg, nfr):
     """The cell-list search (large boxes) and the dense search give the same arrays, bit for bit."""
