@@ -356,10 +356,17 @@ __device__ __forceinline__ double rate_eval(const RateParams &r, double x, doubl
     case CMD_RATE_FERMI_ANGLE:  // jumprate_generators.py:42-43
         return theta < r.par[3] ? 0.0 : fermi_eval(r, x);
     case CMD_RATE_AE: {  // IO/config_parser.py:334-342 (specification text; parity unpinned)
-        double u = x - r.par[3];
+        // E = a u / sqrt(b + 1/u^2) = a u^2 / sqrt(b u^2 + 1) for u > 0: one reciprocal square root
+        // instead of a division, a square root and another division; exp through exp_core.  A few
+        // ulp from the restatement's libm value (the gate is 1e-10 relative).
+        const double u = x - r.par[3];
         if (!(u > 0)) return r.par[0];
-        double e = r.par[1] * u / sqrt(r.par[2] + 1.0 / (u * u));
-        return r.par[0] * exp(-e / (CMD_KB_EV * r.par[4]));
+        const double u2 = u * u;
+        const double e = r.par[1] * u2 * rsqrt(fma(r.par[2], u2, 1.0));
+        const double z = -e * __drcp_rn(CMD_KB_EV * r.par[4]);
+        if (!(z > -700.0) || !(u2 < 1e300))   // cold: underflowing rate, overflowing u^2, nan
+            return r.par[0] * exp(-(r.par[1] * u / sqrt(r.par[2] + 1.0 / (u * u))) / (CMD_KB_EV * r.par[4]));
+        return r.par[0] * exp_core(z);
     }
     case CMD_RATE_EXP:  // IO/config_parser.py:344-345
         return r.par[0] * exp(r.par[1] * x);
