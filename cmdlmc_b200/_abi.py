@@ -39,6 +39,7 @@ SIGNATURES = {
     "cmd_sync": (C.c_int, []),
     "cmd_launch_count": (C.c_int64, []),
     "cmd_fp64_peak": (C.c_int, [C.c_int, dp]),
+    "cmd_smem_peak": (C.c_int, [C.c_int, dp]),
     "cmd_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
     "cmd_host_free": (C.c_int, [vp]),
     "cmd_staging_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), ip]),

@@ -128,6 +128,60 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// Shared-memory read peak: every thread streams 16-byte loads (conflict-free, one wavefront per
+// quarter warp) over a 32 KB window of its CTA's shared memory.
+__global__ void __launch_bounds__(1024) k_smem_peak(double *out, int iters)
+{
+    __shared__ uint4 buf[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) buf[i] = make_uint4(i, i + 1, i + 2, i + 3);
+    __syncthreads();
+    unsigned acc = 0;
+    int at = threadIdx.x;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {   // volatile: the loads are what is measured
+            uint4 v;
+            const unsigned addr = (unsigned)__cvta_generic_to_shared(&buf[(at + u * 128) & 2047]);
+            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+            acc += v.x ^ v.y ^ v.z ^ v.w;
+        }
+        at = (at + 1024) & 2047;
+    }
+    if (acc == 0xdeadbeefu) out[0] = acc;   // keeps the loads alive
+}
+
+extern "C" int cmd_smem_peak(int iters, double *gbs)
+{
+    CMD_REQUIRE_INIT();
+    if (!gbs || iters < 1) return cmd_set_error(CMD_EINVAL, "bad argument");
+    CmdGlobal &g = cmd_global();
+    const int blocks = g.sm_count * 2, threads = 1024;
+    void *buf;
+    int rc = cmd_scratch(5, 64, &buf);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    CMD_CUDA(cudaEventCreate(&e0));
+    CMD_CUDA(cudaEventCreate(&e1));
+    k_smem_peak<<<blocks, threads, 0, g.stream>>>((double *)buf, iters / 8 + 1);  // warm-up
+    CMD_LAUNCHED();
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CMD_CUDA(cudaEventRecord(e0, g.stream));
+        k_smem_peak<<<blocks, threads, 0, g.stream>>>((double *)buf, iters);
+        CMD_LAUNCHED();
+        CMD_CUDA(cudaEventRecord(e1, g.stream));
+        CMD_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        CMD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *gbs = 16.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e9;
+    return CMD_OK;
+}
+
 extern "C" int cmd_fp64_peak(int iters, double *tflops)
 {
     CMD_REQUIRE_INIT();

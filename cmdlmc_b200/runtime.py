@@ -95,6 +95,15 @@ def fp64_peak_tflops(iters=20000):
     return v.value
 
 
+def smem_peak_gbs(iters=4000):
+    """Measured shared-memory read rate of the whole GPU in GB/s (cmd_smem_peak)."""
+    import ctypes as C
+    ensure_init()
+    v = C.c_double(0)
+    _abi.check(_abi.lib().cmd_smem_peak(int(iters), C.byref(v)))
+    return v.value
+
+
 def numa_topology(device=None):
     """What the host says about NUMA placement of this GPU: node count of the machine, the node of
     the GPU's PCIe function (-1: the platform reports none, as on single-node or virtualised

@@ -72,6 +72,10 @@ int64_t cmd_launch_count(void);
 /* Measured-peak helper: runs a dependent-free DFMA loop on every SM and returns the achieved
  * FP64 rate in TFLOP/s (the roofline denominator of the FP64-bound kernels). */
 int cmd_fp64_peak(int iters, double *tflops);
+/* The same for shared memory: conflict-free 16-byte loads on every SM, GB/s over the whole GPU
+ * (the roofline denominator of the KMC replica kernel, which streams the pair lists out of a
+ * shared-memory ring). */
+int cmd_smem_peak(int iters, double *gbs);
 
 /* ---------------------------------------------------------------- AtomBox --------------- */
 /* Replaces AtomBoxCubic.__cinit__ (n_values == 3, PBCHelper.pyx:216-226) and
