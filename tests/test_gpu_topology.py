@@ -576,6 +576,57 @@ def test_full_size_c2_trajectory_properties():
     assert n_pairs > 6000 * total
 
 
+def test_full_size_c2_bruteforce_host_blocks(orc):
+    """BASELINE.json config 2 at its full size in brute-force mode, the way the bench's end-to-end
+    number runs: float32 host blocks of 16 384 frames through cmd_topo_build (chunked upload, chunk
+    kernels on two streams, skin list per persistent CTA).  Size-independent properties on every
+    frame (even counts, finite positive rate sums, counts equal to a second topology that takes the
+    direct filter path), order / symmetry and the oracle's lists on sampled frames -- among them the
+    frames right at the chunk boundaries."""
+    from cmdlmc_b200.topology import DeviceTopology, MODE_BRUTEFORCE, build_with_retry
+    import cmdlmc_b200 as cm
+    import os
+    w = synth.workload("C2")
+    total, block = 98304, 16384
+    box, obox = make_box(w.cell), orc.OracleBox(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    topo = direct = None
+    rng = np.random.RandomState(1)
+    for b0 in range(0, total, block):
+        fr32 = synth.trajectory(w, block, start=b0, dtype=np.float32)
+        if topo is None:
+            topo = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer,
+                                                               MODE_BRUTEFORCE, rate, cap), fr32)
+            os.environ["CMDLMC_B200_DENSE_SKIN"] = "0"
+            try:
+                direct = DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, MODE_BRUTEFORCE, rate,
+                                        topo.stride)
+            finally:
+                del os.environ["CMDLMC_B200_DENSE_SKIN"]
+        else:
+            topo.build(fr32)
+        direct.build(fr32)
+        counts, _, rsum = topo.frame_info()
+        dcounts, _, drsum = direct.frame_info()
+        assert (counts > 0).all() and (counts % 2 == 0).all()
+        np.testing.assert_array_equal(counts, dcounts)
+        np.testing.assert_array_equal(rsum, drsum)
+        edges = [0, 2047, 2048, 2049, 4095, 4096, block - 1]
+        for f in sorted(set(edges) | set(rng.choice(block, 3, replace=False).tolist())):
+            s, d, dist, om = topo.get_frame(int(f), int(counts[f]))
+            key = s.astype(np.int64) * w.n_oxygen + d
+            assert (np.diff(key) > 0).all()
+            mirror = np.argsort(d.astype(np.int64) * w.n_oxygen + s, kind="stable")
+            np.testing.assert_array_equal(dist[mirror], dist)
+            orow, ocol, odist = orc.topology_bruteforce(obox, fr32[f].astype(np.float64), w.cutoff, w.buffer)
+            np.testing.assert_array_equal(s, orow)
+            np.testing.assert_array_equal(d, ocol)
+            np.testing.assert_array_equal(dist, odist)
+    fr, reb, _ = topo.skin_stats()
+    assert fr > 0.9 * total and reb < fr // 4        # the skin list carried most frames
+    assert direct.skin_stats()[0] == 0
+
+
 def test_randomised_sweep_vs_oracle(orc):
     """Seeded sweep over cell shapes (incl. strongly skewed cells that keep periodic images in the
     filter), atom counts (odd / even / tiny / beyond one warp), radii (up to half the smallest
