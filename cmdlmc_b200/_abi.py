@@ -79,6 +79,8 @@ SIGNATURES = {
     "cmd_topo_nframes": (C.c_int64, [vp]),
     "cmd_topo_get_frame": (C.c_int, [vp, C.c_int64, ip, ip, dp, dp]),
     "cmd_topo_set_selection": (C.c_int, [vp, C.c_int, ip]),
+    "cmd_topo_build_async": (C.c_int, [vp, vp, C.c_int, C.c_int64]),
+    "cmd_topo_wait": (C.c_int, [vp]),
     "cmd_topo_get_block": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int64, ip, ip, dp, dp]),
     "cmd_topo_device_arrays": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                          C.POINTER(vp), C.POINTER(vp)]),

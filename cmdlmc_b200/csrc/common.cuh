@@ -49,6 +49,9 @@ struct CmdGlobal {
     // as those of chunk i drain (cmd_topo_build)
     cudaStream_t aux_stream = 0;
     cudaEvent_t aux_event[2] = {0, 0};
+    // read-backs of a block that is complete while later blocks are still queued on `stream`
+    // (cmd_topo_build_async / cmd_topo_wait / cmd_topo_frame_info)
+    cudaStream_t ctl_stream = 0;
     int64_t launches = 0;
     // stream-ordered scratch for the host-pointer entry points
     void *scratch[6] = {0, 0, 0, 0, 0, 0};

@@ -88,6 +88,10 @@ struct cmd_topo {
     // frame, the donors are rows d_sel[0 .. n) of each
     int *d_sel;
     int n_total;
+    // asynchronous blocks (cmd_topo_build_async): `done` fires when the block's last kernel has
+    // finished; `pending` until cmd_topo_wait has checked the capacity
+    cudaEvent_t done;
+    bool done_valid, pending;
     const double *d_frames_last;  // frames of the last block (device)
     int64_t total_frames;
 };
@@ -694,6 +698,7 @@ extern "C" void cmd_topo_destroy(cmd_topo *t)
     cudaFree(t->d_carry_rowoff);
     cudaFree(t->d_sched); cudaFree(t->d_upload); cudaFree(t->d_cap_need); cudaFree(t->d_lists);
     cudaFree(t->d_sel);
+    if (t->done) cudaEventDestroy(t->done);
     cudaFree(t->d_group); cudaFree(t->d_extra_upload);
     cell_free(t);
     free(t);
@@ -1398,6 +1403,7 @@ static int topo_build_impl(cmd_topo *t, const double *d_frames, int64_t nframes,
     CmdGlobal &g = cmd_global();
     cudaStream_t st = g.stream;
     int rc;
+    t->done_valid = false;   // this block completes in stream order, not behind the last pipelined one
     if (t->stride == 0 && (rc = topo_autosize(t, d_frames))) return rc;
     if ((rc = topo_reserve(t, nframes))) return rc;
     if (t->mode == CMD_TOPO_VERLET && !t->d_carry_start) {
@@ -1557,6 +1563,7 @@ extern "C" int cmd_topo_seed_dev(cmd_topo *t, const double *d_frame_rebuild, con
     if (!t || !d_frame_rebuild || !d_frame_prev) return cmd_set_error(CMD_EINVAL, "bad argument");
     if (t->mode != CMD_TOPO_VERLET || t->total_frames == 0 || t->stride == 0)
         return cmd_set_error(CMD_ESTATE, "call cmd_topo_skip_dr_dev first");
+    t->done_valid = false;
     CmdGlobal &g = cmd_global();
     cudaStream_t st = g.stream;
     int rc;
@@ -1612,7 +1619,8 @@ static int topo_stage(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_
 
 // Brute-force blocks from host memory: frames are independent, so the block is cut into chunks and
 // the host->device copy of chunk i+1 (copy stream) overlaps the pair kernel of chunk i.
-static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes)
+static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes,
+                                bool async = false)
 {
     CmdGlobal &g = cmd_global();
     cudaStream_t st = g.stream;
@@ -1650,9 +1658,16 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
     const int nch = nch_env && atoi(nch_env) > 0 ? atoi(nch_env) : TOPO_UPLOAD_CHUNKS;
     int64_t chunk = (nframes + nch - 1) / nch;
     if (chunk < 1024) chunk = 1024;   // several consecutive frames per persistent CTA (skin list)
-    // the staging buffer may still be read by kernels of the previous block
-    CMD_CUDA(cudaEventRecord(g.copy_event[0], st));
-    CMD_CUDA(cudaStreamWaitEvent(g.copy_stream, g.copy_event[0], 0));
+    // the staging buffer may still be read by kernels of the previous block: everything queued on
+    // the stream (blocking call), or this topology's own previous block (asynchronous call -- the
+    // copies must not wait for the blocks of OTHER topologies still queued on the stream)
+    if (!t->done) CMD_CUDA(cudaEventCreateWithFlags(&t->done, cudaEventDisableTiming));
+    if (async) {
+        if (t->done_valid) CMD_CUDA(cudaStreamWaitEvent(g.copy_stream, t->done, 0));
+    } else {
+        CMD_CUDA(cudaEventRecord(g.copy_event[0], st));
+        CMD_CUDA(cudaStreamWaitEvent(g.copy_stream, g.copy_event[0], 0));
+    }
     unsigned char *d_raw = (unsigned char *)(t->d_upload + elems);
     int rc;
     bool sized = t->stride != 0;
@@ -1701,7 +1716,57 @@ static int topo_build_pipelined(cmd_topo *t, const void *h_frames, int dtype_byt
     CMD_CUDA(cudaEventRecord(g.aux_event[1], g.aux_stream));
     CMD_CUDA(cudaStreamWaitEvent(st, g.aux_event[1], 0));
     t->total_frames += nframes;
+    CMD_CUDA(cudaEventRecord(t->done, st));
+    t->done_valid = true;
+    if (async) { t->pending = true; return CMD_OK; }
     return topo_check_capacity(t);
+}
+
+// the stream for read-backs of a finished block: behind the block's `done` event only
+static int topo_ctl_stream(const cmd_topo *t, cudaStream_t *out)
+{
+    CmdGlobal &g = cmd_global();
+    if (!t->done_valid) { *out = g.stream; return CMD_OK; }
+    if (!g.ctl_stream) CMD_CUDA(cudaStreamCreateWithFlags(&g.ctl_stream, cudaStreamNonBlocking));
+    CMD_CUDA(cudaStreamWaitEvent(g.ctl_stream, t->done, 0));
+    *out = g.ctl_stream;
+    return CMD_OK;
+}
+
+extern "C" int cmd_topo_build_async(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes)
+{
+    CMD_REQUIRE_INIT();
+    if (!t || !h_frames || nframes < 1 || (dtype_bytes != 4 && dtype_bytes != 8))
+        return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (nframes > 0x7fffffff / 2) return cmd_set_error(CMD_EINVAL, "block too large");
+    if (t->pending) return cmd_set_error(CMD_ESTATE, "cmd_topo_wait has not been called for the last block");
+    if (t->mode != CMD_TOPO_BRUTEFORCE || t->stride == 0 || nframes < 512)
+        return cmd_set_error(CMD_ESTATE, "asynchronous blocks: brute-force mode, at least 512 frames, and "
+                                         "a topology that has built one block already (capacity known)");
+    return topo_build_pipelined(t, h_frames, dtype_bytes, nframes, true);
+}
+
+extern "C" int cmd_topo_wait(cmd_topo *t)
+{
+    CMD_REQUIRE_INIT();
+    if (!t) return cmd_set_error(CMD_EINVAL, "bad argument");
+    if (!t->pending) return CMD_OK;
+    t->pending = false;
+    cudaStream_t cs;
+    int rc = topo_ctl_stream(t, &cs);
+    if (rc) return rc;
+    int err = 0;
+    CMD_CUDA(cudaMemcpyAsync(&err, t->d_err, sizeof(int), cudaMemcpyDeviceToHost, cs));
+    CMD_CUDA(cudaStreamSynchronize(cs));
+    if (err > 0) {
+        CMD_CUDA(cudaMemsetAsync(t->d_err, 0, sizeof(int), cs));
+        CMD_CUDA(cudaStreamSynchronize(cs));
+        t->capacity_needed = err;
+        return cmd_set_error(CMD_ECAPACITY, "a frame has %d directed pairs but the per-frame "
+                             "capacity is %lld: re-create the topology with a larger "
+                             "capacity_per_frame", err, (long long)t->stride);
+    }
+    return CMD_OK;
 }
 
 extern "C" int cmd_topo_set_selection(cmd_topo *t, int n_total, const int *h_index)
@@ -1757,7 +1822,13 @@ extern "C" int cmd_topo_frame_info(const cmd_topo *t, int64_t *counts, uint8_t *
 {
     CMD_REQUIRE_INIT();
     if (!t || t->nframes < 1) return cmd_set_error(CMD_ESTATE, "no block has been built");
-    cudaStream_t st = cmd_global().stream;
+    // a block built by the pipelined path is read back behind its own completion, not behind
+    // whatever else is queued on the stream (asynchronous blocks of other topologies)
+    cudaStream_t st;
+    {
+        int rc = topo_ctl_stream(t, &st);
+        if (rc) return rc;
+    }
     if (counts) {
         int *tmp = (int *)malloc(t->nframes * sizeof(int));
         if (!tmp) return cmd_set_error(CMD_ENOMEM, "out of host memory");

@@ -154,6 +154,27 @@ class DeviceTopology:
         check(_abi.lib().cmd_topo_build(self._handle, frames.ctypes.data_as(C.c_void_p),
                                         frames.dtype.itemsize, frames.shape[0]))
 
+    def build_async(self, frames):
+        """Queues the upload and the kernels of a brute-force block and returns at once
+        (cmd_topo_build_async); `frames` (page-locked for a real overlap) must stay untouched until
+        wait().  Used alternately on two topologies, the upload of one block overlaps the kernels
+        of the other."""
+        if frames.dtype not in (np.float32, np.float64) or not frames.flags.c_contiguous:
+            raise ValueError("build_async takes a C-contiguous float32 / float64 block as it is")
+        rows = getattr(self, "_n_rows", self.n_atoms)
+        if frames.ndim != 3 or frames.shape[1:] != (rows, 3):
+            raise ValueError("frames must have shape [F, %d, 3]" % rows)
+        self._async_block = frames           # keeps the host block alive
+        check(_abi.lib().cmd_topo_build_async(self._handle, frames.ctypes.data_as(C.c_void_p),
+                                              frames.dtype.itemsize, frames.shape[0]))
+
+    def wait(self):
+        """Completion of the last build_async block; raises on a capacity overflow."""
+        try:
+            check(_abi.lib().cmd_topo_wait(self._handle))
+        finally:
+            self._async_block = None
+
     def skip(self, frames):
         """Walks frames that precede this rank's block through the Verlet schedule pass only
         (frame-block sharding, cmd_topo_skip); produces no per-frame results."""

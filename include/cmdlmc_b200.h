@@ -185,6 +185,16 @@ int cmd_topo_build_dev(cmd_topo *t, const double *d_frames, int64_t nframes);
  * pageable blocks pass through the library's page-locked staging ring (the host copy of one piece
  * overlaps the DMA of the previous one and the kernels of the chunk before). */
 int cmd_topo_build(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes);
+/* Streaming form for brute-force blocks: queues the upload and the kernels of the block and returns
+ * without waiting.  With two topologies used alternately the upload of block k+1 (and its first
+ * chunk in particular, which nothing hides inside one block) overlaps the kernels of block k --
+ * the double-buffered chunk upload of a trajectory reader (IO/trajectory_parser.py:296-337 reads
+ * the next chunk only after the previous one has been consumed).  The host block must stay
+ * untouched until cmd_topo_wait(t) returns; cmd_topo_wait also reports a capacity overflow.
+ * cmd_topo_frame_info of such a block waits for that block only, not for later ones.  Needs a
+ * topology that has built one block already (the per-frame capacity is known). */
+int cmd_topo_build_async(cmd_topo *t, const void *h_frames, int dtype_bytes, int64_t nframes);
+int cmd_topo_wait(cmd_topo *t);
 /* Donor selection on the device: after this call the host blocks handed to cmd_topo_build /
  * cmd_topo_skip hold ALL n_total atoms of every frame ([nframes][n_total][3], as a trajectory file
  * stores them) and the topology's n_atoms donors are rows h_index[0 .. n_atoms) of each frame --

@@ -627,6 +627,58 @@ def test_full_size_c2_bruteforce_host_blocks(orc):
     assert direct.skin_stats()[0] == 0
 
 
+def test_streaming_blocks_on_two_topologies_equal_blocking_builds():
+    """cmd_topo_build_async on two topologies used alternately (the upload of block k+1 overlaps the
+    kernels of block k; results are read one block late) against blocking builds of the same
+    blocks: counts, rate sums and sampled lists are the same bits.  Blocks come from page-locked
+    and from plain memory."""
+    from cmdlmc_b200 import runtime
+    from cmdlmc_b200.topology import DeviceTopology, MODE_BRUTEFORCE, build_with_retry
+    import cmdlmc_b200 as cm
+    w = synth.workload("C2")
+    block, nblocks = 4096, 6
+    box = make_box(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    blocks = [np.ascontiguousarray(synth.trajectory(w, block, start=k * block, dtype=np.float32))
+              for k in range(nblocks)]
+    ref = build_with_retry(lambda cap: DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer,
+                                                      MODE_BRUTEFORCE, rate, cap), blocks[0])
+    want = []
+    for b in blocks:
+        ref.build(b)
+        c, _, r = ref.frame_info()
+        want.append((c, r, ref.get_frame(block - 1, int(c[-1])), ref.get_frame(7, int(c[7]))))
+    two = [DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, MODE_BRUTEFORCE, rate, ref.stride)
+           for _ in range(2)]
+    pinned = [runtime.pinned_empty(blocks[0].shape, np.float32) for _ in range(2)]
+    for t in two:
+        t.build(blocks[0])                       # the first block of a topology is a blocking one
+        with pytest.raises(ValueError):
+            t.build_async(blocks[0][:, ::2])     # not contiguous / wrong shape
+    got = [None] * nblocks
+
+    def collect(k):
+        t = two[k % 2]
+        t.wait()
+        c, _, r = t.frame_info()
+        got[k] = (c, r, t.get_frame(block - 1, int(c[-1])), t.get_frame(7, int(c[7])))
+    for k in range(nblocks):
+        src = blocks[k]
+        if k % 3 != 2:                           # two of three blocks through page-locked memory
+            pinned[k % 2][...] = blocks[k]
+            src = pinned[k % 2]
+        two[k % 2].build_async(src)
+        if k >= 1:
+            collect(k - 1)                       # the previous block, while this one is in flight
+    collect(nblocks - 1)
+    for k in range(nblocks):
+        np.testing.assert_array_equal(got[k][0], want[k][0])
+        np.testing.assert_array_equal(got[k][1], want[k][1])
+        for fa, fb in zip(got[k][2:], want[k][2:]):
+            for a, b in zip(fa, fb):
+                np.testing.assert_array_equal(a, b)
+
+
 def test_randomised_sweep_vs_oracle(orc):
     """Seeded sweep over cell shapes (incl. strongly skewed cells that keep periodic images in the
     filter), atom counts (odd / even / tiny / beyond one warp), radii (up to half the smallest
