@@ -627,6 +627,50 @@ def test_full_size_c2_bruteforce_host_blocks(orc):
     assert direct.skin_stats()[0] == 0
 
 
+def test_skin_list_on_unrelated_frames(orc, monkeypatch):
+    """Brute-force callers may hand over frames that have nothing to do with each other: the
+    displacement test then fails on (nearly) every frame and the list is rebuilt -- same lists as
+    the direct path, and the oracle's on sampled frames.  Uniformly random positions, so pairs
+    come arbitrarily close and the counts fluctuate."""
+    import torch
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.topology import DeviceTopology
+    w = synth.workload("C2")
+    nfr = 2048
+    rng = np.random.RandomState(8)
+    frames = rng.uniform(0, 1, size=(nfr, w.n_oxygen, 3)) @ w.cell_matrix
+    frames[100] = frames[99]                       # and one exact repeat in between
+    box, obox = make_box(w.cell), orc.OracleBox(w.cell)
+    rate = cm.Fermi(*w.rate_params)
+    d = torch.from_numpy(frames).cuda()
+    res = []
+    for skin in ("0", None):
+        if skin is None:
+            monkeypatch.delenv("CMDLMC_B200_DENSE_SKIN", raising=False)
+        else:
+            monkeypatch.setenv("CMDLMC_B200_DENSE_SKIN", skin)
+        t = DeviceTopology(box, w.n_oxygen, w.cutoff, w.buffer, 0, rate, 16384, path=0)
+        t.build_dev(d.data_ptr(), nfr)
+        counts, _, rsum = t.frame_info()
+        assert (counts > 0).all()
+        blk = t.get_block(0, nfr, counts, omega=True)
+        pad = np.arange(blk[0].shape[1])[None, :] >= counts[:, None]
+        for a in blk:
+            a[pad] = 0
+        res.append((t, counts, rsum) + blk)
+    fr, reb, _ = res[1][0].skin_stats()
+    assert fr >= nfr - 16 and reb >= fr - 8         # rebuilt on (nearly) every frame
+    for a, b in zip(res[0][1:], res[1][1:]):
+        np.testing.assert_array_equal(a, b)
+    _, counts, _, start, dest, dist, _ = res[1]
+    for f in (0, 99, 100, 101, 1500, nfr - 1):
+        orow, ocol, odist = orc.topology_bruteforce(obox, frames[f], w.cutoff, w.buffer)
+        c = int(counts[f])
+        np.testing.assert_array_equal(start[f, :c], orow)
+        np.testing.assert_array_equal(dest[f, :c], ocol)
+        np.testing.assert_array_equal(dist[f, :c], odist)
+
+
 def test_streaming_blocks_on_two_topologies_equal_blocking_builds():
     """cmd_topo_build_async on two topologies used alternately (the upload of block k+1 overlaps the
     kernels of block k; results are read one block late) against blocking builds of the same
