@@ -539,7 +539,10 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         if (!direct) {
             // (e) the skin list through the same packed-half filter at the radius itself, two
             // candidates per thread (low / high halves); survivors -> the exact stage's list
-            __syncthreads();   // s.misc[0] == 0, the list and its length visible to the CTA
+            // after a rebuild: s.misc[0] == 0, the list and its length visible to the CTA (a reused
+            // list: the barrier of the displacement test already stands between this point and the
+            // frame's writes of qa / qc / s.misc[0])
+            if (rebuild) __syncthreads();
             const int n_list = s.misc[34];
             const unsigned *my_list = lists + (size_t)blockIdx.x * cap_l;
             if (tid == 0) {   // statistics: frames, rebuilds, list entries filtered
