@@ -501,10 +501,14 @@ k_schedule_cluster(const double *__restrict__ dr, double *__restrict__ displacem
     cluster.sync();   // no CTA leaves while its shared memory may still be written
 }
 
+#ifndef REFRESH_MINB
+#define REFRESH_MINB 6   // 40 registers.  With the next pair prefetched (below): C2 Verlet pipeline 1.63 ->
+                         // 1.52 ms per 16 384 frames; 8 CTAs of 32 registers spill: 1.57 ms
+#endif
 // Refresh of a kept list (topology.py:110): dist = length(frame[row], frame[col]), same pairs.
 // One CTA per refreshed frame; the head list is either a frame of this block or the carry.
 template <bool STAGE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, REFRESH_MINB)
 k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RateParams rp,
           const double *__restrict__ frames, const int *__restrict__ ids,
           const int *__restrict__ n_ids, const int *__restrict__ head, int n, int64_t stride,
@@ -539,8 +543,15 @@ k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RatePara
     double rsum = 0.0;
     const int share = (p + (int)gridDim.y - 1) / (int)gridDim.y;
     const int k_lo = min((int)blockIdx.y * share, p), k_hi = min(k_lo + share, p);
-    for (int k = k_lo + threadIdx.x; k < k_hi; k += blockDim.x) {
-        int a = hs[k], b = hdst[k];
+    // the pair of the NEXT trip is fetched before this trip's arithmetic: the head list may be a
+    // frame of this very block (hs aliases out_start), so the compiler cannot hoist the loads over
+    // the stores itself
+    int k = k_lo + threadIdx.x;
+    int a_nx = k < k_hi ? hs[k] : 0, b_nx = k < k_hi ? hdst[k] : 0;
+    for (; k < k_hi; k += blockDim.x) {
+        const int a = a_nx, b = b_nx;
+        const int kn = k + blockDim.x;
+        if (kn < k_hi) { a_nx = hs[kn]; b_nx = hdst[kn]; }
         double pa[3] = {sp[3 * a], sp[3 * a + 1], sp[3 * a + 2]};
         double pb[3] = {sp[3 * b], sp[3 * b + 1], sp[3 * b + 2]};
         double dist;
