@@ -502,8 +502,9 @@ k_schedule_cluster(const double *__restrict__ dr, double *__restrict__ displacem
 }
 
 #ifndef REFRESH_MINB
-#define REFRESH_MINB 6   // 40 registers.  With the next pair prefetched (below): C2 Verlet pipeline 1.63 ->
-                         // 1.52 ms per 16 384 frames; 8 CTAs of 32 registers spill: 1.57 ms
+#define REFRESH_MINB 5   // 48 registers.  With two pairs per trip and the next trip's pairs prefetched
+                         // (below): C2 Verlet pipeline 1.63 -> 1.50 ms per 16 384 frames (one pair per trip
+                         // at six CTAs of 40 registers: 1.52 ms; eight CTAs of 32 registers spill: 1.57 ms)
 #endif
 // Refresh of a kept list (topology.py:110): dist = length(frame[row], frame[col]), same pairs.
 // One CTA per refreshed frame; the head list is either a frame of this block or the carry.
@@ -546,27 +547,47 @@ k_refresh(const __grid_constant__ BoxParams bx, const __grid_constant__ RatePara
     // the pair of the NEXT trip is fetched before this trip's arithmetic: the head list may be a
     // frame of this very block (hs aliases out_start), so the compiler cannot hoist the loads over
     // the stores itself
+    // two pairs per trip (independent FP64 chains), the pairs of the next trip fetched first
+    const int T = blockDim.x;
     int k = k_lo + threadIdx.x;
-    int a_nx = k < k_hi ? hs[k] : 0, b_nx = k < k_hi ? hdst[k] : 0;
-    for (; k < k_hi; k += blockDim.x) {
-        const int a = a_nx, b = b_nx;
-        const int kn = k + blockDim.x;
-        if (kn < k_hi) { a_nx = hs[kn]; b_nx = hdst[kn]; }
-        double pa[3] = {sp[3 * a], sp[3 * a + 1], sp[3 * a + 2]};
-        double pb[3] = {sp[3 * b], sp[3 * b + 1], sp[3 * b + 2]};
-        double dist;
-        if (bx.kind == 0) dist = length_exact(bx, pa, pb);
-        else {   // zero image + the images kept for the refresh radius == the 27-image minimum here
-            double d[3];
-            if (bx.sparse == 2) diff_general_norm_sp<2>(bx, pa, pb, d);
-            else if (bx.sparse == 1) diff_general_norm_sp<1>(bx, pa, pb, d);
-            else diff_general_norm_exact(bx, pa, pb, d);
-            dist = sqrt(min_image_norm2_kept(bx, d));
+    int a_nx[2], b_nx[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        a_nx[q] = k + q * T < k_hi ? hs[k + q * T] : 0;
+        b_nx[q] = k + q * T < k_hi ? hdst[k + q * T] : 0;
+    }
+    for (; k < k_hi; k += 2 * T) {
+        const int a[2] = {a_nx[0], a_nx[1]}, b[2] = {b_nx[0], b_nx[1]};
+        const bool two = k + T < k_hi;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int kn = k + (2 + q) * T;
+            if (kn < k_hi) { a_nx[q] = hs[kn]; b_nx[q] = hdst[kn]; }
         }
-        double om = rate_eval(rp, dist, 0.0);
-        rsum += om;
-        out_start[base + k] = a; out_dest[base + k] = b;
-        out_dist[base + k] = dist; out_omega[base + k] = om;
+        double dist[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const double pa[3] = {sp[3 * a[q]], sp[3 * a[q] + 1], sp[3 * a[q] + 2]};
+            const double pb[3] = {sp[3 * b[q]], sp[3 * b[q] + 1], sp[3 * b[q] + 2]};
+            if (bx.kind == 0) dist[q] = length_exact(bx, pa, pb);
+            else {   // zero image + the images kept for the refresh radius == the 27-image minimum here
+                double d[3];
+                if (bx.sparse == 2) diff_general_norm_sp<2>(bx, pa, pb, d);
+                else if (bx.sparse == 1) diff_general_norm_sp<1>(bx, pa, pb, d);
+                else diff_general_norm_exact(bx, pa, pb, d);
+                dist[q] = sqrt(min_image_norm2_kept(bx, d));
+            }
+        }
+        double om[2];
+        rate_eval2(rp, dist[0], dist[1], om);
+        rsum += om[0];
+        out_start[base + k] = a[0]; out_dest[base + k] = b[0];
+        out_dist[base + k] = dist[0]; out_omega[base + k] = om[0];
+        if (two) {
+            rsum += om[1];
+            out_start[base + k + T] = a[1]; out_dest[base + k + T] = b[1];
+            out_dist[base + k + T] = dist[1]; out_omega[base + k + T] = om[1];
+        }
     }
     for (int o = 16; o > 0; o >>= 1) rsum += __shfl_down_sync(0xffffffffu, rsum, o);
     __shared__ double wsum[8];
