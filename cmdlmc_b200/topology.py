@@ -478,18 +478,17 @@ class AngleTopology(NeighborTopology):
         # the iteration over the topology starts at the second frame
         first_frame = next(self._frames())
         self._cache.append(first_frame)
-        distances_PO = self.atombox.length_all_to_all(first_frame[self.extra_atoms].atom_positions,
-                                                      first_frame[self.donor_atoms].atom_positions)
-        closest_Os = np.argsort(distances_PO, axis=1)[:, :self.group_size]
-        self.map_O_to_P = {}
-        for P_index, Os in enumerate(closest_Os):
-            for O_index in Os:
-                self.map_O_to_P[int(O_index)] = P_index
-        self.n_extra = distances_PO.shape[0]
-        n_donor = distances_PO.shape[1]
-        self._group = np.full(n_donor, -1, dtype=np.int32)
-        for o, p in self.map_O_to_P.items():
-            self._group[o] = p
+        centres = first_frame[self.extra_atoms].atom_positions
+        donors = first_frame[self.donor_atoms].atom_positions
+        # one all-to-all distance matrix on the device, rows = extra atoms
+        nearest = np.argsort(self.atombox.length_all_to_all(centres, donors), axis=1)[:, :self.group_size]
+        self.n_extra = nearest.shape[0]
+        # donor -> extra atom; a donor claimed by several extra atoms goes to the LAST of them, as
+        # in the dict of the reference (later entries overwrite earlier ones) = the largest index
+        self._group = np.full(donors.shape[0], -1, dtype=np.int32)
+        np.maximum.at(self._group, nearest.ravel(),
+                      np.repeat(np.arange(self.n_extra, dtype=np.int32), nearest.shape[1]))
+        self.map_O_to_P = {int(o): int(p) for o, p in enumerate(self._group) if p >= 0}
 
     def _extra_positions(self, full_frame):
         return np.asarray(full_frame[self.extra_atoms].atom_positions, dtype=float)
@@ -560,10 +559,12 @@ class ReLUTransformation(DistanceTransformation):
 
     def __call__(self, distances):
         distances = np.asarray(distances, dtype=float)
-        rescaled = np.where(distances < self.d0, self.b, self.a * (distances - self.d0) + self.b)
-        mask = (distances <= self.left_bound) | (self.right_bound <= distances)
-        rescaled[mask] = distances[mask]
-        return rescaled
+        # same value per element as topology.py:288-292: inside (left_bound, right_bound) the
+        # constant b below d0 and the line a (d - d0) + b above it, the distance itself elsewhere
+        ramp = np.maximum(distances - self.d0, 0.0)
+        inside = (self.left_bound < distances) & (distances < self.right_bound)
+        return np.where(inside, np.where(ramp > 0.0, self.a * (distances - self.d0) + self.b, self.b),
+                        distances)
 
     def device_parameters(self):
         return 1, np.array([self.a, self.b, self.d0, self.left_bound, self.right_bound], float), None, None
@@ -594,12 +595,11 @@ class InterpolatedTransformation(DistanceTransformation):
         return slope * (d - self.x[lo]) + self.y[lo]
 
     def __call__(self, distances):
-        distances = np.asarray(distances, dtype=float)
-        inside = (self.x_min <= distances) & (distances <= self.x_max)
-        rescaled = np.copy(distances)
-        rescaled[inside] = self._interp(rescaled[inside])
-        rescaled[rescaled < self.x_min] = self.y_min
-        return rescaled
+        # per element the values of topology.py:328-334: the table inside [x_min, x_max], its first
+        # value below it, the distance itself above it
+        d = np.asarray(distances, dtype=float)
+        table = self._interp(np.clip(d, self.x_min, self.x_max))
+        return np.where(d < self.x_min, self.y_min, np.where(d <= self.x_max, table, d))
 
     def device_parameters(self):
         return 2, np.zeros(5), self.x, self.y
@@ -655,14 +655,18 @@ class HydroniumTopology(NeighborTopology):
                     frame_time_step=float(self.trajectory_time_step))
 
     def transform_distances(self, occupied_indices, distances, time):
-        occupied_indices = np.unique(occupied_indices)
-        proton_indices = self._lattice[occupied_indices]
-        last_jump_times = self._time_of_last_jump_vec[proton_indices - 1]
-        residence_times = np.where(last_jump_times >= 0, time - last_jump_times, np.inf)
+        """Host mirror of topology.py:213-229 (the device does this per replica inside the KMC
+        kernel): rescaled distances of the occupied sites, relaxed with the time the proton on
+        each has spent there (infinite for a proton that has not jumped yet)."""
         rescaled = self._distance_transformation_function(distances)
         if self._distance_interpolator is None:
             return rescaled
-        return self._distance_interpolator(residence_times, distances, rescaled)
+        sites = np.unique(occupied_indices)
+        since = self._time_of_last_jump_vec[self._lattice[sites] - 1]       # per proton label
+        residence = np.full(since.shape, np.inf)
+        jumped = since >= 0
+        residence[jumped] = time - since[jumped]
+        return self._distance_interpolator(residence, distances, rescaled)
 
     def _colvars_from_nearest(self, near_dest, near_dist, frame):
         """(start, dest, rescaled distance) of one frame from the device's nearest-neighbour arrays
