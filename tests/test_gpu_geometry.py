@@ -179,3 +179,33 @@ def test_empty_and_errors():
         cm.AtomBoxCubic([10.0, -1, 10])
     with pytest.raises(ValueError):
         box.length(np.zeros((2, 3)), np.zeros((3, 3)))
+
+
+def test_mean_square_displacement_host_mirror_like_the_reference_tests():
+    """tests/LMC/test_output.py:21-47 on the host mirror of mdlmc/LMC/output.py (its distances go
+    through AtomBox.distance, i.e. the CUDA kernels), plus the covalent autocorrelation (:6-14)."""
+    import cmdlmc_b200 as cm
+    from cmdlmc_b200.output import CovalentAutocorrelation, MeanSquareDisplacement
+    atom_positions = np.arange(1, 19).reshape(6, 3)
+    lattice = np.array([0, 3, 0, 0, 1, 2])
+    atombox = cm.AtomBoxCubic([10, 10, 10])
+    msd = MeanSquareDisplacement(atom_positions, lattice, atombox=atombox)
+    np.testing.assert_equal(msd.snapshot, np.array([[13, 14, 15], [16, 17, 18], [4, 5, 6]]))
+    auto = CovalentAutocorrelation(lattice)
+    assert auto.calculate(lattice) == 3
+    # protons 1 and 2 swap positions
+    lattice[-2], lattice[-1] = lattice[-1], lattice[-2]
+    msd.update_displacement(atom_positions, lattice)
+    displacement = np.zeros((3, 3), int)
+    displacement[0] = [3, 3, 3]
+    displacement[1] = [-3, -3, -3]
+    np.testing.assert_equal(msd.displacement, displacement)
+    assert auto.calculate(lattice) == 1
+    # proton 2 jumps to an empty site
+    lattice[-2], lattice[-3] = lattice[-3], lattice[-2]
+    msd.update_displacement(atom_positions, lattice)
+    displacement[1] += np.array([-3, -3, -3])
+    np.testing.assert_equal(msd.displacement, displacement)
+    np.testing.assert_allclose(msd.msd(), (displacement ** 2).sum(axis=0) / 3)
+    msd.reset_displacement()
+    assert (msd.displacement == 0).all()
