@@ -13,6 +13,12 @@
 //              upper-triangular cell matrix (R of h = QR), the squared length and the compare run
 //              as half2 SIMD: ~10 instructions per pair.  The radius is widened by a proven bound
 //              on quantisation + fp16 rounding (topo_filter_params).
+//              Skin list: consecutive frames of a trajectory (one contiguous run per persistent
+//              CTA) share their candidates.  The window filter runs with the radius widened by a
+//              skin and its survivors are kept per CTA (global memory, L2 resident); a later
+//              frame only re-filters that list, as long as the two largest atomic displacements
+//              since the list was built sum to less than the skin (triangle inequality of the
+//              periodic metric) -- otherwise the list is rebuilt on the spot.
 //              FILT_F32 / FILT_F32_IMG: 32-bit fixed point + FP32 (cells so skewed that periodic
 //              images matter, or so large that 10 bits are too coarse).
 //   2 exact    the surviving candidates (~1.1x the hits), densely packed over the CTA, in the
