@@ -38,6 +38,14 @@ def build(force=False, verbose=False, extra=()):
 
 
 if __name__ == "__main__":
+    # --check: a second library with index checks inside the kernels (-DCMD_BOUNDS_CHECK, csrc/common.cuh),
+    # for `CMDLMC_B200_LIB=cmdlmc_b200/libcmdlmc_b200_check.so python -m pytest tests -m gpu`
+    if "--check" in sys.argv:
+        out = os.path.join(HERE, "libcmdlmc_b200_check.so")
+        subprocess.run([os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + ["-DCMD_BOUNDS_CHECK"] + sources() +
+                       ["-o", out], check=True)
+        print(out)
+        sys.exit(0)
     build(force="--force" in sys.argv, verbose=True,
           extra=["-Xptxas", "-v"] if "--ptxas" in sys.argv else [])
     print(LIB)

@@ -99,6 +99,15 @@ inline bool cmd_sync_launches()
         if (cmd_sync_launches()) CMD_CUDA(cudaStreamSynchronize(cmd_global().stream));      \
     } while (0)
 
+// -DCMD_BOUNDS_CHECK: index checks inside the kernels that address shared memory and scratch lists
+// by computed positions (the pool's compute-sanitizer is closed: profiles/r2h_sanitizer_closed.txt);
+// a violated check traps, which the next API call reports as a CUDA error.
+#ifdef CMD_BOUNDS_CHECK
+#define CMD_CHECK(cond) do { if (!(cond)) { printf("CMD_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define CMD_CHECK(cond) do { } while (0)
+#endif
+
 // row pitch (ints) of the per-frame row index: n + 1 entries padded to 16 bytes (TMA bulk copies)
 __host__ __device__ inline int cmd_ro_pitch(int n) { return (n + 4) & ~3; }
 

@@ -317,6 +317,7 @@ k_cell_pairs(const __grid_constant__ BoxParams bx, const __grid_constant__ Filte
                     const int4 me = wbuf[a];
                     const bool ok = filter_pair<KIND, IMAGES>(fp, me, cand) & (a < alim);
                     const unsigned hb = __ballot_sync(full, ok);
+                    CMD_CHECK(np + 32 <= CELL_PLIST + 1 && (!ok || (me.w >= 0 && me.w < n && cand.w >= 0 && cand.w < n)));
                     if (ok) plist[np + __popc(hb & lt)] = make_int2(me.w, cand.w);
                     np += __popc(hb);
                     if (np >= 64) {

@@ -523,6 +523,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
                 ha &= ha - 1;
                 int c = c0 + 2 * (b & 15) + (b >> 4);
                 if (c >= n) c -= n;
+                CMD_CHECK(c >= 0 && c < n && t < n);
                 const unsigned e = my_tag | (unsigned)s.perm[c];
                 if (direct) { if (pos < hit_cap) s.hit_ij[pos] = e; }
                 else if (pos < cap_l) lists[(size_t)blockIdx.x * cap_l + pos] = e;
@@ -583,6 +584,8 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
 #pragma unroll
                     for (int u = 0; u < LIST_U; u++) {
                         const int ka = k0 + 2 * u * T + tid, kb = ka + T;
+                        CMD_CHECK((int)(ija[u] >> 16) < n && (int)(ija[u] & 0xffffu) < n &&
+                                  (int)(ijb[u] >> 16) < n && (int)(ijb[u] & 0xffffu) < n);
                         const uint2 Ca = qc2[ija[u] >> 16], Pa = qa2[ija[u] & 0xffffu];
                         const uint2 Cb = qc2[ijb[u] >> 16], Pb = qa2[ijb[u] & 0xffffu];
                         const uint4 P = make_uint4(__byte_perm(Pa.x, Pb.x, 0x5410), __byte_perm(Pa.x, Pb.x, 0x7632),
@@ -718,6 +721,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const int a = ij[q] >> 16, b = ij[q] & 0xffff;
+                CMD_CHECK(a < n && b < n && a != b);
                 const double pa[3] = {s.c[3 * a], s.c[3 * a + 1], s.c[3 * a + 2]};
                 const double pb[3] = {s.c[3 * b], s.c[3 * b + 1], s.c[3 * b + 2]};
                 double d[3];
@@ -809,6 +813,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
                 }
                 pa += __popc(s.mask[a * W + (b >> 5)] & ((1u << (b & 31)) - 1u));
                 pb += __popc(s.mask[b * W + (a >> 5)] & ((1u << (a & 31)) - 1u));
+                CMD_CHECK(pa >= 0 && pa < total && pb >= 0 && pb < total && pa != pb && total <= 2 * hit_cap);
                 s.slot[pa] = (unsigned short)h;
                 s.slot[pb] = (unsigned short)(h | 0x8000);
             }
@@ -825,6 +830,7 @@ k_pairs_dense(const __grid_constant__ BoxParams bx, const __grid_constant__ Rate
         // (start, dest) of the directed pair behind slot entry e
         auto pair_of = [&](unsigned e, int &st, int &de) -> int {
             const int h = (int)(e & 0x7fffu);
+            CMD_CHECK(h < ncand && h < hit_cap);
             unsigned ij = s.hit_ij[h];
             if (e & 0x8000u) ij = __funnelshift_l(ij, ij, 16);
             st = (int)(ij >> 16);
