@@ -187,6 +187,8 @@ struct WarpCtx {
     double *psum;
     const int *ro;
     double lane_total;
+    double scan_inc;     // inclusive scan of the lane totals of the frame at element offset scan_base
+    int64_t scan_base;
     int nst;
     double *tlast;       // hydronium: [n_sites] last jump time per proton label - 1 (shared memory)
     double t_frame;      // hydronium: frame.time of the frame being consumed
@@ -696,14 +698,21 @@ __device__ bool kmc_move_fast(const KmcArgs &a, WarpCtx &c, double u, int r, lon
                               int *o_start, int *o_dest, int *o_proton, int *o_index,
                               unsigned long long *ties)
 {
-    // lane totals -> inclusive scan over lanes; the last value is the total the draw refers to
+    // lane totals -> inclusive scan over lanes; the last value is the total the draw refers to.
+    // The totals belong to the frame, not to the event: the scan is kept for the frame's further
+    // events (same values, same bits).
     const double lt = c.lane_total;   // == sum over the frame's stages of psum[s][lane], same order
-    double inc = lt;
+    if (c.scan_base != c.base) {
+        double v = lt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (c.lane >= o) inc += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, v, o);
+            if (c.lane >= o) v += t;
+        }
+        c.scan_inc = v;
+        c.scan_base = c.base;
     }
+    const double inc = c.scan_inc;
     const double total = __shfl_sync(0xffffffffu, inc, 31);
     const unsigned have = __ballot_sync(0xffffffffu, lt > 0.0);
     if (!have || !(total > 0.0)) return false;   // nothing was allowed: IndexError upstream
@@ -1708,6 +1717,7 @@ __global__ void __maxnreg__(112) k_kmc_stream(const __grid_constant__ BoxParams 
     c.lat = (int *)((unsigned char *)c.mask0 + mask_bytes);
     c.occ = (unsigned *)(c.lat + a.n_sites);
     c.base = 0; c.p = 0; c.m = 0; c.nst = 0; c.lane_total = 0.0; c.ro = nullptr;
+    c.scan_base = -1; c.scan_inc = 0.0;
     c.comp = c.cum = c.lsum = nullptr;
     c.cidx = c.loff = c.ln = nullptr;
     KmcState st;
